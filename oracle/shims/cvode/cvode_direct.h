@@ -1,0 +1,2 @@
+/* TEST INFRASTRUCTURE ONLY (oracle build shim): see sundials/sundials_types.h */
+#include "sundials/sundials_types.h"
