@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the PION hot path on B200.
+
+Metric (BASELINE.json): 3-D ideal-MHD (HLLD + GLM, FKJ98 eta=0.15, second order)
+cell-updates/s.  One step = calculate_timestep + advance_time on the resident grid
+(predictor, ghost fill, corrector, ghost fill, CFL reduction), exactly the quantity
+the reference prints (source/sim_control/sim_control.cpp:270-277).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl ours|reference]
+
+N=1 workload: "DTE3D_MHD-style" 512^3: cube +-3.086e19 cm,
+outflow on all faces, gamma 5/3, CFL 0.2, rho 2.338e-22, p 1.518e-12, B_x = 14.2e-6
+/ sqrt(4 pi), central sphere r = L/4 with 200x pressure.  N>1 (launched by torchrun, one
+rank per GPU): weak scaling, 512^3 per GPU, block-decomposed exactly like
+MCMDcontrol::decomposeDomain, halos by NCCL send/recv, dt by NCCL all-reduce.
+
+Prints ONE JSON line on rank 0.  --impl reference times the reference's own CPU
+implementation (oracle/_ref when built, else the plain-C oracle port) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+NVAR = 9
+ALG_BYTES_PER_CELL_UPDATE = 5 * NVAR * 8  # predictor R+W, corrector 2R+W, FP64
+METRIC = "3D MHD cell-updates/s per step at 1/2/4/8 B200; % of HBM roofline; vs CPU"
+UNIT = "cell-updates/s"
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text())["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dte_problem(NG, xmin, xmax, bcs=("outflow",) * 6):
+    from harness import Problem
+    return Problem(ndim=3, NG=tuple(NG), eqn="glm-mhd", solver=7, artviscosity=1, etav=0.15, gamma=5.0 / 3.0, cfl=0.2,
+                   xmin=tuple(xmin), xmax=tuple(xmax), bcs=tuple(bcs), ooa=2, finishtime=1.0e30,
+                   refvec=(2.338e-22, 1.518e-12, 1.0e6, 1.0e6, 1.0e6, 4.0e-6, 4.0e-6, 4.0e-6, 4.0e-6) + (1.0,) * 7)
+
+
+def dte_state(prob, gxmin, gxmax, out=None):
+    """Synthetic DTE3D_MHD-style initial state on the padded local grid (float64 SoA)."""
+    shp = prob.padded_shape()
+    P = out if out is not None else np.empty(shp)
+    g = prob.nbc
+    dx = prob.dx
+    ax = [prob.xmin[a] + (np.arange(shp[3 - a]) - g + 0.5) * dx for a in range(3)]
+    L = gxmax[0] - gxmin[0]
+    c = [0.5 * (gxmin[a] + gxmax[a]) for a in range(3)]
+    r2z = (ax[2] - c[2]) ** 2
+    r2y = (ax[1] - c[1]) ** 2
+    r2x = (ax[0] - c[0]) ** 2
+    P[0] = 2.338e-22
+    P[2:5] = 0.0
+    P[5] = 14.2e-6 / math.sqrt(4.0 * math.pi)
+    P[6:9] = 0.0
+    R2 = (0.25 * L) ** 2
+    for k in range(shp[1]):
+        r2 = r2z[k] + r2y[:, None] + r2x[None, :]
+        P[1, k] = np.where(r2 < R2, 200.0 * 1.518e-12, 1.518e-12)
+    return P
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler for the timed region."""
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            for ts, ln in self.lines[-3:]:
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_sample(size, steps, kind):
+    """Run `steps` steps of the same problem family at size^3 on ONE host core; returns
+    cell-updates/s.  kind: 'reference' (oracle/_ref) or 'port' (plain-C oracle)."""
+    from harness import OracleSim, RefSim
+    L = 3.086e19
+    prob = dte_problem((size,) * 3, (-L,) * 3, (L,) * 3)
+    sim = RefSim(prob) if kind == "reference" else OracleSim(prob)
+    sim.set_state(dte_state(prob, (-L,) * 3, (L,) * 3))
+    sim.init_after_state()
+    sim.run(1)  # warm
+    t0 = time.perf_counter()
+    sim.run(steps)
+    dt = time.perf_counter() - t0
+    sim.close()
+    return steps * size ** 3 / dt
+
+
+def _cpu_worker(args):
+    size, steps, kind = args
+    return cpu_sample(size, steps, kind)
+
+
+def cpu_kind():
+    from harness import have_ref
+    return "reference" if have_ref() else "port"
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the same step on all host
+    cores (independent single-threaded instances = what its MPI build would do at best)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    size = 48
+    steps = max(1, args.steps)
+    warm = max(0, args.warmup)
+    t_all0 = time.perf_counter()
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        if warm:
+            pool.map(_cpu_worker, [(size, 1, kind)] * cores)
+        t0 = time.perf_counter()
+        rates = pool.map(_cpu_worker, [(size, steps, kind)] * cores)
+        wall = time.perf_counter() - t0
+    value = float(sum(rates))
+    L = 3.086e19
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"DTE3D_MHD-style 3-D GLM-MHD HLLD+FKJ98 2nd order, bounded CPU sample: {cores} x {size}^3 blocks",
+                   "solver": "HLLD", "eqn": "glm-mhd"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{cores} independent single-thread instances x {size}^3 cells x {steps} steps "
+                                   f"({'unmodified reference TUs, oracle/_ref' if kind == 'reference' else 'plain-C oracle port'})"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t_all0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=512, help="cells per axis PER GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    from harness import gpu_config
+    from pion_b200.capi import Context, load_library
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lib = load_library()
+    S = args.size
+    L = 3.086e19
+    # global grid: weak scaling, S^3 per GPU, decomposed like MCMDcontrol::decomposeDomain
+    nsplit = [1, 1, 1]
+    n = 1
+    a = 0
+    while n < world:
+        nsplit[a % 3] *= 2
+        n *= 2
+        a += 1
+    gNG = [S * nsplit[q] for q in range(3)]
+    gxmin = [-L * nsplit[q] for q in range(3)]
+    gxmax = [L * nsplit[q] for q in range(3)]
+    gprob = dte_problem(gNG, gxmin, gxmax)
+    cfg, keep = gpu_config(gprob, device=local_rank)
+    if world > 1:
+        err = lib.pion_gpu_decompose_domain(cfg, rank, world)
+        assert err == 0, lib.pion_gpu_last_error()
+    lprob = dte_problem([cfg.NG[q] for q in range(3)], [cfg.xmin[q] for q in range(3)], [cfg.xmax[q] for q in range(3)])
+    assert list(lprob.NG) == [S, S, S], lprob.NG
+
+    ctx = Context(cfg, keep)
+    if world > 1:
+        import ctypes as C
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            assert lib.pion_gpu_nccl_unique_id(idbuf) == 0
+        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        ctx.nccl_init(bytes(t.cpu().numpy().tobytes()))
+
+    # initial state in pinned host memory (also the e2e staging buffer)
+    shp = lprob.padded_shape()
+    host = torch.empty(shp, dtype=torch.float64, pin_memory=True)
+    dte_state(lprob, gxmin, gxmax, out=host.numpy())
+    ctx.upload_ptr(host.data_ptr(), 0)
+    ctx.init_after_upload()
+
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    ncell_local = S ** 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        ctx.calculate_timestep()
+        ctx.advance_time()
+
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    ctx.stage_timing(True)
+    l0 = ctx.counters()[2]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    ctx.sync()
+    barrier()
+    tw1 = time.time()
+    ms = e0.elapsed_time(e1)
+    stage_ms, stage_n = ctx.stage_timing(False)
+    launches = ctx.counters()[2] - l0
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    ms_per_step = ms / args.steps
+    value = ncell_local * world * args.steps / (ms * 1e-3)
+
+    # end-to-end through the C ABI with HOST buffers: every step uploads the state from
+    # pinned host memory, advances it, and reads the new state back.
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(2, min(3, args.steps))
+        nbytes = host.numel() * 8
+        barrier()
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            ctx.upload_ptr(host.data_ptr(), 0)
+            step()
+            ctx.download_ptr(host.data_ptr(), 0)
+        e1.record(stream)
+        ctx.sync()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            tmax = torch.tensor([ems], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ems = float(tmax.item())
+        e2e = {"value": ncell_local * world * e2e_steps / (ems * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes), "steps": e2e_steps}
+
+    neg = ctx.counters()[:2]
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        per_launch_bytes = ALG_BYTES_PER_CELL_UPDATE * ncell_local / 2.0  # two stage launches per step
+        stage_avg_ms = stage_ms / max(1, stage_n)
+        achieved = per_launch_bytes / (stage_avg_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"DTE3D_MHD-style 3-D GLM-MHD {S}^3 per GPU, HLLD + GLM + FKJ98(0.15), 2nd order, CFL 0.2, outflow BCs",
+                       "global_grid": gNG, "decomposition": nsplit, "l2_policy": "working set (>20 GB per GPU) far exceeds the 126 MB L2",
+                       "step": "calculate_timestep + advance_time (predictor, BCs, corrector, BCs, CFL reduction)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k_stage<GLM,HLLD,FKJ>",
+                         "alg_bytes_per_cell_update": ALG_BYTES_PER_CELL_UPDATE, "launches_timed": stage_n,
+                         "avg_launch_ms": stage_avg_ms, "stage_share_of_step": stage_ms / ms},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "state_errors": {"negative_density": int(neg[0]), "negative_pressure_fixups": int(neg[1])},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            kind = cpu_kind()
+            t0 = time.perf_counter()
+            csize, csteps = 64, 8
+            v = cpu_sample(csize, csteps, kind)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": f"{csize}^3 cells x {csteps} steps of the same problem on one host core, "
+                                              f"{time.perf_counter() - t0:.1f} s"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

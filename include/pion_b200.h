@@ -1,0 +1,158 @@
+/* pion_b200.h -- C ABI of libpion_b200.so, the B200 (sm_100a) implementation of
+ * PION's finite-volume hydro/MHD dynamics update.
+ *
+ * PION has no FFI: its extension seam is C++ virtual inheritance (SURVEY.md
+ * 8b).  A GPU cannot sit behind the per-cell virtuals of FV_solver_base, so the
+ * drop-in boundary is the GRID-LEVEL seam -- the methods of time_integrator /
+ * calc_timestep / assign_update_bcs that sim_control calls once per step and
+ * that sim_control_pllel / sim_control_NG already override in the reference.
+ * Each entry point below names the reference method it replaces (paths relative
+ * to /root/reference/source).  INTEGRATION.md shows the `sim_control_gpu`
+ * subclass a PION maintainer adds to bind them.
+ *
+ * Conventions kept from the reference: every call returns an int error count,
+ * 0 = success (the caller turns non-zero into rep.error(...), tools/reporting.h
+ * :63-85); FP64 throughout (#define pion_flt double, defines/
+ * functionality_flags.h:31); primitive order {RO,PG,VX,VY,VZ,BX,BY,BZ,SI,
+ * tracers...} and conserved order {RHO,ERG,MMX,MMY,MMZ,BBX,BBY,BBZ,PSI,...}
+ * (constants.h:256-281); B in code units (NEW_B_NORM).  One host thread per
+ * context; the library owns all device memory behind the opaque handle.
+ *
+ * Host <-> device state exchange is structure-of-arrays: double
+ * [nvar][NZ+2g][NY+2g][NX+2g], x fastest, ghost depth g = 2 (second order) or 1,
+ * unused dimensions have extent 1.  That is exactly the reference's cell-id
+ * order (grid/uniform_grid.cpp:449-451) transposed to variable-major.
+ */
+#ifndef PION_B200_H
+#define PION_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PION_GPU_MAXVAR 16
+#define PION_GPU_MAXTR 4
+
+/* integer codes are the reference's (constants.h:166-246, boundaries/boundaries.h:32-52) */
+enum { PION_EQEUL = 1, PION_EQMHD = 2, PION_EQGLM = 3 };
+enum { PION_COORD_CRT = 1, PION_COORD_CYL = 2, PION_COORD_SPH = 3 };
+enum { PION_FLUX_ROE = 4, PION_FLUX_HLLD = 7, PION_FLUX_HLL = 8 };
+enum { PION_AV_NONE = 0, PION_AV_FKJ98 = 1, PION_AV_HCORR = 3, PION_AV_HCORR_FKJ98 = 4 };
+enum {
+  PION_BC_PERIODIC = 1, PION_BC_OUTFLOW = 2, PION_BC_INFLOW = 3, PION_BC_REFLECTING = 4, PION_BC_FIXED = 5,
+  PION_BC_DMACH = 8, PION_BC_DMACH2 = 9, PION_BC_MPI = 10, PION_BC_ONEWAY_OUT = 13, PION_BC_STWIND = 14
+};
+enum { PION_STATE_P = 0, PION_STATE_PH = 1, PION_STATE_DU = 2 };
+
+/* Mirrors the subset of class SimParams (sim_params.h:200-285) the path reads. */
+typedef struct pion_gpu_config {
+  int device;          /* CUDA device ordinal */
+  int ndim;            /* SimPM.ndim */
+  int NG[3];           /* LOCAL interior cells per axis (SimPM.NG / MCMD LocalNG) */
+  int nvar, ntracer;   /* SimPM.nvar, SimPM.ntracer (tracers are the last ntracer variables) */
+  int eqntype;         /* SimPM.eqntype */
+  int coord_sys;       /* SimPM.coord_sys (only PION_COORD_CRT in this round) */
+  int solver;          /* SimPM.solverType: 4 Roe-CV, 7 HLLD, 8 HLL */
+  int artviscosity;    /* SimPM.artviscosity: 0,1,3,4 */
+  int spOOA, tmOOA;    /* SimPM.spOOA / tmOOA: (1,1) or (2,2) */
+  double gamma, cfl, etav;
+  double xmin[3], xmax[3];   /* LOCAL domain; dx = (xmax[0]-xmin[0])/NG[0] */
+  double sim_xmin[3];        /* GLOBAL SimPM.Xmin (cell positions for DMR boundaries) */
+  int bc[6];           /* per LOCAL face XN,XP,YN,YP,ZN,ZP; PION_BC_MPI for a face shared with a neighbour rank */
+  int n_internal_bc;
+  int internal_bc[4];
+  double refvec[PION_GPU_MAXVAR]; /* SimPM.RefVec */
+  double starttime, finishtime;
+  int op_criterion;    /* SimPM.op_criterion, 1: dt limited by next_optime */
+  double opfreq_time;
+  /* microphysics: mp_only_cooling (EP.cooling && !EP.chemistry) */
+  int cooling;         /* EP.cooling (0 none, 8 = WSS09_CIE_LINE_HEAT_COOL) */
+  int mp_timestep_limit;
+  double min_temperature, max_temperature;
+  int n_table;
+  const double *table_T, *table_rrhp, *table_C_rrh, *table_C_ffhe, *table_C_fbdn, *table_C_cie;
+  /* decomposition (decomposition/MCMD_control.cpp:62-221) */
+  int rank, nproc;
+  int ngbprocs[6];     /* neighbour rank per face, -1 = none (MCMDcontrol::ngbprocs) */
+} pion_gpu_config;
+
+typedef struct pion_gpu_ctx pion_gpu_ctx;
+
+/* setup_fixed_grid::setup_grid + set_equations + setup_microphysics
+ * (grid/setup_fixed_grid.cpp:160-246,254-470,1067-1190): allocates the device
+ * SoA grid.  Returns NULL on failure (reason via pion_gpu_last_error). */
+pion_gpu_ctx *pion_gpu_create(const pion_gpu_config *cfg);
+void pion_gpu_destroy(pion_gpu_ctx *ctx);
+const char *pion_gpu_last_error(void);
+
+/* host -> device / device -> host copies of P, Ph or dU (dataio->ReadData /
+ * OutputData side of the seam, sim_init.cpp:213, :671-760) */
+int pion_gpu_upload(pion_gpu_ctx *ctx, int which, const double *soa);
+int pion_gpu_download(pion_gpu_ctx *ctx, int which, double *soa);
+
+/* sim_init::Init after ReadData (sim_init.cpp:215-262): Ph=P, psi=0 for GLM at
+ * step 0, assign_boundary_data (boundaries/assign_update_bcs.cpp:28-120) and
+ * the first TimeUpdateInternal/ExternalBCs. */
+int pion_gpu_init_after_upload(pion_gpu_ctx *ctx);
+
+/* calc_timestep::calc_dynamics_dt / calc_microphysics_dt
+ * (sim_control/calc_timestep.cpp:271-333, :342-463).  LOCAL minima. */
+int pion_gpu_calc_dt(pion_gpu_ctx *ctx, double *t_dyn, double *t_mp);
+/* calc_timestep::calculate_timestep (calc_timestep.cpp:68-153) incl.
+ * Set_GLM_Speeds and timestep_checking_and_limiting (:219-262); with nproc>1
+ * the minima are reduced over ranks (sim_control_MPI.cpp:503-504). */
+int pion_gpu_calculate_timestep(pion_gpu_ctx *ctx, double *dt);
+/* FV_solver_base::Setdt + Set_GLM_Speeds(spatial_solvers/solver_eqn_mhd_adi.cpp:906) */
+int pion_gpu_set_dt(pion_gpu_ctx *ctx, double dt);
+int pion_gpu_set_glm_speeds(pion_gpu_ctx *ctx, double t_dyn, double dx, double cr);
+int pion_gpu_set_time(pion_gpu_ctx *ctx, double simtime, double last_dt, int timestep);
+int pion_gpu_get_time(pion_gpu_ctx *ctx, double *simtime, double *dt, double *last_dt, int *timestep);
+
+/* time_integrator::calc_microphysics_dU (time_integrator.cpp:253, :438) */
+int pion_gpu_calc_microphysics_dU(pion_gpu_ctx *ctx, double dt);
+/* time_integrator::calc_dynamics_dU (time_integrator.cpp:498): preprocess_data +
+ * set_dynamics_dU; accumulates into the device dU array. `step` is OA1 / OA2. */
+int pion_gpu_calc_dynamics_dU(pion_gpu_ctx *ctx, double dt, int step);
+/* time_integrator::grid_update_state_vector (time_integrator.cpp:881) */
+int pion_gpu_grid_update_state_vector(pion_gpu_ctx *ctx, double dt, int step, int ooa);
+/* assign_update_bcs::TimeUpdateInternalBCs + TimeUpdateExternalBCs
+ * (boundaries/assign_update_bcs.cpp:134-246); with nproc>1 the BCMPI faces are
+ * NCCL halo exchanges (boundaries/MCMD_boundaries.cpp:57-236). */
+int pion_gpu_time_update_bcs(pion_gpu_ctx *ctx, double simtime, int cstep, int maxstep);
+/* time_integrator::advance_time (time_integrator.cpp:72-142): the fused fast
+ * path (predictor, BCs, corrector, BCs, next-step CFL reduction); returns dt. */
+int pion_gpu_advance_time(pion_gpu_ctx *ctx, double *dt_done);
+/* nsteps x { calculate_timestep; advance_time } = body of sim_control::Time_Int
+ * (sim_control.cpp:220-266); dts[nsteps] (optional) receives each dt. */
+int pion_gpu_run(pion_gpu_ctx *ctx, int nsteps, double *dts);
+
+/* error / diagnostic counters accumulated on the device:
+ * [0] negative-density events (fatal in the reference), [1] negative-pressure
+ * fix-ups, [2] kernels launched so far */
+int pion_gpu_counters(pion_gpu_ctx *ctx, long long *out3);
+/* block until all queued device work of this context has finished */
+int pion_gpu_sync(pion_gpu_ctx *ctx);
+/* stream the context launches on (cudaStream_t as void*), for CUDA-event timing */
+void *pion_gpu_stream(pion_gpu_ctx *ctx);
+
+/* bench support: with enable!=0 every later stage-kernel launch is bracketed by CUDA
+ * events on the context's stream; the call returns the summed duration and count of
+ * the launches recorded since the previous call and resets the record. */
+int pion_gpu_stage_timing(pion_gpu_ctx *ctx, int enable, double *total_ms, long long *nlaunch);
+
+/* multi-GPU: NCCL communicator for the BCMPI faces and the dt all-reduce
+ * (replaces comms/comm_mpi.cpp).  `unique_id` is the 128-byte ncclUniqueId
+ * produced by pion_gpu_nccl_unique_id on rank 0 and broadcast by the host. */
+int pion_gpu_nccl_unique_id(char *out128);
+int pion_gpu_nccl_init(pion_gpu_ctx *ctx, const char *unique_id128);
+
+/* decomposition helper = MCMDcontrol::decomposeDomain + pointToNeighbours
+ * (decomposition/MCMD_control.cpp:62-221, :316-420): fills local NG, xmin, xmax,
+ * bc[] (PION_BC_MPI on shared faces) and ngbprocs[] of `cfg` for `rank` of
+ * `nproc` from the GLOBAL values already in cfg. */
+int pion_gpu_decompose_domain(pion_gpu_config *cfg, int rank, int nproc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,731 @@
+// pion_b200/csrc/physics.cuh -- per-interface / per-cell device math of the
+// finite-volume dynamics update, FP64, written in the *solver frame*:
+// (n, t1, t2) = (sweep axis, next axis, next-next axis) in cyclic order, which
+// is exactly the permutation eqns_base::SetDirection establishes in the
+// reference (source/equations/eqns_base.cpp:94-131).  The kernels permute at
+// load / accumulate time, so nothing in here indexes a state vector
+// dynamically (everything stays in registers).
+//
+// Reference semantics restated here (paths relative to /root/reference/source):
+//   equations/eqns_hydro_adiabatic.cpp:89-350   PtoU, UtoP(+floors), PUtoFlux, UtoFlux, chydro
+//   equations/eqns_mhd_adiabatic.cpp:79-337,581-660  PtoU, UtoP, check_pressure, cfast, PUtoFlux, GLM
+//   Riemann_solvers/HLL_hydro.cpp:92-170         Euler HLL
+//   Riemann_solvers/HLLD_MHD.cpp:124-417         MHD HLLD / HLL / signal speeds
+//   Riemann_solvers/Roe_Hydro_ConservedVar_solver.cpp:129-436   Euler Roe (conserved variables)
+//   Riemann_solvers/Roe_MHD_ConservedVar_solver.cpp:218-810,1074-1131  MHD Roe (Cargo & Gallice)
+//   spatial_solvers/solver_eqn_hydro_adi.cpp:94-205,283-333      Euler inviscid_flux, AVFalle
+//   spatial_solvers/solver_eqn_mhd_adi.cpp:102-288,662-772       MHD / GLM inviscid_flux, AVFalle
+//   coord_sys/VectorOps.cpp:40-59                minmod ("AvgFalle")
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace pion {
+
+enum : int { EQ_EULER = 1, EQ_MHD = 2, EQ_GLM = 3 };                 // constants.h:166-172
+enum : int { SOLVE_ROE = 4, SOLVE_HLLD = 7, SOLVE_HLL = 8 };         // constants.h:238-246
+enum : int { AV_NONE = 0, AV_FKJ98 = 1, AV_HCORR = 3, AV_HCORR_FKJ98 = 4 };
+
+#define PION_MACHINEACCURACY 5.e-16    // constants.h:151
+#define PION_TINYVALUE 1.0e-100        // constants.h:152
+#define PION_SMALLVALUE 1.0e-12        // constants.h:150
+#define PION_VERY_TINY_VALUE 1.0e-200  // constants.h:153
+#define PION_BASE_RHO 1.0e-5           // constants.h:339
+
+// Primitive state in the solver frame.
+struct Prim {
+  double ro, pg, vn, vt1, vt2, bn, bt1, bt2, psi;
+};
+// Conserved state / flux in the solver frame.
+struct Cons {
+  double rho, erg, mn, mt1, mt2, bbn, bbt1, bbt2, psi;
+};
+
+// Per-launch physics constants (kernel argument, lives in constant bank).
+struct PhysParams {
+  double gamma;
+  double etav;         // FKJ98 viscosity coefficient (FV_etav == FV_etaB)
+  double chyp;         // GLM hyperbolic speed c_h
+  double refvec_ro;    // RefVec[RO] for the (fatal) negative-density reset
+  double min_temp;     // EP.MinTemperature
+  double max_temp;     // EP.MaxTemperature
+  double mu_tot_over_kB;  // mp_only_cooling::Mu_tot_over_kB (0 if no microphysics)
+  int have_mp;
+};
+
+__device__ __forceinline__ double sq(double x) { return x * x; }
+
+// ---------------------------------------------------------------------------
+// minmod: BaseVectorOps::AvgFalle, AVG_MINMOD variant (VectorOps.cpp:40-59).
+// The reference computes r=a/b; min(r,1)*b.  For 0<r<1 that is (a/b)*b which
+// equals `a` to within one rounding; we return `a` directly and save the FP64
+// division (documented deviation, <= 1 ulp of the slope).  PION_STRICT keeps
+// the reference's exact expression.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double minmod(double a, double b, double tiny) {
+  double ab = a * b;
+#ifdef PION_STRICT
+  if (ab <= tiny) return 0.0;
+  double r = a / b;
+  return (r > 0.0) ? fmin(r, 1.0) * b : 0.0;
+#else
+  // a*b > tiny  =>  same sign, both non-zero
+  double m = (fabs(a) < fabs(b)) ? a : b;
+  return (ab <= tiny) ? 0.0 : m;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// Equations of state / conversions
+// ---------------------------------------------------------------------------
+template <int EQ>
+__device__ __forceinline__ void PtoU(const Prim& p, Cons& u, double gm1) {
+  u.rho = p.ro;
+  u.mn = p.ro * p.vn;
+  u.mt1 = p.ro * p.vt1;
+  u.mt2 = p.ro * p.vt2;
+  if (EQ == EQ_EULER) {
+    u.erg = p.ro * (p.vn * p.vn + p.vt1 * p.vt1 + p.vt2 * p.vt2) * 0.5 + p.pg / gm1;
+    u.bbn = u.bbt1 = u.bbt2 = u.psi = 0.0;
+  } else {
+    u.bbn = p.bn;
+    u.bbt1 = p.bt1;
+    u.bbt2 = p.bt2;
+    u.erg = (p.ro * (p.vn * p.vn + p.vt1 * p.vt1 + p.vt2 * p.vt2) * 0.5) + (p.pg / gm1) +
+            ((u.bbn * u.bbn + u.bbt1 * u.bbt1 + u.bbt2 * u.bbt2) * 0.5);
+    if (EQ == EQ_GLM) {
+      u.psi = p.psi;
+      u.erg += 0.5 * u.psi * u.psi;
+    } else {
+      u.psi = 0.0;
+    }
+  }
+}
+// ideal-MHD PtoU without the psi energy (what the Riemann solvers call:
+// eqns_mhd_ideal::PtoU, HLLD_MHD.cpp:139-140)
+__device__ __forceinline__ void PtoU_mhd_ideal(const Prim& p, Cons& u, double gm1) {
+  PtoU<EQ_MHD>(p, u, gm1);
+}
+
+// status bits returned by UtoP
+enum : int { ST_NEG_RHO = 1, ST_NEG_PG = 2 };
+
+// UtoP with the reference's floors (SET_NEGATIVE_PRESSURE_TO_FIXED_TEMPERATURE):
+// Euler eqns_hydro_adiabatic.cpp:117-205, MHD eqns_mhd_adiabatic.cpp:110-224,
+// GLM :618-641.
+template <int EQ>
+__device__ __forceinline__ int UtoP(const Cons& u, Prim& p, const PhysParams& pp) {
+  int st = 0;
+  const double gm1 = pp.gamma - 1.0;
+  p.ro = u.rho;
+#ifdef PION_STRICT
+  p.vn = u.mn / u.rho;
+  p.vt1 = u.mt1 / u.rho;
+  p.vt2 = u.mt2 / u.rho;
+#else
+  const double ir = 1.0 / u.rho;
+  p.vn = u.mn * ir;
+  p.vt1 = u.mt1 * ir;
+  p.vt2 = u.mt2 * ir;
+#endif
+  double ke = p.ro * (p.vn * p.vn + p.vt1 * p.vt1 + p.vt2 * p.vt2);
+  if (EQ == EQ_EULER) {
+    p.pg = gm1 * (u.erg - ke / 2.0);
+    p.bn = p.bt1 = p.bt2 = p.psi = 0.0;
+  } else {
+    double b2 = (u.bbn * u.bbn + u.bbt1 * u.bbt1 + u.bbt2 * u.bbt2);
+    if (EQ == EQ_GLM) {
+      p.psi = u.psi;
+      p.pg = gm1 * (u.erg - ke * 0.5 - 0.5 * u.psi * u.psi - b2 * 0.5);
+    } else {
+      p.psi = 0.0;
+      p.pg = gm1 * (u.erg - ke / 2. - b2 / 2.);
+    }
+    p.bn = u.bbn;
+    p.bt1 = u.bbt1;
+    p.bt2 = u.bbt2;
+  }
+  if (p.ro <= 0.0) {
+    // fatal in the reference (rep.error); we flag it and apply the code that
+    // follows the rep.error call so that the kernel stays finite.
+    st |= ST_NEG_RHO;
+    if (EQ == EQ_EULER) {
+      p.ro = PION_BASE_RHO;
+      p.vn = u.mn / p.ro;
+      p.vt1 = u.mt1 / p.ro;
+      p.vt2 = u.mt2 / p.ro;
+      p.pg = gm1 * (u.erg - p.ro * (p.vn * p.vn + p.vt1 * p.vt1 + p.vt2 * p.vt2) / 2.0);
+    } else {
+      p.ro = PION_BASE_RHO * pp.refvec_ro;
+      double f = u.rho / p.ro;
+      p.vn *= f;
+      p.vt1 *= f;
+      p.vt2 *= f;
+      p.pg = gm1 * (u.erg - p.ro * (p.vn * p.vn + p.vt1 * p.vt1 + p.vt2 * p.vt2) / 2. -
+                    (u.bbn * u.bbn + u.bbt1 * u.bbt1 + u.bbt2 * u.bbt2) / 2.);
+    }
+  }
+  if (p.pg <= 0.0) {
+    st |= ST_NEG_PG;
+    if (pp.have_mp) p.pg = p.ro * pp.min_temp / pp.mu_tot_over_kB;  // MP->Set_Temp(p,MinTemp)
+    else p.pg = 0.01 * p.ro;
+  } else if (pp.have_mp && (p.pg * pp.mu_tot_over_kB / p.ro < pp.min_temp)) {
+    p.pg = p.ro * pp.min_temp / pp.mu_tot_over_kB;
+  }
+  return st;
+}
+
+// eqns_Euler::PUtoFlux (eqns_hydro_adiabatic.cpp:296-308) /
+// eqns_mhd_ideal::PUtoFlux (eqns_mhd_adiabatic.cpp:307-328)
+template <int EQ>
+__device__ __forceinline__ void PUtoFlux(const Prim& p, const Cons& u, Cons& f) {
+  f.rho = u.mn;
+  if (EQ == EQ_EULER) {
+    f.mn = u.mn * p.vn + p.pg;
+    f.mt1 = u.mn * p.vt1;
+    f.mt2 = u.mn * p.vt2;
+    f.erg = p.vn * (u.erg + p.pg);
+    f.bbn = f.bbt1 = f.bbt2 = f.psi = 0.0;
+  } else {
+    double pm = (u.bbn * u.bbn + u.bbt1 * u.bbt1 + u.bbt2 * u.bbt2) / 2.;
+    f.mn = u.mn * p.vn + p.pg + pm - u.bbn * u.bbn;
+    f.mt1 = u.mn * p.vt1 - u.bbn * u.bbt1;
+    f.mt2 = u.mn * p.vt2 - u.bbn * u.bbt2;
+    f.erg = p.vn * (u.erg + p.pg + pm) - u.bbn * (p.vn * u.bbn + p.vt1 * u.bbt1 + p.vt2 * u.bbt2);
+    f.bbn = 0.;
+    f.bbt1 = p.vn * p.bt1 - p.vt1 * p.bn;
+    f.bbt2 = p.vn * p.bt2 - p.vt2 * p.bn;
+    f.psi = 0.0;
+  }
+}
+
+__device__ __forceinline__ double chydro(double ro, double pg, double g) { return sqrt(g * pg / ro); }
+
+// eqns_mhd_ideal::cfast_components (eqns_mhd_adiabatic.cpp:263-276)
+__device__ __forceinline__ double cfast_components(double ro, double pg, double bx, double by, double bz, double g) {
+#ifdef PION_STRICT
+  double ch = sqrt(g * pg / ro);
+  double temp1 = ch * ch + (bx * bx + by * by + bz * bz) / ro;
+  double temp2 = 4. * ch * ch * bx * bx / ro;
+#else
+  // one reciprocal instead of a sqrt + three divisions; ch*ch == g*pg/ro to 1 ulp
+  double ir = 1.0 / ro;
+  double ch2 = g * pg * ir;
+  double temp1 = ch2 + (bx * bx + by * by + bz * bz) * ir;
+  double temp2 = 4. * ch2 * bx * bx * ir;
+#endif
+  temp2 = fmax(PION_MACHINEACCURACY, temp1 * temp1 - temp2);
+  return sqrt((temp1 + sqrt(temp2)) / 2.);
+}
+
+// ---------------------------------------------------------------------------
+// Riemann solvers.  All take edge states in the solver frame and return the
+// flux; `ustar`/`pstar` is only produced when the FKJ98 viscosity needs it.
+// ---------------------------------------------------------------------------
+
+// HLL_hydro::hydro_HLL_flux_solver (HLL_hydro.cpp:118-170)
+__device__ __forceinline__ void hydro_HLL(const Prim& L, const Prim& R, const PhysParams& pp, Cons& flux, Cons& ustar) {
+  const double gm1 = pp.gamma - 1.0;
+  Cons UL, UR, FL, FR;
+  PtoU<EQ_EULER>(L, UL, gm1);
+  PtoU<EQ_EULER>(R, UR, gm1);
+  PUtoFlux<EQ_EULER>(L, UL, FL);
+  PUtoFlux<EQ_EULER>(R, UR, FR);
+  double cf_max = fmax(chydro(L.ro, L.pg, pp.gamma), chydro(R.ro, R.pg, pp.gamma));
+  double Sl = fmin(L.vn, R.vn) - cf_max;
+  double Sr = fmax(L.vn, R.vn) + cf_max;
+  double idS = 1.0 / (Sr - Sl);
+#define PION_HLL_COMP(c)                                                             \
+  flux.c = (Sl > 0) ? FL.c : (Sr < 0) ? FR.c : (Sr * FL.c - Sl * FR.c + Sr * Sl * (UR.c - UL.c)) * idS; \
+  ustar.c = (Sr * UR.c - Sl * UL.c + FL.c - FR.c) * idS;
+  PION_HLL_COMP(rho) PION_HLL_COMP(erg) PION_HLL_COMP(mn) PION_HLL_COMP(mt1) PION_HLL_COMP(mt2)
+#undef PION_HLL_COMP
+  flux.bbn = flux.bbt1 = flux.bbt2 = flux.psi = 0.0;
+  ustar.bbn = ustar.bbt1 = ustar.bbt2 = ustar.psi = 0.0;
+}
+
+// constants::equalD (constants.cpp:48-69)
+__device__ __forceinline__ bool equalD(double a, double b) {
+  if (a == b) return true;
+  if (fabs(a) + fabs(b) < PION_TINYVALUE) return true;
+  return (fabs(a - b) / (fabs(a) + fabs(b) + PION_TINYVALUE)) < PION_SMALLVALUE;
+}
+
+// eqns_Euler::UtoFlux (eqns_hydro_adiabatic.cpp:317-333)
+__device__ __forceinline__ void euler_UtoFlux(const Cons& u, Cons& f, double gm1) {
+  double ir = 1.0 / u.rho;
+  double pg = gm1 * (u.erg - (u.mn * u.mn + u.mt1 * u.mt1 + u.mt2 * u.mt2) * 0.5 * ir);
+  f.rho = u.mn;
+  f.mn = u.mn * u.mn * ir + pg;
+  f.mt1 = u.mn * u.mt1 * ir;
+  f.mt2 = u.mn * u.mt2 * ir;
+  f.erg = u.mn * (u.erg + pg) * ir;
+}
+
+// Riemann_Roe_Hydro_CV::Roe_flux_solver_symmetric
+// (Roe_Hydro_ConservedVar_solver.cpp:129-175 + helpers :215-436)
+__device__ __forceinline__ void hydro_RoeCV(const Prim& L, const Prim& R, const PhysParams& pp, double hc_eta, Cons& flux,
+                                            Prim& pstar) {
+  const double g = pp.gamma, gm1 = g - 1.0;
+  double rl = sqrt(L.ro), rr = sqrt(R.ro);
+  double lH = 0.5 * (L.vn * L.vn + L.vt1 * L.vt1 + L.vt2 * L.vt2) + g * L.pg / gm1 / L.ro;
+  double rH = 0.5 * (R.vn * R.vn + R.vt1 * R.vt1 + R.vt2 * R.vt2) + g * R.pg / gm1 / R.ro;
+  double denom = 1.0 / (rl + rr);
+  double m_ro = rl * rr;
+  double m_vn = (rl * L.vn + rr * R.vn) * denom;
+  double m_vt1 = (rl * L.vt1 + rr * R.vt1) * denom;
+  double m_vt2 = (rl * L.vt2 + rr * R.vt2) * denom;
+  double m_H = (rl * lH + rr * rH) * denom;
+  double v2 = m_vn * m_vn + m_vt1 * m_vt1 + m_vt2 * m_vt2;
+  double a = sqrt(gm1 * fmax(m_H - 0.5 * v2, 1.0e-12 * v2));
+  double ev[5] = {m_vn - a, m_vn, m_vn, m_vn, m_vn + a};
+#pragma unroll
+  for (int v = 0; v < 5; v++) ev[v] = (ev[v] < 0.0) ? fmin(ev[v], -hc_eta) : fmax(ev[v], hc_eta);
+  Cons ul, ur;
+  PtoU<EQ_EULER>(L, ul, gm1);
+  PtoU<EQ_EULER>(R, ur, gm1);
+  double d_rho = equalD(ur.rho, ul.rho) ? 0.0 : ur.rho - ul.rho;
+  double d_erg = equalD(ur.erg, ul.erg) ? 0.0 : ur.erg - ul.erg;
+  double d_mn = equalD(ur.mn, ul.mn) ? 0.0 : ur.mn - ul.mn;
+  double d_mt1 = equalD(ur.mt1, ul.mt1) ? 0.0 : ur.mt1 - ul.mt1;
+  double d_mt2 = equalD(ur.mt2, ul.mt2) ? 0.0 : ur.mt2 - ul.mt2;
+  double s2 = d_mt1 - m_vt1 * d_rho;
+  double s3 = d_mt2 - m_vt2 * d_rho;
+  double u5bar = d_erg - s2 * m_vt1 - s3 * m_vt2;
+  double s1 = (d_rho * (m_H - m_vn * m_vn) + m_vn * d_mn - u5bar) * gm1 / a / a;
+  double s0 = 0.5 * (d_rho * (m_vn + a) - d_mn - a * s1) / a;
+  double s4 = d_rho - s0 - s1;
+  Cons fl, fr;
+  euler_UtoFlux(ul, fl, gm1);
+  euler_UtoFlux(ur, fr, gm1);
+  flux.rho = fl.rho + fr.rho;
+  flux.mn = fl.mn + fr.mn;
+  flux.mt1 = fl.mt1 + fr.mt1;
+  flux.mt2 = fl.mt2 + fr.mt2;
+  flux.erg = fl.erg + fr.erg;
+  // wave 0: (1, vn-a, vt1, vt2, H - vn a)
+  double w = s0 * fabs(ev[0]);
+  flux.rho -= w; flux.mn -= w * (m_vn - a); flux.mt1 -= w * m_vt1; flux.mt2 -= w * m_vt2; flux.erg -= w * (m_H - m_vn * a);
+  // wave 1: (1, vn, vt1, vt2, v2/2)
+  w = s1 * fabs(ev[1]);
+  flux.rho -= w; flux.mn -= w * m_vn; flux.mt1 -= w * m_vt1; flux.mt2 -= w * m_vt2; flux.erg -= w * (0.5 * v2);
+  // wave 2: (0,0,1,0,vt1)
+  w = s2 * fabs(ev[2]);
+  flux.mt1 -= w; flux.erg -= w * m_vt1;
+  // wave 3: (0,0,0,1,vt2)
+  w = s3 * fabs(ev[3]);
+  flux.mt2 -= w; flux.erg -= w * m_vt2;
+  // wave 4: (1, vn+a, vt1, vt2, H + vn a)
+  w = s4 * fabs(ev[4]);
+  flux.rho -= w; flux.mn -= w * (m_vn + a); flux.mt1 -= w * m_vt1; flux.mt2 -= w * m_vt2; flux.erg -= w * (m_H + m_vn * a);
+  flux.rho *= 0.5; flux.mn *= 0.5; flux.mt1 *= 0.5; flux.mt2 *= 0.5; flux.erg *= 0.5;
+  flux.bbn = flux.bbt1 = flux.bbt2 = flux.psi = 0.0;
+  pstar.ro = m_ro; pstar.vn = m_vn; pstar.vt1 = m_vt1; pstar.vt2 = m_vt2;
+  pstar.pg = m_ro * a * a / g;
+  pstar.bn = pstar.bt1 = pstar.bt2 = pstar.psi = 0.0;
+}
+
+// HLLD_MHD::HLLD_signal_speeds (HLLD_MHD.cpp:342-368); Bx is the same on both
+// sides in the GLM case but the formula is kept general.
+__device__ __forceinline__ void hlld_speeds(const Prim& L, const Prim& R, double g, double& Sl, double& Sr) {
+  double Bx = 0.5 * (L.bn + R.bn);
+  double cf_l = cfast_components(L.ro, L.pg, Bx, L.bt1, L.bt2, g);
+  double cf_r = cfast_components(R.ro, R.pg, Bx, R.bt1, R.bt2, g);
+  double cf_max = fmax(cf_l, cf_r);
+  Sl = fmin(L.vn, R.vn) - cf_max;
+  Sr = fmax(L.vn, R.vn) + cf_max;
+}
+
+// HLLD_MHD::MHD_HLL_flux_solver (HLLD_MHD.cpp:377-417)
+template <bool NEED_USTAR>
+__device__ __forceinline__ void mhd_HLL(const Prim& L, const Prim& R, const PhysParams& pp, Cons& flux, Cons& ustar) {
+  const double gm1 = pp.gamma - 1.0;
+  Cons UL, UR, FL, FR;
+  PtoU_mhd_ideal(L, UL, gm1);
+  PtoU_mhd_ideal(R, UR, gm1);
+  PUtoFlux<EQ_MHD>(L, UL, FL);
+  PUtoFlux<EQ_MHD>(R, UR, FR);
+  double l0, l1;
+  hlld_speeds(L, R, pp.gamma, l0, l1);
+  double idl = 1.0 / (l1 - l0);
+#define PION_HLLM_COMP(c)                                                                         \
+  flux.c = (l0 > 0.0) ? FL.c : (l1 < 0.0) ? FR.c : (l1 * FL.c - l0 * FR.c + l1 * l0 * (UR.c - UL.c)) * idl; \
+  if (NEED_USTAR) ustar.c = (l0 > 0.0) ? UL.c : (l1 < 0.0) ? UR.c : (l1 * UR.c - l0 * UL.c - FR.c + FL.c) * idl;
+  PION_HLLM_COMP(rho) PION_HLLM_COMP(erg) PION_HLLM_COMP(mn) PION_HLLM_COMP(mt1) PION_HLLM_COMP(mt2)
+  PION_HLLM_COMP(bbn) PION_HLLM_COMP(bbt1) PION_HLLM_COMP(bbt2)
+#undef PION_HLLM_COMP
+  flux.psi = 0.0;
+  if (NEED_USTAR) ustar.psi = 0.0;
+}
+
+// HLLD_MHD::MHD_HLLD_flux_solver (HLLD_MHD.cpp:124-333), Miyoshi & Kusano 2005.
+// Region select is done first so that only the needed intermediate states are
+// formed; every expression inside a region is the reference's.
+template <bool NEED_USTAR>
+__device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const PhysParams& pp, Cons& flux, Cons& ustar) {
+  const double gm1 = pp.gamma - 1.0;
+  const double BX = 0.5 * (L.bn + R.bn);
+  Cons UL, UR, FL, FR;
+  PtoU_mhd_ideal(L, UL, gm1);
+  PtoU_mhd_ideal(R, UR, gm1);
+  PUtoFlux<EQ_MHD>(L, UL, FL);
+  PUtoFlux<EQ_MHD>(R, UR, FR);
+  double lam0, lam4;
+  hlld_speeds(L, R, pp.gamma, lam0, lam4);
+
+  double sl_vl = lam0 - L.vn;
+  double sr_vr = lam4 - R.vn;
+  double tp_r = R.pg + 0.5 * (R.bn * R.bn + R.bt1 * R.bt1 + R.bt2 * R.bt2);
+  double tp_l = L.pg + 0.5 * (L.bn * L.bn + L.bt1 * L.bt1 + L.bt2 * L.bt2);
+  double temp = sr_vr * R.ro - sl_vl * L.ro;
+  double itemp = 1.0 / temp;
+  double lam2 = (sr_vr * UR.mn - sl_vl * UL.mn - tp_r + tp_l) * itemp;
+  double tp_s = (sr_vr * R.ro * tp_l - sl_vl * L.ro * tp_r + L.ro * R.ro * sr_vr * sl_vl * (R.vn - L.vn)) * itemp;
+  double sl_sm = lam0 - lam2;
+  double sr_sm = lam4 - lam2;
+  double isl_sm = 1.0 / sl_sm, isr_sm = 1.0 / sr_sm;
+
+  Cons ULs, URs;
+  ULs.rho = L.ro * sl_vl * isl_sm;
+  URs.rho = R.ro * sr_vr * isr_sm;
+  ULs.mn = lam2 * ULs.rho;
+  URs.mn = lam2 * URs.rho;
+  double temp_l1 = lam2 - L.vn;
+  double temp_l2 = L.ro * sl_vl * sl_sm - BX * BX;
+  double temp_r1 = lam2 - R.vn;
+  double temp_r2 = R.ro * sr_vr * sr_sm - BX * BX;
+  double vys_l = L.vt1, vys_r = R.vt1, vzs_l = L.vt2, vzs_r = R.vt2;
+  double ql = temp_l1 / temp_l2, qr = temp_r1 / temp_r2;
+  if (isfinite(ql)) {
+    vys_l = L.vt1 - BX * L.bt1 * ql;
+    vzs_l = L.vt2 - BX * L.bt2 * ql;
+  }
+  if (isfinite(qr)) {
+    vys_r = R.vt1 - BX * R.bt1 * qr;
+    vzs_r = R.vt2 - BX * R.bt2 * qr;
+  }
+  ULs.mt1 = vys_l * ULs.rho;
+  URs.mt1 = vys_r * URs.rho;
+  ULs.mt2 = vzs_l * ULs.rho;
+  URs.mt2 = vzs_r * URs.rho;
+  ULs.bbn = URs.bbn = BX;
+  temp_l1 = L.ro * sl_vl * sl_vl - BX * BX;
+  temp_r1 = R.ro * sr_vr * sr_vr - BX * BX;
+  ULs.bbt1 = 0.0; URs.bbt1 = 0.0; ULs.bbt2 = 0.0; URs.bbt2 = 0.0;
+  ql = temp_l1 / temp_l2;
+  qr = temp_r1 / temp_r2;
+  if (isfinite(ql)) {
+    ULs.bbt1 = L.bt1 * ql;
+    ULs.bbt2 = L.bt2 * ql;
+  }
+  if (isfinite(qr)) {
+    URs.bbt1 = R.bt1 * qr;
+    URs.bbt2 = R.bt2 * qr;
+  }
+  temp_l1 = L.vn * BX + L.vt1 * L.bt1 + L.vt2 * L.bt2;
+  temp_r1 = R.vn * BX + R.vt1 * R.bt1 + R.vt2 * R.bt2;
+  temp_l2 = lam2 * ULs.bbn + vys_l * ULs.bbt1 + vzs_l * ULs.bbt2;
+  temp_r2 = lam2 * URs.bbn + vys_r * URs.bbt1 + vzs_r * URs.bbt2;
+  ULs.erg = (sl_vl * UL.erg - tp_l * L.vn + tp_s * lam2 + BX * (temp_l1 - temp_l2)) * isl_sm;
+  URs.erg = (sr_vr * UR.erg - tp_r * R.vn + tp_s * lam2 + BX * (temp_r1 - temp_r2)) * isr_sm;
+  double sq_l = sqrt(ULs.rho), sq_r = sqrt(URs.rho);
+  double lam1 = lam2 - fabs(BX) / sq_l;
+  double lam3 = lam2 + fabs(BX) / sq_r;
+  ULs.psi = URs.psi = 0.0;
+
+  Cons ULss = ULs, URss = URs;
+  if (BX != 0) {
+    double sgn = (BX > 0) - (BX < 0);
+    double tsum = sq_l + sq_r;
+    double itsum = 1.0 / tsum;
+    double vy_ss = (sq_l * vys_l + sq_r * vys_r + (URs.bbt1 - ULs.bbt1) * sgn) * itsum;
+    double vz_ss = (sq_l * vzs_l + sq_r * vzs_r + (URs.bbt2 - ULs.bbt2) * sgn) * itsum;
+    ULss.mt1 = vy_ss * ULss.rho;
+    URss.mt1 = vy_ss * URss.rho;
+    ULss.mt2 = vz_ss * ULss.rho;
+    URss.mt2 = vz_ss * URss.rho;
+    double by_ss = (sq_l * URs.bbt1 + sq_r * ULs.bbt1 + sq_l * sq_r * (vys_r - vys_l) * sgn) * itsum;
+    double bz_ss = (sq_l * URs.bbt2 + sq_r * ULs.bbt2 + sq_l * sq_r * (vzs_r - vzs_l) * sgn) * itsum;
+    ULss.bbt1 = URss.bbt1 = by_ss;
+    ULss.bbt2 = URss.bbt2 = bz_ss;
+    double bv = lam2 * BX + vy_ss * by_ss + vz_ss * bz_ss;
+    ULss.erg = ULs.erg - sq_l * (temp_l2 - bv) * sgn;
+    URss.erg = URs.erg + sq_r * (temp_r2 - bv) * sgn;
+  }
+
+#define PION_HLLD_COMP(c)                                                                   \
+  if (lam0 > 0) { flux.c = FL.c; if (NEED_USTAR) ustar.c = UL.c; }                              \
+  else if (lam1 >= 0) { flux.c = FL.c + lam0 * (ULs.c - UL.c); if (NEED_USTAR) ustar.c = ULs.c; } \
+  else if (lam2 >= 0) { flux.c = FL.c + lam1 * ULss.c - (lam1 - lam0) * ULs.c - lam0 * UL.c; if (NEED_USTAR) ustar.c = ULss.c; } \
+  else if (lam3 >= 0) { flux.c = FR.c + lam3 * URss.c - (lam3 - lam4) * URs.c - lam4 * UR.c; if (NEED_USTAR) ustar.c = URss.c; } \
+  else if (lam4 >= 0) { flux.c = FR.c + lam4 * (URs.c - UR.c); if (NEED_USTAR) ustar.c = URs.c; } \
+  else { flux.c = FR.c; if (NEED_USTAR) ustar.c = UR.c; }
+  PION_HLLD_COMP(rho) PION_HLLD_COMP(erg) PION_HLLD_COMP(mn) PION_HLLD_COMP(mt1) PION_HLLD_COMP(mt2)
+  PION_HLLD_COMP(bbn) PION_HLLD_COMP(bbt1) PION_HLLD_COMP(bbt2)
+#undef PION_HLLD_COMP
+  flux.psi = 0.0;
+  if (NEED_USTAR) ustar.psi = 0.0;
+}
+
+// Riemann_Roe_MHD_CV::MHD_Roe_CV_flux_solver_symmetric
+// (Roe_MHD_ConservedVar_solver.cpp:218-262; average state :300-352, difference
+// states :358-393, wave speeds :399-470, eigenvalues + H-correction :476-510,
+// wave strengths :516-580, Cargo & Gallice right eigenvectors :699-810,
+// symmetric flux :1074-1131, pstar :283-295)
+__device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const PhysParams& pp, double hc_etamax, Cons& flux,
+                                          Prim& pstar) {
+  enum { FN = 0, AN = 1, SN = 2, CT = 3, SP = 4, AP = 5, FP = 6 };
+  const double g = pp.gamma, gm1 = g - 1.0;
+  Cons UL, UR;
+  PtoU_mhd_ideal(L, UL, gm1);
+  PtoU_mhd_ideal(R, UR, gm1);
+  double rl = sqrt(L.ro), rr = sqrt(R.ro);
+  double lH = (L.ro * (L.vn * L.vn + L.vt1 * L.vt1 + L.vt2 * L.vt2) / 2.0 + (g * L.pg / gm1) +
+               (L.bn * L.bn + L.bt1 * L.bt1 + L.bt2 * L.bt2)) / L.ro;
+  double rH = (R.ro * (R.vn * R.vn + R.vt1 * R.vt1 + R.vt2 * R.vt2) / 2.0 + (g * R.pg / gm1) +
+               (R.bn * R.bn + R.bt1 * R.bt1 + R.bt2 * R.bt2)) / R.ro;
+  double Roe_denom = 1.0 / (rl + rr);
+  double m_ro = rl * rr;
+  double m_vn = (rl * L.vn + rr * R.vn) * Roe_denom;
+  double m_vt1 = (rl * L.vt1 + rr * R.vt1) * Roe_denom;
+  double m_vt2 = (rl * L.vt2 + rr * R.vt2) * Roe_denom;
+  double m_bt1 = (rr * L.bt1 + rl * R.bt1) * Roe_denom;
+  double m_bt2 = (rr * L.bt2 + rl * R.bt2) * Roe_denom;
+  double m_bn = 0.5 * (L.bn + R.bn);
+  double signBX = (m_bn >= 0.0) ? 1.0 : -1.0;
+  double m_H = (rl * lH + rr * rH) * Roe_denom;
+  double Roe_V = sqrt(m_vn * m_vn + m_vt1 * m_vt1 + m_vt2 * m_vt2);
+  double Roe_B = sqrt(m_bn * m_bn + m_bt1 * m_bt1 + m_bt2 * m_bt2);
+  double Roe_Bt = sqrt(m_bt1 * m_bt1 + m_bt2 * m_bt2);
+  double betay, betaz;
+  if (Roe_Bt >= PION_TINYVALUE) {
+    betay = m_bt1 / Roe_Bt;
+    betaz = m_bt2 / Roe_Bt;
+  } else {
+    betay = 1.0 / sqrt(2.0);
+    betaz = 1.0 / sqrt(2.0);
+  }
+  // difference states
+  double ud_mn = UR.mn - UL.mn, ud_mt1 = UR.mt1 - UL.mt1, ud_mt2 = UR.mt2 - UL.mt2, ud_erg = UR.erg - UL.erg;
+  double pd_ro = R.ro - L.ro, pd_vn = R.vn - L.vn, pd_vt1 = R.vt1 - L.vt1, pd_vt2 = R.vt2 - L.vt2;
+  double pd_bt1 = R.bt1 - L.bt1, pd_bt2 = R.bt2 - L.bt2;
+  double CGX = (pd_bt1 * pd_bt1 + pd_bt2 * pd_bt2) * 0.5 * Roe_denom * Roe_denom;
+  double pd_pg = ((0.5 * Roe_V * Roe_V - CGX) * pd_ro - (m_vn * ud_mn + m_vt1 * ud_mt1 + m_vt2 * ud_mt2) + ud_erg -
+                  (m_bt1 * pd_bt1 + m_bt2 * pd_bt2)) * gm1;
+  // wave speeds
+  double b2 = Roe_B * Roe_B / m_ro;
+  double Roe_a = sqrt((2.0 - g) * CGX + gm1 * fmax((m_H - 0.5 * Roe_V * Roe_V - b2), 1.0e-12 * Roe_V * Roe_V));
+  double astar2 = Roe_a * Roe_a + b2;
+  double Roe_ca = sqrt(m_bn * m_bn / m_ro);
+  double Roe_cs = astar2 * astar2 - 4.0 * Roe_a * Roe_a * Roe_ca * Roe_ca;
+  Roe_cs = (Roe_cs <= 0.0) ? 0.0 : sqrt(Roe_cs);
+  double Roe_cf = sqrt(0.5 * (astar2 + Roe_cs));
+  Roe_cs = astar2 - Roe_cs;
+  Roe_cs = (Roe_cs <= 0.0) ? 0.0 : sqrt(0.5 * Roe_cs);
+  if (Roe_ca > Roe_cf) Roe_ca = Roe_cf;
+  if (Roe_cs > Roe_ca) Roe_cs = Roe_ca;
+  double cf2diff = Roe_cf * Roe_cf - Roe_cs * Roe_cs, alphaf, alphas;
+  if (cf2diff > PION_MACHINEACCURACY) {
+    alphaf = Roe_a * Roe_a - Roe_cs * Roe_cs;
+    if (alphaf < 0.0) alphaf = 0.;
+    alphas = Roe_cf * Roe_cf - Roe_a * Roe_a;
+    if (alphas < 0.0) alphas = 0.;
+    alphaf = sqrt(alphaf / cf2diff);
+    if (alphaf > 1.0) alphaf = 1.0;
+    alphas = sqrt(alphas / cf2diff);
+    if (alphas > 1.0) alphas = 1.0;
+  } else {
+    alphaf = alphas = 1.0 / sqrt(2.0);
+  }
+  double ev[7];
+  ev[FN] = m_vn - Roe_cf; ev[AN] = m_vn - Roe_ca; ev[SN] = m_vn - Roe_cs; ev[CT] = m_vn;
+  ev[SP] = m_vn + Roe_cs; ev[AP] = m_vn + Roe_ca; ev[FP] = m_vn + Roe_cf;
+#pragma unroll
+  for (int v = 0; v < 7; v++) ev[v] = (ev[v] < 0.0) ? fmin(ev[v], -hc_etamax) : fmax(ev[v], hc_etamax);
+  // wave strengths
+  double rootrho = sqrt(m_ro);
+  double str[7];
+  {
+    double t_p = (CGX * pd_ro + pd_pg);
+    double t_v = (betay * pd_vt1 + betaz * pd_vt2);
+    double t_b = (betay * pd_bt1 + betaz * pd_bt2);
+    str[FN] = 0.5 * (alphaf * t_p + m_ro * alphas * Roe_cs * signBX * t_v - m_ro * alphaf * Roe_cf * pd_vn +
+                     rootrho * alphas * Roe_a * t_b);
+    str[FP] = 0.5 * (alphaf * t_p - m_ro * alphas * Roe_cs * signBX * t_v + m_ro * alphaf * Roe_cf * pd_vn +
+                     rootrho * alphas * Roe_a * t_b);
+    str[SN] = 0.5 * (alphas * t_p - m_ro * alphaf * Roe_cf * signBX * t_v - m_ro * alphas * Roe_cs * pd_vn -
+                     rootrho * alphaf * Roe_a * t_b);
+    str[SP] = 0.5 * (alphas * t_p + m_ro * alphaf * Roe_cf * signBX * t_v + m_ro * alphas * Roe_cs * pd_vn -
+                     rootrho * alphaf * Roe_a * t_b);
+    str[AN] = 0.5 * (+betay * pd_vt2 - betaz * pd_vt1 + signBX * (betay * pd_bt2 - betaz * pd_bt1) / rootrho);
+    str[AP] = 0.5 * (-betay * pd_vt2 + betaz * pd_vt1 + signBX * (betay * pd_bt2 - betaz * pd_bt1) / rootrho);
+    str[CT] = (Roe_a * Roe_a - CGX) * pd_ro - pd_pg;
+  }
+  // right eigenvectors, component order {rho, mn, mt1, mt2, bt1, bt2, e}
+  double rev[7][7];
+  double ia2 = 1.0 / (Roe_a * Roe_a);
+  rev[CT][0] = ia2; rev[CT][1] = m_vn * ia2; rev[CT][2] = m_vt1 * ia2; rev[CT][3] = m_vt2 * ia2;
+  rev[CT][4] = 0.0; rev[CT][5] = 0.0;
+  rev[CT][6] = (0.5 * Roe_V * Roe_V + CGX * (g - 2) / gm1) * ia2;
+  rev[AN][0] = 0.0; rev[AN][1] = 0.0;
+  rev[AN][2] = -m_ro * betaz;
+  rev[AN][3] = +m_ro * betay;
+  rev[AN][4] = -signBX * rootrho * betaz;
+  rev[AN][5] = +signBX * rootrho * betay;
+  rev[AN][6] = -m_ro * (m_vt1 * betaz - m_vt2 * betay);
+  rev[AP][0] = 0.0; rev[AP][1] = 0.0;
+  rev[AP][2] = -rev[AN][2]; rev[AP][3] = -rev[AN][3]; rev[AP][4] = rev[AN][4]; rev[AP][5] = rev[AN][5];
+  rev[AP][6] = -rev[AN][6];
+  double das = m_ro * alphas, daf = m_ro * alphaf;
+  double hb = m_H - Roe_B * Roe_B / m_ro;
+  double vb = (m_vt1 * betay + m_vt2 * betaz);
+  double inorm = 1.0 / (m_ro * Roe_a * Roe_a);
+  rev[SN][0] = das;
+  rev[SN][1] = das * (m_vn - Roe_cs);
+  rev[SN][2] = das * m_vt1 - daf * Roe_cf * betay * signBX;
+  rev[SN][3] = das * m_vt2 - daf * Roe_cf * betaz * signBX;
+  rev[SN][4] = -rootrho * alphaf * Roe_a * betay;
+  rev[SN][5] = -rootrho * alphaf * Roe_a * betaz;
+  rev[SN][6] = das * (hb - m_vn * Roe_cs) - daf * Roe_cf * signBX * vb - rootrho * alphaf * Roe_a * Roe_Bt;
+  rev[SP][0] = das;
+  rev[SP][1] = das * (m_vn + Roe_cs);
+  rev[SP][2] = das * m_vt1 + daf * Roe_cf * betay * signBX;
+  rev[SP][3] = das * m_vt2 + daf * Roe_cf * betaz * signBX;
+  rev[SP][4] = rev[SN][4];
+  rev[SP][5] = rev[SN][5];
+  rev[SP][6] = das * (hb + m_vn * Roe_cs) + daf * Roe_cf * signBX * vb - rootrho * alphaf * Roe_a * Roe_Bt;
+  rev[FN][0] = daf;
+  rev[FN][1] = daf * (m_vn - Roe_cf);
+  rev[FN][2] = daf * m_vt1 + das * Roe_cs * betay * signBX;
+  rev[FN][3] = daf * m_vt2 + das * Roe_cs * betaz * signBX;
+  rev[FN][4] = rootrho * alphas * Roe_a * betay;
+  rev[FN][5] = rootrho * alphas * Roe_a * betaz;
+  rev[FN][6] = daf * (hb - m_vn * Roe_cf) + das * Roe_cs * signBX * vb + rootrho * alphas * Roe_a * Roe_Bt;
+  rev[FP][0] = daf;
+  rev[FP][1] = daf * (m_vn + Roe_cf);
+  rev[FP][2] = daf * m_vt1 - das * Roe_cs * betay * signBX;
+  rev[FP][3] = daf * m_vt2 - das * Roe_cs * betaz * signBX;
+  rev[FP][4] = rev[FN][4];
+  rev[FP][5] = rev[FN][5];
+  rev[FP][6] = daf * (hb + m_vn * Roe_cf) - das * Roe_cs * signBX * vb + rootrho * alphas * Roe_a * Roe_Bt;
+#pragma unroll
+  for (int v = 0; v < 7; v++) {
+    rev[SN][v] *= inorm; rev[SP][v] *= inorm; rev[FN][v] *= inorm; rev[FP][v] *= inorm;
+  }
+  Cons FL, FR;
+  PUtoFlux<EQ_MHD>(L, UL, FL);
+  PUtoFlux<EQ_MHD>(R, UR, FR);
+  double f[7] = {FL.rho + FR.rho, FL.mn + FR.mn, FL.mt1 + FR.mt1, FL.mt2 + FR.mt2, FL.bbt1 + FR.bbt1, FL.bbt2 + FR.bbt2,
+                 FL.erg + FR.erg};
+#pragma unroll
+  for (int iw = 0; iw < 7; iw++) {
+    double w = str[iw] * fabs(ev[iw]);
+#pragma unroll
+    for (int c = 0; c < 7; c++) f[c] -= w * rev[iw][c];
+  }
+  flux.rho = 0.5 * f[0]; flux.mn = 0.5 * f[1]; flux.mt1 = 0.5 * f[2]; flux.mt2 = 0.5 * f[3];
+  flux.bbt1 = 0.5 * f[4]; flux.bbt2 = 0.5 * f[5]; flux.erg = 0.5 * f[6];
+  flux.bbn = 0.5 * (FL.bbn + FR.bbn);
+  flux.psi = 0.0;
+  pstar.ro = m_ro; pstar.vn = m_vn; pstar.vt1 = m_vt1; pstar.vt2 = m_vt2;
+  pstar.bn = m_bn; pstar.bt1 = m_bt1; pstar.bt2 = m_bt2; pstar.psi = 0.0;
+  pstar.pg = m_ro * Roe_a * Roe_a / g;
+}
+
+// ---------------------------------------------------------------------------
+// InterCellFlux: inviscid flux + FKJ98 viscosity, for one interface.
+// FV_solver_base::InterCellFlux (solver_eqn_base.cpp:152-204) minus the tracer
+// flux (done by the caller, which owns the tracer edge states).
+//   use_hll  : HLLD->HLL switch already evaluated from divV / |grad p|/p
+//   hc_etamax: H-correction eta (0 when AV != 3,4)
+// ---------------------------------------------------------------------------
+template <int EQ, int SOLVER, int AV>
+__device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, const PhysParams& pp, bool use_hll,
+                                               double hc_etamax, Cons& flux) {
+  constexpr bool FKJ = (AV == AV_FKJ98 || AV == AV_HCORR_FKJ98);
+  Prim pstar;
+  if (EQ == EQ_EULER) {
+    if (SOLVER == SOLVE_ROE) {
+      hydro_RoeCV(eL, eR, pp, hc_etamax, flux, pstar);
+    } else {
+      Cons ustar;
+      hydro_HLL(eL, eR, pp, flux, ustar);
+      if (FKJ) UtoP<EQ_EULER>(ustar, pstar, pp);
+    }
+    if (FKJ) {
+      // FV_solver_Hydro_Euler::AVFalle (solver_eqn_hydro_adi.cpp:283-333)
+      double prefactor = chydro(pstar.ro, pstar.pg, pp.gamma) * pp.etav * pstar.ro;
+      double momvisc = prefactor * (eR.vn - eL.vn);
+      double ergvisc = momvisc * pstar.vn;
+      flux.mn -= momvisc;
+      momvisc = prefactor * (eR.vt1 - eL.vt1);
+      flux.mt1 -= momvisc;
+      ergvisc += momvisc * pstar.vt1;
+      momvisc = prefactor * (eR.vt2 - eL.vt2);
+      flux.mt2 -= momvisc;
+      ergvisc += momvisc * pstar.vt2;
+      flux.erg -= ergvisc;
+    }
+  } else {
+    // GLM: Dedner 2x2 star state, Bx := Bx*, psi := 0 in the states handed to
+    // the ideal-MHD solver (solver_eqn_mhd_adi.cpp:726-742)
+    Prim l = eL, r = eR;
+    double psistar = 0.0, bxstar = 0.0;
+    if (EQ == EQ_GLM) {
+      psistar = 0.5 * (eL.psi + eR.psi - (eR.bn - eL.bn));
+      bxstar = 0.5 * (eL.bn + eR.bn - (eR.psi - eL.psi));
+      l.psi = r.psi = 0.0;
+      l.bn = r.bn = bxstar;
+    }
+    if (SOLVER == SOLVE_ROE) {
+      mhd_RoeCV(l, r, pp, hc_etamax, flux, pstar);
+    } else {
+      Cons ustar;
+      if (SOLVER == SOLVE_HLLD && !use_hll) mhd_HLLD<FKJ>(l, r, pp, flux, ustar);
+      else mhd_HLL<FKJ>(l, r, pp, flux, ustar);
+      if (FKJ) {
+        // virtual UtoP: GLM version with psi==0 equals the ideal one
+        UtoP<EQ_MHD>(ustar, pstar, pp);
+      }
+    }
+    if (EQ == EQ_GLM) {
+      flux.erg += pp.chyp * bxstar * psistar;
+      flux.bbn = pp.chyp * psistar;
+      flux.psi = pp.chyp * bxstar;
+    }
+    if (FKJ) {
+      // FV_solver_mhd_ideal_adi::AVFalle (solver_eqn_mhd_adi.cpp:209-288) on the
+      // ORIGINAL edge states (InterCellFlux passes lp,rp)
+      double prefactor = cfast_components(0.5 * (eL.ro + eR.ro), 0.5 * (eL.pg + eR.pg), 0.5 * (eL.bn + eR.bn),
+                                          0.5 * (eL.bt1 + eR.bt1), 0.5 * (eL.bt2 + eR.bt2), pp.gamma) *
+                         pp.etav * pstar.ro;
+      double momvisc = prefactor * (eR.vn - eL.vn);
+      double ergvisc = momvisc * pstar.vn;
+      flux.mn -= momvisc;
+      momvisc = prefactor * (eR.vt1 - eL.vt1);
+      flux.mt1 -= momvisc;
+      ergvisc += momvisc * pstar.vt1;
+      momvisc = prefactor * (eR.vt2 - eL.vt2);
+      flux.mt2 -= momvisc;
+      ergvisc += momvisc * pstar.vt2;
+      prefactor *= pp.etav / (pp.etav * pstar.ro);
+      momvisc = prefactor * (eR.bt1 - eL.bt1);
+      flux.bbt1 -= momvisc;
+      ergvisc += momvisc * pstar.bt1;
+      momvisc = prefactor * (eR.bt2 - eL.bt2);
+      flux.bbt2 -= momvisc;
+      ergvisc += momvisc * pstar.bt2;
+      flux.erg -= ergvisc;
+    }
+  }
+}
+
+// maxspeed() used by the H-correction (solver_eqn_base.cpp:579-599): chydro for
+// Euler, cfast along the sweep axis for MHD.
+template <int EQ>
+__device__ __forceinline__ double maxspeed(const Prim& p, double g) {
+  if (EQ == EQ_EULER) return chydro(p.ro, p.pg, g);
+  return cfast_components(p.ro, p.pg, p.bn, p.bt1, p.bt2, g);
+}
+
+}  // namespace pion

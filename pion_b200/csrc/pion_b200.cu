@@ -1,0 +1,820 @@
+// pion_b200/csrc/pion_b200.cu -- context, host-side orchestration and the C ABI
+// of libpion_b200.so (see include/pion_b200.h for the reference method each
+// entry point replaces).  The host logic mirrors, call for call,
+//   sim_control/time_integrator.cpp:72-243   advance_time / first_order_update / second_order_update
+//   sim_control/calc_timestep.cpp:68-262     calculate_timestep / timestep_checking_and_limiting
+//   boundaries/assign_update_bcs.cpp:28-246  assign_boundary_data / TimeUpdate{Internal,External}BCs
+//   sim_control/sim_init.cpp:215-280         Init after ReadData
+// There is no CPU fallback: every numerical step is a kernel launch on the
+// context's stream; the host only sequences launches and reads back scalars.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pion_b200.h"
+#include "aux_kernels.cuh"
+
+using namespace pion;
+
+static thread_local std::string g_last_error;
+static void set_error(const std::string& s) { g_last_error = s; }
+
+#define CUDA_OK(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                        \
+      return 1;                                                                             \
+    }                                                                                       \
+  } while (0)
+#define NCCL_OK(call)                                                                       \
+  do {                                                                                      \
+    ncclResult_t r_ = (call);                                                               \
+    if (r_ != ncclSuccess) {                                                                \
+      set_error(std::string(#call) + ": " + ncclGetErrorString(r_));                        \
+      return 1;                                                                             \
+    }                                                                                       \
+  } while (0)
+
+struct pion_gpu_ctx {
+  pion_gpu_config cfg;
+  GridD g;
+  PhysParams pp;
+  int nvar, nbase_, ntr;
+  size_t arr_elems;  // doubles per state array
+  double *P = nullptr, *Ph = nullptr, *dU = nullptr, *eta = nullptr;
+  unsigned char *hll = nullptr, *mask = nullptr;
+  unsigned long long* d_dtmin = nullptr;  // [0] running min for the next step, [1] scratch
+  long long* d_counters = nullptr;
+  unsigned long long* h_pinned = nullptr;  // pinned mirror for scalar read-back
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  // time state (SimParams: simtime, dt, last_dt, timestep, next_optime)
+  double simtime = 0, dt = 0, last_dt = 1.e100, next_optime = 0;
+  int timestep = 0;
+  double FV_dt = 0, chyp = 0, cr = 0;
+  bool ph_valid = true;      // false after a fused full step: Ph's interior is stale, P is the truth
+  bool next_dt_valid = false;  // d_dtmin[0] holds min CellTimeStep(P) for the current P
+  double bc_refval[10][PION_MAXVAR];
+  long long launches = 0;
+  // optional per-launch timing of the stage kernel (bench.py roofline leg)
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;  // begin/end pairs
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  double *sendbuf[6] = {nullptr}, *recvbuf[6] = {nullptr};
+  size_t halo_elems[6] = {0};
+};
+
+static inline int nblocks(long n, int block, int cap = 148 * 16) {
+  long b = (n + block - 1) / block;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+// ---------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------
+extern "C" const char* pion_gpu_last_error(void) { return g_last_error.c_str(); }
+
+static int check_config(const pion_gpu_config& c) {
+  if (c.ndim < 1 || c.ndim > 3) { set_error("ndim must be 1..3"); return 1; }
+  if (c.eqntype != PION_EQEUL && c.eqntype != PION_EQMHD && c.eqntype != PION_EQGLM) { set_error("unsupported eqntype"); return 1; }
+  if (c.coord_sys != PION_COORD_CRT) { set_error("only Cartesian coordinates in this round"); return 1; }
+  if (c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL) { set_error("solver must be 4 (Roe-CV), 7 (HLLD) or 8 (HLL)"); return 1; }
+  if (c.eqntype == PION_EQEUL && c.solver == PION_FLUX_HLLD) { set_error("HLLD needs MHD equations"); return 1; }
+  if (c.artviscosity != 0 && c.artviscosity != 1 && c.artviscosity != 3 && c.artviscosity != 4) { set_error("artviscosity must be 0,1,3,4"); return 1; }
+  if (!((c.spOOA == 1 && c.tmOOA == 1) || (c.spOOA == 2 && c.tmOOA == 2))) { set_error("Bad OOA requests; choose (1,1) or (2,2)"); return 1; }
+  if (c.ntracer < 0 || c.ntracer > PION_MAXTR) { set_error("ntracer must be 0..4"); return 1; }
+  int nb0 = (c.eqntype == PION_EQEUL) ? 5 : (c.eqntype == PION_EQMHD) ? 8 : 9;
+  if (c.nvar != nb0 + c.ntracer) { set_error("nvar inconsistent with eqntype/ntracer"); return 1; }
+  for (int d = 0; d < 2 * c.ndim; d++) {
+    int t = c.bc[d];
+    if (t == PION_BC_FIXED && c.ndim > 1 && d >= 2) { set_error("FIXED boundary on a Y/Z face: the reference's BC_assign_FIXED never terminates there (fixed_boundaries.cpp:50-58)"); return 1; }
+    if (t != PION_BC_PERIODIC && t != PION_BC_OUTFLOW && t != PION_BC_INFLOW && t != PION_BC_REFLECTING &&
+        t != PION_BC_FIXED && t != PION_BC_DMACH && t != PION_BC_ONEWAY_OUT && t != PION_BC_MPI) { set_error("unsupported boundary type"); return 1; }
+    if (c.eqntype == PION_EQGLM && c.ndim == 1 && (t == PION_BC_OUTFLOW || t == PION_BC_ONEWAY_OUT)) { set_error("Psi outflow boundary condition doesn't work for 1D! (outflow_boundaries.cpp:57)"); return 1; }
+  }
+  return 0;
+}
+
+extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
+  if (!cfg) { set_error("null config"); return nullptr; }
+  if (check_config(*cfg)) return nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: libpion_b200 has no CPU fallback");
+    return nullptr;
+  }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+  pion_gpu_ctx* c = new pion_gpu_ctx();
+  c->cfg = *cfg;
+  // ics/get_sim_info.cpp:452-468
+  if (c->cfg.artviscosity == 0) c->cfg.etav = 0.0;
+  if (c->cfg.artviscosity == 3) c->cfg.etav = 0.1;
+  GridD& g = c->g;
+  g.ndim = cfg->ndim;
+  const int nbc = (cfg->spOOA == 2) ? 2 : 1;  // setup_fixed_grid.cpp:183-184
+  for (int a = 0; a < 3; a++) {
+    g.NG[a] = (a < g.ndim) ? cfg->NG[a] : 1;
+    g.nb[a] = (a < g.ndim) ? nbc : 0;
+    g.NGa[a] = g.NG[a] + 2 * g.nb[a];
+  }
+  g.xoff = 16 - g.nb[0];
+  long pitch = ((long)g.xoff + g.NGa[0] + 15) / 16 * 16;
+  g.sy = pitch;
+  g.sz = pitch * g.NGa[1];
+  g.vs = ((pitch * g.NGa[1] * g.NGa[2]) + 15) / 16 * 16;
+  g.dx = (cfg->xmax[0] - cfg->xmin[0]) / g.NG[0];  // UniformGrid::set_cell_size
+  c->nvar = cfg->nvar;
+  c->ntr = cfg->ntracer;
+  c->nbase_ = cfg->nvar - cfg->ntracer;
+  c->arr_elems = (size_t)g.vs * c->nvar;
+  PhysParams& pp = c->pp;
+  pp.gamma = cfg->gamma;
+  pp.etav = c->cfg.etav;
+  pp.chyp = 0.0;
+  pp.refvec_ro = cfg->refvec[0];
+  pp.min_temp = cfg->min_temperature;
+  pp.max_temp = cfg->max_temperature;
+  pp.have_mp = cfg->cooling ? 1 : 0;
+  pp.mu_tot_over_kB = cfg->cooling ? (0.609 * 1.6726231e-24) / 1.380658e-16 : 0.0;
+  c->simtime = cfg->starttime;
+
+  bool ok = true;
+  ok &= cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming) == cudaSuccess;
+  ok &= cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming) == cudaSuccess;
+  ok &= cudaMalloc(&c->P, c->arr_elems * sizeof(double)) == cudaSuccess;
+  ok &= cudaMalloc(&c->Ph, c->arr_elems * sizeof(double)) == cudaSuccess;
+  ok &= cudaMalloc(&c->d_dtmin, 2 * sizeof(unsigned long long)) == cudaSuccess;
+  ok &= cudaMalloc(&c->d_counters, 4 * sizeof(long long)) == cudaSuccess;
+  ok &= cudaMallocHost(&c->h_pinned, 8 * sizeof(unsigned long long)) == cudaSuccess;
+  if (cfg->solver == PION_FLUX_HLLD) ok &= cudaMalloc(&c->hll, (size_t)g.vs) == cudaSuccess;
+  if (cfg->solver == PION_FLUX_ROE && (cfg->artviscosity == 3 || cfg->artviscosity == 4))
+    ok &= cudaMalloc(&c->eta, (size_t)g.vs * 3 * sizeof(double)) == cudaSuccess;
+  if (!ok) {
+    set_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    pion_gpu_destroy(c);
+    return nullptr;
+  }
+  cudaMemsetAsync(c->P, 0, c->arr_elems * sizeof(double), c->stream);
+  cudaMemsetAsync(c->Ph, 0, c->arr_elems * sizeof(double), c->stream);
+  cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(long long), c->stream);
+  if (c->hll) cudaMemsetAsync(c->hll, 0, (size_t)g.vs, c->stream);
+  if (c->eta) cudaMemsetAsync(c->eta, 0, (size_t)g.vs * 3 * sizeof(double), c->stream);
+  cudaStreamSynchronize(c->stream);
+  return c;
+}
+
+extern "C" void pion_gpu_destroy(pion_gpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm) ncclCommDestroy(c->comm);
+  cudaFree(c->P); cudaFree(c->Ph); cudaFree(c->dU); cudaFree(c->eta); cudaFree(c->hll); cudaFree(c->mask);
+  cudaFree(c->d_dtmin); cudaFree(c->d_counters);
+  for (int f = 0; f < 6; f++) { cudaFree(c->sendbuf[f]); cudaFree(c->recvbuf[f]); }
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->ev_a) cudaEventDestroy(c->ev_a);
+  if (c->ev_b) cudaEventDestroy(c->ev_b);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  delete c;
+}
+
+static int ensure_dU(pion_gpu_ctx* c) {
+  if (c->dU) return 0;
+  CUDA_OK(cudaMalloc(&c->dU, c->arr_elems * sizeof(double)));
+  CUDA_OK(cudaMemsetAsync(c->dU, 0, c->arr_elems * sizeof(double), c->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// upload / download: compact padded SoA on the host <-> pitched SoA on the device
+// ---------------------------------------------------------------------------
+static double* state_ptr(pion_gpu_ctx* c, int which) {
+  if (which == PION_STATE_P) return c->P;
+  if (which == PION_STATE_PH) return c->ph_valid ? c->Ph : c->P;  // after a fused full step Ph == P
+  return c->dU;
+}
+
+extern "C" int pion_gpu_upload(pion_gpu_ctx* c, int which, const double* soa) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (which == PION_STATE_DU && ensure_dU(c)) return 1;
+  if (which == PION_STATE_PH && !c->ph_valid) {
+    CUDA_OK(cudaMemcpyAsync(c->Ph, c->P, c->arr_elems * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->ph_valid = true;
+  }
+  double* dst = (which == PION_STATE_P) ? c->P : (which == PION_STATE_PH) ? c->Ph : c->dU;
+  const GridD& g = c->g;
+  const size_t rows = (size_t)g.NGa[1] * g.NGa[2];
+  for (int v = 0; v < c->nvar; v++) {
+    CUDA_OK(cudaMemcpy2DAsync(dst + (size_t)v * g.vs + g.xoff, g.sy * sizeof(double),
+                              soa + (size_t)v * rows * g.NGa[0], g.NGa[0] * sizeof(double), g.NGa[0] * sizeof(double),
+                              rows, cudaMemcpyHostToDevice, c->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (which == PION_STATE_P) c->next_dt_valid = false;
+  return 0;
+}
+
+extern "C" int pion_gpu_download(pion_gpu_ctx* c, int which, double* soa) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (which == PION_STATE_DU && ensure_dU(c)) return 1;
+  const double* src = state_ptr(c, which);
+  const GridD& g = c->g;
+  const size_t rows = (size_t)g.NGa[1] * g.NGa[2];
+  for (int v = 0; v < c->nvar; v++) {
+    CUDA_OK(cudaMemcpy2DAsync(soa + (size_t)v * rows * g.NGa[0], g.NGa[0] * sizeof(double),
+                              src + (size_t)v * g.vs + g.xoff, g.sy * sizeof(double), g.NGa[0] * sizeof(double), rows,
+                              cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// boundaries
+// ---------------------------------------------------------------------------
+static void fill_bc_args(pion_gpu_ctx* c, BCArgs& b, int face, int type, double* A0, double* A1, double simtime,
+                         const double* refval) {
+  b.g = c->g;
+  b.A[0] = A0;
+  b.A[1] = A1;
+  b.narr = A1 ? 2 : 1;
+  b.face = face;
+  b.type = type;
+  b.nvar = c->nvar;
+  b.eq = c->cfg.eqntype;
+  b.ftr = c->nbase_;
+  for (int v = 0; v < PION_MAXVAR; v++) b.refval[v] = refval ? refval[v] : 0.0;
+  b.simtime = simtime;
+  for (int a = 0; a < 3; a++) b.sim_xmin[a] = c->cfg.xmin[a];
+}
+
+static long face_cells(const GridD& g, int face) {
+  long n = g.nb[face >> 1];
+  for (int q = 0; q < 3; q++)
+    if (q != (face >> 1)) n *= g.NGa[q];
+  return n;
+}
+
+static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A);
+
+// TimeUpdateInternalBCs + TimeUpdateExternalBCs on the given arrays (A1 may be null)
+static int update_bcs_arrays(pion_gpu_ctx* c, double* A0, double* A1, double simtime) {
+  const GridD& g = c->g;
+  for (int ax = 0; ax < g.ndim; ax++) {
+    bool mpi_face = false;
+    for (int s = 0; s < 2; s++) {
+      const int face = 2 * ax + s;
+      const int type = c->cfg.bc[face];
+      if (type == PION_BC_MPI) { mpi_face = true; continue; }
+      BCArgs b;
+      fill_bc_args(c, b, face, type, A0, A1, simtime, c->bc_refval[face]);
+      k_bc_face<<<nblocks(face_cells(g, face), 128), 128, 0, c->stream>>>(b);
+      c->launches++;
+    }
+    if (mpi_face) {
+      if (halo_exchange_axis(c, ax, A0)) return 1;
+      if (A1 && halo_exchange_axis(c, ax, A1)) return 1;
+    }
+  }
+  for (int i = 0; i < c->cfg.n_internal_bc; i++) {
+    if (c->cfg.internal_bc[i] == PION_BC_DMACH2) {
+      BCArgs b;
+      fill_bc_args(c, b, 2, PION_BC_DMACH2, A0, A1, simtime, c->bc_refval[6 + i]);
+      k_bc_dmach2<<<nblocks((long)g.NG[0] * g.nb[1], 128), 128, 0, c->stream>>>(b);
+      c->launches++;
+    }
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pion_gpu_time_update_bcs(pion_gpu_ctx* c, double simtime, int cstep, int maxstep) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (!c->ph_valid) {  // make Ph a true copy before it is used as a separate array again
+    CUDA_OK(cudaMemcpyAsync(c->Ph, c->P, c->arr_elems * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->ph_valid = true;
+  }
+  return update_bcs_arrays(c, c->Ph, (cstep == maxstep) ? c->P : nullptr, simtime);
+}
+
+// one device->host read of `n` doubles starting at element `idx` of variable planes of A
+static int fetch_cell(pion_gpu_ctx* c, const double* A, long cidx_, double* out) {
+  for (int v = 0; v < c->nvar; v++)
+    CUDA_OK(cudaMemcpyAsync(out + v, A + (size_t)v * c->g.vs + cidx_, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// sim_init::Init after ReadData (sim_init.cpp:215-262)
+extern "C" int pion_gpu_init_after_upload(pion_gpu_ctx* c) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const GridD& g = c->g;
+  const long ncell = (long)g.NG[0] * g.NG[1] * g.NG[2];
+  // Ph = P on the grid; psi = 0 at step 0 for GLM (:215-241)
+  const int zero_var = (c->cfg.eqntype == PION_EQGLM && c->timestep == 0) ? 8 : -1;
+  if (zero_var >= 0) {
+    k_zero_var_interior<<<nblocks(ncell, 256), 256, 0, c->stream>>>(g, c->P, zero_var);
+    c->launches++;
+  }
+  k_copy_interior<<<nblocks(ncell, 256), 256, 0, c->stream>>>(g, c->P, c->Ph, c->nvar, -1);
+  c->launches++;
+  c->ph_valid = true;
+  // assign_boundary_data (assign_update_bcs.cpp:28-120), face by face in list order;
+  // reference values of INFLOW / FIXED / REFLECTING / DMACH are fixed here.
+  for (int face = 0; face < 2 * g.ndim; face++) {
+    const int type = c->cfg.bc[face];
+    const int ax = face >> 1, pos = face & 1;
+    double* rv = c->bc_refval[face];
+    for (int v = 0; v < PION_MAXVAR; v++) rv[v] = 0.0;
+    if (type == PION_BC_MPI) continue;
+    if (type == PION_BC_REFLECTING) {  // reflecting_boundaries.cpp:36-75
+      for (int v = 0; v < c->nvar; v++) rv[v] = 1.0;
+      rv[2 + ax] = -1.0;
+      if (c->cfg.eqntype != PION_EQEUL) rv[5 + ax] = -1.0;
+    } else if (type == PION_BC_DMACH) {  // double_Mach_ref_boundaries.cpp:33-38
+      rv[0] = 1.4; rv[1] = 1.0; rv[2] = rv[3] = rv[4] = 0.0;
+      for (int v = c->nbase_; v < c->nvar; v++) rv[v] = -1.0;
+    } else if (type == PION_BC_INFLOW || type == PION_BC_FIXED) {
+      // INFLOW: P of the source of the LAST ghost cell in the list (inflow_boundaries.cpp:36-52);
+      // FIXED: P of the source of the FIRST ghost cell (fixed_boundaries.cpp:45-63).
+      int lo[3], hi[3];
+      for (int q = 0; q < 3; q++) { lo[q] = 0; hi[q] = g.NGa[q]; }
+      if (ax == 0) { for (int q = 1; q < 3; q++) { lo[q] = g.nb[q]; hi[q] = g.NGa[q] - g.nb[q]; } }
+      else if (ax == 1) { lo[2] = g.nb[2]; hi[2] = g.NGa[2] - g.nb[2]; }
+      int ijk[3];
+      for (int q = 0; q < 3; q++) ijk[q] = (type == PION_BC_INFLOW) ? hi[q] - 1 : lo[q];
+      ijk[ax] = pos ? g.NGa[ax] - g.nb[ax] - 1 : g.nb[ax];  // the edge cell
+      if (fetch_cell(c, c->P, gidx(g, ijk[0], ijk[1], ijk[2]), rv)) return 1;
+    }
+    BCArgs b;
+    // BC_assign_ONEWAY_OUT is BC_assign_OUTFLOW: no velocity clamp at assign time
+    // (oneway_out_boundaries.cpp:24-32)
+    fill_bc_args(c, b, face, (type == PION_BC_ONEWAY_OUT) ? PION_BC_OUTFLOW : type, c->P, c->Ph, c->simtime, rv);
+    k_bc_face<<<nblocks(face_cells(g, face), 128), 128, 0, c->stream>>>(b);
+    c->launches++;
+  }
+  for (int i = 0; i < c->cfg.n_internal_bc; i++) {
+    double* rv = c->bc_refval[6 + i];
+    for (int v = 0; v < PION_MAXVAR; v++) rv[v] = 0.0;
+    if (c->cfg.internal_bc[i] == PION_BC_DMACH2) {  // double_Mach_ref_boundaries.cpp:104-110
+      rv[0] = 8.0; rv[1] = 116.5; rv[2] = 7.14470958; rv[3] = -4.125; rv[4] = 0.0;
+      for (int v = c->nbase_; v < c->nvar; v++) rv[v] = 1.0;
+    } else {
+      set_error("unsupported internal boundary");
+      return 1;
+    }
+  }
+  // first TimeUpdateInternal/ExternalBCs (sim_init.cpp:259-262), cstep==maxstep
+  if (update_bcs_arrays(c, c->Ph, c->P, c->simtime)) return 1;
+  if (c->cfg.op_criterion == 1) {  // sim_init.cpp:270-280
+    c->next_optime = c->simtime + c->cfg.opfreq_time;
+    double tmp = ((c->simtime / c->cfg.opfreq_time) - floor(c->simtime / c->cfg.opfreq_time)) * c->cfg.opfreq_time;
+    c->next_optime -= tmp;
+  }
+  c->next_dt_valid = false;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// time step
+// ---------------------------------------------------------------------------
+static const unsigned long long DT_INIT_BITS = 0x54B249AD2594C37DULL;  // bits of 1.0e100
+
+static int launch_calc_dt(pion_gpu_ctx* c) {
+  const GridD& g = c->g;
+  const long ncell = (long)g.NG[0] * g.NG[1] * g.NG[2];
+  CUDA_OK(cudaMemcpyAsync(c->d_dtmin, &DT_INIT_BITS, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  const int blocks = nblocks(ncell, 256, 148 * 8);
+  switch (c->cfg.eqntype) {
+    case PION_EQEUL: k_calc_dt<EQ_EULER><<<blocks, 256, 0, c->stream>>>(g, c->pp, c->P, nullptr, c->cfg.cfl, c->d_dtmin); break;
+    case PION_EQMHD: k_calc_dt<EQ_MHD><<<blocks, 256, 0, c->stream>>>(g, c->pp, c->P, nullptr, c->cfg.cfl, c->d_dtmin); break;
+    default: k_calc_dt<EQ_GLM><<<blocks, 256, 0, c->stream>>>(g, c->pp, c->P, nullptr, c->cfg.cfl, c->d_dtmin); break;
+  }
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  c->next_dt_valid = true;
+  return 0;
+}
+
+static int read_dtmin(pion_gpu_ctx* c, double* out) {
+  CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->d_dtmin, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  double d;
+  memcpy(&d, c->h_pinned, sizeof(double));
+  *out = d;
+  return 0;
+}
+
+extern "C" int pion_gpu_calc_dt(pion_gpu_ctx* c, double* t_dyn, double* t_mp) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (!c->next_dt_valid && launch_calc_dt(c)) return 1;
+  double d;
+  if (read_dtmin(c, &d)) return 1;
+  if (t_dyn) *t_dyn = d;
+  if (t_mp) *t_mp = 1.0e99;  // calc_microphysics_dt without MP (calc_timestep.cpp:355-357)
+  return 0;
+}
+
+extern "C" int pion_gpu_calculate_timestep(pion_gpu_ctx* c, double* dt_out) {
+  double t_dyn, t_mp;
+  if (pion_gpu_calc_dt(c, &t_dyn, &t_mp)) return 1;
+  if (c->comm) {  // sim_control_MPI.cpp:503-504: global MIN of both
+    double* d_red = reinterpret_cast<double*>(c->d_dtmin + 1);
+    double h[1] = {fmin(t_dyn, 1.0e100)};
+    // the two minima travel as one 2-element all-reduce
+    double hv[2] = {t_dyn, t_mp};
+    (void)h;
+    static_assert(sizeof(double) == sizeof(unsigned long long), "size");
+    double* d2 = nullptr;
+    CUDA_OK(cudaMalloc(&d2, 2 * sizeof(double)));
+    CUDA_OK(cudaMemcpyAsync(d2, hv, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCCL_OK(ncclAllReduce(d2, d2, 2, ncclDouble, ncclMin, c->comm, c->stream));
+    CUDA_OK(cudaMemcpyAsync(hv, d2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(d2));
+    (void)d_red;
+    t_dyn = hv[0];
+    t_mp = hv[1];
+  }
+  if (!(t_dyn > 0.0)) { set_error("CellTimeStep function returned failing value"); return 1; }
+  c->dt = fmin(t_dyn, t_mp);
+  // Set_GLM_Speeds(td, dx, cr): c_h = CFL*dx/t_dyn, c_r = 0.25/dx (calc_timestep.cpp:121-131)
+  if (c->cfg.eqntype == PION_EQGLM) {
+    c->chyp = c->cfg.cfl * c->g.dx / t_dyn;
+    c->cr = 0.25 / c->g.dx;
+  }
+  // timestep_checking_and_limiting (:219-262)
+  c->dt = fmin(c->dt, 1.3 * c->last_dt);
+  if (c->cfg.op_criterion == 1) {
+    c->dt = fmin(c->dt, c->next_optime - c->simtime);
+    if (c->dt <= 0.0) { set_error("Went past output time without outputting!"); return 1; }
+  }
+  c->dt = fmin(c->dt, c->cfg.finishtime - c->simtime);
+  if (c->dt <= 0.0) { set_error("Negative timestep!"); return 1; }
+  c->FV_dt = c->dt;
+  if (dt_out) *dt_out = c->dt;
+  return 0;
+}
+
+extern "C" int pion_gpu_set_dt(pion_gpu_ctx* c, double dt) {
+  c->dt = dt;
+  c->FV_dt = dt;
+  return 0;
+}
+extern "C" int pion_gpu_set_glm_speeds(pion_gpu_ctx* c, double t_dyn, double dx, double cr) {
+  c->chyp = c->cfg.cfl * dx / t_dyn;  // solver_eqn_mhd_adi.cpp:916
+  c->cr = cr;
+  return 0;
+}
+extern "C" int pion_gpu_set_time(pion_gpu_ctx* c, double simtime, double last_dt, int timestep) {
+  c->simtime = simtime;
+  c->last_dt = last_dt;
+  c->timestep = timestep;
+  return 0;
+}
+extern "C" int pion_gpu_get_time(pion_gpu_ctx* c, double* simtime, double* dt, double* last_dt, int* timestep) {
+  if (simtime) *simtime = c->simtime;
+  if (dt) *dt = c->dt;
+  if (last_dt) *last_dt = c->last_dt;
+  if (timestep) *timestep = c->timestep;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// dynamics
+// ---------------------------------------------------------------------------
+static int launch_preprocess(pion_gpu_ctx* c, const double* S, int order) {
+  const GridD& g = c->g;
+  if (c->hll) {  // solver_eqn_base.cpp:398-412
+    long n = (long)(g.NGa[0] - 2) * ((g.ndim > 1) ? g.NGa[1] - 2 : 1) * ((g.ndim > 2) ? g.NGa[2] - 2 : 1);
+    k_hlld_flags<<<nblocks(n, 256), 256, 0, c->stream>>>(g, S, c->hll);
+    c->launches++;
+  }
+  if (c->eta) {  // solver_eqn_base.cpp:423-573
+    long n = (long)g.NGa[0] * g.NGa[1] * g.NGa[2];
+    const double tiny2 = PION_VERY_TINY_VALUE * g.dx * g.dx;
+    switch (c->cfg.eqntype) {
+      case PION_EQEUL: k_hcorr_eta<EQ_EULER><<<nblocks(n, 128), 128, 0, c->stream>>>(g, S, c->eta, order, c->pp.gamma, tiny2); break;
+      case PION_EQMHD: k_hcorr_eta<EQ_MHD><<<nblocks(n, 128), 128, 0, c->stream>>>(g, S, c->eta, order, c->pp.gamma, tiny2); break;
+      default: k_hcorr_eta<EQ_GLM><<<nblocks(n, 128), 128, 0, c->stream>>>(g, S, c->eta, order, c->pp.gamma, tiny2); break;
+    }
+    c->launches++;
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double* dU, double dt, int order,
+                        bool fused, bool want_dt) {
+  StageArgs a;
+  a.g = c->g;
+  a.pp = c->pp;
+  a.pp.chyp = c->chyp;
+  a.S = S;
+  a.Pb = Pb;
+  a.out = out;
+  a.dU = dU;
+  a.hll = c->hll;
+  a.eta = c->eta;
+  a.mask = c->mask;
+  a.dt = dt;
+  a.tiny2 = PION_VERY_TINY_VALUE * c->g.dx * c->g.dx;
+  a.glm_damp = exp(-dt * c->chyp * c->cr);  // eqns_mhd_adiabatic.cpp:650-660 with FV_dt
+  a.cfl = c->cfg.cfl;
+  a.dtmin = want_dt ? c->d_dtmin : nullptr;
+  a.counters = c->d_counters;
+  a.order = order;
+  a.ntr = c->ntr;
+  a.fused = fused ? 1 : 0;
+  const int fkj = (c->cfg.artviscosity == 1 || c->cfg.artviscosity == 4) ? 1 : 0;
+  a.fkj = fkj;
+  if (want_dt)
+    CUDA_OK(cudaMemcpyAsync(c->d_dtmin, &DT_INIT_BITS, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->timing) {
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    CUDA_OK(cudaEventRecord(e0, c->stream));
+  }
+  switch (c->cfg.eqntype) {
+    case PION_EQEUL: launch_stage_euler(c->cfg.solver, fkj, a, c->stream); break;
+    case PION_EQMHD: launch_stage_mhd(c->cfg.solver, fkj, a, c->stream); break;
+    default: launch_stage_glm(c->cfg.solver, fkj, a, c->stream); break;
+  }
+  if (c->timing) {
+    CUDA_OK(cudaEventRecord(e1, c->stream));
+    c->tev.push_back(e0);
+    c->tev.push_back(e1);
+  }
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pion_gpu_calc_microphysics_dU(pion_gpu_ctx* c, double dt) {
+  (void)dt;
+  if (!c->cfg.cooling) return 0;  // time_integrator.cpp:264: no MP -> nothing to do
+  set_error("cooling source term not built yet");
+  return 1;
+}
+
+extern "C" int pion_gpu_calc_dynamics_dU(pion_gpu_ctx* c, double dt, int step) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (ensure_dU(c)) return 1;
+  if (!c->ph_valid) {
+    CUDA_OK(cudaMemcpyAsync(c->Ph, c->P, c->arr_elems * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->ph_valid = true;
+  }
+  c->FV_dt = dt;
+  const int order = (step == 1) ? 1 : 2;
+  if (launch_preprocess(c, c->Ph, order)) return 1;
+  return launch_stage(c, c->Ph, c->P, nullptr, c->dU, dt, order, false, false);
+}
+
+extern "C" int pion_gpu_grid_update_state_vector(pion_gpu_ctx* c, double dt, int step, int ooa) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (ensure_dU(c)) return 1;
+  if (!c->ph_valid) {
+    CUDA_OK(cudaMemcpyAsync(c->Ph, c->P, c->arr_elems * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->ph_valid = true;
+  }
+  c->FV_dt = dt;
+  UpdateArgs a;
+  a.g = c->g;
+  a.pp = c->pp;
+  a.P = c->P;
+  a.Ph = c->Ph;
+  a.dU = c->dU;
+  a.mask = c->mask;
+  a.counters = c->d_counters;
+  a.glm_damp = exp(-dt * c->chyp * c->cr);
+  a.ntr = c->ntr;
+  a.full = (step == ooa) ? 1 : 0;
+  const long n = (long)c->g.NGa[0] * c->g.NGa[1] * c->g.NGa[2];
+  switch (c->cfg.eqntype) {
+    case PION_EQEUL: k_update_state<EQ_EULER><<<nblocks(n, 256), 256, 0, c->stream>>>(a); break;
+    case PION_EQMHD: k_update_state<EQ_MHD><<<nblocks(n, 256), 256, 0, c->stream>>>(a); break;
+    default: k_update_state<EQ_GLM><<<nblocks(n, 256), 256, 0, c->stream>>>(a); break;
+  }
+  c->launches++;
+  if (a.full) c->next_dt_valid = false;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// time_integrator::advance_time (time_integrator.cpp:72-142), fused fast path.
+//   predictor : stencil from P (== Ph at the start of a step), writes Ph
+//   corrector : stencil from Ph, base state P, writes P in place and reduces the
+//               next step's CFL dt; Ph's interior is then stale until the next predictor.
+// HBM traffic per cell-update: read P, write Ph, read Ph + P, write P = 5*nvar*8 B.
+extern "C" int pion_gpu_advance_time(pion_gpu_ctx* c, double* dt_done) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  const double dt = c->dt;
+  if (c->cfg.cooling) { set_error("cooling source term not built yet"); return 1; }
+  if (c->cfg.tmOOA == 1) {
+    // first_order_update(dt, OA1) + BCs (OA1, OA1): full step in one stage
+    c->FV_dt = dt;
+    const double* S = c->ph_valid ? c->Ph : c->P;
+    // the single stage reads P's stencil and must not write P in place: go through Ph
+    if (launch_preprocess(c, c->P, 1)) return 1;
+    (void)S;
+    if (launch_stage(c, c->P, c->P, c->Ph, nullptr, dt, 1, true, true)) return 1;
+    // P = Ph on the interior, then boundaries of both
+    const long ncell = (long)c->g.NG[0] * c->g.NG[1] * c->g.NG[2];
+    k_copy_interior<<<nblocks(ncell, 256), 256, 0, c->stream>>>(c->g, c->Ph, c->P, c->nvar, -1);
+    c->launches++;
+    c->ph_valid = true;
+    if (update_bcs_arrays(c, c->Ph, c->P, c->simtime)) return 1;
+    c->next_dt_valid = true;
+  } else {
+    // first_order_update(0.5 dt, OA2): Setdt(0.5dt), dynamics OA1, update Ph
+    c->FV_dt = 0.5 * dt;
+    if (launch_preprocess(c, c->P, 1)) return 1;
+    if (launch_stage(c, c->P, c->P, c->Ph, nullptr, 0.5 * dt, 1, true, false)) return 1;
+    // boundaries of Ph (cstep=OA1 != maxstep=OA2), simtime = start of step
+    if (update_bcs_arrays(c, c->Ph, nullptr, c->simtime)) return 1;
+    // second_order_update(dt, OA2): Setdt(dt), dynamics OA2 from Ph, update P
+    c->FV_dt = dt;
+    if (launch_preprocess(c, c->Ph, 2)) return 1;
+    if (launch_stage(c, c->Ph, c->P, c->P, nullptr, dt, 2, true, true)) return 1;
+    // boundaries of P (and Ph == P): only P is kept current
+    if (update_bcs_arrays(c, c->P, nullptr, c->simtime)) return 1;
+    c->ph_valid = false;
+    c->next_dt_valid = true;
+  }
+  c->simtime += dt;
+  c->last_dt = dt;
+  c->timestep++;
+  if (dt_done) *dt_done = dt;
+  return 0;
+}
+
+extern "C" int pion_gpu_run(pion_gpu_ctx* c, int nsteps, double* dts) {
+  for (int i = 0; i < nsteps; i++) {
+    double dt;
+    if (pion_gpu_calculate_timestep(c, &dt)) return 1;
+    if (pion_gpu_advance_time(c, nullptr)) return 1;
+    if (dts) dts[i] = dt;
+  }
+  return 0;
+}
+
+extern "C" int pion_gpu_counters(pion_gpu_ctx* c, long long* out3) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  long long h[2];
+  CUDA_OK(cudaMemcpyAsync(h, c->d_counters, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  out3[0] = h[0];
+  out3[1] = h[1];
+  out3[2] = c->launches;
+  return 0;
+}
+extern "C" int pion_gpu_sync(pion_gpu_ctx* c) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" void* pion_gpu_stream(pion_gpu_ctx* c) { return (void*)c->stream; }
+
+extern "C" int pion_gpu_stage_timing(pion_gpu_ctx* c, int enable, double* total_ms, long long* nlaunch) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < c->tev.size(); i += 2) {
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, c->tev[i], c->tev[i + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (nlaunch) *nlaunch = (long long)(c->tev.size() / 2);
+  for (auto e : c->tev) cudaEventDestroy(e);
+  c->tev.clear();
+  c->timing = enable != 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU: NCCL halo exchange + decomposition
+// ---------------------------------------------------------------------------
+extern "C" int pion_gpu_nccl_unique_id(char* out128) {
+  ncclUniqueId id;
+  NCCL_OK(ncclGetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+extern "C" int pion_gpu_nccl_init(pion_gpu_ctx* c, const char* unique_id128) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  ncclUniqueId id;
+  memcpy(&id, unique_id128, 128);
+  NCCL_OK(ncclCommInitRank(&c->comm, c->cfg.nproc, id, c->cfg.rank));
+  for (int f = 0; f < 2 * c->g.ndim; f++) {
+    if (c->cfg.bc[f] != PION_BC_MPI) continue;
+    c->halo_elems[f] = (size_t)face_cells(c->g, f) * c->nvar;
+    CUDA_OK(cudaMalloc(&c->sendbuf[f], c->halo_elems[f] * sizeof(double)));
+    CUDA_OK(cudaMalloc(&c->recvbuf[f], c->halo_elems[f] * sizeof(double)));
+  }
+  return 0;
+}
+
+// BC_update_BCMPI for both faces of one axis (MCMD_boundaries.cpp:122-236):
+// pack -> grouped ncclSend/ncclRecv -> unpack, all on the compute stream.
+static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A) {
+  if (!c->comm) { set_error("BCMPI face but no NCCL communicator (call pion_gpu_nccl_init)"); return 1; }
+  const GridD& g = c->g;
+  for (int s = 0; s < 2; s++) {
+    const int f = 2 * ax + s;
+    if (c->cfg.bc[f] != PION_BC_MPI) continue;
+    HaloArgs h;
+    h.g = g; h.A = A; h.buf = c->sendbuf[f]; h.face = f; h.nvar = c->nvar; h.pack = 1;
+    k_halo<<<nblocks((long)c->halo_elems[f], 256), 256, 0, c->stream>>>(h);
+    c->launches++;
+  }
+  NCCL_OK(ncclGroupStart());
+  for (int s = 0; s < 2; s++) {
+    const int f = 2 * ax + s;
+    if (c->cfg.bc[f] != PION_BC_MPI) continue;
+    NCCL_OK(ncclSend(c->sendbuf[f], c->halo_elems[f], ncclDouble, c->cfg.ngbprocs[f], c->comm, c->stream));
+    NCCL_OK(ncclRecv(c->recvbuf[f], c->halo_elems[f], ncclDouble, c->cfg.ngbprocs[f], c->comm, c->stream));
+  }
+  NCCL_OK(ncclGroupEnd());
+  for (int s = 0; s < 2; s++) {
+    const int f = 2 * ax + s;
+    if (c->cfg.bc[f] != PION_BC_MPI) continue;
+    HaloArgs h;
+    h.g = g; h.A = A; h.buf = c->recvbuf[f]; h.face = f; h.nvar = c->nvar; h.pack = 0;
+    k_halo<<<nblocks((long)c->halo_elems[f], 256), 256, 0, c->stream>>>(h);
+    c->launches++;
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// MCMDcontrol::decomposeDomain (MCMD_control.cpp:62-221): halve the longest local
+// axis until nproc sub-blocks (ties -> lowest axis); rank = nx*ny*iz + nx*iy + ix;
+// pointToNeighbours (:316-420): neighbour ranks, periodic wrap.
+extern "C" int pion_gpu_decompose_domain(pion_gpu_config* cfg, int rank, int nproc) {
+  if (nproc < 1 || (nproc & (nproc - 1))) { set_error("nproc must be a power of two (MCMD_control.cpp:98-104)"); return 1; }
+  int nx[3] = {1, 1, 1};
+  double range[3], locrange[3];
+  int locNG[3];
+  for (int a = 0; a < 3; a++) {
+    range[a] = (a < cfg->ndim) ? cfg->xmax[a] - cfg->xmin[a] : 0.0;
+    locrange[a] = range[a];
+    locNG[a] = (a < cfg->ndim) ? cfg->NG[a] : 1;
+  }
+  int npcounter = 1;
+  while (npcounter < nproc) {
+    int dsplit = 0;
+    double maxrange = 0.;
+    for (int a = 0; a < cfg->ndim; a++) {
+      if (locrange[a] > maxrange * (1.0 + 1.0e-12)) { maxrange = locrange[a]; dsplit = a; }  // ties keep the lowest axis
+    }
+    locrange[dsplit] /= 2.;
+    if (locNG[dsplit] % 2) { set_error("grid not divisible by the decomposition"); return 1; }
+    locNG[dsplit] /= 2;
+    nx[dsplit] *= 2;
+    npcounter *= 2;
+  }
+  int ix[3];
+  ix[0] = rank % nx[0];
+  ix[1] = (rank / nx[0]) % nx[1];
+  ix[2] = rank / (nx[0] * nx[1]);
+  cfg->rank = rank;
+  cfg->nproc = nproc;
+  double gxmin[3], dxg = range[0] / cfg->NG[0];
+  (void)dxg;
+  for (int a = 0; a < 3; a++) gxmin[a] = cfg->xmin[a];
+  for (int a = 0; a < cfg->ndim; a++) {
+    cfg->sim_xmin[a] = gxmin[a];
+    cfg->NG[a] = locNG[a];
+    cfg->xmin[a] = gxmin[a] + ix[a] * locrange[a];
+    cfg->xmax[a] = gxmin[a] + (ix[a] + 1) * locrange[a];
+    const int stride = (a == 0) ? 1 : (a == 1) ? nx[0] : nx[0] * nx[1];
+    const int lo = 2 * a, hi = 2 * a + 1;
+    const int bc_lo = cfg->bc[lo], bc_hi = cfg->bc[hi];
+    cfg->ngbprocs[lo] = cfg->ngbprocs[hi] = -1;
+    if (ix[a] > 0) { cfg->ngbprocs[lo] = rank - stride; cfg->bc[lo] = PION_BC_MPI; }
+    else if (bc_lo == PION_BC_PERIODIC && nx[a] > 1) { cfg->ngbprocs[lo] = rank + (nx[a] - 1) * stride; cfg->bc[lo] = PION_BC_MPI; }
+    if (ix[a] < nx[a] - 1) { cfg->ngbprocs[hi] = rank + stride; cfg->bc[hi] = PION_BC_MPI; }
+    else if (bc_hi == PION_BC_PERIODIC && nx[a] > 1) { cfg->ngbprocs[hi] = rank - (nx[a] - 1) * stride; cfg->bc[hi] = PION_BC_MPI; }
+  }
+  return 0;
+}

@@ -1,0 +1,13 @@
+// Euler instantiations of the stage kernel (HLL, Roe-CV; FKJ98 on/off).
+#include "stage_kernel.cuh"
+namespace pion {
+void launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s) {
+  if (solver == SOLVE_ROE) {
+    if (fkj) launch_stage_t<EQ_EULER, SOLVE_ROE, true>(a, s);
+    else launch_stage_t<EQ_EULER, SOLVE_ROE, false>(a, s);
+  } else {
+    if (fkj) launch_stage_t<EQ_EULER, SOLVE_HLL, true>(a, s);
+    else launch_stage_t<EQ_EULER, SOLVE_HLL, false>(a, s);
+  }
+}
+}  // namespace pion

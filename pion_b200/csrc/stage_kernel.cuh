@@ -1,0 +1,329 @@
+// pion_b200/csrc/stage_kernel.cuh -- one predictor or corrector stage of the
+// finite-volume update as ONE kernel (gather form).
+//
+// Reference path restated (paths relative to /root/reference/source):
+//   sim_control/time_integrator.cpp:498-873  calc_dynamics_dU / set_dynamics_dU /
+//                                            dynamics_dU_column (per-axis column sweeps
+//                                            scattering into dU)
+//   coord_sys/VectorOps.cpp:535-644          SetEdgeState, SetSlope, DivStateVectorComponent
+//   spatial_solvers/solver_eqn_base.cpp:152-342  InterCellFlux, tracer flux, select_Hcorr_eta
+//   spatial_solvers/solver_eqn_mhd_adi.cpp:368-443,782-844  dU_Cell, Powell + GLM sources,
+//                                            CellAdvanceTime (+GLMsource)
+//   sim_control/time_integrator.cpp:881-958  grid_update_state_vector
+//   sim_control/calc_timestep.cpp:271-333    calc_dynamics_dt (fused into the corrector)
+//
+// The reference walks 1-D columns and scatters each interface's contribution into
+// the two adjacent cells' dU.  Here each thread GATHERS everything that lands in
+// its own cell, in the reference's accumulation order
+//   dU = [microphysics] ; for axis in x,y,z: + src_R(i-1,i) ; - src_L(i,i+1) ; + dt*(F_{i-1/2}-F_{i+1/2})/dx
+// and (fused mode) immediately applies CellAdvanceTime, so dU, slopes, edge states
+// and fluxes never touch HBM.  The axis loop is a real loop: the solver frame is
+// rotated in registers between axes, so the Riemann solver is instantiated once.
+#pragma once
+#include "grid.cuh"
+
+namespace pion {
+
+struct StageArgs {
+  GridD g;
+  PhysParams pp;
+  const double* S;    // stencil source: Ph (or P on the fused predictor, where Ph==P)
+  const double* Pb;   // base state P of U = PtoU(P) + dU
+  double* out;        // fused: destination primitive array (Ph on predictor, P on corrector)
+  double* dU;         // unfused: accumulated into; fused: optional microphysics dU (read), else null
+  const unsigned char* hll;  // HLLD->HLL switch flags per cell (null unless solver==HLLD)
+  const double* eta;         // H-correction eta, 3 planes of vs doubles (null unless AV 3/4)
+  const unsigned char* mask; // 1 = cell is updated (isdomain); null = every interior cell
+  double dt;          // stage dt == FV_dt
+  double tiny2;       // VERY_TINY_VALUE * dx^2 (minmod cut-off for undivided differences)
+  double glm_damp;    // exp(-FV_dt * c_h * c_r)
+  double cfl;
+  unsigned long long* dtmin;  // corrector: ordered-bits min of the next CFL dt (null = skip)
+  long long* counters;        // [0] negative density, [1] negative pressure fix-ups
+  int order;          // spatial order of this stage (1 or 2)
+  int ntr;            // tracers
+  int fused;          // 1: apply CellAdvanceTime and write `out`; 0: dU += ...
+  int fkj;            // FKJ98 viscosity on (AV 1 or 4)
+};
+
+// sCMA corrector of one tracer value (microphysics_base.cpp:80-126 with no element
+// tracers): the second assignment wins, so only values > 1 are rescaled.
+__device__ __forceinline__ double scma_corr(double tr) { return (tr > 1.0) ? 1.0 / tr : 1.0; }
+
+// CellTimeStep: Euler solver_eqn_hydro_adi.cpp:460-500, MHD solver_eqn_mhd_adi.cpp:516-574
+template <int EQ>
+__device__ __forceinline__ double cell_time_step(const Prim& p, const PhysParams& pp, int ndim, double dx, double cfl) {
+  double temp;
+  if (EQ == EQ_EULER) {
+    temp = p.vn * p.vn;
+    if (ndim > 1) temp += p.vt1 * p.vt1;
+    if (ndim > 2) temp += p.vt2 * p.vt2;
+    temp = sqrt(temp) + chydro(p.ro, p.pg, pp.gamma);
+  } else {
+    temp = fabs(p.vn);
+    if (ndim > 1) temp = fmax(temp, fabs(p.vt1));
+    if (ndim > 2) temp = fmax(temp, fabs(p.vt2));
+    double bx = p.bn, by = p.bt1, bz = p.bt2;
+    if (ndim > 1) {
+      // rotate to the axis of smallest |B| component (:541-563)
+      int newdir = 0;
+      if (fabs(p.bt1) < fabs(p.bn)) {
+        newdir = 1;
+        if (fabs(p.bt2) < fabs(p.bt1)) newdir = 2;
+      } else if (fabs(p.bt2) < fabs(p.bn)) newdir = 2;
+      if (newdir == 1) { bx = p.bt1; by = p.bt2; bz = p.bn; }
+      if (newdir == 2) { bx = p.bt2; by = p.bn; bz = p.bt1; }
+    }
+    temp += cfast_components(p.ro, p.pg, bx, by, bz, pp.gamma);
+  }
+  return (dx / temp) * cfl;
+}
+
+__device__ __forceinline__ unsigned long long dbl_ordered_bits(double x) {
+  // positive finite doubles order like their bit patterns
+  return (unsigned long long)__double_as_longlong(x);
+}
+
+template <int EQ, int SOLVER, bool FKJ>
+__global__ void __launch_bounds__(128) k_stage(const __grid_constant__ StageArgs a) {
+  const GridD& g = a.g;
+  const int NX = g.NG[0], NY = g.NG[1];
+  const long ncell = (long)NX * NY * g.NG[2];
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = t < ncell;
+  double my_dt = 1.0e100;
+  int status = 0;
+
+  if (active) {
+    const int i = (int)(t % NX), j = (int)((t / NX) % NY), k = (int)(t / ((long)NX * NY));
+    const long c = gidx(g, i + g.nb[0], j + g.nb[1], k + g.nb[2]);
+    const long vs = g.vs;
+    const bool domain = a.mask ? (a.mask[c] != 0) : true;
+    constexpr int NB = nbase(EQ);
+    const double idx = 1.0 / g.dx;
+    const double dt = a.dt;
+
+    Cons acc;
+    acc.rho = acc.erg = acc.mn = acc.mt1 = acc.mt2 = acc.bbn = acc.bbt1 = acc.bbt2 = acc.psi = 0.0;
+    double acctr[PION_MAXTR];
+#pragma unroll
+    for (int q = 0; q < PION_MAXTR; q++) acctr[q] = 0.0;
+
+    if (a.fused && a.dU) {  // microphysics dU computed by the cooling kernel (frame x)
+      acc.rho = a.dU[c]; acc.erg = a.dU[vs + c]; acc.mn = a.dU[2 * vs + c]; acc.mt1 = a.dU[3 * vs + c];
+      acc.mt2 = a.dU[4 * vs + c];
+      if (EQ != EQ_EULER) { acc.bbn = a.dU[5 * vs + c]; acc.bbt1 = a.dU[6 * vs + c]; acc.bbt2 = a.dU[7 * vs + c]; }
+      if (EQ == EQ_GLM) acc.psi = a.dU[8 * vs + c];
+#pragma unroll
+      for (int q = 0; q < PION_MAXTR; q++)
+        if (q < a.ntr) acctr[q] = a.dU[(NB + q) * vs + c];
+    }
+
+    Prim C = load_prim<EQ>(a.S, c, vs, 0, 1, 2);
+
+    if (domain || !a.fused) {
+#pragma unroll 1
+      for (int ax = 0; ax < g.ndim; ax++) {
+        const int a1 = (ax == 2) ? 0 : ax + 1;
+        const int a2 = (a1 == 2) ? 0 : a1 + 1;
+        const long st = axis_stride(g, ax);
+        const Prim M1 = load_prim<EQ>(a.S, c - st, vs, ax, a1, a2);
+        const Prim P1 = load_prim<EQ>(a.S, c + st, vs, ax, a1, a2);
+        // edge states at the low (i-1/2) and high (i+1/2) faces
+        Prim lowL = M1, lowR = C, highL = C, highR = P1;
+        if (a.order == 2) {
+          const Prim M2 = load_prim<EQ>(a.S, c - 2 * st, vs, ax, a1, a2);
+          const Prim P2 = load_prim<EQ>(a.S, c + 2 * st, vs, ax, a1, a2);
+#define PION_EDGE(f)                                                              \
+  {                                                                               \
+    double d0 = M1.f - M2.f, d1 = C.f - M1.f, d2 = P1.f - C.f, d3 = P2.f - P1.f;  \
+    double sm = minmod(d0, d1, a.tiny2), sc = minmod(d1, d2, a.tiny2), sp = minmod(d2, d3, a.tiny2); \
+    lowL.f = M1.f + sm * 0.5;                                                     \
+    lowR.f = C.f - sc * 0.5;                                                      \
+    highL.f = C.f + sc * 0.5;                                                     \
+    highR.f = P1.f - sp * 0.5;                                                    \
+  }
+          PION_EDGE(ro) PION_EDGE(pg) PION_EDGE(vn) PION_EDGE(vt1) PION_EDGE(vt2)
+          if (EQ != EQ_EULER) { PION_EDGE(bn) PION_EDGE(bt1) PION_EDGE(bt2) }
+          if (EQ == EQ_GLM) { PION_EDGE(psi) }
+#undef PION_EDGE
+        }
+        // HLLD -> HLL switch (solver_eqn_mhd_adi.cpp:167-177)
+        bool hll_low = false, hll_high = false;
+        if (SOLVER == SOLVE_HLLD) {
+          unsigned char fm = a.hll[c - st], fc = a.hll[c], fp = a.hll[c + st];
+          hll_low = (fm | fc) != 0;
+          hll_high = (fc | fp) != 0;
+        }
+        // H-correction eta_max (solver_eqn_base.cpp:608-678); consumed by Roe only
+        double eta_low = 0.0, eta_high = 0.0;
+        if (SOLVER == SOLVE_ROE && a.eta) {
+          const double* en = a.eta + (long)ax * vs;
+          eta_low = en[c - st];
+          eta_high = en[c];
+          // NB perpendicular axes are taken modulo ndim here (solver_eqn_base.cpp:639,648),
+          // unlike the velocity permutation which is always modulo 3
+          if (g.ndim > 1) {
+            const double* e1 = a.eta + (long)((ax + 1) % g.ndim) * vs;
+            eta_low = fmax(eta_low, fmax(fmax(e1[c - st], e1[c]), e1[c - 2 * st]));
+            eta_high = fmax(eta_high, fmax(fmax(e1[c], e1[c + st]), e1[c - st]));
+          }
+          if (g.ndim > 2) {
+            const double* e2 = a.eta + (long)((ax + 2) % g.ndim) * vs;
+            eta_low = fmax(eta_low, fmax(fmax(e2[c - st], e2[c]), e2[c - 2 * st]));
+            eta_high = fmax(eta_high, fmax(fmax(e2[c], e2[c + st]), e2[c - st]));
+          }
+        }
+        Cons Flow, Fhigh;
+        intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(lowL, lowR, a.pp, hll_low, eta_low, Flow);
+        intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(highL, highR, a.pp, hll_high, eta_high, Fhigh);
+
+        // Powell + GLM sources from cell-centre states (solver_eqn_mhd_adi.cpp:396-443,782-813):
+        // R part of interface (i-1,i) first, then L part of interface (i,i+1)
+        if (EQ != EQ_EULER) {
+          const double uB = C.bn * C.vn + C.bt1 * C.vt1 + C.bt2 * C.vt2;
+          double f = dt * (0.5 * (M1.bn + C.bn));
+          acc.mn += f * C.bn * idx; acc.mt1 += f * C.bt1 * idx; acc.mt2 += f * C.bt2 * idx; acc.erg += f * uB * idx;
+          acc.bbn += f * C.vn * idx; acc.bbt1 += f * C.vt1 * idx; acc.bbt2 += f * C.vt2 * idx;
+          if (EQ == EQ_GLM) {
+            double fs = dt * (0.5 * (M1.psi + C.psi));
+            acc.erg += fs * (C.vn * C.psi) * idx;
+            acc.psi += fs * C.vn * idx;
+          }
+          f = dt * (0.5 * (C.bn + P1.bn));
+          acc.mn -= f * C.bn * idx; acc.mt1 -= f * C.bt1 * idx; acc.mt2 -= f * C.bt2 * idx; acc.erg -= f * uB * idx;
+          acc.bbn -= f * C.vn * idx; acc.bbt1 -= f * C.vt1 * idx; acc.bbt2 -= f * C.vt2 * idx;
+          if (EQ == EQ_GLM) {
+            double fs = dt * (0.5 * (C.psi + P1.psi));
+            acc.erg -= fs * (C.vn * C.psi) * idx;
+            acc.psi -= fs * C.vn * idx;
+          }
+        }
+        // flux difference (dU_Cell + DivStateVectorComponent)
+        acc.rho += dt * ((Flow.rho - Fhigh.rho) * idx);
+        acc.erg += dt * ((Flow.erg - Fhigh.erg) * idx);
+        acc.mn += dt * ((Flow.mn - Fhigh.mn) * idx);
+        acc.mt1 += dt * ((Flow.mt1 - Fhigh.mt1) * idx);
+        acc.mt2 += dt * ((Flow.mt2 - Fhigh.mt2) * idx);
+        if (EQ != EQ_EULER) {
+          acc.bbn += dt * ((Flow.bbn - Fhigh.bbn) * idx);
+          acc.bbt1 += dt * ((Flow.bbt1 - Fhigh.bbt1) * idx);
+          acc.bbt2 += dt * ((Flow.bbt2 - Fhigh.bbt2) * idx);
+        }
+        if (EQ == EQ_GLM) acc.psi += dt * ((Flow.psi - Fhigh.psi) * idx);
+        // tracers: upwind on the sign of the mass flux (solver_eqn_base.cpp:281-342)
+#pragma unroll
+        for (int q = 0; q < PION_MAXTR; q++) {
+          if (q < a.ntr) {
+            const double* T = a.S + (long)(NB + q) * vs;
+            double tm1 = __ldg(T + c - st), tc = __ldg(T + c), tp1 = __ldg(T + c + st);
+            double lL = tm1, lR = tc, hL = tc, hR = tp1;
+            if (a.order == 2) {
+              double tm2 = __ldg(T + c - 2 * st), tp2 = __ldg(T + c + 2 * st);
+              double sm = minmod(tm1 - tm2, tc - tm1, a.tiny2), sc = minmod(tc - tm1, tp1 - tc, a.tiny2),
+                     sp = minmod(tp1 - tc, tp2 - tp1, a.tiny2);
+              lL = tm1 + sm * 0.5; lR = tc - sc * 0.5; hL = tc + sc * 0.5; hR = tp1 - sp * 0.5;
+            }
+            double fl = 0.0, fh = 0.0;
+            if (Flow.rho > 0.0) fl = lL * Flow.rho * (a.pp.have_mp ? scma_corr(lL) : 1.0);
+            else if (Flow.rho < 0.0) fl = lR * Flow.rho * (a.pp.have_mp ? scma_corr(lR) : 1.0);
+            if (Fhigh.rho > 0.0) fh = hL * Fhigh.rho * (a.pp.have_mp ? scma_corr(hL) : 1.0);
+            else if (Fhigh.rho < 0.0) fh = hR * Fhigh.rho * (a.pp.have_mp ? scma_corr(hR) : 1.0);
+            acctr[q] += dt * ((fl - fh) * idx);
+          }
+        }
+        // rotate the centre state and the accumulators into the next axis' frame
+        rot3(C.vn, C.vt1, C.vt2);
+        rot3(acc.mn, acc.mt1, acc.mt2);
+        if (EQ != EQ_EULER) {
+          rot3(C.bn, C.bt1, C.bt2);
+          rot3(acc.bbn, acc.bbt1, acc.bbt2);
+        }
+      }
+      // back to the x frame after ndim rotations
+      if (g.ndim == 2) {  // frame is (z,x,y)
+        rot3(acc.mn, acc.mt1, acc.mt2);
+        if (EQ != EQ_EULER) rot3(acc.bbn, acc.bbt1, acc.bbt2);
+      } else if (g.ndim == 1) {  // frame is (y,z,x)
+        rot3(acc.mn, acc.mt1, acc.mt2); rot3(acc.mn, acc.mt1, acc.mt2);
+        if (EQ != EQ_EULER) { rot3(acc.bbn, acc.bbt1, acc.bbt2); rot3(acc.bbn, acc.bbt1, acc.bbt2); }
+      }
+    }
+
+    if (!a.fused) {
+      double* d = a.dU;
+      d[c] += acc.rho; d[vs + c] += acc.erg; d[2 * vs + c] += acc.mn; d[3 * vs + c] += acc.mt1; d[4 * vs + c] += acc.mt2;
+      if (EQ != EQ_EULER) { d[5 * vs + c] += acc.bbn; d[6 * vs + c] += acc.bbt1; d[7 * vs + c] += acc.bbt2; }
+      if (EQ == EQ_GLM) d[8 * vs + c] += acc.psi;
+#pragma unroll
+      for (int q = 0; q < PION_MAXTR; q++)
+        if (q < a.ntr) d[(NB + q) * vs + c] += acctr[q];
+    } else if (domain) {
+      // CellAdvanceTime (solver_eqn_mhd_adi.cpp:452-504, :822-844; Euler solver_eqn_hydro_adi.cpp:372-451)
+      Prim Pb = load_prim<EQ>(a.Pb, c, vs, 0, 1, 2);
+      Cons U;
+      PtoU<EQ>(Pb, U, a.pp.gamma - 1.0);
+      U.rho += acc.rho; U.erg += acc.erg; U.mn += acc.mn; U.mt1 += acc.mt1; U.mt2 += acc.mt2;
+      if (EQ != EQ_EULER) { U.bbn += acc.bbn; U.bbt1 += acc.bbt1; U.bbt2 += acc.bbt2; }
+      if (EQ == EQ_GLM) U.psi += acc.psi;
+      Prim Pn;
+      status = UtoP<EQ>(U, Pn, a.pp);
+      if (EQ == EQ_GLM) Pn.psi *= a.glm_damp;
+      // temperature cap of grid_update_state_vector (time_integrator.cpp:926-932)
+      if (a.pp.have_mp && (Pn.pg * a.pp.mu_tot_over_kB / Pn.ro > a.pp.max_temp))
+        Pn.pg = Pn.ro * a.pp.max_temp / a.pp.mu_tot_over_kB;
+      store_prim<EQ>(a.out, c, vs, Pn);
+#pragma unroll
+      for (int q = 0; q < PION_MAXTR; q++) {
+        if (q < a.ntr) {
+          double pb = __ldg(a.Pb + (long)(NB + q) * vs + c);
+          if (a.pp.have_mp) pb *= scma_corr(pb);
+          double u = pb * Pb.ro + acctr[q];
+          double pn = u / U.rho;
+          if (a.pp.have_mp) pn *= scma_corr(pn);
+          a.out[(long)(NB + q) * vs + c] = pn;
+        }
+      }
+      if (a.dtmin) my_dt = cell_time_step<EQ>(Pn, a.pp, g.ndim, g.dx, a.cfl);
+    } else {
+      // cell cut out of the domain (time_integrator.cpp:905-908): state untouched
+      if (a.out != a.S) {
+        for (int v = 0; v < NB + a.ntr; v++) a.out[(long)v * vs + c] = a.S[(long)v * vs + c];
+      }
+    }
+  }
+
+  // block-level reductions: min dt (warp shuffles) and error counters
+  if (a.dtmin) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_dt = fmin(my_dt, __shfl_xor_sync(0xffffffffu, my_dt, o));
+    __shared__ double s_dt[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_dt[w] = my_dt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = s_dt[0];
+      for (int q = 1; q < (int)(blockDim.x >> 5); q++) m = fmin(m, s_dt[q]);
+      if (m < 1.0e100) atomicMin(a.dtmin, dbl_ordered_bits(m));
+    }
+  }
+  if (status && a.counters) {
+    if (status & ST_NEG_RHO) atomicAdd((unsigned long long*)&a.counters[0], 1ULL);
+    if (status & ST_NEG_PG) atomicAdd((unsigned long long*)&a.counters[1], 1ULL);
+  }
+}
+
+// host-side launcher implemented per equation set in stage_{euler,mhd,glm}.cu
+void launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+void launch_stage_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+void launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+
+template <int EQ, int SOLVER, bool FKJ>
+inline void launch_stage_t(const StageArgs& a, cudaStream_t s) {
+  const long ncell = (long)a.g.NG[0] * a.g.NG[1] * a.g.NG[2];
+  const int block = 128;
+  const long grid = (ncell + block - 1) / block;
+  k_stage<EQ, SOLVER, FKJ><<<(unsigned)grid, block, 0, s>>>(a);
+}
+
+}  // namespace pion

@@ -419,3 +419,116 @@ def rel_err(a, b, scale=None):
         s = s if s > 0 else 1.0
         errs.append(float(np.max(np.abs(a[v] - b[v])) / s))
     return np.array(errs)
+
+
+# --------------------------------------------------------------------------
+def gpu_config(prob: Problem, device=0, tables=None):
+    """Problem -> struct pion_gpu_config of the product library."""
+    import sys
+    sys.path.insert(0, str(ROOT))
+    from pion_b200.capi import GpuConfig
+    c = GpuConfig()
+    c.device, c.ndim = device, prob.ndim
+    for a in range(3):
+        c.NG[a] = prob.NG[a] if a < prob.ndim else 1
+        c.xmin[a] = prob.xmin[a]
+        c.xmax[a] = prob.xmax[a]
+        c.sim_xmin[a] = prob.xmin[a]
+    c.nvar, c.ntracer, c.eqntype = prob.nvar, prob.ntracer, EQN_NAMES[prob.eqn]
+    c.coord_sys, c.solver, c.artviscosity = 1, prob.solver, prob.artviscosity
+    c.spOOA = c.tmOOA = prob.ooa
+    c.gamma, c.cfl, c.etav = prob.gamma, prob.cfl, prob.etav
+    for d in range(6):
+        c.bc[d] = BC_CODES[prob.bcs[d]] if d < 2 * prob.ndim else 0
+        c.ngbprocs[d] = -1
+    c.n_internal_bc = len(prob.internal_bcs)
+    for i, b in enumerate(prob.internal_bcs):
+        c.internal_bc[i] = BC_CODES[b]
+    for v in range(PO_MAXVAR):
+        c.refvec[v] = prob.refvec[v]
+    c.starttime, c.finishtime = prob.starttime, prob.finishtime
+    c.op_criterion, c.opfreq_time = prob.op_criterion, prob.opfreq_time
+    c.cooling, c.mp_timestep_limit = prob.cooling, prob.mp_timestep_limit
+    c.min_temperature, c.max_temperature = prob.min_temperature, prob.max_temperature
+    c.rank, c.nproc = 0, 1
+    keep = []
+    if tables is not None:
+        c.n_table = len(tables["T"])
+        for name, key in [("table_T", "T"), ("table_rrhp", "rrhp"), ("table_C_rrh", "C_rrh"),
+                          ("table_C_ffhe", "C_ffhe"), ("table_C_fbdn", "C_fbdn"), ("table_C_cie", "C_cie")]:
+            arr = np.ascontiguousarray(tables[key], dtype=np.float64)
+            keep.append(arr)
+            setattr(c, name, arr.ctypes.data)
+    return c, keep
+
+
+class GpuSim:
+    """The product (libpion_b200.so through its C ABI) behind the same method
+    names as RefSim / OracleSim."""
+
+    def __init__(self, prob: Problem, device=0, tables=None):
+        import sys
+        sys.path.insert(0, str(ROOT))
+        from pion_b200.capi import Context
+        self.prob = prob
+        cfg, keep = gpu_config(prob, device, tables)
+        self.ctx = Context(cfg, keep)
+
+    def shape(self):
+        return self.ctx.shape
+
+    def get_state(self, which=0):
+        return self.ctx.download(which)
+
+    def set_state(self, arr, which=0):
+        self.ctx.upload(arr, which)
+
+    def init_after_state(self):
+        self.ctx.init_after_upload()
+        return 0
+
+    def calc_timestep(self):
+        return self.ctx.calculate_timestep()
+
+    def advance(self):
+        return self.ctx.advance_time()
+
+    def dynamics_dt(self):
+        return self.ctx.calc_dt()[0]
+
+    def microphysics_dt(self):
+        return self.ctx.calc_dt()[1]
+
+    def run(self, n):
+        return self.ctx.run(n)
+
+    def update_bcs(self, cstep, maxstep):
+        self.ctx.time_update_bcs(self.ctx.get_time()[0], cstep, maxstep)
+        return 0
+
+    def dynamics_dU(self, dt, step):
+        self.ctx.calc_dynamics_dU(dt, step)
+        return 0
+
+    def microphysics_dU(self, dt):
+        self.ctx.calc_microphysics_dU(dt)
+        return 0
+
+    def update_state(self, dt, step, ooa):
+        self.ctx.grid_update_state_vector(dt, step, ooa)
+        return 0
+
+    def set_dt(self, dt):
+        self.ctx.set_dt(dt)
+
+    def set_glm_speeds(self, tdyn, dx, cr):
+        self.ctx.set_glm_speeds(tdyn, dx, cr)
+
+    def set_time(self, simtime, last_dt, timestep):
+        self.ctx.set_time(simtime, last_dt, timestep)
+
+    def error_counts(self):
+        return self.ctx.counters()[:2]
+
+    def close(self):
+        self.ctx.close()
