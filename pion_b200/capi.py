@@ -6,7 +6,10 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "libpion_b200.so"
+import os
+
+# PION_B200_LIB selects an alternative build of the SAME library (kernel tuning experiments)
+LIB_PATH = Path(os.environ.get("PION_B200_LIB", Path(__file__).resolve().parent / "libpion_b200.so"))
 MAXVAR = 16
 
 _lib = None

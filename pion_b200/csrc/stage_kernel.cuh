@@ -84,8 +84,11 @@ __device__ __forceinline__ unsigned long long dbl_ordered_bits(double x) {
   return (unsigned long long)__double_as_longlong(x);
 }
 
+#ifndef PION_STAGE_MINBLOCKS
+#define PION_STAGE_MINBLOCKS 2
+#endif
 template <int EQ, int SOLVER, bool FKJ>
-__global__ void __launch_bounds__(128) k_stage(const __grid_constant__ StageArgs a) {
+__global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __grid_constant__ StageArgs a) {
   const GridD& g = a.g;
   const int NX = g.NG[0], NY = g.NG[1];
   const long ncell = (long)NX * NY * g.NG[2];

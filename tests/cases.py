@@ -1,0 +1,29 @@
+"""Shared parity-case definitions (equation set x solver x viscosity x boundaries)."""
+from harness import Problem
+
+EQ_SOLVERS = [("euler", 8), ("euler", 4), ("i-mhd", 8), ("i-mhd", 7), ("i-mhd", 4),
+              ("glm-mhd", 8), ("glm-mhd", 7), ("glm-mhd", 4)]
+AVS = [0, 1, 3, 4]
+DX = 0.0625  # cells must be cubic (uniform_grid.cpp:866-874); a power of two keeps xmax exact
+
+BCSETS = {
+    "periodic": ("periodic",) * 6,
+    "outflow": ("outflow",) * 6,
+    "reflect-outflow": ("reflecting", "outflow") * 3,
+    "mixed1": ("fixed", "one-way-outflow", "reflecting", "inflow", "periodic", "periodic"),
+    "mixed2": ("one-way-outflow", "fixed", "one-way-outflow", "one-way-outflow", "inflow", "inflow"),
+}
+
+
+def case_2d(eqn, solver, av, bcs="periodic", ntracer=0, NG=(24, 16, 1)):
+    return Problem(ndim=2, NG=NG, eqn=eqn, solver=solver, artviscosity=av, xmax=(NG[0] * DX, NG[1] * DX, 1.0),
+                   bcs=BCSETS[bcs], ntracer=ntracer)
+
+
+def case_3d(eqn, solver, av, bcs="periodic", ntracer=0, NG=(12, 10, 8), ooa=2):
+    return Problem(ndim=3, NG=NG, eqn=eqn, solver=solver, artviscosity=av, xmax=(NG[0] * DX, NG[1] * DX, NG[2] * DX),
+                   bcs=BCSETS[bcs], ntracer=ntracer, ooa=ooa)
+
+
+def case_1d(eqn, solver, av, bcs=("outflow", "outflow")):
+    return Problem(ndim=1, NG=(64, 1, 1), eqn=eqn, solver=solver, artviscosity=av, bcs=tuple(bcs) + ("periodic",) * 4)

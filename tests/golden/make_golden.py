@@ -1,0 +1,83 @@
+"""Generates the golden vectors in this directory FROM THE COMPILED REFERENCE
+(oracle/_ref/libpion_ref.so = unmodified PION translation units).  Run in the build
+container (needs /root/reference at build time):
+
+    python tests/golden/make_golden.py
+
+Each fixture holds the seeded input state, the per-step dt sequence and the full padded
+state after N steps; tests/test_golden.py replays them through the plain-C oracle
+(bit-exact) and, on the GPU box, through the CUDA path (tolerance)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent))
+from cases import case_1d, case_2d, case_3d  # noqa: E402
+from harness import RefSim, random_state  # noqa: E402
+
+CASES = {
+    "glm_hlld_fkj_3d_periodic": (case_3d("glm-mhd", 7, 1, NG=(12, 10, 8)), 4),
+    "glm_hlld_fkj_3d_outflow": (case_3d("glm-mhd", 7, 1, bcs="outflow", NG=(12, 10, 8)), 4),
+    "glm_roe_hcorr_2d_periodic": (case_2d("glm-mhd", 4, 4), 4),
+    "imhd_hll_2d_reflect": (case_2d("i-mhd", 8, 1, bcs="reflect-outflow"), 4),
+    "euler_roe_fkj_3d_mixed": (case_3d("euler", 4, 1, bcs="mixed1", ntracer=1, NG=(10, 8, 6)), 4),
+    "euler_hll_1d_reflect_inflow": (case_1d("euler", 8, 1, bcs=("reflecting", "inflow")), 6),
+}
+
+
+# The reference's own test problems, initial conditions produced by the reference's IC
+# classes (ics/basic_tests.cpp:553-812, ics/blast_wave.cpp:626-695) at reduced resolution.
+from harness import Problem  # noqa: E402
+
+TEST_PROBLEMS = {
+    # test_problems/double_Mach_reflection/params_DMR_n065.txt
+    "tp_DMR_n065_roe": (Problem(ndim=2, NG=(65, 20, 1), eqn="euler", solver=4, artviscosity=1, etav=0.1, gamma=1.4, cfl=0.4,
+                                xmax=(3.25, 1.0, 1.0), bcs=("inflow", "outflow", "reflecting", "DMR", "periodic", "periodic"),
+                                internal_bcs=("DMR2",), ics="DoubleMachRef", finishtime=0.2, op_criterion=1, opfreq_time=0.05,
+                                extra={"DMRmach": 10.0, "DMRtheta": 60}), 12),
+    "tp_DMR_n065_hll": (Problem(ndim=2, NG=(65, 20, 1), eqn="euler", solver=8, artviscosity=1, etav=0.1, gamma=1.4, cfl=0.4,
+                                xmax=(3.25, 1.0, 1.0), bcs=("inflow", "outflow", "reflecting", "DMR", "periodic", "periodic"),
+                                internal_bcs=("DMR2",), ics="DoubleMachRef", finishtime=0.2, op_criterion=1, opfreq_time=0.05,
+                                extra={"DMRmach": 10.0, "DMRtheta": 60}), 12),
+    # test_problems/FieldLoop/params_FieldLoop200.txt at 64x32, HLLD (7) and the shipped Roe (4)
+    "tp_FieldLoop_64x32_hlld": (Problem(ndim=2, NG=(64, 32, 1), eqn="glm-mhd", solver=7, artviscosity=1, etav=0.1,
+                                        gamma=1.666666666666666666666, cfl=0.4, xmin=(-1.0, -0.5, 0.0), xmax=(1.0, 0.5, 1.0),
+                                        ics="FieldLoop", finishtime=2.0, op_criterion=1, opfreq_time=1.0), 12),
+    "tp_FieldLoop_64x32_roe": (Problem(ndim=2, NG=(64, 32, 1), eqn="glm-mhd", solver=4, artviscosity=1, etav=0.1,
+                                       gamma=1.666666666666666666666, cfl=0.4, xmin=(-1.0, -0.5, 0.0), xmax=(1.0, 0.5, 1.0),
+                                       ics="FieldLoop", finishtime=2.0, op_criterion=1, opfreq_time=1.0), 12),
+    # test_problems/blastwave_crt3d/params_BWcrt3D_Octant_NR016.txt
+    "tp_BWcrt3D_octant_n016": (Problem(ndim=3, NG=(16, 16, 16), eqn="euler", solver=4, artviscosity=1, etav=0.1,
+                                       gamma=1.666666666666666666666, cfl=0.3, xmax=(30.86e18,) * 3,
+                                       bcs=("reflecting", "outflow") * 3, ics="BlastWave", finishtime=1.58e12, op_criterion=1,
+                                       opfreq_time=6.32e10,
+                                       extra={"BWpressure": 1.38e-11, "BWdensity": 2.34e-22, "BWmagfieldX": 0.0, "BWmagfieldY": 0.0,
+                                              "BWmagfieldZ": 0.0, "BW_energy": 1.0e51, "BW_nzones": 2, "BW_blast_dens": 2.34e-22,
+                                              "BW_interface": 1.0e50, "BW_amb2_RO": 0.0, "BW_amb2_PG": 0.0, "BW_amb2_VX": 0.0,
+                                              "BW_amb2_VY": 0.0, "BW_amb2_VZ": 0.0, "InitIons": "LEAVE"}), 12),
+}
+CASES.update(TEST_PROBLEMS)
+
+
+def main():
+    for name, (prob, nsteps) in CASES.items():
+        if name in TEST_PROBLEMS:
+            r = RefSim(prob, run_ics=True)
+            P0 = r.get_state(0)
+        else:
+            P0 = random_state(prob, seed=2024)
+            r = RefSim(prob)
+            r.set_state(P0)
+        r.init_after_state()
+        Pinit = r.get_state(0)
+        dts = r.run(nsteps)
+        P = r.get_state(0)
+        r.close()
+        np.savez_compressed(HERE / f"{name}.npz", P0=P0, Pinit=Pinit, dts=dts, P=P, nsteps=nsteps)
+        print(name, P.shape, dts)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,77 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pion_b200.h declares;
+without a GPU it refuses to create a context (there is no CPU fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    txt = (ROOT / "include" / "pion_b200.h").read_text()
+    return sorted(set(re.findall(r"\b(pion_gpu_[A-Za-z_0-9]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pion_b200.capi import EXPORTED_SYMBOLS, LIB_PATH, load_library
+    assert LIB_PATH.exists(), "libpion_b200.so not built: run __graft_entry__.build()"
+    lib = load_library()
+    decl = declared_symbols()
+    assert len(decl) >= 24
+    for name in decl:
+        assert hasattr(lib, name), name
+    assert set(decl) == set(EXPORTED_SYMBOLS)
+
+
+def test_product_does_not_link_the_oracle():
+    import subprocess
+    from pion_b200.capi import LIB_PATH
+    out = subprocess.run(["ldd", str(LIB_PATH)], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "pion_ref" not in out
+    syms = subprocess.run(["nm", "-D", str(LIB_PATH)], capture_output=True, text=True).stdout
+    assert " po_" not in syms and " pref_" not in syms
+    for src in (ROOT / "pion_b200").rglob("*"):
+        if src.suffix in (".cu", ".cuh", ".cpp", ".h", ".py"):
+            assert "oracle" not in src.read_text().replace("no CPU fallback", ""), src
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from harness import GpuSim, Problem
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        GpuSim(Problem())
+
+
+def test_config_validation_matches_reference_errors():
+    from pion_b200.capi import GpuConfig, load_library
+    lib = load_library()
+    c = GpuConfig()
+    c.ndim = 2
+    c.eqntype, c.nvar, c.solver, c.coord_sys, c.spOOA, c.tmOOA = 3, 9, 7, 1, 2, 1
+    assert not lib.pion_gpu_create(ctypes.byref(c))
+    assert b"Bad OOA requests" in lib.pion_gpu_last_error()  # time_integrator.cpp:130
+
+
+def test_decompose_domain_matches_mcmd():
+    """MCMDcontrol::decomposeDomain: 8 ranks on a cube -> 2x2x2, rank = nx*ny*iz + nx*iy + ix."""
+    from harness import Problem, gpu_config
+    from pion_b200.capi import load_library
+    lib = load_library()
+    prob = Problem(ndim=3, NG=(64, 64, 64), xmin=(0, 0, 0), xmax=(1, 1, 1), bcs=("periodic", "periodic", "outflow", "outflow", "reflecting", "outflow"))
+    for rank in range(8):
+        cfg, _ = gpu_config(prob)
+        assert lib.pion_gpu_decompose_domain(cfg, rank, 8) == 0
+        ix, iy, iz = rank % 2, (rank // 2) % 2, rank // 4
+        assert list(cfg.NG) == [32, 32, 32]
+        assert cfg.xmin[0] == 0.5 * ix and cfg.xmin[1] == 0.5 * iy and cfg.xmin[2] == 0.5 * iz
+        # x is periodic: both faces talk to the other x-rank
+        assert cfg.bc[0] == 10 and cfg.bc[1] == 10 and cfg.ngbprocs[0] == cfg.ngbprocs[1] == rank ^ 1
+        assert cfg.bc[2] == (10 if iy else 2) and cfg.bc[3] == (2 if iy else 10)
+        assert cfg.bc[4] == (10 if iz else 4) and cfg.bc[5] == (2 if iz else 10)
+    cfg, _ = gpu_config(Problem(ndim=2, NG=(64, 32, 1), xmax=(2.0, 1.0, 1.0)))
+    assert lib.pion_gpu_decompose_domain(cfg, 1, 2) == 0
+    assert list(cfg.NG)[:2] == [32, 32] and cfg.xmin[0] == 1.0  # longest axis split first

@@ -1,0 +1,54 @@
+"""Golden vectors produced by the compiled reference (tests/golden/make_golden.py):
+the plain-C oracle must reproduce them bit-for-bit (CPU), the CUDA path within the
+stated tolerance (GPU)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from harness import GpuSim, OracleSim, rel_err
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def load(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", GOLD / "make_golden.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    prob, nsteps = mod.CASES[name]
+    return prob, nsteps, np.load(GOLD / f"{name}.npz")
+
+
+NAMES = sorted(p.stem for p in GOLD.glob("*.npz"))
+
+
+def test_golden_fixtures_exist():
+    assert len(NAMES) >= 6
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_reference_golden(name):
+    prob, nsteps, z = load(name)
+    o = OracleSim(prob)
+    o.set_state(z["P0"])
+    o.init_after_state()
+    assert np.array_equal(o.get_state(0), z["Pinit"])
+    dts = o.run(nsteps)
+    assert np.array_equal(dts, z["dts"])
+    assert np.array_equal(o.get_state(0), z["P"])
+    o.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_reproduces_reference_golden(name):
+    prob, nsteps, z = load(name)
+    g = GpuSim(prob)
+    g.set_state(z["P0"])
+    g.init_after_state()
+    assert np.array_equal(g.get_state(0), z["Pinit"])
+    dts = g.run(nsteps)
+    assert np.allclose(dts, z["dts"], rtol=1e-13, atol=0)
+    assert rel_err(g.get_state(0), z["P"]).max() < 5e-12
+    g.close()

@@ -1,0 +1,86 @@
+"""CPU: pins the plain-C oracle (oracle/pion_oracle.c) to the UNMODIFIED reference
+translation units compiled into oracle/_ref/libpion_ref.so.  The bar is BIT-EXACT
+equality of the full padded state (ghost cells included) and of every dt."""
+import numpy as np
+import pytest
+
+from cases import AVS, EQ_SOLVERS, case_1d, case_2d, case_3d
+from harness import OracleSim, RefSim, have_ref, random_state
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
+
+
+def run_pair(prob, nsteps=3, seed=1):
+    r, o = RefSim(prob), OracleSim(prob)
+    try:
+        assert r.shape() == o.shape() == prob.padded_shape()
+        P = random_state(prob, seed)
+        for s in (r, o):
+            s.set_state(P)
+            assert s.init_after_state() == 0
+        assert np.array_equal(r.get_state(0), o.get_state(0))
+        assert np.array_equal(r.get_state(1), o.get_state(1))
+        dr, do = r.run(nsteps), o.run(nsteps)
+        Pr, Po = r.get_state(0), o.get_state(0)
+        assert np.array_equal(dr, do), (dr, do)
+        assert np.max(np.abs(Pr - P)) > 1e-6, "state did not evolve"
+        assert np.array_equal(Pr, Po), float(np.max(np.abs(Pr - Po)))
+        assert o.error_counts()[0] == 0
+    finally:
+        r.close()
+        o.close()
+
+
+@pytest.mark.parametrize("eqn,solver", EQ_SOLVERS)
+@pytest.mark.parametrize("av", AVS)
+def test_2d_periodic_bit_exact(eqn, solver, av):
+    run_pair(case_2d(eqn, solver, av))
+
+
+@pytest.mark.parametrize("eqn,solver,av,ntr", [("glm-mhd", 7, 1, 0), ("glm-mhd", 4, 4, 2), ("euler", 4, 3, 1),
+                                               ("i-mhd", 7, 0, 1), ("euler", 8, 1, 0)])
+def test_3d_periodic_bit_exact(eqn, solver, av, ntr):
+    run_pair(case_3d(eqn, solver, av, ntracer=ntr))
+
+
+@pytest.mark.parametrize("bcs", ["outflow", "reflect-outflow", "mixed1", "mixed2"])
+@pytest.mark.parametrize("eqn,solver", [("glm-mhd", 7), ("euler", 8), ("i-mhd", 4)])
+def test_boundary_types_bit_exact(bcs, eqn, solver):
+    run_pair(case_3d(eqn, solver, 1, bcs=bcs, NG=(10, 8, 6)))
+    run_pair(case_2d(eqn, solver, 4, bcs=bcs, ntracer=1, NG=(10, 8, 1)))
+
+
+def test_1d_and_first_order():
+    run_pair(case_1d("i-mhd", 7, 1))
+    run_pair(case_1d("euler", 8, 1, bcs=("reflecting", "inflow")))
+    run_pair(case_3d("glm-mhd", 7, 1, ooa=1))
+
+
+def test_per_call_seam_bit_exact():
+    """The grid-level seam one call at a time: dU after calc_dynamics_dU, Ph after the
+    half-step update, ghost cells after TimeUpdateBCs, the HLLD switch scalars."""
+    prob = case_3d("glm-mhd", 7, 1, bcs="reflect-outflow")
+    r, o = RefSim(prob), OracleSim(prob)
+    P = random_state(prob, 3)
+    for s in (r, o):
+        s.set_state(P)
+        s.init_after_state()
+    dt = r.dynamics_dt()
+    assert dt == o.dynamics_dt()
+    for s in (r, o):
+        s.set_glm_speeds(dt, prob.dx, 0.25 / prob.dx)
+        s.set_dt(0.5 * dt)
+        s.dynamics_dU(0.5 * dt, 1)
+    assert np.array_equal(r.get_state(2), o.get_state(2))
+    assert np.array_equal(r.get_extra(0), o.get_extra(0))  # divV
+    assert np.array_equal(r.get_extra(1), o.get_extra(1))  # |grad p|/p
+    for s in (r, o):
+        s.update_state(0.5 * dt, 1, 2)
+        s.update_bcs(1, 2)
+    assert np.array_equal(r.get_state(1), o.get_state(1))
+    for s in (r, o):
+        s.set_dt(dt)
+        s.dynamics_dU(dt, 2)
+    assert np.array_equal(r.get_state(2), o.get_state(2))
+    r.close()
+    o.close()
