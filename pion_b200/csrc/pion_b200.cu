@@ -69,6 +69,7 @@ struct pion_gpu_ctx {
   std::vector<cudaEvent_t> tev;  // begin/end pairs
   // multi-GPU
   ncclComm_t comm = nullptr;
+  double* d_red = nullptr;  // 2 doubles for the dt all-reduce
   double *sendbuf[6] = {nullptr}, *recvbuf[6] = {nullptr};
   size_t halo_elems[6] = {0};
 };
@@ -182,7 +183,7 @@ extern "C" void pion_gpu_destroy(pion_gpu_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm) ncclCommDestroy(c->comm);
   cudaFree(c->P); cudaFree(c->Ph); cudaFree(c->dU); cudaFree(c->eta); cudaFree(c->hll); cudaFree(c->mask);
-  cudaFree(c->d_dtmin); cudaFree(c->d_counters);
+  cudaFree(c->d_dtmin); cudaFree(c->d_counters); cudaFree(c->d_red);
   for (int f = 0; f < 6; f++) { cudaFree(c->sendbuf[f]); cudaFree(c->recvbuf[f]); }
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -259,7 +260,7 @@ static void fill_bc_args(pion_gpu_ctx* c, BCArgs& b, int face, int type, double*
   b.ftr = c->nbase_;
   for (int v = 0; v < PION_MAXVAR; v++) b.refval[v] = refval ? refval[v] : 0.0;
   b.simtime = simtime;
-  for (int a = 0; a < 3; a++) b.sim_xmin[a] = c->cfg.xmin[a];
+  for (int a = 0; a < 3; a++) b.sim_xmin[a] = c->cfg.xmin[a];  // local origin: positions are xmin + (2i+1)dx/2
 }
 
 static long face_cells(const GridD& g, int face) {
@@ -433,21 +434,14 @@ extern "C" int pion_gpu_calc_dt(pion_gpu_ctx* c, double* t_dyn, double* t_mp) {
 extern "C" int pion_gpu_calculate_timestep(pion_gpu_ctx* c, double* dt_out) {
   double t_dyn, t_mp;
   if (pion_gpu_calc_dt(c, &t_dyn, &t_mp)) return 1;
-  if (c->comm) {  // sim_control_MPI.cpp:503-504: global MIN of both
-    double* d_red = reinterpret_cast<double*>(c->d_dtmin + 1);
-    double h[1] = {fmin(t_dyn, 1.0e100)};
-    // the two minima travel as one 2-element all-reduce
-    double hv[2] = {t_dyn, t_mp};
-    (void)h;
-    static_assert(sizeof(double) == sizeof(unsigned long long), "size");
-    double* d2 = nullptr;
-    CUDA_OK(cudaMalloc(&d2, 2 * sizeof(double)));
-    CUDA_OK(cudaMemcpyAsync(d2, hv, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    NCCL_OK(ncclAllReduce(d2, d2, 2, ncclDouble, ncclMin, c->comm, c->stream));
-    CUDA_OK(cudaMemcpyAsync(hv, d2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (c->comm) {  // sim_control_MPI.cpp:503-504: global MIN of t_dyn and t_mp, one 2-element all-reduce
+    double* hv = reinterpret_cast<double*>(c->h_pinned + 2);
+    hv[0] = t_dyn;
+    hv[1] = t_mp;
+    CUDA_OK(cudaMemcpyAsync(c->d_red, hv, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCCL_OK(ncclAllReduce(c->d_red, c->d_red, 2, ncclDouble, ncclMin, c->comm, c->stream));
+    CUDA_OK(cudaMemcpyAsync(hv, c->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    CUDA_OK(cudaFree(d2));
-    (void)d_red;
     t_dyn = hv[0];
     t_mp = hv[1];
   }
@@ -629,10 +623,8 @@ extern "C" int pion_gpu_advance_time(pion_gpu_ctx* c, double* dt_done) {
   if (c->cfg.tmOOA == 1) {
     // first_order_update(dt, OA1) + BCs (OA1, OA1): full step in one stage
     c->FV_dt = dt;
-    const double* S = c->ph_valid ? c->Ph : c->P;
     // the single stage reads P's stencil and must not write P in place: go through Ph
     if (launch_preprocess(c, c->P, 1)) return 1;
-    (void)S;
     if (launch_stage(c, c->P, c->P, c->Ph, nullptr, dt, 1, true, true)) return 1;
     // P = Ph on the interior, then boundaries of both
     const long ncell = (long)c->g.NG[0] * c->g.NG[1] * c->g.NG[2];
@@ -725,6 +717,7 @@ extern "C" int pion_gpu_nccl_init(pion_gpu_ctx* c, const char* unique_id128) {
   ncclUniqueId id;
   memcpy(&id, unique_id128, 128);
   NCCL_OK(ncclCommInitRank(&c->comm, c->cfg.nproc, id, c->cfg.rank));
+  CUDA_OK(cudaMalloc(&c->d_red, 2 * sizeof(double)));
   for (int f = 0; f < 2 * c->g.ndim; f++) {
     if (c->cfg.bc[f] != PION_BC_MPI) continue;
     c->halo_elems[f] = (size_t)face_cells(c->g, f) * c->nvar;
@@ -747,11 +740,20 @@ static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A) {
     k_halo<<<nblocks((long)c->halo_elems[f], 256), 256, 0, c->stream>>>(h);
     c->launches++;
   }
+  // Sends go out in face order (N, P) and receives are posted in the opposite order
+  // (P, N): when both neighbours of this axis are the SAME rank (2 ranks, periodic) NCCL
+  // matches operations per peer in order, and the peer's N-side slab must land in our P
+  // ghost layers.  (The reference gets the same pairing from its even/odd send ordering,
+  // assign_update_bcs_MPI.cpp:104-124.)
   NCCL_OK(ncclGroupStart());
   for (int s = 0; s < 2; s++) {
     const int f = 2 * ax + s;
     if (c->cfg.bc[f] != PION_BC_MPI) continue;
     NCCL_OK(ncclSend(c->sendbuf[f], c->halo_elems[f], ncclDouble, c->cfg.ngbprocs[f], c->comm, c->stream));
+  }
+  for (int s = 1; s >= 0; s--) {
+    const int f = 2 * ax + s;
+    if (c->cfg.bc[f] != PION_BC_MPI) continue;
     NCCL_OK(ncclRecv(c->recvbuf[f], c->halo_elems[f], ncclDouble, c->cfg.ngbprocs[f], c->comm, c->stream));
   }
   NCCL_OK(ncclGroupEnd());

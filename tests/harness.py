@@ -409,14 +409,38 @@ def random_state(prob: Problem, seed=12345, smooth=True, amp=0.5):
     return out
 
 
-def rel_err(a, b, scale=None):
-    """max |a-b| / scale per variable; scale defaults to max|b| per variable."""
+def state_scales(b, gamma=5.0 / 3.0):
+    """Per-variable normalisation for primitive-state comparisons: density and pressure by
+    their maxima; every velocity component by max(|v|, sound speed); every B component and
+    psi by max |B| (vector components that are identically zero in the problem, e.g. v_z in
+    a 2-D run, only carry rounding noise and must not be normalised by themselves)."""
+    b = np.asarray(b)
+    nv = b.shape[0]
+    sc = np.ones(nv)
+    sc[0] = np.max(np.abs(b[0]))
+    sc[1] = np.max(np.abs(b[1]))
+    cs = float(np.sqrt(gamma * np.max(np.abs(b[1])) / max(np.min(np.abs(b[0])), 1e-300)))
+    sc[2:5] = max(float(np.max(np.abs(b[2:5]))), cs)
+    if nv >= 8:
+        bmax = float(np.max(np.abs(b[5:8])))
+        sc[5:8] = bmax if bmax > 0 else 1.0
+        if nv >= 9:
+            sc[8] = sc[5]
+    for v in range(9 if nv >= 9 else (8 if nv >= 8 else 5), nv):
+        m = float(np.max(np.abs(b[v])))
+        sc[v] = m if m > 0 else 1.0
+    return sc
+
+
+def rel_err(a, b, scale=None, primitive=True):
+    """max |a-b| / scale per variable (scale: state_scales(b) for primitive states)."""
     a = np.asarray(a)
     b = np.asarray(b)
+    if scale is None:
+        scale = state_scales(b) if primitive and b.shape[0] >= 5 else [np.max(np.abs(b[v])) for v in range(b.shape[0])]
     errs = []
     for v in range(a.shape[0]):
-        s = np.max(np.abs(b[v])) if scale is None else scale[v]
-        s = s if s > 0 else 1.0
+        s = scale[v] if scale[v] > 0 else 1.0
         errs.append(float(np.max(np.abs(a[v] - b[v])) / s))
     return np.array(errs)
 
