@@ -30,13 +30,13 @@ __global__ void k_hlld_flags(GridD g, const double* __restrict__ S, unsigned cha
     int k = (int)(t / ((long)ex * ey)) + ((g.ndim > 2) ? 1 : 0);
     long c = gidx(g, i, j, k);
     double divv = 0.0, gradp = 0.0;
-    const double d2 = 2.0 * g.dx;
+    const double id2 = 1.0 / (2.0 * g.dx);
     for (int ax = 0; ax < g.ndim; ax++) {
       long st = axis_stride(g, ax);
       const double* V = S + (2 + ax) * g.vs;
-      divv += (__ldg(V + c + st) - __ldg(V + c - st)) / d2;
+      divv += (__ldg(V + c + st) - __ldg(V + c - st)) * id2;
       double pp = __ldg(S + g.vs + c + st), pn = __ldg(S + g.vs + c - st);
-      gradp += fabs(pp - pn) / fmin(pp, pn);
+      gradp += fabs(pp - pn) * fast_rcp(fmin(pp, pn));
     }
     flag[c] = (divv < 0. && gradp > 5.) ? 1 : 0;
   }

@@ -1,0 +1,65 @@
+// pion_b200/csrc/fastmath.cuh -- branch-free FP64 reciprocal / square root.
+//
+// CUDA's `a / b` and `sqrt(x)` expand to a MUFU seed + Newton steps + a range check
+// that CALLs a slow path (denormal / zero / huge operands; for `a / b` the check is on
+// the NUMERATOR, so an exactly-zero numerator -- a static medium -- takes the slow path
+// every time).  The dynamics update only divides by strictly positive, well-scaled
+// quantities (densities, wave-speed differences) or guards the result with isfinite
+// (HLLD_MHD.cpp:189-224), so the kernels use these sequences instead: the MUFU.RCP64H /
+// MUFU.RSQ64H seed (>= 20 good bits) refined to <= 1-2 ulp, no branches, no calls.
+// Zero / infinite / NaN operands propagate as inf / NaN exactly where the reference's
+// IEEE division would produce a non-finite value (what the isfinite guards test).
+// tools/micro/fp64_pipe.cu measures the error against IEEE division on the device.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pion {
+
+__device__ __forceinline__ double fast_rcp(double x) {
+#ifdef PION_STRICT
+  return 1.0 / x;
+#else
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);        // e + e^2: cubic convergence, 2^-20 -> 2^-60
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);     // one more correction brings the result to <= 1 ulp
+  return fma(r, e, r);
+#endif
+}
+
+// 1/sqrt(x), x > 0
+__device__ __forceinline__ double fast_rsqrt(double x) {
+#ifdef PION_STRICT
+  return 1.0 / sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  // y <- y (1 + e/2 + 3 e^2/8), e = 1 - x y^2  (cubic)
+  double e = fma(-x * y, y, 1.0);
+  double t = fma(0.375, e, 0.5);
+  y = fma(y * e, t, y);
+  e = fma(-x * y, y, 1.0);
+  return fma(y * e, 0.5, y);
+#endif
+}
+
+// sqrt(x), x >= 0 (x == 0 returns 0)
+__device__ __forceinline__ double fast_sqrt(double x) {
+#ifdef PION_STRICT
+  return sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  double t = fma(0.375, e, 0.5);
+  y = fma(y * e, t, y);
+  double g = x * y;                       // ~ sqrt(x)
+  double d = fma(-g, g, x);               // residual
+  g = fma(d * 0.5, y, g);
+  return (x > 0.0) ? g : 0.0;
+#endif
+}
+
+}  // namespace pion

@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include "fastmath.cuh"
 
 namespace pion {
 
@@ -55,6 +56,13 @@ struct PhysParams {
 
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
+// p/(gamma-1): gamma is launch-uniform, so the reciprocal is loop-invariant and hoisted
+#ifdef PION_STRICT
+#define PION_OVER_GM1(x, gm1) ((x) / (gm1))
+#else
+#define PION_OVER_GM1(x, gm1) ((x) * fast_rcp(gm1))
+#endif
+
 // ---------------------------------------------------------------------------
 // minmod: BaseVectorOps::AvgFalle, AVG_MINMOD variant (VectorOps.cpp:40-59).
 // The reference computes r=a/b; min(r,1)*b.  For 0<r<1 that is (a/b)*b which
@@ -85,13 +93,13 @@ __device__ __forceinline__ void PtoU(const Prim& p, Cons& u, double gm1) {
   u.mt1 = p.ro * p.vt1;
   u.mt2 = p.ro * p.vt2;
   if (EQ == EQ_EULER) {
-    u.erg = p.ro * (p.vn * p.vn + p.vt1 * p.vt1 + p.vt2 * p.vt2) * 0.5 + p.pg / gm1;
+    u.erg = p.ro * (p.vn * p.vn + p.vt1 * p.vt1 + p.vt2 * p.vt2) * 0.5 + PION_OVER_GM1(p.pg, gm1);
     u.bbn = u.bbt1 = u.bbt2 = u.psi = 0.0;
   } else {
     u.bbn = p.bn;
     u.bbt1 = p.bt1;
     u.bbt2 = p.bt2;
-    u.erg = (p.ro * (p.vn * p.vn + p.vt1 * p.vt1 + p.vt2 * p.vt2) * 0.5) + (p.pg / gm1) +
+    u.erg = (p.ro * (p.vn * p.vn + p.vt1 * p.vt1 + p.vt2 * p.vt2) * 0.5) + PION_OVER_GM1(p.pg, gm1) +
             ((u.bbn * u.bbn + u.bbt1 * u.bbt1 + u.bbt2 * u.bbt2) * 0.5);
     if (EQ == EQ_GLM) {
       u.psi = p.psi;
@@ -123,7 +131,7 @@ __device__ __forceinline__ int UtoP(const Cons& u, Prim& p, const PhysParams& pp
   p.vt1 = u.mt1 / u.rho;
   p.vt2 = u.mt2 / u.rho;
 #else
-  const double ir = 1.0 / u.rho;
+  const double ir = fast_rcp(u.rho);
   p.vn = u.mn * ir;
   p.vt1 = u.mt1 * ir;
   p.vt2 = u.mt2 * ir;
@@ -199,23 +207,35 @@ __device__ __forceinline__ void PUtoFlux(const Prim& p, const Cons& u, Cons& f) 
   }
 }
 
-__device__ __forceinline__ double chydro(double ro, double pg, double g) { return sqrt(g * pg / ro); }
+__device__ __forceinline__ double chydro(double ro, double pg, double g) {
+#ifdef PION_STRICT
+  return sqrt(g * pg / ro);
+#else
+  return fast_sqrt(g * pg * fast_rcp(ro));
+#endif
+}
 
-// eqns_mhd_ideal::cfast_components (eqns_mhd_adiabatic.cpp:263-276)
+// eqns_mhd_ideal::cfast_components (eqns_mhd_adiabatic.cpp:263-276).
+// cfast2_ir returns the SQUARE of the fast speed given 1/ro, so that callers needing
+// max(cf_l, cf_r) take one square root of the larger square (sqrt is monotonic: same value).
+__device__ __forceinline__ double cfast2_ir(double ir, double pg, double bx, double by, double bz, double g) {
+  // one reciprocal instead of a sqrt + three divisions; ch*ch == g*pg/ro to 1 ulp
+  double ch2 = g * pg * ir;
+  double temp1 = ch2 + (bx * bx + by * by + bz * bz) * ir;
+  double temp2 = 4. * ch2 * bx * bx * ir;
+  temp2 = fmax(PION_MACHINEACCURACY, temp1 * temp1 - temp2);
+  return (temp1 + fast_sqrt(temp2)) / 2.;
+}
 __device__ __forceinline__ double cfast_components(double ro, double pg, double bx, double by, double bz, double g) {
 #ifdef PION_STRICT
   double ch = sqrt(g * pg / ro);
   double temp1 = ch * ch + (bx * bx + by * by + bz * bz) / ro;
   double temp2 = 4. * ch * ch * bx * bx / ro;
-#else
-  // one reciprocal instead of a sqrt + three divisions; ch*ch == g*pg/ro to 1 ulp
-  double ir = 1.0 / ro;
-  double ch2 = g * pg * ir;
-  double temp1 = ch2 + (bx * bx + by * by + bz * bz) * ir;
-  double temp2 = 4. * ch2 * bx * bx * ir;
-#endif
   temp2 = fmax(PION_MACHINEACCURACY, temp1 * temp1 - temp2);
   return sqrt((temp1 + sqrt(temp2)) / 2.);
+#else
+  return fast_sqrt(cfast2_ir(fast_rcp(ro), pg, bx, by, bz, g));
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -234,7 +254,7 @@ __device__ __forceinline__ void hydro_HLL(const Prim& L, const Prim& R, const Ph
   double cf_max = fmax(chydro(L.ro, L.pg, pp.gamma), chydro(R.ro, R.pg, pp.gamma));
   double Sl = fmin(L.vn, R.vn) - cf_max;
   double Sr = fmax(L.vn, R.vn) + cf_max;
-  double idS = 1.0 / (Sr - Sl);
+  double idS = fast_rcp(Sr - Sl);
 #define PION_HLL_COMP(c)                                                             \
   flux.c = (Sl > 0) ? FL.c : (Sr < 0) ? FR.c : (Sr * FL.c - Sl * FR.c + Sr * Sl * (UR.c - UL.c)) * idS; \
   ustar.c = (Sr * UR.c - Sl * UL.c + FL.c - FR.c) * idS;
@@ -329,9 +349,14 @@ __device__ __forceinline__ void hydro_RoeCV(const Prim& L, const Prim& R, const 
 // sides in the GLM case but the formula is kept general.
 __device__ __forceinline__ void hlld_speeds(const Prim& L, const Prim& R, double g, double& Sl, double& Sr) {
   double Bx = 0.5 * (L.bn + R.bn);
+#ifdef PION_STRICT
   double cf_l = cfast_components(L.ro, L.pg, Bx, L.bt1, L.bt2, g);
   double cf_r = cfast_components(R.ro, R.pg, Bx, R.bt1, R.bt2, g);
   double cf_max = fmax(cf_l, cf_r);
+#else
+  double cf_max = fast_sqrt(fmax(cfast2_ir(fast_rcp(L.ro), L.pg, Bx, L.bt1, L.bt2, g),
+                                 cfast2_ir(fast_rcp(R.ro), R.pg, Bx, R.bt1, R.bt2, g)));
+#endif
   Sl = fmin(L.vn, R.vn) - cf_max;
   Sr = fmax(L.vn, R.vn) + cf_max;
 }
@@ -347,7 +372,7 @@ __device__ __forceinline__ void mhd_HLL(const Prim& L, const Prim& R, const Phys
   PUtoFlux<EQ_MHD>(R, UR, FR);
   double l0, l1;
   hlld_speeds(L, R, pp.gamma, l0, l1);
-  double idl = 1.0 / (l1 - l0);
+  double idl = fast_rcp(l1 - l0);
 #define PION_HLLM_COMP(c)                                                                         \
   flux.c = (l0 > 0.0) ? FL.c : (l1 < 0.0) ? FR.c : (l1 * FL.c - l0 * FR.c + l1 * l0 * (UR.c - UL.c)) * idl; \
   if (NEED_USTAR) ustar.c = (l0 > 0.0) ? UL.c : (l1 < 0.0) ? UR.c : (l1 * UR.c - l0 * UL.c - FR.c + FL.c) * idl;
@@ -359,112 +384,126 @@ __device__ __forceinline__ void mhd_HLL(const Prim& L, const Prim& R, const Phys
 }
 
 // HLLD_MHD::MHD_HLLD_flux_solver (HLLD_MHD.cpp:124-333), Miyoshi & Kusano 2005.
-// Region select is done first so that only the needed intermediate states are
-// formed; every expression inside a region is the reference's.
-template <bool NEED_USTAR>
-__device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const PhysParams& pp, Cons& flux, Cons& ustar) {
-  const double gm1 = pp.gamma - 1.0;
+//
+// The reference forms UL, UR, FL, FR and all four intermediate states, then picks
+// one of six fan regions.  Only ONE side's states ever reach the flux, so this
+// version computes the two-sided scalars the wave speeds and the double-star
+// averages need (rho*, v_t*, B_t*, sqrt(rho*) of both sides), picks the side K of
+// the contact (lam2 >= 0 -> left), and forms U_K, F_K, U_K*, U_K** for that side only:
+//   F = F_K + c2 (U* - U_K) + c1 (U** - U*),   c2 = 0 in the outer region else the outer
+//   speed (lam0 | lam4),  c1 = inner speed (lam1 | lam3) in the double-star region else 0,
+// which is the reference's  F_K + lam_in U** - (lam_in - lam_out) U* - lam_out U_K
+// regrouped.  The 0/0 guards (isfinite, HLLD_MHD.cpp:189-224) and the exact BX==0
+// special case (:248) are kept.  `pstar` (NEED_PSTAR) is the primitive form of the
+// selected region's state, i.e. UtoP(ustar) of solver_eqn_mhd_adi.cpp:183 without the
+// round trip through conserved variables (v = (rho v)/rho); only ro, v and B_t are set
+// (all that AVFalle reads, solver_eqn_mhd_adi.cpp:254-284).
+template <bool NEED_PSTAR>
+__device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const PhysParams& pp, Cons& flux, Prim& pstar) {
+  const double g = pp.gamma, gm1 = g - 1.0;
   const double BX = 0.5 * (L.bn + R.bn);
-  Cons UL, UR, FL, FR;
-  PtoU_mhd_ideal(L, UL, gm1);
-  PtoU_mhd_ideal(R, UR, gm1);
-  PUtoFlux<EQ_MHD>(L, UL, FL);
-  PUtoFlux<EQ_MHD>(R, UR, FR);
-  double lam0, lam4;
-  hlld_speeds(L, R, pp.gamma, lam0, lam4);
+  const double BX2 = BX * BX;
+  // HLLD_signal_speeds (:342-368)
+  const double cf_max = fast_sqrt(fmax(cfast2_ir(fast_rcp(L.ro), L.pg, BX, L.bt1, L.bt2, g),
+                                       cfast2_ir(fast_rcp(R.ro), R.pg, BX, R.bt1, R.bt2, g)));
+  const double lam0 = fmin(L.vn, R.vn) - cf_max;
+  const double lam4 = fmax(L.vn, R.vn) + cf_max;
+  const double sl_vl = lam0 - L.vn, sr_vr = lam4 - R.vn;
+  const double pm_l = 0.5 * (L.bn * L.bn + L.bt1 * L.bt1 + L.bt2 * L.bt2);
+  const double pm_r = 0.5 * (R.bn * R.bn + R.bt1 * R.bt1 + R.bt2 * R.bt2);
+  const double tp_l = L.pg + pm_l, tp_r = R.pg + pm_r;
+  const double rsl = L.ro * sl_vl, rsr = R.ro * sr_vr;
+  const double itemp = fast_rcp(rsr - rsl);
+  const double lam2 = (sr_vr * (R.ro * R.vn) - sl_vl * (L.ro * L.vn) - tp_r + tp_l) * itemp;
+  const double tp_s = (rsr * tp_l - rsl * tp_r + L.ro * R.ro * sr_vr * sl_vl * (R.vn - L.vn)) * itemp;
+  const double sl_sm = lam0 - lam2, sr_sm = lam4 - lam2;
+  const double isl_sm = fast_rcp(sl_sm), isr_sm = fast_rcp(sr_sm);
+  const double rho_ls = rsl * isl_sm, rho_rs = rsr * isr_sm;
+  // transverse velocity and field of the single-star states, both sides
+  const double id_l = fast_rcp(rsl * sl_sm - BX2), id_r = fast_rcp(rsr * sr_sm - BX2);
+  double vys_l = L.vt1, vzs_l = L.vt2, vys_r = R.vt1, vzs_r = R.vt2;
+  double bys_l = 0.0, bzs_l = 0.0, bys_r = 0.0, bzs_r = 0.0;
+  {
+    const double ql = (lam2 - L.vn) * id_l, qr = (lam2 - R.vn) * id_r;
+    if (isfinite(ql)) { vys_l = L.vt1 - BX * L.bt1 * ql; vzs_l = L.vt2 - BX * L.bt2 * ql; }
+    if (isfinite(qr)) { vys_r = R.vt1 - BX * R.bt1 * qr; vzs_r = R.vt2 - BX * R.bt2 * qr; }
+    const double pl = (rsl * sl_vl - BX2) * id_l, pr = (rsr * sr_vr - BX2) * id_r;
+    if (isfinite(pl)) { bys_l = L.bt1 * pl; bzs_l = L.bt2 * pl; }
+    if (isfinite(pr)) { bys_r = R.bt1 * pr; bzs_r = R.bt2 * pr; }
+  }
+  const double isq_l = fast_rsqrt(rho_ls), isq_r = fast_rsqrt(rho_rs);
+  const double sq_l = rho_ls * isq_l, sq_r = rho_rs * isq_r;
+  const double aBX = fabs(BX);
+  const double lam1 = lam2 - aBX * isq_l;
+  const double lam3 = lam2 + aBX * isq_r;
 
-  double sl_vl = lam0 - L.vn;
-  double sr_vr = lam4 - R.vn;
-  double tp_r = R.pg + 0.5 * (R.bn * R.bn + R.bt1 * R.bt1 + R.bt2 * R.bt2);
-  double tp_l = L.pg + 0.5 * (L.bn * L.bn + L.bt1 * L.bt1 + L.bt2 * L.bt2);
-  double temp = sr_vr * R.ro - sl_vl * L.ro;
-  double itemp = 1.0 / temp;
-  double lam2 = (sr_vr * UR.mn - sl_vl * UL.mn - tp_r + tp_l) * itemp;
-  double tp_s = (sr_vr * R.ro * tp_l - sl_vl * L.ro * tp_r + L.ro * R.ro * sr_vr * sl_vl * (R.vn - L.vn)) * itemp;
-  double sl_sm = lam0 - lam2;
-  double sr_sm = lam4 - lam2;
-  double isl_sm = 1.0 / sl_sm, isr_sm = 1.0 / sr_sm;
+  // side and region of the interface (the reference's if-chain, first true wins)
+  const bool left = (lam0 > 0) || (lam1 >= 0) || (lam2 >= 0);
+  const bool outer = left ? (lam0 > 0) : !(lam3 >= 0 || lam4 >= 0);
+  const bool dstar = left ? !(lam0 > 0 || lam1 >= 0) : (lam3 >= 0);
 
-  Cons ULs, URs;
-  ULs.rho = L.ro * sl_vl * isl_sm;
-  URs.rho = R.ro * sr_vr * isr_sm;
-  ULs.mn = lam2 * ULs.rho;
-  URs.mn = lam2 * URs.rho;
-  double temp_l1 = lam2 - L.vn;
-  double temp_l2 = L.ro * sl_vl * sl_sm - BX * BX;
-  double temp_r1 = lam2 - R.vn;
-  double temp_r2 = R.ro * sr_vr * sr_sm - BX * BX;
-  double vys_l = L.vt1, vys_r = R.vt1, vzs_l = L.vt2, vzs_r = R.vt2;
-  double ql = temp_l1 / temp_l2, qr = temp_r1 / temp_r2;
-  if (isfinite(ql)) {
-    vys_l = L.vt1 - BX * L.bt1 * ql;
-    vzs_l = L.vt2 - BX * L.bt2 * ql;
-  }
-  if (isfinite(qr)) {
-    vys_r = R.vt1 - BX * R.bt1 * qr;
-    vzs_r = R.vt2 - BX * R.bt2 * qr;
-  }
-  ULs.mt1 = vys_l * ULs.rho;
-  URs.mt1 = vys_r * URs.rho;
-  ULs.mt2 = vzs_l * ULs.rho;
-  URs.mt2 = vzs_r * URs.rho;
-  ULs.bbn = URs.bbn = BX;
-  temp_l1 = L.ro * sl_vl * sl_vl - BX * BX;
-  temp_r1 = R.ro * sr_vr * sr_vr - BX * BX;
-  ULs.bbt1 = 0.0; URs.bbt1 = 0.0; ULs.bbt2 = 0.0; URs.bbt2 = 0.0;
-  ql = temp_l1 / temp_l2;
-  qr = temp_r1 / temp_r2;
-  if (isfinite(ql)) {
-    ULs.bbt1 = L.bt1 * ql;
-    ULs.bbt2 = L.bt2 * ql;
-  }
-  if (isfinite(qr)) {
-    URs.bbt1 = R.bt1 * qr;
-    URs.bbt2 = R.bt2 * qr;
-  }
-  temp_l1 = L.vn * BX + L.vt1 * L.bt1 + L.vt2 * L.bt2;
-  temp_r1 = R.vn * BX + R.vt1 * R.bt1 + R.vt2 * R.bt2;
-  temp_l2 = lam2 * ULs.bbn + vys_l * ULs.bbt1 + vzs_l * ULs.bbt2;
-  temp_r2 = lam2 * URs.bbn + vys_r * URs.bbt1 + vzs_r * URs.bbt2;
-  ULs.erg = (sl_vl * UL.erg - tp_l * L.vn + tp_s * lam2 + BX * (temp_l1 - temp_l2)) * isl_sm;
-  URs.erg = (sr_vr * UR.erg - tp_r * R.vn + tp_s * lam2 + BX * (temp_r1 - temp_r2)) * isr_sm;
-  double sq_l = sqrt(ULs.rho), sq_r = sqrt(URs.rho);
-  double lam1 = lam2 - fabs(BX) / sq_l;
-  double lam3 = lam2 + fabs(BX) / sq_r;
-  ULs.psi = URs.psi = 0.0;
-
-  Cons ULss = ULs, URss = URs;
-  if (BX != 0) {
-    double sgn = (BX > 0) - (BX < 0);
-    double tsum = sq_l + sq_r;
-    double itsum = 1.0 / tsum;
-    double vy_ss = (sq_l * vys_l + sq_r * vys_r + (URs.bbt1 - ULs.bbt1) * sgn) * itsum;
-    double vz_ss = (sq_l * vzs_l + sq_r * vzs_r + (URs.bbt2 - ULs.bbt2) * sgn) * itsum;
-    ULss.mt1 = vy_ss * ULss.rho;
-    URss.mt1 = vy_ss * URss.rho;
-    ULss.mt2 = vz_ss * ULss.rho;
-    URss.mt2 = vz_ss * URss.rho;
-    double by_ss = (sq_l * URs.bbt1 + sq_r * ULs.bbt1 + sq_l * sq_r * (vys_r - vys_l) * sgn) * itsum;
-    double bz_ss = (sq_l * URs.bbt2 + sq_r * ULs.bbt2 + sq_l * sq_r * (vzs_r - vzs_l) * sgn) * itsum;
-    ULss.bbt1 = URss.bbt1 = by_ss;
-    ULss.bbt2 = URss.bbt2 = bz_ss;
-    double bv = lam2 * BX + vy_ss * by_ss + vz_ss * bz_ss;
-    ULss.erg = ULs.erg - sq_l * (temp_l2 - bv) * sgn;
-    URss.erg = URs.erg + sq_r * (temp_r2 - bv) * sgn;
+  // double-star transverse state (shared by both sides, :248-290); equals the star state if BX == 0
+  const double sgn = (double)((BX > 0) - (BX < 0));
+  double vy_ss, vz_ss, by_ss, bz_ss;
+  {
+    const double itsum = fast_rcp(sq_l + sq_r);
+    vy_ss = (sq_l * vys_l + sq_r * vys_r + (bys_r - bys_l) * sgn) * itsum;
+    vz_ss = (sq_l * vzs_l + sq_r * vzs_r + (bzs_r - bzs_l) * sgn) * itsum;
+    by_ss = (sq_l * bys_r + sq_r * bys_l + sq_l * sq_r * (vys_r - vys_l) * sgn) * itsum;
+    bz_ss = (sq_l * bzs_r + sq_r * bzs_l + sq_l * sq_r * (vzs_r - vzs_l) * sgn) * itsum;
   }
 
-#define PION_HLLD_COMP(c)                                                                   \
-  if (lam0 > 0) { flux.c = FL.c; if (NEED_USTAR) ustar.c = UL.c; }                              \
-  else if (lam1 >= 0) { flux.c = FL.c + lam0 * (ULs.c - UL.c); if (NEED_USTAR) ustar.c = ULs.c; } \
-  else if (lam2 >= 0) { flux.c = FL.c + lam1 * ULss.c - (lam1 - lam0) * ULs.c - lam0 * UL.c; if (NEED_USTAR) ustar.c = ULss.c; } \
-  else if (lam3 >= 0) { flux.c = FR.c + lam3 * URss.c - (lam3 - lam4) * URs.c - lam4 * UR.c; if (NEED_USTAR) ustar.c = URss.c; } \
-  else if (lam4 >= 0) { flux.c = FR.c + lam4 * (URs.c - UR.c); if (NEED_USTAR) ustar.c = URs.c; } \
-  else { flux.c = FR.c; if (NEED_USTAR) ustar.c = UR.c; }
-  PION_HLLD_COMP(rho) PION_HLLD_COMP(erg) PION_HLLD_COMP(mn) PION_HLLD_COMP(mt1) PION_HLLD_COMP(mt2)
-  PION_HLLD_COMP(bbn) PION_HLLD_COMP(bbt1) PION_HLLD_COMP(bbt2)
-#undef PION_HLLD_COMP
+  // everything below is for side K only
+  const double K_ro = left ? L.ro : R.ro, K_pg = left ? L.pg : R.pg, K_vn = left ? L.vn : R.vn;
+  const double K_vt1 = left ? L.vt1 : R.vt1, K_vt2 = left ? L.vt2 : R.vt2;
+  const double K_bn = left ? L.bn : R.bn, K_bt1 = left ? L.bt1 : R.bt1, K_bt2 = left ? L.bt2 : R.bt2;
+  const double s_v = left ? sl_vl : sr_vr, is_m = left ? isl_sm : isr_sm;
+  const double rho_s = left ? rho_ls : rho_rs, sq_K = left ? -sq_l : sq_r;  // sign of the ** energy jump folded in
+  const double vys = left ? vys_l : vys_r, vzs = left ? vzs_l : vzs_r;
+  const double bys = left ? bys_l : bys_r, bzs = left ? bzs_l : bzs_r;
+  const double pm_K = left ? pm_l : pm_r, tp_K = left ? tp_l : tp_r;
+  const double c2 = outer ? 0.0 : (left ? lam0 : lam4);
+  const double c1 = (dstar && BX != 0) ? (left ? lam1 : lam3) : 0.0;
+
+  // U_K (eqns_mhd_ideal::PtoU) and F_K (PUtoFlux)
+  const double K_mn = K_ro * K_vn, K_mt1 = K_ro * K_vt1, K_mt2 = K_ro * K_vt2;
+  const double K_erg = (K_ro * (K_vn * K_vn + K_vt1 * K_vt1 + K_vt2 * K_vt2) * 0.5) + PION_OVER_GM1(K_pg, gm1) + pm_K;
+  const double vb_own = K_vn * K_bn + K_vt1 * K_bt1 + K_vt2 * K_bt2;
+  // star-state energy (:226-239) -- note v.B there is taken with BX, not the side's own B_n
+  const double vb_K = K_vn * BX + K_vt1 * K_bt1 + K_vt2 * K_bt2;
+  const double vbs_K = lam2 * BX + vys * bys + vzs * bzs;
+  const double erg_s = (s_v * K_erg - tp_K * K_vn + tp_s * lam2 + BX * (vb_K - vbs_K)) * is_m;
+  const double bv = lam2 * BX + vy_ss * by_ss + vz_ss * bz_ss;
+  const double derg_ss = sq_K * (vbs_K - bv) * sgn;  // U**.erg - U*.erg
+
+  flux.rho = K_mn + c2 * (rho_s - K_ro);
+  flux.mn = (K_mn * K_vn + K_pg + pm_K - K_bn * K_bn) + c2 * (lam2 * rho_s - K_mn);
+  flux.mt1 = (K_mn * K_vt1 - K_bn * K_bt1) + c2 * (vys * rho_s - K_mt1) + c1 * ((vy_ss - vys) * rho_s);
+  flux.mt2 = (K_mn * K_vt2 - K_bn * K_bt2) + c2 * (vzs * rho_s - K_mt2) + c1 * ((vz_ss - vzs) * rho_s);
+  flux.erg = (K_vn * (K_erg + K_pg + pm_K) - K_bn * vb_own) + c2 * (erg_s - K_erg) + c1 * derg_ss;
+  flux.bbn = c2 * (BX - K_bn);
+  flux.bbt1 = (K_vn * K_bt1 - K_vt1 * K_bn) + c2 * (bys - K_bt1) + c1 * (by_ss - bys);
+  flux.bbt2 = (K_vn * K_bt2 - K_vt2 * K_bn) + c2 * (bzs - K_bt2) + c1 * (bz_ss - bzs);
   flux.psi = 0.0;
-  if (NEED_USTAR) ustar.psi = 0.0;
+
+  if (NEED_PSTAR) {
+    const bool dd = dstar && (BX != 0);  // in the ** region with BX==0 the state is the * state
+    pstar.ro = outer ? K_ro : rho_s;
+    pstar.vn = outer ? K_vn : lam2;
+    pstar.vt1 = outer ? K_vt1 : (dd ? vy_ss : vys);
+    pstar.vt2 = outer ? K_vt2 : (dd ? vz_ss : vzs);
+    pstar.bt1 = outer ? K_bt1 : (dd ? by_ss : bys);
+    pstar.bt2 = outer ? K_bt2 : (dd ? bz_ss : bzs);
+    pstar.bn = outer ? K_bn : BX;
+    pstar.pg = 0.0;
+    pstar.psi = 0.0;
+    if (pstar.ro <= 0.0) {  // UtoP's (fatal in the reference) negative-density reset, eqns_mhd_adiabatic.cpp:137-160
+      const double r0 = PION_BASE_RHO * pp.refvec_ro;
+      const double f = pstar.ro / r0;
+      pstar.vn *= f; pstar.vt1 *= f; pstar.vt2 *= f;
+      pstar.ro = r0;
+    }
+  }
 }
 
 // Riemann_Roe_MHD_CV::MHD_Roe_CV_flux_solver_symmetric
@@ -679,14 +718,13 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
     }
     if (SOLVER == SOLVE_ROE) {
       mhd_RoeCV(l, r, pp, hc_etamax, flux, pstar);
+    } else if (SOLVER == SOLVE_HLLD && !use_hll) {
+      mhd_HLLD<FKJ>(l, r, pp, flux, pstar);
     } else {
       Cons ustar;
-      if (SOLVER == SOLVE_HLLD && !use_hll) mhd_HLLD<FKJ>(l, r, pp, flux, ustar);
-      else mhd_HLL<FKJ>(l, r, pp, flux, ustar);
-      if (FKJ) {
-        // virtual UtoP: GLM version with psi==0 equals the ideal one
-        UtoP<EQ_MHD>(ustar, pstar, pp);
-      }
+      mhd_HLL<FKJ>(l, r, pp, flux, ustar);
+      // virtual UtoP: GLM version with psi==0 equals the ideal one
+      if (FKJ) UtoP<EQ_MHD>(ustar, pstar, pp);
     }
     if (EQ == EQ_GLM) {
       flux.erg += pp.chyp * bxstar * psistar;

@@ -66,6 +66,7 @@ struct pion_gpu_ctx {
   long long launches = 0;
   // optional per-launch timing of the stage kernel (bench.py roofline leg)
   bool timing = false;
+  bool force_gather = false;  // PION_B200_GATHER=1: run the gather kernel on the fused path too (A/B tests)
   std::vector<cudaEvent_t> tev;  // begin/end pairs
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -149,6 +150,7 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   pp.have_mp = cfg->cooling ? 1 : 0;
   pp.mu_tot_over_kB = cfg->cooling ? (0.609 * 1.6726231e-24) / 1.380658e-16 : 0.0;
   c->simtime = cfg->starttime;
+  { const char* e = getenv("PION_B200_GATHER"); c->force_gather = e && e[0] == '1'; }
 
   bool ok = true;
   ok &= cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -545,10 +547,13 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
     CUDA_OK(cudaEventCreate(&e1));
     CUDA_OK(cudaEventRecord(e0, c->stream));
   }
+  // fused 2-D/3-D stages run the flux-once sweep kernel; 1-D grids and the unfused seam
+  // call (calc_dynamics_dU) run the per-cell gather kernel
+  const bool sweep = fused && c->g.ndim >= 2 && !c->force_gather;
   switch (c->cfg.eqntype) {
-    case PION_EQEUL: launch_stage_euler(c->cfg.solver, fkj, a, c->stream); break;
-    case PION_EQMHD: launch_stage_mhd(c->cfg.solver, fkj, a, c->stream); break;
-    default: launch_stage_glm(c->cfg.solver, fkj, a, c->stream); break;
+    case PION_EQEUL: (sweep ? launch_sweep_euler : launch_stage_euler)(c->cfg.solver, fkj, a, c->stream); break;
+    case PION_EQMHD: (sweep ? launch_sweep_mhd : launch_stage_mhd)(c->cfg.solver, fkj, a, c->stream); break;
+    default: (sweep ? launch_sweep_glm : launch_stage_glm)(c->cfg.solver, fkj, a, c->stream); break;
   }
   if (c->timing) {
     CUDA_OK(cudaEventRecord(e1, c->stream));

@@ -84,6 +84,63 @@ __device__ __forceinline__ unsigned long long dbl_ordered_bits(double x) {
   return (unsigned long long)__double_as_longlong(x);
 }
 
+// CellAdvanceTime for one cell (solver_eqn_mhd_adi.cpp:452-504, :822-844; Euler
+// solver_eqn_hydro_adi.cpp:372-451) + the temperature cap and P=Ph of
+// grid_update_state_vector (time_integrator.cpp:881-958): U = PtoU(Pb) + dU,
+// out = UtoP(U) with floors; optionally the next step's CellTimeStep.
+template <int EQ>
+__device__ __forceinline__ int cell_advance_time(const StageArgs& a, long c, const Cons& acc, const double* acctr, int ntr, double& my_dt) {
+  constexpr int NB = nbase(EQ);
+  const long vs = a.g.vs;
+  Prim Pb = load_prim<EQ>(a.Pb, c, vs, 0, 1, 2);
+  Cons U;
+  PtoU<EQ>(Pb, U, a.pp.gamma - 1.0);
+  U.rho += acc.rho; U.erg += acc.erg; U.mn += acc.mn; U.mt1 += acc.mt1; U.mt2 += acc.mt2;
+  if (EQ != EQ_EULER) { U.bbn += acc.bbn; U.bbt1 += acc.bbt1; U.bbt2 += acc.bbt2; }
+  if (EQ == EQ_GLM) U.psi += acc.psi;
+  Prim Pn;
+  const int status = UtoP<EQ>(U, Pn, a.pp);
+  if (EQ == EQ_GLM) Pn.psi *= a.glm_damp;
+  // temperature cap of grid_update_state_vector (time_integrator.cpp:926-932)
+  if (a.pp.have_mp && (Pn.pg * a.pp.mu_tot_over_kB / Pn.ro > a.pp.max_temp))
+    Pn.pg = Pn.ro * a.pp.max_temp / a.pp.mu_tot_over_kB;
+  store_prim<EQ>(a.out, c, vs, Pn);
+#pragma unroll
+  for (int q = 0; q < PION_MAXTR; q++) {
+    if (q < ntr) {
+      double pb = __ldg(a.Pb + (long)(NB + q) * vs + c);
+      if (a.pp.have_mp) pb *= scma_corr(pb);
+      double u = pb * Pb.ro + acctr[q];
+      double pn = u / U.rho;
+      if (a.pp.have_mp) pn *= scma_corr(pn);
+      a.out[(long)(NB + q) * vs + c] = pn;
+    }
+  }
+  if (a.dtmin) my_dt = fmin(my_dt, cell_time_step<EQ>(Pn, a.pp, a.g.ndim, a.g.dx, a.cfl));
+  return status;
+}
+
+// block-level reductions: min dt (warp shuffles + one atomicMin per block) and error counters
+__device__ __forceinline__ void stage_block_epilogue(const StageArgs& a, double my_dt, int status) {
+  if (a.dtmin) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_dt = fmin(my_dt, __shfl_xor_sync(0xffffffffu, my_dt, o));
+    __shared__ double s_dt[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_dt[w] = my_dt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = s_dt[0];
+      for (int q = 1; q < (int)(blockDim.x >> 5); q++) m = fmin(m, s_dt[q]);
+      if (m < 1.0e100) atomicMin(a.dtmin, dbl_ordered_bits(m));
+    }
+  }
+  if (status && a.counters) {
+    if (status & ST_NEG_RHO) atomicAdd((unsigned long long*)&a.counters[0], 1ULL);
+    if (status & ST_NEG_PG) atomicAdd((unsigned long long*)&a.counters[1], 1ULL);
+  }
+}
+
 #ifndef PION_STAGE_MINBLOCKS
 #define PION_STAGE_MINBLOCKS 2
 #endif
@@ -262,32 +319,7 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
       for (int q = 0; q < PION_MAXTR; q++)
         if (q < a.ntr) d[(NB + q) * vs + c] += acctr[q];
     } else if (domain) {
-      // CellAdvanceTime (solver_eqn_mhd_adi.cpp:452-504, :822-844; Euler solver_eqn_hydro_adi.cpp:372-451)
-      Prim Pb = load_prim<EQ>(a.Pb, c, vs, 0, 1, 2);
-      Cons U;
-      PtoU<EQ>(Pb, U, a.pp.gamma - 1.0);
-      U.rho += acc.rho; U.erg += acc.erg; U.mn += acc.mn; U.mt1 += acc.mt1; U.mt2 += acc.mt2;
-      if (EQ != EQ_EULER) { U.bbn += acc.bbn; U.bbt1 += acc.bbt1; U.bbt2 += acc.bbt2; }
-      if (EQ == EQ_GLM) U.psi += acc.psi;
-      Prim Pn;
-      status = UtoP<EQ>(U, Pn, a.pp);
-      if (EQ == EQ_GLM) Pn.psi *= a.glm_damp;
-      // temperature cap of grid_update_state_vector (time_integrator.cpp:926-932)
-      if (a.pp.have_mp && (Pn.pg * a.pp.mu_tot_over_kB / Pn.ro > a.pp.max_temp))
-        Pn.pg = Pn.ro * a.pp.max_temp / a.pp.mu_tot_over_kB;
-      store_prim<EQ>(a.out, c, vs, Pn);
-#pragma unroll
-      for (int q = 0; q < PION_MAXTR; q++) {
-        if (q < a.ntr) {
-          double pb = __ldg(a.Pb + (long)(NB + q) * vs + c);
-          if (a.pp.have_mp) pb *= scma_corr(pb);
-          double u = pb * Pb.ro + acctr[q];
-          double pn = u / U.rho;
-          if (a.pp.have_mp) pn *= scma_corr(pn);
-          a.out[(long)(NB + q) * vs + c] = pn;
-        }
-      }
-      if (a.dtmin) my_dt = cell_time_step<EQ>(Pn, a.pp, g.ndim, g.dx, a.cfl);
+      status = cell_advance_time<EQ>(a, c, acc, acctr, a.ntr, my_dt);
     } else {
       // cell cut out of the domain (time_integrator.cpp:905-908): state untouched
       if (a.out != a.S) {
@@ -296,30 +328,17 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
     }
   }
 
-  // block-level reductions: min dt (warp shuffles) and error counters
-  if (a.dtmin) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_dt = fmin(my_dt, __shfl_xor_sync(0xffffffffu, my_dt, o));
-    __shared__ double s_dt[4];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) s_dt[w] = my_dt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double m = s_dt[0];
-      for (int q = 1; q < (int)(blockDim.x >> 5); q++) m = fmin(m, s_dt[q]);
-      if (m < 1.0e100) atomicMin(a.dtmin, dbl_ordered_bits(m));
-    }
-  }
-  if (status && a.counters) {
-    if (status & ST_NEG_RHO) atomicAdd((unsigned long long*)&a.counters[0], 1ULL);
-    if (status & ST_NEG_PG) atomicAdd((unsigned long long*)&a.counters[1], 1ULL);
-  }
+  stage_block_epilogue(a, my_dt, status);
 }
 
 // host-side launcher implemented per equation set in stage_{euler,mhd,glm}.cu
 void launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_stage_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+// flux-once sweep kernel (stage_sweep.cuh), instantiated in sweep_{euler,mhd,glm}.cu
+void launch_sweep_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+void launch_sweep_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+void launch_sweep_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 
 template <int EQ, int SOLVER, bool FKJ>
 inline void launch_stage_t(const StageArgs& a, cudaStream_t s) {

@@ -1,0 +1,339 @@
+// pion_b200/csrc/stage_sweep.cuh -- the production stage kernel: one predictor
+// or corrector stage of the finite-volume update with every interface flux
+// computed exactly ONCE.
+//
+// Same reference path as stage_kernel.cuh (time_integrator.cpp:498-958,
+// VectorOps.cpp:535-644, solver_eqn_base.cpp:152-342, solver_eqn_mhd_adi.cpp:
+// 368-443,782-844), different work decomposition:
+//
+//   * a thread block is a 32 x TY tile of the xy plane that MARCHES in z over a
+//     chunk of planes; warp w is row j0+w, lane l is cell i0+l;
+//   * every thread computes the flux through the LOW x face and the LOW y face
+//     of its cell and the HIGH z face (= low face of the cell above);
+//       x: the high-face flux is the next lane's low-face flux  -> __shfl_down
+//       y: the high-face flux is the next warp's low-face flux  -> shared memory
+//       z: the low-face flux is the one this thread computed one plane earlier
+//          -> stays in registers
+//     so lane 31 and row TY-1 only produce fluxes for their neighbours (the
+//     extra row computes nothing but its y flux): 31 x (TY-1) cells are updated
+//     per plane by 32 x TY threads, and a chunk pays one extra z-flux plane;
+//   * contributions are accumulated in the reference's order (x, y, z; sources
+//     before the flux difference), then CellAdvanceTime is applied in registers:
+//     dU, slopes, edge states and fluxes never touch HBM.
+//
+// The axis loop is a real loop with ONE inlined Riemann solver (the solver frame
+// is rotated in registers), which keeps the kernel inside the instruction cache.
+#pragma once
+#include "stage_kernel.cuh"
+
+namespace pion {
+
+template <int EQ>
+__device__ __forceinline__ void cons_zero(Cons& f) {
+  f.rho = f.erg = f.mn = f.mt1 = f.mt2 = f.bbn = f.bbt1 = f.bbt2 = f.psi = 0.0;
+}
+
+template <int EQ>
+__device__ __forceinline__ Cons cons_shfl_down(const Cons& f) {
+  Cons r;
+  const unsigned m = 0xffffffffu;
+  r.rho = __shfl_down_sync(m, f.rho, 1);
+  r.erg = __shfl_down_sync(m, f.erg, 1);
+  r.mn = __shfl_down_sync(m, f.mn, 1);
+  r.mt1 = __shfl_down_sync(m, f.mt1, 1);
+  r.mt2 = __shfl_down_sync(m, f.mt2, 1);
+  if (EQ != EQ_EULER) {
+    r.bbn = __shfl_down_sync(m, f.bbn, 1);
+    r.bbt1 = __shfl_down_sync(m, f.bbt1, 1);
+    r.bbt2 = __shfl_down_sync(m, f.bbt2, 1);
+  } else {
+    r.bbn = r.bbt1 = r.bbt2 = 0.0;
+  }
+  r.psi = (EQ == EQ_GLM) ? __shfl_down_sync(m, f.psi, 1) : 0.0;
+  return r;
+}
+
+// shared-memory flux slab of one plane: [component][row][lane]
+template <int EQ, int TY>
+__device__ __forceinline__ void cons_to_smem(double* s, int row, int lane, const Cons& f) {
+  double* p = s + row * 32 + lane;
+  constexpr int CS = TY * 32;
+  p[0] = f.rho; p[CS] = f.erg; p[2 * CS] = f.mn; p[3 * CS] = f.mt1; p[4 * CS] = f.mt2;
+  if (EQ != EQ_EULER) { p[5 * CS] = f.bbn; p[6 * CS] = f.bbt1; p[7 * CS] = f.bbt2; }
+  if (EQ == EQ_GLM) p[8 * CS] = f.psi;
+}
+template <int EQ, int TY>
+__device__ __forceinline__ Cons cons_from_smem(const double* s, int row, int lane) {
+  const double* p = s + row * 32 + lane;
+  constexpr int CS = TY * 32;
+  Cons f;
+  f.rho = p[0]; f.erg = p[CS]; f.mn = p[2 * CS]; f.mt1 = p[3 * CS]; f.mt2 = p[4 * CS];
+  if (EQ != EQ_EULER) { f.bbn = p[5 * CS]; f.bbt1 = p[6 * CS]; f.bbt2 = p[7 * CS]; } else { f.bbn = f.bbt1 = f.bbt2 = 0.0; }
+  f.psi = (EQ == EQ_GLM) ? p[8 * CS] : 0.0;
+  return f;
+}
+
+// Flux through the LOW face of cell X along the axis with stride `st`, in that
+// axis' solver frame: slopes + edge states (VectorOps.cpp:535-617), HLLD->HLL
+// switch (solver_eqn_mhd_adi.cpp:167-177), H-correction eta (solver_eqn_base.cpp:
+// 608-678) and InterCellFlux.
+template <int EQ, int SOLVER, bool FKJ>
+__device__ __forceinline__ void low_face_flux(const StageArgs& a, long X, long st, int ax, int a1, int a2, Cons& F) {
+  const GridD& g = a.g;
+  const long vs = g.vs;
+  Prim eL = load_prim<EQ>(a.S, X - st, vs, ax, a1, a2);
+  Prim eR = load_prim<EQ>(a.S, X, vs, ax, a1, a2);
+  if (a.order == 2) {
+    const Prim Q0 = load_prim<EQ>(a.S, X - 2 * st, vs, ax, a1, a2);
+    const Prim Q3 = load_prim<EQ>(a.S, X + st, vs, ax, a1, a2);
+#define PION_EDGE2(f)                                                     \
+  {                                                                       \
+    const double d0 = eL.f - Q0.f, d1 = eR.f - eL.f, d2 = Q3.f - eR.f;    \
+    eL.f += minmod(d0, d1, a.tiny2) * 0.5;                                \
+    eR.f -= minmod(d1, d2, a.tiny2) * 0.5;                                \
+  }
+    PION_EDGE2(ro) PION_EDGE2(pg) PION_EDGE2(vn) PION_EDGE2(vt1) PION_EDGE2(vt2)
+    if (EQ != EQ_EULER) { PION_EDGE2(bn) PION_EDGE2(bt1) PION_EDGE2(bt2) }
+    if (EQ == EQ_GLM) { PION_EDGE2(psi) }
+#undef PION_EDGE2
+  }
+  bool use_hll = false;
+  if (SOLVER == SOLVE_HLLD) use_hll = (a.hll[X - st] | a.hll[X]) != 0;
+  double eta = 0.0;
+  if (SOLVER == SOLVE_ROE && a.eta) {
+    const double* en = a.eta + (long)ax * vs;
+    eta = en[X - st];
+    if (g.ndim > 1) {
+      const double* e1 = a.eta + (long)((ax + 1) % g.ndim) * vs;
+      eta = fmax(eta, fmax(fmax(e1[X - st], e1[X]), e1[X - 2 * st]));
+    }
+    if (g.ndim > 2) {
+      const double* e2 = a.eta + (long)((ax + 2) % g.ndim) * vs;
+      eta = fmax(eta, fmax(fmax(e2[X - st], e2[X]), e2[X - 2 * st]));
+    }
+  }
+  intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(eL, eR, a.pp, use_hll, eta, F);
+}
+
+// Upwinded tracer flux through the low face of cell X (solver_eqn_base.cpp:281-342)
+__device__ __forceinline__ double tracer_low_face_flux(const StageArgs& a, const double* __restrict__ T, long X, long st,
+                                                       double Frho) {
+  double L = __ldg(T + X - st), R = __ldg(T + X);
+  if (a.order == 2) {
+    const double q0 = __ldg(T + X - 2 * st), q3 = __ldg(T + X + st);
+    const double d0 = L - q0, d1 = R - L, d2 = q3 - R;
+    L += minmod(d0, d1, a.tiny2) * 0.5;
+    R -= minmod(d1, d2, a.tiny2) * 0.5;
+  }
+  double f = 0.0;
+  if (Frho > 0.0) f = L * Frho * (a.pp.have_mp ? scma_corr(L) : 1.0);
+  else if (Frho < 0.0) f = R * Frho * (a.pp.have_mp ? scma_corr(R) : 1.0);
+  return f;
+}
+
+#ifndef PION_SWEEP_MINBLOCKS
+#define PION_SWEEP_MINBLOCKS 2
+#endif
+
+template <int EQ, int SOLVER, bool FKJ, int TY, bool TR>
+__global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(const __grid_constant__ StageArgs a, const int kchunk) {
+  extern __shared__ double s_flux[];  // [2][NB][TY][32]
+  constexpr int NB = nbase(EQ);
+  const GridD& g = a.g;
+  const int NX = g.NG[0], NY = g.NG[1], NZ = g.NG[2];
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  int i = blockIdx.x * 31 + lane, j = blockIdx.y * (TY - 1) + row;
+  const bool row_active = (row < TY - 1) && (j < NY);               // warp-uniform
+  const bool upd_xy = row_active && (lane < 31) && (i < NX);
+  i = min(i, NX);  // clamped threads recompute a neighbour's (valid) face; their results are never used
+  j = min(j, NY);
+  const int k0 = blockIdx.z * kchunk, k1 = min(k0 + kchunk, NZ);
+  const bool has_z = g.ndim > 2;
+  const long vs = g.vs;
+  const double idx = 1.0 / g.dx;
+  const double dt = a.dt;
+  const int ntr = TR ? a.ntr : 0;  // TR=false instantiation: no tracer registers at all
+  double my_dt = 1.0e100;
+  int status = 0;
+
+  Cons Fz;  // flux through the low z face of the current cell
+  cons_zero<EQ>(Fz);
+  double Fz_tr[PION_MAXTR];
+#pragma unroll
+  for (int q = 0; q < PION_MAXTR; q++) Fz_tr[q] = 0.0;
+
+  for (int k = has_z ? k0 - 1 : k0; k < k1; k++) {
+    const bool warm = k < k0;  // first iteration of a 3-D chunk: only the z flux into plane k0
+    const long c = gidx(g, i + g.nb[0], j + g.nb[1], k + g.nb[2]);
+    double* sbuf = s_flux + (size_t)((k - k0) & 1) * (NB * TY * 32);
+
+    Cons acc;
+    cons_zero<EQ>(acc);
+    double acctr[PION_MAXTR];
+#pragma unroll
+    for (int q = 0; q < PION_MAXTR; q++) acctr[q] = 0.0;
+    Prim C;
+    const bool domain = upd_xy && !warm && (a.mask ? (a.mask[c] != 0) : true);
+    if (!warm) {
+      C = load_prim<EQ>(a.S, c, vs, 0, 1, 2);
+      if (a.dU && upd_xy) {  // microphysics dU computed by the cooling kernel (frame x)
+        acc.rho = a.dU[c]; acc.erg = a.dU[vs + c]; acc.mn = a.dU[2 * vs + c]; acc.mt1 = a.dU[3 * vs + c];
+        acc.mt2 = a.dU[4 * vs + c];
+        if (EQ != EQ_EULER) { acc.bbn = a.dU[5 * vs + c]; acc.bbt1 = a.dU[6 * vs + c]; acc.bbt2 = a.dU[7 * vs + c]; }
+        if (EQ == EQ_GLM) acc.psi = a.dU[8 * vs + c];
+#pragma unroll
+        for (int q = 0; q < PION_MAXTR; q++)
+          if (q < ntr) acctr[q] = a.dU[(NB + q) * vs + c];
+      }
+    }
+
+#pragma unroll 1
+    for (int ax = warm ? 2 : 0; ax < g.ndim; ax++) {
+      const int a1 = (ax == 2) ? 0 : ax + 1;
+      const int a2 = (a1 == 2) ? 0 : a1 + 1;
+      const long st = axis_stride(g, ax);
+      const long X = (ax == 2) ? c + st : c;  // z: the HIGH face of this cell = low face of the cell above
+      Cons Fnew;
+      cons_zero<EQ>(Fnew);
+      if (row_active || ax == 1) low_face_flux<EQ, SOLVER, FKJ>(a, X, st, ax, a1, a2, Fnew);
+      double Fnew_tr[PION_MAXTR];
+#pragma unroll
+      for (int q = 0; q < PION_MAXTR; q++) {
+        Fnew_tr[q] = 0.0;
+        if (q < ntr && (row_active || ax == 1))
+          Fnew_tr[q] = tracer_low_face_flux(a, a.S + (long)(NB + q) * vs, X, st, Fnew.rho);
+      }
+
+      Cons Flow, Fhigh;
+      double Flow_tr[PION_MAXTR], Fhigh_tr[PION_MAXTR];
+      if (ax == 0) {
+        Flow = Fnew;
+        Fhigh = cons_shfl_down<EQ>(Fnew);
+#pragma unroll
+        for (int q = 0; q < PION_MAXTR; q++) {
+          Flow_tr[q] = Fnew_tr[q];
+          Fhigh_tr[q] = (q < ntr) ? __shfl_down_sync(0xffffffffu, Fnew_tr[q], 1) : 0.0;
+        }
+      } else if (ax == 1) {
+        cons_to_smem<EQ, TY>(sbuf, row, lane, Fnew);
+        double* st_tr = s_flux + 2 * (NB * TY * 32) + (size_t)((k - k0) & 1) * (PION_MAXTR * TY * 32);
+#pragma unroll
+        for (int q = 0; q < PION_MAXTR; q++)
+          if (q < ntr) st_tr[(q * TY + row) * 32 + lane] = Fnew_tr[q];
+        __syncthreads();
+        Flow = Fnew;
+        const int rn = min(row + 1, TY - 1);
+        Fhigh = cons_from_smem<EQ, TY>(sbuf, rn, lane);
+#pragma unroll
+        for (int q = 0; q < PION_MAXTR; q++) {
+          Flow_tr[q] = Fnew_tr[q];
+          Fhigh_tr[q] = (q < ntr) ? st_tr[(q * TY + rn) * 32 + lane] : 0.0;
+        }
+      } else {
+        Flow = Fz;
+        Fhigh = Fnew;
+        Fz = Fnew;
+#pragma unroll
+        for (int q = 0; q < PION_MAXTR; q++) {
+          Flow_tr[q] = Fz_tr[q];
+          Fhigh_tr[q] = Fnew_tr[q];
+          Fz_tr[q] = Fnew_tr[q];
+        }
+      }
+
+      if (!warm) {
+        // Powell + GLM sources from cell-centre states (solver_eqn_mhd_adi.cpp:396-443,782-813):
+        // R part of interface (i-1,i) first, then L part of interface (i,i+1)
+        if (EQ != EQ_EULER) {
+          const double* Bn = a.S + (long)(5 + ax) * vs;
+          const double bm = __ldg(Bn + c - st), bp = __ldg(Bn + c + st);
+          const double uB = C.bn * C.vn + C.bt1 * C.vt1 + C.bt2 * C.vt2;
+          double f = dt * (0.5 * (bm + C.bn));
+          acc.mn += f * C.bn * idx; acc.mt1 += f * C.bt1 * idx; acc.mt2 += f * C.bt2 * idx; acc.erg += f * uB * idx;
+          acc.bbn += f * C.vn * idx; acc.bbt1 += f * C.vt1 * idx; acc.bbt2 += f * C.vt2 * idx;
+          double psm = 0.0, psp = 0.0;
+          if (EQ == EQ_GLM) {
+            psm = __ldg(a.S + 8 * vs + c - st);
+            psp = __ldg(a.S + 8 * vs + c + st);
+            double fs = dt * (0.5 * (psm + C.psi));
+            acc.erg += fs * (C.vn * C.psi) * idx;
+            acc.psi += fs * C.vn * idx;
+          }
+          f = dt * (0.5 * (C.bn + bp));
+          acc.mn -= f * C.bn * idx; acc.mt1 -= f * C.bt1 * idx; acc.mt2 -= f * C.bt2 * idx; acc.erg -= f * uB * idx;
+          acc.bbn -= f * C.vn * idx; acc.bbt1 -= f * C.vt1 * idx; acc.bbt2 -= f * C.vt2 * idx;
+          if (EQ == EQ_GLM) {
+            double fs = dt * (0.5 * (C.psi + psp));
+            acc.erg -= fs * (C.vn * C.psi) * idx;
+            acc.psi -= fs * C.vn * idx;
+          }
+        }
+        // flux difference (dU_Cell + DivStateVectorComponent)
+        acc.rho += dt * ((Flow.rho - Fhigh.rho) * idx);
+        acc.erg += dt * ((Flow.erg - Fhigh.erg) * idx);
+        acc.mn += dt * ((Flow.mn - Fhigh.mn) * idx);
+        acc.mt1 += dt * ((Flow.mt1 - Fhigh.mt1) * idx);
+        acc.mt2 += dt * ((Flow.mt2 - Fhigh.mt2) * idx);
+        if (EQ != EQ_EULER) {
+          acc.bbn += dt * ((Flow.bbn - Fhigh.bbn) * idx);
+          acc.bbt1 += dt * ((Flow.bbt1 - Fhigh.bbt1) * idx);
+          acc.bbt2 += dt * ((Flow.bbt2 - Fhigh.bbt2) * idx);
+        }
+        if (EQ == EQ_GLM) acc.psi += dt * ((Flow.psi - Fhigh.psi) * idx);
+#pragma unroll
+        for (int q = 0; q < PION_MAXTR; q++)
+          if (q < ntr) acctr[q] += dt * ((Flow_tr[q] - Fhigh_tr[q]) * idx);
+        // rotate the centre state and the accumulators into the next axis' frame
+        rot3(C.vn, C.vt1, C.vt2);
+        rot3(acc.mn, acc.mt1, acc.mt2);
+        if (EQ != EQ_EULER) {
+          rot3(C.bn, C.bt1, C.bt2);
+          rot3(acc.bbn, acc.bbt1, acc.bbt2);
+        }
+      }
+    }
+    if (warm) continue;
+    if (g.ndim == 2) {  // frame is (z,x,y): one more rotation returns to x
+      rot3(acc.mn, acc.mt1, acc.mt2);
+      if (EQ != EQ_EULER) rot3(acc.bbn, acc.bbt1, acc.bbt2);
+    }
+
+    if (domain) {
+      status |= cell_advance_time<EQ>(a, c, acc, acctr, ntr, my_dt);
+    } else if (upd_xy && a.out != a.S) {
+      // cell cut out of the domain (time_integrator.cpp:905-908): state untouched
+      for (int v = 0; v < NB + ntr; v++) a.out[(long)v * vs + c] = a.S[(long)v * vs + c];
+    }
+  }
+
+  stage_block_epilogue(a, my_dt, status);
+}
+
+template <int EQ, int SOLVER, bool FKJ>
+inline void launch_sweep_t(const StageArgs& a, cudaStream_t s) {
+#ifndef PION_SWEEP_TY
+#define PION_SWEEP_TY 8
+#endif
+  constexpr int TY = PION_SWEEP_TY;
+  constexpr int NB = nbase(EQ);
+  const int NX = a.g.NG[0], NY = a.g.NG[1], NZ = a.g.NG[2];
+  const int bx = (NX + 30) / 31, by = (NY + TY - 2) / (TY - 1);
+  // z chunks: enough blocks to fill 148 SMs a few times over, long enough to amortise the extra flux plane
+  int kchunk = NZ;
+  if (a.g.ndim > 2) {
+    kchunk = 64;
+    while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
+  }
+  const int bz = (NZ + kchunk - 1) / kchunk;
+  const size_t smem = (size_t)2 * (NB + PION_MAXTR) * TY * 32 * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  if (a.ntr > 0) k_stage_sweep<EQ, SOLVER, FKJ, TY, true><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, kchunk);
+  else k_stage_sweep<EQ, SOLVER, FKJ, TY, false><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, kchunk);
+}
+
+}  // namespace pion
