@@ -131,14 +131,43 @@ __device__ __forceinline__ double tracer_low_face_flux(const StageArgs& a, const
   return f;
 }
 
+#ifndef PION_SWEEP_PREFETCH
+#define PION_SWEEP_PREFETCH 0
+#endif
+#ifndef PION_SWEEP_MBAR
+#define PION_SWEEP_MBAR 1
+#endif
 #ifndef PION_SWEEP_MINBLOCKS
 #define PION_SWEEP_MINBLOCKS 2
 #endif
 
+// split-phase block barrier (mbarrier): a thread ARRIVES right after publishing its y flux
+// and only WAITS after it has computed its x flux, so warp skew hides behind useful work.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PION_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra PION_MBAR_WAIT;\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int EQ, int SOLVER, bool FKJ, int TY, bool TR>
 __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(const __grid_constant__ StageArgs a, const int kchunk) {
-  extern __shared__ double s_flux[];  // [2][NB][TY][32]
+  extern __shared__ double s_flux[];  // [2][NB + MAXTR][TY][32]
+  __shared__ unsigned long long s_bar;
   constexpr int NB = nbase(EQ);
+  constexpr int SLAB = (NB + PION_MAXTR) * TY * 32;
   const GridD& g = a.g;
   const int NX = g.NG[0], NY = g.NG[1], NZ = g.NG[2];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
@@ -155,6 +184,9 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
   const int ntr = TR ? a.ntr : 0;  // TR=false instantiation: no tracer registers at all
   double my_dt = 1.0e100;
   int status = 0;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 32 * TY);
+  __syncthreads();
+  unsigned phase = 0;
 
   Cons Fz;  // flux through the low z face of the current cell
   cons_zero<EQ>(Fz);
@@ -165,7 +197,17 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
   for (int k = has_z ? k0 - 1 : k0; k < k1; k++) {
     const bool warm = k < k0;  // first iteration of a 3-D chunk: only the z flux into plane k0
     const long c = gidx(g, i + g.nb[0], j + g.nb[1], k + g.nb[2]);
-    double* sbuf = s_flux + (size_t)((k - k0) & 1) * (NB * TY * 32);
+    double* sbuf = s_flux + (size_t)((k - k0) & 1) * SLAB;
+    double* sbuf_tr = sbuf + NB * TY * 32;
+
+    // pull the plane the NEXT iteration touches for the first time towards L1
+#if PION_SWEEP_PREFETCH
+    if (has_z && k + 1 < k1) {
+      const long cn = c + (long)(a.order == 2 ? 3 : 2) * g.sz;
+#pragma unroll
+      for (int v = 0; v < NB; v++) prefetch_l1(a.S + (long)v * vs + cn);
+    }
+#endif
 
     Cons acc;
     cons_zero<EQ>(acc);
@@ -187,26 +229,42 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
       }
     }
 
+    // Schedule of one plane (ONE flux call site, ONE accumulate site):
+    //   step 0: y flux -> shared memory, arrive      step 1: x flux (shfl), accumulate x
+    //   step 2: wait, accumulate y from shared memory step 3: z flux, accumulate z
+    // so dU is still summed in the reference's order x, y, z.
 #pragma unroll 1
-    for (int ax = warm ? 2 : 0; ax < g.ndim; ax++) {
+    for (int step = warm ? 3 : 0; step < (has_z ? 4 : 3); step++) {
+      const int ax = (step == 1) ? 0 : (step == 3) ? 2 : 1;
       const int a1 = (ax == 2) ? 0 : ax + 1;
       const int a2 = (a1 == 2) ? 0 : a1 + 1;
       const long st = axis_stride(g, ax);
       const long X = (ax == 2) ? c + st : c;  // z: the HIGH face of this cell = low face of the cell above
       Cons Fnew;
       cons_zero<EQ>(Fnew);
-      if (row_active || ax == 1) low_face_flux<EQ, SOLVER, FKJ>(a, X, st, ax, a1, a2, Fnew);
       double Fnew_tr[PION_MAXTR];
 #pragma unroll
-      for (int q = 0; q < PION_MAXTR; q++) {
-        Fnew_tr[q] = 0.0;
-        if (q < ntr && (row_active || ax == 1))
-          Fnew_tr[q] = tracer_low_face_flux(a, a.S + (long)(NB + q) * vs, X, st, Fnew.rho);
+      for (int q = 0; q < PION_MAXTR; q++) Fnew_tr[q] = 0.0;
+      if (step != 2 && (row_active || ax == 1)) {
+        low_face_flux<EQ, SOLVER, FKJ>(a, X, st, ax, a1, a2, Fnew);
+#pragma unroll
+        for (int q = 0; q < PION_MAXTR; q++)
+          if (q < ntr) Fnew_tr[q] = tracer_low_face_flux(a, a.S + (long)(NB + q) * vs, X, st, Fnew.rho);
+      }
+      if (step == 0) {
+        cons_to_smem<EQ, TY>(sbuf, row, lane, Fnew);
+#pragma unroll
+        for (int q = 0; q < PION_MAXTR; q++)
+          if (q < ntr) sbuf_tr[(q * TY + row) * 32 + lane] = Fnew_tr[q];
+#if PION_SWEEP_MBAR
+        mbar_arrive(&s_bar);
+#endif
+        continue;
       }
 
       Cons Flow, Fhigh;
       double Flow_tr[PION_MAXTR], Fhigh_tr[PION_MAXTR];
-      if (ax == 0) {
+      if (step == 1) {
         Flow = Fnew;
         Fhigh = cons_shfl_down<EQ>(Fnew);
 #pragma unroll
@@ -214,20 +272,20 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
           Flow_tr[q] = Fnew_tr[q];
           Fhigh_tr[q] = (q < ntr) ? __shfl_down_sync(0xffffffffu, Fnew_tr[q], 1) : 0.0;
         }
-      } else if (ax == 1) {
-        cons_to_smem<EQ, TY>(sbuf, row, lane, Fnew);
-        double* st_tr = s_flux + 2 * (NB * TY * 32) + (size_t)((k - k0) & 1) * (PION_MAXTR * TY * 32);
-#pragma unroll
-        for (int q = 0; q < PION_MAXTR; q++)
-          if (q < ntr) st_tr[(q * TY + row) * 32 + lane] = Fnew_tr[q];
+      } else if (step == 2) {
+#if PION_SWEEP_MBAR
+        mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+#else
         __syncthreads();
-        Flow = Fnew;
+#endif
         const int rn = min(row + 1, TY - 1);
+        Flow = cons_from_smem<EQ, TY>(sbuf, row, lane);
         Fhigh = cons_from_smem<EQ, TY>(sbuf, rn, lane);
 #pragma unroll
         for (int q = 0; q < PION_MAXTR; q++) {
-          Flow_tr[q] = Fnew_tr[q];
-          Fhigh_tr[q] = (q < ntr) ? st_tr[(q * TY + rn) * 32 + lane] : 0.0;
+          Flow_tr[q] = (q < ntr) ? sbuf_tr[(q * TY + row) * 32 + lane] : 0.0;
+          Fhigh_tr[q] = (q < ntr) ? sbuf_tr[(q * TY + rn) * 32 + lane] : 0.0;
         }
       } else {
         Flow = Fz;
