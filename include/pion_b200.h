@@ -108,7 +108,8 @@ int pion_gpu_set_glm_speeds(pion_gpu_ctx *ctx, double t_dyn, double dx, double c
 int pion_gpu_set_time(pion_gpu_ctx *ctx, double simtime, double last_dt, int timestep);
 int pion_gpu_get_time(pion_gpu_ctx *ctx, double *simtime, double *dt, double *last_dt, int *timestep);
 
-/* time_integrator::calc_microphysics_dU (time_integrator.cpp:253, :438) */
+/* time_integrator::calc_microphysics_dU (time_integrator.cpp:253, :438): per-cell
+ * mp_only_cooling::TimeUpdateMP (adaptive RK5 Cash-Karp) from P, dU[ERG] += ... */
 int pion_gpu_calc_microphysics_dU(pion_gpu_ctx *ctx, double dt);
 /* time_integrator::calc_dynamics_dU (time_integrator.cpp:498): preprocess_data +
  * set_dynamics_dU; accumulates into the device dU array. `step` is OA1 / OA2. */
@@ -130,6 +131,9 @@ int pion_gpu_run(pion_gpu_ctx *ctx, int nsteps, double *dts);
  * [0] negative-density events (fatal in the reference), [1] negative-pressure
  * fix-ups, [2] kernels launched so far */
 int pion_gpu_counters(pion_gpu_ctx *ctx, long long *out3);
+/* cells whose cooling integration failed so far (mp_only_cooling.cpp:203-207: fatal in the
+ * reference; the caller should turn a non-zero count into rep.error) */
+int pion_gpu_mp_failures(pion_gpu_ctx *ctx, long long *out);
 /* block until all queued device work of this context has finished */
 int pion_gpu_sync(pion_gpu_ctx *ctx);
 /* stream the context launches on (cudaStream_t as void*), for CUDA-event timing */

@@ -1350,6 +1350,9 @@ static double calc_dynamics_dt(pion_oracle *s) {
 static double calc_microphysics_dt(pion_oracle *s) {
   if (!s->have_mp) return 1.0e99;
   if (s->cfg.mp_timestep_limit == 0) return 1.0e99;
+  /* limit 4 = recombination time only: mp_only_cooling::timescales returns 1e99 when tc is
+   * false (mp_only_cooling.cpp:341, calc_timestep.cpp:441-443) */
+  if (s->cfg.mp_timestep_limit == 4) return 1.0e99;
   double dt = 1.e99;
   int nv = s->nv;
   for (long c = 0; c < s->ncell; c++) {
@@ -1721,7 +1724,7 @@ pion_oracle *po_create(const pion_oracle_config *cfg) {
   }
   if (cfg->cooling) {
     /* mp_only_cooling constructor (mp_only_cooling.cpp:96-160); m_p, k_B from constants.h */
-    const double m_p = 1.6726231e-24, kB = 1.380658e-16;
+    const double m_p = 1.672621898e-24, kB = 1.38064852e-16; /* constants.h:53,64 */
     s->have_mp = 1;
     s->Mu = 1.40 * m_p;
     double Mu_tot = 0.609 * m_p;

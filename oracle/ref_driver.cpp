@@ -41,6 +41,7 @@
 #include "ics/get_sim_info.h"
 #include "dataIO/readparams.h"
 #include "microphysics/microphysics_base.h"
+#include "microphysics/mp_only_cooling.h"
 #include "spatial_solvers/solver_eqn_base.h"
 
 using namespace std;
@@ -386,4 +387,28 @@ int pref_intercell_flux(void *h, int axis, const double *Pl, const double *Pr, d
   return err;
 }
 
+// The lookup tables mp_only_cooling builds at set-up (private member `lt`,
+// microphysics/mp_only_cooling.cpp:528-556) re-evaluated through the SAME public
+// rate functions of the reference's MP object, so that the oracle port and the GPU
+// library can be fed bit-identical tables (the GSL spline behind
+// cooling_rate_SD93CIE is a shim here, SURVEY 8c "parity unpinned" for its values).
+int pref_cooling_tables(void *h, int n, double *T, double *rrhp, double *C_rrh, double *C_ffhe, double *C_fbdn,
+                        double *C_cie) {
+  RefSim *s = static_cast<RefSim *>(h);
+  class mp_only_cooling *mp = dynamic_cast<class mp_only_cooling *>(MP);
+  if (!mp || n < 2) return 1;
+  const double Tmin = s->SimPM.EP.MinTemperature, Tmax = s->SimPM.EP.MaxTemperature;
+  const double dlogT = (log10(Tmax) - log10(Tmin)) / (n - 1);
+  for (int i = 0; i < n; i++) {
+    T[i] = pow(10.0, log10(Tmin) + i * dlogT);
+    rrhp[i] = mp->Hii_rad_recomb_rate(T[i]);
+    C_rrh[i] = mp->Hii_total_cooling(T[i]);
+    C_ffhe[i] = 6.72e-28 * sqrt(T[i]);
+    C_fbdn[i] = 1.20e-22 * exp(-33610.0 / T[i] - (2180.0 * 2180.0 / T[i] / T[i])) * exp(-T[i] * T[i] / 5.0e10);
+    C_cie[i] = mp->cooling_rate_SD93CIE(T[i]);
+  }
+  return 0;
+}
+
 }  // extern "C"
+

@@ -1,0 +1,240 @@
+// pion_b200/csrc/cooling.cuh -- per-cell radiative cooling source term
+// (microphysics without chemistry: mp_only_cooling with EP_cooling = 8).
+//
+// Reference path restated (paths relative to /root/reference/source):
+//   sim_control/time_integrator.cpp:438-489   calc_noRT_microphysics_dU: for every isdomain
+//                                             cell  dU += PtoU(TimeUpdateMP(P, dt)) - PtoU(P)
+//   microphysics/mp_only_cooling.cpp:167-221  TimeUpdateMP (integrates from the UNCLAMPED
+//                                             Eint0; T clamp applied to the result)
+//   microphysics/mp_only_cooling.cpp:470-521  Edot_WSS09CIE_heat_cool_metallines: binary
+//                                             search in the 200-point T table + linear interp.
+//   microphysics/mp_only_cooling.cpp:333-358  timescales (cooling time)
+//   microphysics/integrator.cpp:285-371       Step_RK5CK (first-order shortcut if |k1|dt/E<1e-6)
+//   microphysics/integrator.cpp:401-530       Stepper_RKCK (bisection on the error estimate)
+//   microphysics/integrator.cpp:540-606       Int_Adaptive_RKCK (<= 25 sub-steps)
+//   sim_control/calc_timestep.cpp:342-463     calc_microphysics_dt
+//
+// One thread per cell; the 11 table columns (T, 5 rates, 5 slopes) sit in shared memory
+// (17.6 KB) so the data-dependent binary search never leaves the SM.  The integrator keeps
+// the reference's exact control flow (trip counts vary per cell: divergence is inherent);
+// arithmetic here is plain IEEE FP64 (divisions included) -- this kernel moves 24 B per cell
+// and is nowhere near any roofline that matters for the step.
+#pragma once
+#include "stage_kernel.cuh"
+
+namespace pion {
+
+struct CoolParams {
+  const double* tables;  // device: [11][nT] = T, rrhp, C_rrh, C_ffhe, C_fbdn, C_cie, then the 5 slopes
+  int nT;
+  double inv_Mu2, inv_Mu2_elec_H, Mu_tot_over_kB, MinT, MaxT;
+};
+
+struct CoolArgs {
+  GridD g;
+  CoolParams cp;
+  const double* P;            // state the source term is integrated from (start-of-step P)
+  double* dE;                 // fused path: energy source per cell (one plane), overwritten
+  double* dU;                 // seam path: full dU array, energy plane accumulated (+=)
+  const unsigned char* mask;  // isdomain
+  double dt, gamma;
+  long long* counters;        // [2] integration failures (fatal in the reference)
+  unsigned long long* dtmin;  // k_mp_dt: ordered-bits min of the cooling time
+  int mp_timestep_limit;
+};
+
+struct CoolTab {
+  const double *T, *rrhp, *Crrh, *Cffhe, *Cfbdn, *Ccie, *s_rrhp, *s_Crrh, *s_Cffhe, *s_Cfbdn, *s_Ccie;
+  int nT;
+  double inv_Mu2, inv_Mu2_elec_H;
+};
+
+__device__ __forceinline__ CoolTab cool_tables_to_smem(const CoolParams& cp, double* s) {
+  for (int t = threadIdx.x; t < 11 * cp.nT; t += blockDim.x) s[t] = cp.tables[t];
+  __syncthreads();
+  CoolTab ct;
+  const int n = cp.nT;
+  ct.T = s; ct.rrhp = s + n; ct.Crrh = s + 2 * n; ct.Cffhe = s + 3 * n; ct.Cfbdn = s + 4 * n; ct.Ccie = s + 5 * n;
+  ct.s_rrhp = s + 6 * n; ct.s_Crrh = s + 7 * n; ct.s_Cffhe = s + 8 * n; ct.s_Cfbdn = s + 9 * n; ct.s_Ccie = s + 10 * n;
+  ct.nT = n;
+  ct.inv_Mu2 = cp.inv_Mu2;
+  ct.inv_Mu2_elec_H = cp.inv_Mu2_elec_H;
+  return ct;
+}
+
+// mp_only_cooling::Edot_WSS09CIE_heat_cool_metallines (mp_only_cooling.cpp:470-521)
+__device__ __forceinline__ double cool_Edot(const CoolTab& t, double rho, double T) {
+  int ihi = t.nT - 1, ilo = 0;
+  do {
+    const int imid = ilo + ((ihi - ilo) >> 1);  // ilo + floor((ihi-ilo)/2.0)
+    if (t.T[imid] < T) ilo = imid;
+    else ihi = imid;
+  } while (ihi - ilo > 1);
+  const int iT = ilo;
+  const double dT = T - t.T[iT];
+  const double rho2 = rho * rho;
+  double rate = -(t.Cfbdn[iT] + dT * t.s_Cfbdn[iT]) * rho2 * t.inv_Mu2_elec_H;
+  rate = fmin(rate, -(t.Ccie[iT] + dT * t.s_Ccie[iT]) * rho2 * t.inv_Mu2);
+  rate -= (t.Crrh[iT] + dT * t.s_Crrh[iT]) * rho2 * t.inv_Mu2_elec_H;
+  rate -= (t.Cffhe[iT] + dT * t.s_Cffhe[iT]) * rho2 * t.inv_Mu2_elec_H;
+  rate += 8.01e-12 * (t.rrhp[iT] + dT * t.s_rrhp[iT]) * rho2 * t.inv_Mu2_elec_H;
+  return rate;
+}
+
+struct CoolCell {
+  double rho, gm1, Mu_tot_over_kB;
+};
+// mp_only_cooling::dPdt (:227-236)
+__device__ __forceinline__ double cool_dPdt(const CoolTab& t, const CoolCell& c, double E) {
+  return cool_Edot(t, c.rho, E * c.gm1 * c.Mu_tot_over_kB / c.rho);
+}
+
+// Integrator_Base::Step_RK5CK for one variable (integrator.cpp:285-371)
+__device__ __forceinline__ void cool_step_rk5ck(const CoolTab& t, const CoolCell& c, double p0, double dt, double& pf, double& dp) {
+  const double b21 = 0.2, b31 = 3. / 40., b32 = 9. / 40., b41 = 0.3, b42 = -0.9, b43 = 1.2, b51 = -11. / 54., b52 = 2.5,
+               b53 = -70. / 27., b54 = 35. / 27., b61 = 1631. / 55296., b62 = 175. / 512., b63 = 575. / 13824.,
+               b64 = 44275. / 110592., b65 = 253. / 4096., c1 = 37. / 378., c3 = 250. / 621., c4 = 125. / 594.,
+               c6 = 512. / 1771.;
+  const double dc1 = c1 - 2825. / 27648., dc3 = c3 - 18575. / 48384., dc4 = c4 - 13525. / 55296., dc5 = -277. / 14336.,
+               dc6 = c6 - 0.25;
+  double k1 = cool_dPdt(t, c, p0);
+  double ptemp = 0.0;
+  ptemp += fabs(k1) * dt / (p0 + 1.0e-100);
+  if (ptemp < 1.e-6) {
+    pf = p0 + k1 * dt;
+    dp = k1 * dt;
+    return;
+  }
+  k1 *= dt;
+  ptemp = p0 + b21 * k1;
+  double k2 = cool_dPdt(t, c, ptemp) * dt;
+  ptemp = p0 + b31 * k1 + b32 * k2;
+  double k3 = cool_dPdt(t, c, ptemp) * dt;
+  ptemp = p0 + b41 * k1 + b42 * k2 + b43 * k3;
+  double k4 = cool_dPdt(t, c, ptemp) * dt;
+  ptemp = p0 + b51 * k1 + b52 * k2 + b53 * k3 + b54 * k4;
+  double k5 = cool_dPdt(t, c, ptemp) * dt;
+  ptemp = p0 + b61 * k1 + b62 * k2 + b63 * k3 + b64 * k4 + b65 * k5;
+  double k6 = cool_dPdt(t, c, ptemp) * dt;
+  pf = p0 + c1 * k1 + c3 * k3 + c4 * k4 + c6 * k6;
+  dp = dc1 * k1 + dc3 * k3 + dc4 * k4 + dc5 * k5 + dc6 * k6;
+}
+
+// Integrator_Base::Stepper_RKCK, BISECTION_STEPPER variant (integrator.cpp:401-530)
+__device__ __forceinline__ int cool_stepper(const CoolTab& t, const CoolCell& c, double p0, double t0, double htry,
+                                            double errtol, double& p1, double& hdid, double& hnext) {
+  int rval = 0, ct = 0;
+  double h = htry, maxerr, err = 0.0, ptemp = 0.0;
+  if (h < 0) return 1;
+  do {
+    cool_step_rk5ck(t, c, p0, h, ptemp, err);
+    maxerr = 0;
+    if (!isfinite(err) || !isfinite(ptemp) || ptemp < 0.0) {
+      maxerr = fmax(maxerr, 1000.0);
+    } else {
+      err /= fabs(ptemp) + 1.e-100;
+      err = fabs(err / errtol);
+      maxerr = fmax(maxerr, err);
+    }
+    if (maxerr > 1.) h /= 2.0;
+    if (t0 + h == t0) return -2;
+    ct++;
+  } while (maxerr > 1.0 && ct < 50);
+  if (maxerr > 1.0) rval += ct + (int)(fabs(maxerr));
+  hnext = h * 2.0;
+  hdid = h;
+  p1 = ptemp;
+  if (isnan(p1) || isinf(p1)) { p1 = -1.e100; rval++; }
+  return rval;
+}
+
+// Integrator_Base::Int_Adaptive_RKCK (integrator.cpp:540-606)
+__device__ __forceinline__ int cool_integrate(const CoolTab& t, const CoolCell& c, double p0, double dt, double& pf) {
+  double tt = 0.0, p1 = p0, p2 = 0.0;
+  const double tf = 0.0 + dt;
+  double h = dt, hdid = 0.0, hnext = 0.0;
+  int err = 0, ct = 0;
+  do {
+    err += cool_stepper(t, c, p1, tt, h, 1.0e-2, p2, hdid, hnext);
+    tt += hdid;
+    h = fmin(hnext, tf - tt);
+    ct++;
+    p1 = p2;
+  } while (tt < tf && (err == 0) && (ct < 25));
+  pf = p1;
+  return err;
+}
+
+// calc_noRT_microphysics_dU: one thread per interior cell.
+template <int EQ>
+__global__ void __launch_bounds__(128) k_cooling_dU(const __grid_constant__ CoolArgs a) {
+  extern __shared__ double s_tab[];
+  const CoolTab t = cool_tables_to_smem(a.cp, s_tab);
+  const GridD& g = a.g;
+  const long ncell = (long)g.NG[0] * g.NG[1] * g.NG[2];
+  int fails = 0;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(q % g.NG[0]), j = (int)((q / g.NG[0]) % g.NG[1]), k = (int)(q / ((long)g.NG[0] * g.NG[1]));
+    const long c = gidx(g, i + g.nb[0], j + g.nb[1], k + g.nb[2]);
+    double dE = 0.0;
+    if (!a.mask || a.mask[c]) {
+      Prim p = load_prim<EQ>(a.P, c, g.vs, 0, 1, 2);
+      CoolCell cc;
+      cc.rho = p.ro;
+      cc.gm1 = a.gamma - 1.0;
+      cc.Mu_tot_over_kB = a.cp.Mu_tot_over_kB;
+      const double Eint0 = p.pg / (a.gamma - 1.0);
+      double Eint;
+      fails += (cool_integrate(t, cc, Eint0, a.dt, Eint) != 0);
+      Prim po = p;
+      po.pg = Eint * (a.gamma - 1);
+      const double Tf = po.pg * a.cp.Mu_tot_over_kB / po.ro;
+      if (Tf > a.cp.MaxT) po.pg *= a.cp.MaxT / Tf;
+      else if (Tf < a.cp.MinT) po.pg *= a.cp.MinT / Tf;
+      // dU += PtoU(p') - PtoU(P): every component but the energy cancels exactly
+      Cons ui, uf;
+      PtoU<EQ>(p, ui, a.gamma - 1.0);
+      PtoU<EQ>(po, uf, a.gamma - 1.0);
+      dE = uf.erg - ui.erg;
+    }
+    if (a.dE) a.dE[c] = dE;
+    if (a.dU) a.dU[g.vs + c] += dE;
+  }
+  if (fails && a.counters) atomicAdd((unsigned long long*)&a.counters[2], (unsigned long long)fails);
+}
+
+// calc_microphysics_dt / get_mp_timescales_no_radiation + mp_only_cooling::timescales
+template <int EQ>
+__global__ void __launch_bounds__(256) k_mp_dt(const __grid_constant__ CoolArgs a) {
+  extern __shared__ double s_tab[];
+  const CoolTab t = cool_tables_to_smem(a.cp, s_tab);
+  const GridD& g = a.g;
+  const long ncell = (long)g.NG[0] * g.NG[1] * g.NG[2];
+  double my = 1.0e99;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(q % g.NG[0]), j = (int)((q / g.NG[0]) % g.NG[1]), k = (int)(q / ((long)g.NG[0] * g.NG[1]));
+    const long c = gidx(g, i + g.nb[0], j + g.nb[1], k + g.nb[2]);
+    if (a.mask && !a.mask[c]) continue;  // isbd cells (internal boundaries) are skipped (:435)
+    const double ro = __ldg(a.P + c), pg = __ldg(a.P + g.vs + c);
+    const double Eint = pg / (a.gamma - 1.0);
+    const double T = pg * a.cp.Mu_tot_over_kB / ro;
+    if (T >= 1.1 * a.cp.MinT) {
+      const double rate = fmax(fabs(cool_Edot(t, ro, T)), fabs(cool_Edot(t, ro, fmax(a.cp.MinT, 0.5 * T))));
+      my = fmin(my, Eint / rate);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my = fmin(my, __shfl_xor_sync(0xffffffffu, my, o));
+  __shared__ double s[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) s[w] = my;
+  __syncthreads();
+  if (w == 0) {
+    my = (lane < (int)(blockDim.x >> 5)) ? s[lane] : 1.0e99;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my = fmin(my, __shfl_xor_sync(0xffffffffu, my, o));
+    if (lane == 0) atomicMin(a.dtmin, dbl_ordered_bits(my));
+  }
+}
+
+}  // namespace pion

@@ -20,6 +20,7 @@
 
 #include "../../include/pion_b200.h"
 #include "aux_kernels.cuh"
+#include "cooling.cuh"
 
 using namespace pion;
 
@@ -71,6 +72,10 @@ struct pion_gpu_ctx {
   // multi-GPU
   ncclComm_t comm = nullptr;
   double* d_red = nullptr;  // 2 doubles for the dt all-reduce
+  // microphysics (mp_only_cooling)
+  CoolParams cool;
+  double *d_tables = nullptr, *mp_dE = nullptr;
+  long long mp_failures = 0;
   double *sendbuf[6] = {nullptr}, *recvbuf[6] = {nullptr};
   size_t halo_elems[6] = {0};
 };
@@ -104,6 +109,14 @@ static int check_config(const pion_gpu_config& c) {
     if (t != PION_BC_PERIODIC && t != PION_BC_OUTFLOW && t != PION_BC_INFLOW && t != PION_BC_REFLECTING &&
         t != PION_BC_FIXED && t != PION_BC_DMACH && t != PION_BC_ONEWAY_OUT && t != PION_BC_MPI) { set_error("unsupported boundary type"); return 1; }
     if (c.eqntype == PION_EQGLM && c.ndim == 1 && (t == PION_BC_OUTFLOW || t == PION_BC_ONEWAY_OUT)) { set_error("Psi outflow boundary condition doesn't work for 1D! (outflow_boundaries.cpp:57)"); return 1; }
+  }
+  if (c.cooling) {
+    if (c.cooling != 8) { set_error("only EP_cooling 8 (WSS09_CIE_LINE_HEAT_COOL, mp_only_cooling) is built"); return 1; }
+    if (c.n_table < 2 || !c.table_T || !c.table_rrhp || !c.table_C_rrh || !c.table_C_ffhe || !c.table_C_fbdn || !c.table_C_cie) {
+      set_error("cooling needs the mp_only_cooling lookup tables (n_table, table_*)");
+      return 1;
+    }
+    if (c.mp_timestep_limit < 0 || c.mp_timestep_limit > 4) { set_error("Bad MP_timestep_limit"); return 1; }
   }
   return 0;
 }
@@ -148,7 +161,7 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   pp.min_temp = cfg->min_temperature;
   pp.max_temp = cfg->max_temperature;
   pp.have_mp = cfg->cooling ? 1 : 0;
-  pp.mu_tot_over_kB = cfg->cooling ? (0.609 * 1.6726231e-24) / 1.380658e-16 : 0.0;
+  pp.mu_tot_over_kB = cfg->cooling ? (0.609 * 1.672621898e-24) / 1.38064852e-16 : 0.0;
   c->simtime = cfg->starttime;
   { const char* e = getenv("PION_B200_GATHER"); c->force_gather = e && e[0] == '1'; }
 
@@ -165,6 +178,34 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   if (cfg->solver == PION_FLUX_HLLD) ok &= cudaMalloc(&c->hll, (size_t)g.vs) == cudaSuccess;
   if (cfg->solver == PION_FLUX_ROE && (cfg->artviscosity == 3 || cfg->artviscosity == 4))
     ok &= cudaMalloc(&c->eta, (size_t)g.vs * 3 * sizeof(double)) == cudaSuccess;
+  if (cfg->cooling) {
+    // mp_only_cooling constructor + gen_mpoc_lookup_tables (mp_only_cooling.cpp:51-160, :528-579)
+    const double m_p = 1.672621898e-24;  // constants.h:64
+    const double Mu = 1.40 * m_p, Mu_elec = 1.167 * m_p;
+    CoolParams& cp = c->cool;
+    cp.nT = cfg->n_table;
+    cp.inv_Mu2 = 1.0 / (Mu * Mu);
+    cp.inv_Mu2_elec_H = 1.0 / (Mu_elec * Mu);
+    cp.Mu_tot_over_kB = pp.mu_tot_over_kB;
+    cp.MinT = cfg->min_temperature;
+    cp.MaxT = cfg->max_temperature;
+    if (cp.MinT < 1.0 || cp.MinT > 1.0e6) cp.MinT = 1.0;      // microphysics_base / mp_only_cooling limits
+    if (cp.MaxT < 1.0e2 || cp.MaxT > 3.0e10) cp.MaxT = 1.0e8;
+    const int n = cp.nT;
+    std::vector<double> h(11 * (size_t)n, 0.0);
+    const double* src[6] = {cfg->table_T, cfg->table_rrhp, cfg->table_C_rrh, cfg->table_C_ffhe, cfg->table_C_fbdn, cfg->table_C_cie};
+    for (int q = 0; q < 6; q++) memcpy(&h[(size_t)q * n], src[q], n * sizeof(double));
+    for (int q = 1; q < 6; q++)
+      for (int i = 0; i < n - 1; i++) h[(size_t)(5 + q) * n + i] = (h[(size_t)q * n + i + 1] - h[(size_t)q * n + i]) / (h[i + 1] - h[i]);
+    ok &= cudaMalloc(&c->d_tables, h.size() * sizeof(double)) == cudaSuccess;
+    ok &= cudaMalloc(&c->mp_dE, (size_t)g.vs * sizeof(double)) == cudaSuccess;
+    if (ok) {
+      ok &= cudaMemcpy(c->d_tables, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+      ok &= cudaMemset(c->mp_dE, 0, (size_t)g.vs * sizeof(double)) == cudaSuccess;
+    }
+    cp.tables = c->d_tables;
+    c->cfg.table_T = c->cfg.table_rrhp = c->cfg.table_C_rrh = c->cfg.table_C_ffhe = c->cfg.table_C_fbdn = c->cfg.table_C_cie = nullptr;
+  }
   if (!ok) {
     set_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     pion_gpu_destroy(c);
@@ -185,7 +226,7 @@ extern "C" void pion_gpu_destroy(pion_gpu_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm) ncclCommDestroy(c->comm);
   cudaFree(c->P); cudaFree(c->Ph); cudaFree(c->dU); cudaFree(c->eta); cudaFree(c->hll); cudaFree(c->mask);
-  cudaFree(c->d_dtmin); cudaFree(c->d_counters); cudaFree(c->d_red);
+  cudaFree(c->d_dtmin); cudaFree(c->d_counters); cudaFree(c->d_red); cudaFree(c->d_tables); cudaFree(c->mp_dE);
   for (int f = 0; f < 6; f++) { cudaFree(c->sendbuf[f]); cudaFree(c->recvbuf[f]); }
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -429,7 +470,30 @@ extern "C" int pion_gpu_calc_dt(pion_gpu_ctx* c, double* t_dyn, double* t_mp) {
   double d;
   if (read_dtmin(c, &d)) return 1;
   if (t_dyn) *t_dyn = d;
-  if (t_mp) *t_mp = 1.0e99;  // calc_microphysics_dt without MP (calc_timestep.cpp:355-357)
+  if (t_mp) {
+    *t_mp = 1.0e99;  // calc_microphysics_dt without MP / without a limit (calc_timestep.cpp:348-357)
+    const int lim = c->cfg.mp_timestep_limit;
+    if (c->cfg.cooling && lim >= 1 && lim <= 3) {  // 4 = recombination time only: none for mp_only_cooling
+      static const unsigned long long MP_INIT_BITS = 0x547D42AEA2879F2EULL;  // bits of 1.0e99
+      CUDA_OK(cudaMemcpyAsync(c->d_dtmin + 1, &MP_INIT_BITS, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+      CoolArgs a;
+      a.g = c->g; a.cp = c->cool; a.P = c->ph_valid ? c->Ph : c->P;  // timescales(c->Ph)
+      a.dE = nullptr; a.dU = nullptr; a.mask = c->mask; a.dt = 0.0; a.gamma = c->pp.gamma; a.counters = c->d_counters;
+      a.dtmin = c->d_dtmin + 1; a.mp_timestep_limit = lim;
+      const long ncell = (long)c->g.NG[0] * c->g.NG[1] * c->g.NG[2];
+      const size_t smem = 11 * (size_t)c->cool.nT * sizeof(double);
+      switch (c->cfg.eqntype) {
+        case PION_EQEUL: k_mp_dt<EQ_EULER><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
+        case PION_EQMHD: k_mp_dt<EQ_MHD><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
+        default: k_mp_dt<EQ_GLM><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
+      }
+      c->launches++;
+      CUDA_OK(cudaMemcpyAsync(c->h_pinned + 1, c->d_dtmin + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_OK(cudaStreamSynchronize(c->stream));
+      memcpy(t_mp, c->h_pinned + 1, sizeof(double));
+      if (!(*t_mp > 0.0)) { set_error("get_mp_timescales_no_radiation() returned error"); return 1; }
+    }
+  }
   return 0;
 }
 
@@ -525,6 +589,7 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   a.Pb = Pb;
   a.out = out;
   a.dU = dU;
+  a.mp_dE = (fused && c->cfg.cooling) ? c->mp_dE : nullptr;
   a.hll = c->hll;
   a.eta = c->eta;
   a.mask = c->mask;
@@ -565,11 +630,29 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   return 0;
 }
 
+// calc_noRT_microphysics_dU (time_integrator.cpp:438-489): always integrates from P
+static int launch_cooling(pion_gpu_ctx* c, double dt, double* dE, double* dU) {
+  CoolArgs a;
+  a.g = c->g; a.cp = c->cool; a.P = c->P; a.dE = dE; a.dU = dU; a.mask = c->mask; a.dt = dt; a.gamma = c->pp.gamma;
+  a.counters = c->d_counters; a.dtmin = nullptr; a.mp_timestep_limit = 0;
+  const long ncell = (long)c->g.NG[0] * c->g.NG[1] * c->g.NG[2];
+  const size_t smem = 11 * (size_t)c->cool.nT * sizeof(double);
+  const int blocks = nblocks(ncell, 128, 148 * 32);
+  switch (c->cfg.eqntype) {
+    case PION_EQEUL: k_cooling_dU<EQ_EULER><<<blocks, 128, smem, c->stream>>>(a); break;
+    case PION_EQMHD: k_cooling_dU<EQ_MHD><<<blocks, 128, smem, c->stream>>>(a); break;
+    default: k_cooling_dU<EQ_GLM><<<blocks, 128, smem, c->stream>>>(a); break;
+  }
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int pion_gpu_calc_microphysics_dU(pion_gpu_ctx* c, double dt) {
-  (void)dt;
   if (!c->cfg.cooling) return 0;  // time_integrator.cpp:264: no MP -> nothing to do
-  set_error("cooling source term not built yet");
-  return 1;
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (ensure_dU(c)) return 1;
+  return launch_cooling(c, dt, nullptr, c->dU);
 }
 
 extern "C" int pion_gpu_calc_dynamics_dU(pion_gpu_ctx* c, double dt, int step) {
@@ -624,11 +707,11 @@ extern "C" int pion_gpu_grid_update_state_vector(pion_gpu_ctx* c, double dt, int
 extern "C" int pion_gpu_advance_time(pion_gpu_ctx* c, double* dt_done) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
   const double dt = c->dt;
-  if (c->cfg.cooling) { set_error("cooling source term not built yet"); return 1; }
   if (c->cfg.tmOOA == 1) {
     // first_order_update(dt, OA1) + BCs (OA1, OA1): full step in one stage
     c->FV_dt = dt;
     // the single stage reads P's stencil and must not write P in place: go through Ph
+    if (c->cfg.cooling && launch_cooling(c, dt, c->mp_dE, nullptr)) return 1;
     if (launch_preprocess(c, c->P, 1)) return 1;
     if (launch_stage(c, c->P, c->P, c->Ph, nullptr, dt, 1, true, true)) return 1;
     // P = Ph on the interior, then boundaries of both
@@ -641,12 +724,14 @@ extern "C" int pion_gpu_advance_time(pion_gpu_ctx* c, double* dt_done) {
   } else {
     // first_order_update(0.5 dt, OA2): Setdt(0.5dt), dynamics OA1, update Ph
     c->FV_dt = 0.5 * dt;
+    if (c->cfg.cooling && launch_cooling(c, 0.5 * dt, c->mp_dE, nullptr)) return 1;  // calc_microphysics_dU(0.5dt)
     if (launch_preprocess(c, c->P, 1)) return 1;
     if (launch_stage(c, c->P, c->P, c->Ph, nullptr, 0.5 * dt, 1, true, false)) return 1;
     // boundaries of Ph (cstep=OA1 != maxstep=OA2), simtime = start of step
     if (update_bcs_arrays(c, c->Ph, nullptr, c->simtime)) return 1;
     // second_order_update(dt, OA2): Setdt(dt), dynamics OA2 from Ph, update P
     c->FV_dt = dt;
+    if (c->cfg.cooling && launch_cooling(c, dt, c->mp_dE, nullptr)) return 1;  // from P again (time_integrator.cpp:472)
     if (launch_preprocess(c, c->Ph, 2)) return 1;
     if (launch_stage(c, c->Ph, c->P, c->P, nullptr, dt, 2, true, true)) return 1;
     // boundaries of P (and Ph == P): only P is kept current
@@ -673,12 +758,19 @@ extern "C" int pion_gpu_run(pion_gpu_ctx* c, int nsteps, double* dts) {
 
 extern "C" int pion_gpu_counters(pion_gpu_ctx* c, long long* out3) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
-  long long h[2];
-  CUDA_OK(cudaMemcpyAsync(h, c->d_counters, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  long long h[3];
+  CUDA_OK(cudaMemcpyAsync(h, c->d_counters, 3 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   out3[0] = h[0];
   out3[1] = h[1];
   out3[2] = c->launches;
+  c->mp_failures = h[2];
+  return 0;
+}
+extern "C" int pion_gpu_mp_failures(pion_gpu_ctx* c, long long* out) {
+  long long t[3];
+  if (pion_gpu_counters(c, t)) return 1;
+  *out = c->mp_failures;
   return 0;
 }
 extern "C" int pion_gpu_sync(pion_gpu_ctx* c) {

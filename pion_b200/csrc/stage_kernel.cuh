@@ -30,7 +30,8 @@ struct StageArgs {
   const double* S;    // stencil source: Ph (or P on the fused predictor, where Ph==P)
   const double* Pb;   // base state P of U = PtoU(P) + dU
   double* out;        // fused: destination primitive array (Ph on predictor, P on corrector)
-  double* dU;         // unfused: accumulated into; fused: optional microphysics dU (read), else null
+  double* dU;         // unfused: accumulated into; unused by the fused path
+  const double* mp_dE;  // fused: microphysics energy source per cell (cooling.cuh), null without microphysics
   const unsigned char* hll;  // HLLD->HLL switch flags per cell (null unless solver==HLLD)
   const double* eta;         // H-correction eta, 3 planes of vs doubles (null unless AV 3/4)
   const unsigned char* mask; // 1 = cell is updated (isdomain); null = every interior cell
@@ -169,15 +170,7 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
 #pragma unroll
     for (int q = 0; q < PION_MAXTR; q++) acctr[q] = 0.0;
 
-    if (a.fused && a.dU) {  // microphysics dU computed by the cooling kernel (frame x)
-      acc.rho = a.dU[c]; acc.erg = a.dU[vs + c]; acc.mn = a.dU[2 * vs + c]; acc.mt1 = a.dU[3 * vs + c];
-      acc.mt2 = a.dU[4 * vs + c];
-      if (EQ != EQ_EULER) { acc.bbn = a.dU[5 * vs + c]; acc.bbt1 = a.dU[6 * vs + c]; acc.bbt2 = a.dU[7 * vs + c]; }
-      if (EQ == EQ_GLM) acc.psi = a.dU[8 * vs + c];
-#pragma unroll
-      for (int q = 0; q < PION_MAXTR; q++)
-        if (q < a.ntr) acctr[q] = a.dU[(NB + q) * vs + c];
-    }
+    if (a.fused && a.mp_dE) acc.erg = a.mp_dE[c];  // cooling source term (only the energy component is non-zero)
 
     Prim C = load_prim<EQ>(a.S, c, vs, 0, 1, 2);
 

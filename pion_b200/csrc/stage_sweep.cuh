@@ -218,15 +218,7 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
     const bool domain = upd_xy && !warm && (a.mask ? (a.mask[c] != 0) : true);
     if (!warm) {
       C = load_prim<EQ>(a.S, c, vs, 0, 1, 2);
-      if (a.dU && upd_xy) {  // microphysics dU computed by the cooling kernel (frame x)
-        acc.rho = a.dU[c]; acc.erg = a.dU[vs + c]; acc.mn = a.dU[2 * vs + c]; acc.mt1 = a.dU[3 * vs + c];
-        acc.mt2 = a.dU[4 * vs + c];
-        if (EQ != EQ_EULER) { acc.bbn = a.dU[5 * vs + c]; acc.bbt1 = a.dU[6 * vs + c]; acc.bbt2 = a.dU[7 * vs + c]; }
-        if (EQ == EQ_GLM) acc.psi = a.dU[8 * vs + c];
-#pragma unroll
-        for (int q = 0; q < PION_MAXTR; q++)
-          if (q < ntr) acctr[q] = a.dU[(NB + q) * vs + c];
-      }
+      if (a.mp_dE && upd_xy) acc.erg = a.mp_dE[c];  // cooling source term (energy only)
     }
 
     // Schedule of one plane (ONE flux call site, ONE accumulate site):

@@ -27,3 +27,12 @@ def case_3d(eqn, solver, av, bcs="periodic", ntracer=0, NG=(12, 10, 8), ooa=2):
 
 def case_1d(eqn, solver, av, bcs=("outflow", "outflow")):
     return Problem(ndim=1, NG=(64, 1, 1), eqn=eqn, solver=solver, artviscosity=av, bcs=tuple(bcs) + ("periodic",) * 4)
+
+
+def case_cooling(eqn="euler", solver=8, ndim=3, NG=(12, 10, 8), ntracer=1, mp_limit=1, bcs="reflect-outflow", ooa=2):
+    """Wind3D-style units: cgs, dx = 1e17 cm, EP_cooling 8, T in [5e3, 1e8] K."""
+    dx = 1.0e17
+    return Problem(ndim=ndim, NG=NG, eqn=eqn, solver=solver, artviscosity=1, etav=0.1, cfl=0.3,
+                   xmax=(NG[0] * dx, NG[1] * dx, NG[2] * dx if ndim > 2 else 1.0), bcs=BCSETS[bcs], ntracer=ntracer, ooa=ooa,
+                   cooling=8, mp_timestep_limit=mp_limit, min_temperature=5.0e3, max_temperature=1.0e8,
+                   refvec=(2.0e-24, 3.0e-10, 1.0e6, 1.0e6, 1.0e6, 1.0e-6, 1.0e-6, 1.0e-6, 1.0e-6) + (1.0,) * 7)

@@ -14,8 +14,8 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent))
-from cases import case_1d, case_2d, case_3d  # noqa: E402
-from harness import RefSim, random_state  # noqa: E402
+from cases import case_1d, case_2d, case_3d, case_cooling  # noqa: E402
+from harness import COOLING_TABLES, TABLE_KEYS, RefSim, cooling_state, random_state  # noqa: E402
 
 CASES = {
     "glm_hlld_fkj_3d_periodic": (case_3d("glm-mhd", 7, 1, NG=(12, 10, 8)), 4),
@@ -60,10 +60,26 @@ TEST_PROBLEMS = {
 }
 CASES.update(TEST_PROBLEMS)
 
+# Per-cell cooling source term (mp_only_cooling, EP_cooling 8) on cgs states; `dense` puts the
+# cooling time near the CFL step (adaptive sub-stepping + MP_timestep_limit active).
+COOLING = {
+    "cool_euler_hll_3d_tracer": (case_cooling("euler", 8, ntracer=1), 4, 2.0e-24),
+    "cool_euler_hll_3d_dense": (case_cooling("euler", 8, ntracer=1), 4, 2.0e-21),
+    "cool_glm_hlld_3d_dense": (case_cooling("glm-mhd", 7, ntracer=0, bcs="periodic"), 3, 2.0e-22),
+}
+CASES.update({k: v[:2] for k, v in COOLING.items()})
+
 
 def main():
     for name, (prob, nsteps) in CASES.items():
-        if name in TEST_PROBLEMS:
+        if name in COOLING:
+            r = RefSim(prob)
+            if not COOLING_TABLES.exists() or name == next(iter(COOLING)):
+                tab = r.cooling_tables()
+                np.savez_compressed(COOLING_TABLES, **tab)
+            P0 = cooling_state(prob, seed=2024, rho0=COOLING[name][2])
+            r.set_state(P0)
+        elif name in TEST_PROBLEMS:
             r = RefSim(prob, run_ics=True)
             P0 = r.get_state(0)
         else:

@@ -233,6 +233,15 @@ class _CSim:
 
 
 _ref_lib = None
+TABLE_KEYS = ["T", "rrhp", "C_rrh", "C_ffhe", "C_fbdn", "C_cie"]
+COOLING_TABLES = ROOT / "tests" / "golden" / "cooling_tables_wss09_T5e3_1e8.npz"
+
+
+def load_cooling_tables():
+    """Committed fixture: the reference's EP_cooling=8 lookup tables for T in [5e3, 1e8] K
+    (generated by tests/golden/make_golden.py from oracle/_ref)."""
+    z = np.load(COOLING_TABLES)
+    return {k: z[k] for k in TABLE_KEYS}
 
 
 def have_ref():
@@ -262,6 +271,16 @@ class RefSim(_CSim):
         finally:
             os.unlink(path)
         assert self.h, "reference set-up failed"
+
+    def cooling_tables(self, n=200):
+        """mp_only_cooling's 200-point lookup tables, re-evaluated through the reference's own
+        rate functions (pref_cooling_tables in oracle/ref_driver.cpp)."""
+        arrs = {k: np.zeros(n) for k in TABLE_KEYS}
+        self.lib.pref_cooling_tables.restype = C.c_int
+        self.lib.pref_cooling_tables.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        err = self.lib.pref_cooling_tables(self.h, n, *[arrs[k].ctypes.data for k in TABLE_KEYS])
+        assert err == 0, "reference has no mp_only_cooling object"
+        return arrs
 
     def intercell_flux(self, axis, Pl, Pr, divv_l=0.0, gradp_l=0.0, divv_r=0.0, gradp_r=0.0):
         Pl = np.ascontiguousarray(Pl, dtype=np.float64)
@@ -409,35 +428,62 @@ def random_state(prob: Problem, seed=12345, smooth=True, amp=0.5):
     return out
 
 
-def state_scales(b, gamma=5.0 / 3.0):
+MU_TOT_OVER_KB = (0.609 * 1.672621898e-24) / 1.38064852e-16  # mp_only_cooling.cpp:79-81 with constants.h:53,64
+
+
+def cooling_state(prob: Problem, seed=4242, rho0=2.0e-24):
+    """Seeded cgs state for the cooling tests: rho ~ 2e-24 g/cm3 x [0.3,3], T log-uniform in
+    [6e3, 5e7] K (both sides of the cooling-curve peak), |v| <~ 3e6 cm/s, weak B, tracers in
+    [0,1.1] (exercises the sCMA clamp).  rho0 = 2e-22 makes the cooling time comparable to the
+    CFL step, so the adaptive integrator bisects and sub-steps."""
+    P = random_state(prob, seed)
+    shp = prob.padded_shape()
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    nv_phys = EQN_NVAR[prob.eqn]
+    rho = rho0 * 10.0 ** (P[0] - 1.0)
+    T = 10.0 ** (np.log10(6.0e3) + (np.log10(5.0e7) - np.log10(6.0e3)) * np.clip((P[1] - 0.5) * 1.6 - 0.3 + 0.4 * rng.random(shp[1:]), 0, 1))
+    out = np.zeros(shp)
+    out[0] = rho
+    out[1] = rho * T / MU_TOT_OVER_KB
+    out[2:5] = 6.0e6 * P[2:5]
+    if nv_phys >= 8:
+        out[5:8] = 2.0e-6 * P[5:8]
+    for v in range(nv_phys, prob.nvar):
+        out[v] = 1.1 * P[v]
+    return out
+
+
+def state_scales(b, gamma=5.0 / 3.0, nphys=None):
     """Per-variable normalisation for primitive-state comparisons: density and pressure by
     their maxima; every velocity component by max(|v|, sound speed); every B component and
     psi by max |B| (vector components that are identically zero in the problem, e.g. v_z in
     a 2-D run, only carry rounding noise and must not be normalised by themselves)."""
     b = np.asarray(b)
     nv = b.shape[0]
+    if nphys is None:  # without the equation set, assume no tracers beyond the 9 GLM variables
+        nphys = 9 if nv >= 9 else (8 if nv >= 8 else 5)
     sc = np.ones(nv)
     sc[0] = np.max(np.abs(b[0]))
     sc[1] = np.max(np.abs(b[1]))
     cs = float(np.sqrt(gamma * np.max(np.abs(b[1])) / max(np.min(np.abs(b[0])), 1e-300)))
     sc[2:5] = max(float(np.max(np.abs(b[2:5]))), cs)
-    if nv >= 8:
+    if nphys >= 8:
         bmax = float(np.max(np.abs(b[5:8])))
         sc[5:8] = bmax if bmax > 0 else 1.0
-        if nv >= 9:
+        if nphys >= 9:
             sc[8] = sc[5]
-    for v in range(9 if nv >= 9 else (8 if nv >= 8 else 5), nv):
+    for v in range(nphys, nv):
         m = float(np.max(np.abs(b[v])))
         sc[v] = m if m > 0 else 1.0
     return sc
 
 
-def rel_err(a, b, scale=None, primitive=True):
+def rel_err(a, b, scale=None, primitive=True, nphys=None):
     """max |a-b| / scale per variable (scale: state_scales(b) for primitive states)."""
     a = np.asarray(a)
     b = np.asarray(b)
     if scale is None:
-        scale = state_scales(b) if primitive and b.shape[0] >= 5 else [np.max(np.abs(b[v])) for v in range(b.shape[0])]
+        scale = state_scales(b, nphys=nphys) if primitive and b.shape[0] >= 5 else [np.max(np.abs(b[v])) for v in range(b.shape[0])]
     errs = []
     for v in range(a.shape[0]):
         s = scale[v] if scale[v] > 0 else 1.0

@@ -26,7 +26,7 @@ def run_pair(prob, nsteps=3, seed=7, checker=OracleSim):
         assert np.allclose(do, dg, rtol=1e-13, atol=0), (do, dg)
         Po, Pg = o.get_state(0), g.get_state(0)
         assert np.max(np.abs(Po - P)) > 1e-6
-        err = rel_err(Pg, Po)
+        err = rel_err(Pg, Po, nphys=prob.nvar - prob.ntracer)
         assert err.max() < TOL, err
         assert g.error_counts() == [0, 0]
         # after a full step Ph == P (time_integrator.cpp:938-940)
@@ -144,3 +144,49 @@ def test_full_size_properties_512_cubed_slab():
     m1, p1 = totals(g.get_state(0))
     assert abs(m1 - m0) / m0 < 1e-12
     g.close()
+
+
+# ------------------------------------------------------------------------------------------
+# cooling source term (a17): k_cooling_dU / k_mp_dt against the oracle, tables from the
+# committed fixture (reference-generated).  The integrator's control flow is reproduced
+# exactly; arithmetic differs by FMA contraction only, so the same 5e-12 bar holds.
+from cases import case_cooling  # noqa: E402
+from harness import cooling_state, load_cooling_tables  # noqa: E402
+
+
+@pytest.mark.parametrize("eqn,solver,ndim,NG,ntr,lim,rho0", [
+    ("euler", 8, 3, (12, 10, 8), 1, 1, 2.0e-24),
+    ("euler", 8, 3, (12, 10, 8), 1, 1, 2.0e-21),
+    ("glm-mhd", 7, 3, (12, 10, 8), 0, 2, 2.0e-22),
+    ("euler", 4, 2, (16, 12, 1), 1, 0, 2.0e-21),
+    ("i-mhd", 8, 2, (16, 12, 1), 2, 4, 2.0e-22),
+])
+def test_cooling_source_term(eqn, solver, ndim, NG, ntr, lim, rho0):
+    prob = case_cooling(eqn, solver, ndim=ndim, NG=NG, ntracer=ntr, mp_limit=lim)
+    tab = load_cooling_tables()
+    o, g = OracleSim(prob, tables=tab), GpuSim(prob, tables=tab)
+    try:
+        P = cooling_state(prob, seed=11, rho0=rho0)
+        for s in (o, g):
+            s.set_state(P)
+            s.init_after_state()
+        tmo, tmg = o.microphysics_dt(), g.microphysics_dt()
+        assert abs(tmo - tmg) <= 1e-13 * tmo, (tmo, tmg)
+        do, dg = o.run(3), g.run(3)
+        assert np.allclose(do, dg, rtol=1e-13, atol=0), (do, dg)
+        err = rel_err(g.get_state(0), o.get_state(0), nphys=prob.nvar - prob.ntracer)
+        assert err.max() < TOL, err
+        assert g.error_counts() == [0, 0] and g.ctx.mp_failures() == 0
+        # seam call: dU after calc_microphysics_dU alone (energy plane only)
+        o.microphysics_dU(0.5 * do[-1])
+        g.microphysics_dU(0.5 * do[-1])
+        dUo, dUg = o.get_state(2), g.get_state(2)
+        inner = prob.interior()
+        assert np.max(np.abs(dUo[1])) > 0
+        # dU[ERG] = E(p') - E(P) is a difference of total energies: it is defined to rounding of E
+        escale = float(np.max(o.get_state(0)[1])) / (prob.gamma - 1.0)
+        assert np.max(np.abs(dUg[inner][1] - dUo[inner][1])) <= 1e-13 * escale
+        assert np.all(dUg[inner][[0, 2, 3, 4]] == 0)
+    finally:
+        o.close()
+        g.close()

@@ -84,3 +84,50 @@ def test_per_call_seam_bit_exact():
     assert np.array_equal(r.get_state(2), o.get_state(2))
     r.close()
     o.close()
+
+
+# ------------------------------------------------------------------------------------------
+# cooling source term (mp_only_cooling, EP_cooling 8): tables taken from the reference's own
+# rate functions, then the whole step -- adaptive RKCK integration included -- is bit-exact.
+from cases import case_cooling  # noqa: E402
+from harness import cooling_state  # noqa: E402
+
+
+@pytest.mark.parametrize("eqn,solver,ndim,NG,ntr,lim,rho0", [
+    ("euler", 8, 3, (12, 10, 8), 1, 1, 2.0e-24),
+    ("euler", 8, 3, (12, 10, 8), 1, 1, 2.0e-21),   # cooling time < CFL step: MP limit + bisection
+    ("glm-mhd", 7, 3, (12, 10, 8), 0, 2, 2.0e-22),
+    ("euler", 4, 2, (16, 12, 1), 1, 0, 2.0e-21),
+    ("i-mhd", 8, 2, (16, 12, 1), 2, 4, 2.0e-22),
+])
+def test_cooling_bit_exact(eqn, solver, ndim, NG, ntr, lim, rho0):
+    prob = case_cooling(eqn, solver, ndim=ndim, NG=NG, ntracer=ntr, mp_limit=lim)
+    r = RefSim(prob)
+    tab = r.cooling_tables()
+    o = OracleSim(prob, tables=tab)
+    try:
+        P = cooling_state(prob, seed=11, rho0=rho0)
+        for s in (r, o):
+            s.set_state(P)
+            assert s.init_after_state() == 0
+        assert r.microphysics_dt() == o.microphysics_dt()
+        dr, do = r.run(3), o.run(3)
+        assert np.array_equal(dr, do), (dr, do)
+        assert np.array_equal(r.get_state(0), o.get_state(0))
+        # the seam call on its own: dU after calc_microphysics_dU
+        assert r.microphysics_dU(0.5 * dr[-1]) == 0 and o.microphysics_dU(0.5 * dr[-1]) == 0
+        dUr, dUo = r.get_state(2), o.get_state(2)
+        assert np.max(np.abs(dUr[1])) > 0
+        assert np.array_equal(dUr, dUo)
+    finally:
+        r.close()
+        o.close()
+
+
+def test_committed_cooling_tables_match_reference():
+    from harness import TABLE_KEYS, load_cooling_tables
+    r = RefSim(case_cooling())
+    tab, gold = r.cooling_tables(), load_cooling_tables()
+    r.close()
+    for k in TABLE_KEYS:
+        assert np.array_equal(tab[k], gold[k]), k
