@@ -48,6 +48,16 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(size):
+    """dram__bytes_read.sum + dram__bytes_write.sum per stage launch (mean of the predictor and the
+    corrector launch) from the committed `ncu --set full` capture of this workload size, or None."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get(str(size), {}).get("bytes_per_launch")
+    return None
+
+
 def dte_problem(NG, xmin, xmax, bcs=("outflow",) * 6):
     from harness import Problem
     return Problem(ndim=3, NG=tuple(NG), eqn="glm-mhd", solver=7, artviscosity=1, etav=0.15, gamma=5.0 / 3.0, cfl=0.2,
@@ -347,7 +357,7 @@ def main():
                        "global_grid": gNG, "decomposition": nsplit, "l2_policy": "working set (>20 GB per GPU) far exceeds the 126 MB L2",
                        "step": "calculate_timestep + advance_time (predictor, BCs, corrector, BCs, CFL reduction)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_stage<GLM,HLLD,FKJ>",
+                         "traffic": ncu_traffic(S), "peak_source": peak_src, "kernel": "k_stage_sweep<GLM,HLLD,FKJ98,TY=8> (one launch per stage, two per step)",
                          "alg_bytes_per_cell_update": ALG_BYTES_PER_CELL_UPDATE, "launches_timed": stage_n,
                          "avg_launch_ms": stage_avg_ms, "stage_share_of_step": stage_ms / ms},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
