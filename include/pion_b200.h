@@ -44,6 +44,20 @@ enum {
 };
 enum { PION_STATE_P = 0, PION_STATE_PH = 1, PION_STATE_DU = 2 };
 
+/* One constant stellar-wind source: the arguments of stellar_wind::add_source
+ * (grid/stellar_wind_BC.cpp:125-140) in parameter-file units (SWP.params[i],
+ * sim_params.h:340-380; WINDTYPE_CONSTANT only). */
+typedef struct pion_gpu_wind_source {
+  double dpos[3];    /* position, cm */
+  double radius;     /* boundary radius, cm */
+  double mdot;       /* Msun/yr */
+  double vinf, vrot; /* km/s */
+  double temp;       /* wind temperature, K */
+  double rstar;      /* stellar radius, cm */
+  double bsrf;       /* surface split-monopole field, Gauss */
+  double tr[PION_GPU_MAXTR]; /* tracer values */
+} pion_gpu_wind_source;
+
 /* Mirrors the subset of class SimParams (sim_params.h:200-285) the path reads. */
 typedef struct pion_gpu_config {
   int device;          /* CUDA device ordinal */
@@ -74,6 +88,10 @@ typedef struct pion_gpu_config {
   /* decomposition (decomposition/MCMD_control.cpp:62-221) */
   int rank, nproc;
   int ngbprocs[6];     /* neighbour rank per face, -1 = none (MCMDcontrol::ngbprocs) */
+  /* internal boundary PION_BC_STWIND ("stellar-wind"): BC_assign_STWIND / BC_update_STWIND
+   * (boundaries/stellar_wind_boundaries.cpp:29-341) for constant sources */
+  int n_wind;
+  pion_gpu_wind_source wind[2];
 } pion_gpu_config;
 
 typedef struct pion_gpu_ctx pion_gpu_ctx;

@@ -55,7 +55,7 @@ struct pion_oracle {
   double *P, *Ph, *dU; /* [ncell][nv] */
   double *hcorr;       /* [ncell][3] */
   double *divv, *gradp;
-  unsigned char *isgd, *isdomain, *tsflag;
+  unsigned char *isgd, *isdomain, *tsflag, *iswind; /* isbd = !isgd || iswind */
   /* solver "class" state: eqns_base.cpp:94-131, solver_eqn_base.h */
   int dir, eVX, eVY, eVZ, eBX, eBY, eBZ, eMX, eMY, eMZ, eBBX, eBBY, eBBZ;
   double FV_dt, chyp, cr, HC_etamax, gamma;
@@ -72,6 +72,10 @@ struct pion_oracle {
   double *s_rrhp, *s_Crrh, *s_Cffhe, *s_Cfbdn, *s_Ccie;
   int nT;
   double mp_rho, mp_gamma; /* integrator "members" */
+  /* stellar wind (grid/stellar_wind_BC.cpp): cells of every source in add order */
+  long wind_n;
+  long *wind_cell;
+  double *wind_p; /* [wind_n][nv] */
 };
 
 /* ------------------------------------------------------------------ */
@@ -1338,11 +1342,14 @@ static double calc_dynamics_dt(pion_oracle *s) {
   int nv = s->nv;
   for (long c = 0; c < s->ncell; c++) {
     if (!s->isgd[c]) continue;
-    if (s->tsflag[c]) {
+    if (s->tsflag[c] && !s->iswind[c]) { /* c->timestep && !c->isbd (calc_timestep.cpp:295) */
       double tempdt = cell_time_step(s, s->P + c * nv);
       dt = fmin(dt, tempdt);
     }
   }
+  /* first step with stellar winds: limit dt by the wind speed (calc_timestep.cpp:318-323) */
+  if (s->timestep == 0)
+    for (int v = 0; v < s->cfg.n_wind; v++) dt = fmin(dt, 0.1 * s->cfg.cfl * s->dx / (s->cfg.wind[v].vinf * 1.0e5));
   return dt;
 }
 /* calc_timestep::calc_microphysics_dt / get_mp_timescales_no_radiation
@@ -1425,6 +1432,8 @@ static void setup_bc_lists(pion_oracle *s) {
         }
   }
 }
+static void wind_assign(pion_oracle *s);
+static void wind_update(pion_oracle *s);
 /* walk `n` steps from c in direction dir */
 static long walk(const pion_oracle *s, long c, int dir, int n) {
   for (int v = 0; v < n; v++) c = nextpt(s, c, dir);
@@ -1540,6 +1549,9 @@ static int assign_boundary_data(pion_oracle *s) {
           }
         } while ((c = nextpt(s, c, XP)) >= 0 && (dpos(s, c, 0) <= 1. / 6.));
       } break;
+      case PO_BC_STWIND: /* stellar_wind_boundaries.cpp:29-250 */
+        wind_assign(s);
+        break;
       default:
         fprintf(stderr, "pion_oracle: BC type %d not restated\n", b->type);
         return 1;
@@ -1547,11 +1559,120 @@ static int assign_boundary_data(pion_oracle *s) {
   }
   return 0;
 }
+/* ------------------------------------------------------------------ */
+/* stellar wind internal boundary (STWIND), constant sources only      */
+/* ------------------------------------------------------------------ */
+/* stellar_wind::set_wind_cell_reference_state (stellar_wind_BC.cpp:375-596) for a
+ * WINDTYPE_CONSTANT source in Cartesian coordinates; gamma is the literal 5./3. that
+ * add_cell passes (:339). */
+static void wind_reference_state(const pion_oracle *s, const po_wind_source *w, long c, double dist, double *p) {
+  const double kB = 1.38064852e-16, m_p = 1.672621898e-24, Msun = 1.9891e33, year = 3.1558150e7; /* constants.h */
+  const double gamma = 5. / 3.;
+  const int nd = s->ndim;
+  const double Mdot = w->mdot * Msun / year, Vinf = w->vinf * 1.0e5, v_rot = w->vrot * 1.0e5; /* add_source :163-166 */
+  for (int v = 0; v < s->nv; v++) p[v] = 0.0;
+  int set_rho = 1;
+  if (dist < 0.75 * w->radius && nd > 1) { p[RO] = 1.0e-31; p[PG] = 1.0e-31; set_rho = 0; }
+  if (nd == 2) { /* ndim==2 && COORD_CRT (:407-413) */
+    p[RO] = Mdot / (Vinf * 2.0 * M_PI * dist);
+    p[PG] = kB * w->temp / m_p;
+    p[PG] *= exp((gamma - 1.0) * log(2.0 * M_PI * w->rstar * Vinf / Mdot));
+    p[PG] *= exp((gamma)*log(p[RO]));
+  } else if (set_rho) {
+    p[RO] = 1.0 / (dist);
+    p[RO] *= p[RO];
+    p[RO] *= Mdot / (Vinf * 4.0 * M_PI);
+    p[PG] = kB * w->temp / m_p;
+    p[PG] *= exp((gamma - 1.0) * log(4.0 * M_PI * w->rstar * w->rstar * Vinf / Mdot));
+    p[PG] *= exp((gamma)*log(p[RO]));
+  }
+  double x = dpos(s, c, 0) - w->dpos[0], y = (nd > 1) ? dpos(s, c, 1) - w->dpos[1] : 0.0,
+         z = (nd > 2) ? dpos(s, c, 2) - w->dpos[2] : 0.0;
+  const double d2 = exp(2 * log(dist)); /* pconst.pow_fast(dist,2) */
+  if (nd == 1) {
+    p[VX] = Vinf * x / dist; p[VY] = 0.0; p[VZ] = 0.0;
+  } else if (nd == 2) {
+    p[VX] = Vinf * x / dist;
+    p[VY] = Vinf * y / dist;
+    p[VZ] = v_rot * w->rstar * y / d2;
+  } else {
+    p[VX] = Vinf * x / dist;
+    p[VY] = Vinf * y / dist;
+    p[VZ] = Vinf * z / dist;
+    p[VX] += -v_rot * w->rstar * y / d2;
+    p[VY] += v_rot * w->rstar * x / d2;
+  }
+  if (s->cfg.eqntype == PO_EQMHD || s->cfg.eqntype == PO_EQGLM) {
+    double B_s = w->bsrf / sqrt(4.0 * M_PI);
+    double D_s = w->rstar / dist;
+    double D_2 = D_s * D_s;
+    double beta_B_sint = (v_rot / Vinf) * B_s * D_s;
+    if (nd == 2) {
+      p[BX] = B_s * D_2 * fabs(x) / dist;
+      p[BY] = B_s * D_2 / dist;
+      p[BY] = (x > 0.0) ? y * p[BY] : -y * p[BY];
+      beta_B_sint = beta_B_sint * y / dist;
+      p[BZ] = (x > 0.0) ? -beta_B_sint : beta_B_sint;
+    } else if (nd == 3) {
+      p[BX] = B_s * D_2 / dist;
+      p[BX] = (z > 0.0) ? x * p[BX] : -x * p[BX];
+      p[BY] = B_s * D_2 / dist;
+      p[BY] = (z > 0.0) ? y * p[BY] : -y * p[BY];
+      p[BZ] = B_s * D_2 * fabs(z) / dist;
+      beta_B_sint *= sqrt(x * x + y * y) / dist;
+      beta_B_sint = (z > 0.0) ? -beta_B_sint : beta_B_sint;
+      p[BX] += -beta_B_sint * y / dist;
+      p[BY] += beta_B_sint * x / dist;
+    }
+  }
+  if (s->cfg.eqntype == PO_EQGLM) p[SI] = 0.0;
+  for (int v = 0; v < s->ntr; v++) p[s->ftr + v] = w->tr[v];
+  /* SET_NEGATIVE_PRESSURE_TO_FIXED_TEMPERATURE (:583-594); Tmin = EP.MinTemperature */
+  if (s->have_mp) {
+    if (mp_temperature(s, p) < s->cfg.min_temperature) mp_set_temp(s, p, s->cfg.min_temperature);
+  } else {
+    p[PG] = fmax(p[PG], s->cfg.min_temperature * p[RO] * kB * 0.78625 / m_p);
+  }
+}
+/* BC_assign_STWIND + BC_assign_STWIND_add_cells2src + stellar_wind::add_cell
+ * (stellar_wind_boundaries.cpp:29-250, stellar_wind_BC.cpp:247-347) */
+static void wind_assign(pion_oracle *s) {
+  int nv = s->nv;
+  for (int id = 0; id < s->cfg.n_wind; id++) {
+    const po_wind_source *w = &s->cfg.wind[id];
+    for (long c = 0; c < s->ncell; c++) { /* FirstPt_All .. NextPt_All: ghost cells included */
+      double d = 0.0;
+      for (int a = 0; a < s->ndim; a++) d += pow(w->dpos[a] - dpos(s, c, a), 2.0);
+      d = sqrt(d);
+      if (d <= w->radius) {
+        s->wind_cell = (long *)realloc(s->wind_cell, (s->wind_n + 1) * sizeof(long));
+        s->wind_p = (double *)realloc(s->wind_p, (size_t)(s->wind_n + 1) * nv * sizeof(double));
+        s->wind_cell[s->wind_n] = c;
+        s->isdomain[c] = 0; /* isbd = true, isdomain = false (:268-269) */
+        s->iswind[c] = 1;
+        s->tsflag[c] = (d < 0.8 * w->radius) ? 0 : 1; /* c->timestep (:273-276) */
+        wind_reference_state(s, w, c, d, s->wind_p + (size_t)s->wind_n * nv);
+        s->wind_n++;
+      }
+    }
+  }
+}
+/* BC_update_STWIND -> stellar_wind::set_cell_values (:642-670): P and Ph, every call */
+static void wind_update(pion_oracle *s) {
+  int nv = s->nv;
+  for (long q = 0; q < s->wind_n; q++) {
+    long c = s->wind_cell[q];
+    for (int v = 0; v < nv; v++) s->P[c * nv + v] = s->wind_p[q * nv + v];
+    for (int v = 0; v < nv; v++) s->Ph[c * nv + v] = s->wind_p[q * nv + v];
+  }
+}
+
 /* assign_update_bcs::TimeUpdateExternalBCs (assign_update_bcs.cpp:182-246) and
  * the BC_update_* functions; TimeUpdateInternalBCs (:134-176) only acts on
- * STWIND which this oracle does not restate yet. */
+ * STWIND and runs first (time_integrator.cpp:104-107). */
 static int time_update_bcs(pion_oracle *s, int cstep, int maxstep) {
   int nv = s->nv;
+  if (s->wind_n) wind_update(s); /* TimeUpdateInternalBCs: BC_update_STWIND */
   for (int ib = 0; ib < s->nbcs; ib++) {
     bc_list *b = &s->bcs[ib];
     int ondir = (b->dir >= 0) ? (b->dir ^ 1) : -1;
@@ -1630,6 +1751,8 @@ static int time_update_bcs(pion_oracle *s, int cstep, int maxstep) {
             for (int v = 0; v < nv; v++) s->P[c * nv + v] = ph[v];
         }
         break;
+      case PO_BC_STWIND: /* updated by TimeUpdateInternalBCs above; skipped here (:238) */
+        break;
       default:
         return 1;
     }
@@ -1700,6 +1823,7 @@ pion_oracle *po_create(const pion_oracle_config *cfg) {
   s->isgd = (unsigned char *)calloc(s->ncell, 1);
   s->isdomain = (unsigned char *)calloc(s->ncell, 1);
   s->tsflag = (unsigned char *)calloc(s->ncell, 1);
+  s->iswind = (unsigned char *)calloc(s->ncell, 1);
   for (long c = 0; c < s->ncell; c++) {
     int ijk[3], in = 1;
     cijk(s, c, ijk);
@@ -1759,7 +1883,7 @@ pion_oracle *po_create(const pion_oracle_config *cfg) {
 void po_destroy(pion_oracle *s) {
   if (!s) return;
   free(s->P); free(s->Ph); free(s->dU); free(s->hcorr); free(s->divv); free(s->gradp);
-  free(s->isgd); free(s->isdomain); free(s->tsflag);
+  free(s->isgd); free(s->isdomain); free(s->tsflag); free(s->iswind); free(s->wind_cell); free(s->wind_p);
   for (int i = 0; i < s->nbcs; i++) { free(s->bcs[i].cell); free(s->bcs[i].npt); free(s->bcs[i].isedge); }
   free(s->tT); free(s->t_rrhp); free(s->t_Crrh); free(s->t_Cffhe); free(s->t_Cfbdn); free(s->t_Ccie);
   free(s->s_rrhp); free(s->s_Crrh); free(s->s_Cffhe); free(s->s_Cfbdn); free(s->s_Ccie);
@@ -1793,7 +1917,7 @@ int po_set_state(pion_oracle *s, int which, const double *in) {
 }
 int po_get_flags(pion_oracle *s, int *out) {
   for (long c = 0; c < s->ncell; c++)
-    out[c] = (s->isgd[c] ? 1 : 0) | (s->isgd[c] ? 0 : 2) | (s->isdomain[c] ? 4 : 0) | 8 | (s->tsflag[c] ? 16 : 0);
+    out[c] = (s->isgd[c] ? 1 : 0) | ((!s->isgd[c] || s->iswind[c]) ? 2 : 0) | (s->isdomain[c] ? 4 : 0) | 8 | (s->tsflag[c] ? 16 : 0);
   return 0;
 }
 int po_get_extra(pion_oracle *s, int what, int axis, double *out) {

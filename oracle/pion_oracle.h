@@ -30,6 +30,19 @@ enum {
   PO_BC_FIXED = 5, PO_BC_DMACH = 8, PO_BC_DMACH2 = 9, PO_BC_ONEWAY_OUT = 13, PO_BC_STWIND = 14
 };
 
+/* one constant stellar-wind source: arguments of stellar_wind::add_source
+ * (grid/stellar_wind_BC.cpp:125-140), units as in the parameter file */
+typedef struct po_wind_source {
+  double dpos[3];   /* cm */
+  double radius;    /* cm */
+  double mdot;      /* Msun/yr */
+  double vinf, vrot;/* km/s */
+  double temp;      /* K */
+  double rstar;     /* cm */
+  double bsrf;      /* Gauss */
+  double tr[4];     /* tracer values */
+} po_wind_source;
+
 typedef struct pion_oracle_config {
   int ndim;
   int NG[3];
@@ -55,6 +68,9 @@ typedef struct pion_oracle_config {
   double min_temperature, max_temperature;
   int n_table;        /* 200 */
   const double *table_T, *table_rrhp, *table_C_rrh, *table_C_ffhe, *table_C_fbdn, *table_C_cie;
+  /* internal boundary PO_BC_STWIND: constant wind sources (SWP, sim_params.h) */
+  int n_wind;
+  po_wind_source wind[2];
 } pion_oracle_config;
 
 typedef struct pion_oracle pion_oracle;

@@ -80,6 +80,10 @@ class RefSim : public sim_control {
   int setup(const char *pfile, int run_ics) {
     int err = 0;
     MP = 0;
+    // the reference keeps its wind-source list in a process-wide global that read_gridparams
+    // appends to (ics/get_sim_info.cpp:875): start every instance from an empty list
+    SWP.params.clear();
+    SWP.Nsources = 0;
     {
       class get_sim_info siminfo;
       err += siminfo.read_gridparams(pfile, SimPM);

@@ -15,6 +15,13 @@ MAXVAR = 16
 _lib = None
 
 
+class WindSource(C.Structure):
+    """struct pion_gpu_wind_source (include/pion_b200.h)."""
+    _fields_ = [("dpos", C.c_double * 3), ("radius", C.c_double), ("mdot", C.c_double), ("vinf", C.c_double),
+                ("vrot", C.c_double), ("temp", C.c_double), ("rstar", C.c_double), ("bsrf", C.c_double),
+                ("tr", C.c_double * 4)]
+
+
 class GpuConfig(C.Structure):
     """struct pion_gpu_config (include/pion_b200.h)."""
     _fields_ = [
@@ -33,6 +40,7 @@ class GpuConfig(C.Structure):
         ("table_T", C.c_void_p), ("table_rrhp", C.c_void_p), ("table_C_rrh", C.c_void_p),
         ("table_C_ffhe", C.c_void_p), ("table_C_fbdn", C.c_void_p), ("table_C_cie", C.c_void_p),
         ("rank", C.c_int), ("nproc", C.c_int), ("ngbprocs", C.c_int * 6),
+        ("n_wind", C.c_int), ("wind", WindSource * 2),
     ]
 
 

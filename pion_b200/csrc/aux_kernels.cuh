@@ -323,6 +323,19 @@ __global__ void k_calc_dt(GridD g, PhysParams pp, const double* __restrict__ P, 
   }
 }
 
+// BC_update_STWIND -> stellar_wind::set_cell_values (grid/stellar_wind_BC.cpp:642-670): the
+// wind cells' reference states overwrite P AND Ph on every boundary update.
+__global__ void k_wind_set(long vs, int nvar, long nw, const long* __restrict__ idx, const double* __restrict__ val,
+                           double* __restrict__ P, double* __restrict__ Ph) {
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < nw * nvar; t += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(t / nw);
+    const long c = idx[t % nw];
+    const double x = val[t];
+    P[(long)v * vs + c] = x;
+    Ph[(long)v * vs + c] = x;
+  }
+}
+
 // small utility kernels
 __global__ void k_copy_interior(GridD g, const double* __restrict__ src, double* __restrict__ dst, int nvar, int zero_var) {
   const long ncell = (long)g.NG[0] * g.NG[1] * g.NG[2];

@@ -76,6 +76,10 @@ struct pion_gpu_ctx {
   CoolParams cool;
   double *d_tables = nullptr, *mp_dE = nullptr;
   long long mp_failures = 0;
+  // stellar-wind internal boundary: cell list (device linear indices) and reference states [nvar][n]
+  long wind_n = 0;
+  long* d_wind_idx = nullptr;
+  double* d_wind_val = nullptr;
   double *sendbuf[6] = {nullptr}, *recvbuf[6] = {nullptr};
   size_t halo_elems[6] = {0};
 };
@@ -110,6 +114,11 @@ static int check_config(const pion_gpu_config& c) {
         t != PION_BC_FIXED && t != PION_BC_DMACH && t != PION_BC_ONEWAY_OUT && t != PION_BC_MPI) { set_error("unsupported boundary type"); return 1; }
     if (c.eqntype == PION_EQGLM && c.ndim == 1 && (t == PION_BC_OUTFLOW || t == PION_BC_ONEWAY_OUT)) { set_error("Psi outflow boundary condition doesn't work for 1D! (outflow_boundaries.cpp:57)"); return 1; }
   }
+  for (int i = 0; i < c.n_internal_bc; i++) {
+    if (c.internal_bc[i] == PION_BC_STWIND) {
+      if (c.n_wind < 1 || c.n_wind > 2) { set_error("BC_assign_STWIND() No Sources! (n_wind must be 1 or 2)"); return 1; }
+    } else if (c.internal_bc[i] != PION_BC_DMACH2) { set_error("unsupported internal boundary"); return 1; }
+  }
   if (c.cooling) {
     if (c.cooling != 8) { set_error("only EP_cooling 8 (WSS09_CIE_LINE_HEAT_COOL, mp_only_cooling) is built"); return 1; }
     if (c.n_table < 2 || !c.table_T || !c.table_rrhp || !c.table_C_rrh || !c.table_C_ffhe || !c.table_C_fbdn || !c.table_C_cie) {
@@ -118,6 +127,114 @@ static int check_config(const pion_gpu_config& c) {
     }
     if (c.mp_timestep_limit < 0 || c.mp_timestep_limit > 4) { set_error("Bad MP_timestep_limit"); return 1; }
   }
+  return 0;
+}
+
+// BC_assign_STWIND + BC_assign_STWIND_add_cells2src + stellar_wind::add_cell +
+// set_wind_cell_reference_state (boundaries/stellar_wind_boundaries.cpp:29-250,
+// grid/stellar_wind_BC.cpp:125-596) for constant sources on a Cartesian grid: every cell
+// (ghost cells included) whose centre lies within `radius` of the source joins the list,
+// becomes !isdomain (mask = 0) and carries a fixed reference state.  Host code, run once.
+static int build_wind_cells(pion_gpu_ctx* c) {
+  const pion_gpu_config& cfg = c->cfg;
+  const GridD& g = c->g;
+  const double kB = 1.38064852e-16, m_p = 1.672621898e-24, Msun = 1.9891e33, year = 3.1558150e7;  // constants.h
+  const double gamma = 5. / 3.;  // the literal add_cell passes (:339)
+  const int nd = g.ndim, nv = c->nvar;
+  std::vector<long> idx;
+  std::vector<double> val;  // [cell][var] while building
+  std::vector<unsigned char> mask((size_t)g.vs, 1);
+  auto dpos = [&](int i, int a) { return cfg.xmin[a] + (2 * (i - g.nb[a]) + 1) * (0.5 * g.dx); };
+  for (int id = 0; id < cfg.n_wind; id++) {
+    const pion_gpu_wind_source& w = cfg.wind[id];
+    const double Mdot = w.mdot * Msun / year, Vinf = w.vinf * 1.0e5, v_rot = w.vrot * 1.0e5;
+    for (int k = 0; k < g.NGa[2]; k++)
+      for (int j = 0; j < g.NGa[1]; j++)
+        for (int i = 0; i < g.NGa[0]; i++) {
+          const int ijk[3] = {i, j, k};
+          double dist = 0.0;
+          for (int a = 0; a < nd; a++) dist += pow(w.dpos[a] - dpos(ijk[a], a), 2.0);
+          dist = sqrt(dist);
+          if (!(dist <= w.radius)) continue;
+          double p[PION_MAXVAR] = {0};
+          bool set_rho = true;
+          if (dist < 0.75 * w.radius && nd > 1) { p[0] = 1.0e-31; p[1] = 1.0e-31; set_rho = false; }
+          if (nd == 2) {
+            p[0] = Mdot / (Vinf * 2.0 * M_PI * dist);
+            p[1] = kB * w.temp / m_p;
+            p[1] *= exp((gamma - 1.0) * log(2.0 * M_PI * w.rstar * Vinf / Mdot));
+            p[1] *= exp((gamma)*log(p[0]));
+          } else if (set_rho) {
+            p[0] = 1.0 / (dist);
+            p[0] *= p[0];
+            p[0] *= Mdot / (Vinf * 4.0 * M_PI);
+            p[1] = kB * w.temp / m_p;
+            p[1] *= exp((gamma - 1.0) * log(4.0 * M_PI * w.rstar * w.rstar * Vinf / Mdot));
+            p[1] *= exp((gamma)*log(p[0]));
+          }
+          const double x = dpos(i, 0) - w.dpos[0], y = (nd > 1) ? dpos(j, 1) - w.dpos[1] : 0.0,
+                       z = (nd > 2) ? dpos(k, 2) - w.dpos[2] : 0.0;
+          const double d2 = exp(2 * log(dist));  // pconst.pow_fast(dist,2)
+          if (nd == 1) {
+            p[2] = Vinf * x / dist;
+          } else if (nd == 2) {
+            p[2] = Vinf * x / dist;
+            p[3] = Vinf * y / dist;
+            p[4] = v_rot * w.rstar * y / d2;
+          } else {
+            p[2] = Vinf * x / dist;
+            p[3] = Vinf * y / dist;
+            p[4] = Vinf * z / dist;
+            p[2] += -v_rot * w.rstar * y / d2;
+            p[3] += v_rot * w.rstar * x / d2;
+          }
+          if (cfg.eqntype != PION_EQEUL) {
+            if (nd == 1) { set_error("1D spherical but MHD?"); return 1; }
+            const double B_s = w.bsrf / sqrt(4.0 * M_PI), D_s = w.rstar / dist, D_2 = D_s * D_s;
+            double beta = (v_rot / Vinf) * B_s * D_s;
+            if (nd == 2) {
+              p[5] = B_s * D_2 * fabs(x) / dist;
+              p[6] = B_s * D_2 / dist;
+              p[6] = (x > 0.0) ? y * p[6] : -y * p[6];
+              beta = beta * y / dist;
+              p[7] = (x > 0.0) ? -beta : beta;
+            } else {
+              p[5] = B_s * D_2 / dist;
+              p[5] = (z > 0.0) ? x * p[5] : -x * p[5];
+              p[6] = B_s * D_2 / dist;
+              p[6] = (z > 0.0) ? y * p[6] : -y * p[6];
+              p[7] = B_s * D_2 * fabs(z) / dist;
+              beta *= sqrt(x * x + y * y) / dist;
+              beta = (z > 0.0) ? -beta : beta;
+              p[5] += -beta * y / dist;
+              p[6] += beta * x / dist;
+            }
+          }
+          if (cfg.eqntype == PION_EQGLM) p[8] = 0.0;
+          for (int t = 0; t < c->ntr; t++) p[c->nbase_ + t] = w.tr[t];
+          // SET_NEGATIVE_PRESSURE_TO_FIXED_TEMPERATURE (:583-594), Tmin = EP.MinTemperature
+          if (cfg.cooling) {
+            if (p[1] * c->pp.mu_tot_over_kB / p[0] < cfg.min_temperature) p[1] = p[0] * cfg.min_temperature / c->pp.mu_tot_over_kB;
+          } else {
+            p[1] = fmax(p[1], cfg.min_temperature * p[0] * kB * 0.78625 / m_p);
+          }
+          const long ci = gidx(g, i, j, k);
+          idx.push_back(ci);
+          mask[ci] = 0;
+          for (int v = 0; v < nv; v++) val.push_back(p[v]);
+        }
+  }
+  c->wind_n = (long)idx.size();
+  if (c->wind_n == 0) return 0;
+  std::vector<double> soa((size_t)nv * c->wind_n);
+  for (long q = 0; q < c->wind_n; q++)
+    for (int v = 0; v < nv; v++) soa[(size_t)v * c->wind_n + q] = val[(size_t)q * nv + v];
+  CUDA_OK(cudaMalloc(&c->d_wind_idx, idx.size() * sizeof(long)));
+  CUDA_OK(cudaMalloc(&c->d_wind_val, soa.size() * sizeof(double)));
+  if (!c->mask) CUDA_OK(cudaMalloc(&c->mask, (size_t)g.vs));
+  CUDA_OK(cudaMemcpy(c->d_wind_idx, idx.data(), idx.size() * sizeof(long), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(c->d_wind_val, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(c->mask, mask.data(), (size_t)g.vs, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -206,6 +323,10 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
     cp.tables = c->d_tables;
     c->cfg.table_T = c->cfg.table_rrhp = c->cfg.table_C_rrh = c->cfg.table_C_ffhe = c->cfg.table_C_fbdn = c->cfg.table_C_cie = nullptr;
   }
+  for (int ib = 0; ib < cfg->n_internal_bc; ib++) {
+    if (cfg->internal_bc[ib] != PION_BC_STWIND) continue;
+    if (build_wind_cells(c)) { pion_gpu_destroy(c); return nullptr; }
+  }
   if (!ok) {
     set_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     pion_gpu_destroy(c);
@@ -226,7 +347,7 @@ extern "C" void pion_gpu_destroy(pion_gpu_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm) ncclCommDestroy(c->comm);
   cudaFree(c->P); cudaFree(c->Ph); cudaFree(c->dU); cudaFree(c->eta); cudaFree(c->hll); cudaFree(c->mask);
-  cudaFree(c->d_dtmin); cudaFree(c->d_counters); cudaFree(c->d_red); cudaFree(c->d_tables); cudaFree(c->mp_dE);
+  cudaFree(c->d_dtmin); cudaFree(c->d_counters); cudaFree(c->d_red); cudaFree(c->d_tables); cudaFree(c->mp_dE); cudaFree(c->d_wind_idx); cudaFree(c->d_wind_val);
   for (int f = 0; f < 6; f++) { cudaFree(c->sendbuf[f]); cudaFree(c->recvbuf[f]); }
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -318,6 +439,10 @@ static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A);
 // TimeUpdateInternalBCs + TimeUpdateExternalBCs on the given arrays (A1 may be null)
 static int update_bcs_arrays(pion_gpu_ctx* c, double* A0, double* A1, double simtime) {
   const GridD& g = c->g;
+  if (c->wind_n) {  // TimeUpdateInternalBCs: BC_update_STWIND writes P and Ph, before the external faces
+    k_wind_set<<<nblocks(c->wind_n * c->nvar, 256), 256, 0, c->stream>>>(g.vs, c->nvar, c->wind_n, c->d_wind_idx, c->d_wind_val, c->P, c->Ph);
+    c->launches++;
+  }
   for (int ax = 0; ax < g.ndim; ax++) {
     bool mpi_face = false;
     for (int s = 0; s < 2; s++) {
@@ -417,7 +542,7 @@ extern "C" int pion_gpu_init_after_upload(pion_gpu_ctx* c) {
     if (c->cfg.internal_bc[i] == PION_BC_DMACH2) {  // double_Mach_ref_boundaries.cpp:104-110
       rv[0] = 8.0; rv[1] = 116.5; rv[2] = 7.14470958; rv[3] = -4.125; rv[4] = 0.0;
       for (int v = c->nbase_; v < c->nvar; v++) rv[v] = 1.0;
-    } else {
+    } else if (c->cfg.internal_bc[i] != PION_BC_STWIND) {
       set_error("unsupported internal boundary");
       return 1;
     }
@@ -445,9 +570,9 @@ static int launch_calc_dt(pion_gpu_ctx* c) {
   CUDA_OK(cudaMemcpyAsync(c->d_dtmin, &DT_INIT_BITS, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
   const int blocks = nblocks(ncell, 256, 148 * 8);
   switch (c->cfg.eqntype) {
-    case PION_EQEUL: k_calc_dt<EQ_EULER><<<blocks, 256, 0, c->stream>>>(g, c->pp, c->P, nullptr, c->cfg.cfl, c->d_dtmin); break;
-    case PION_EQMHD: k_calc_dt<EQ_MHD><<<blocks, 256, 0, c->stream>>>(g, c->pp, c->P, nullptr, c->cfg.cfl, c->d_dtmin); break;
-    default: k_calc_dt<EQ_GLM><<<blocks, 256, 0, c->stream>>>(g, c->pp, c->P, nullptr, c->cfg.cfl, c->d_dtmin); break;
+    case PION_EQEUL: k_calc_dt<EQ_EULER><<<blocks, 256, 0, c->stream>>>(g, c->pp, c->P, c->mask, c->cfg.cfl, c->d_dtmin); break;
+    case PION_EQMHD: k_calc_dt<EQ_MHD><<<blocks, 256, 0, c->stream>>>(g, c->pp, c->P, c->mask, c->cfg.cfl, c->d_dtmin); break;
+    default: k_calc_dt<EQ_GLM><<<blocks, 256, 0, c->stream>>>(g, c->pp, c->P, c->mask, c->cfg.cfl, c->d_dtmin); break;
   }
   c->launches++;
   CUDA_OK(cudaGetLastError());
@@ -469,6 +594,9 @@ extern "C" int pion_gpu_calc_dt(pion_gpu_ctx* c, double* t_dyn, double* t_mp) {
   if (!c->next_dt_valid && launch_calc_dt(c)) return 1;
   double d;
   if (read_dtmin(c, &d)) return 1;
+  // first step with stellar winds: limit dt by the wind speed (calc_timestep.cpp:318-323)
+  if (c->timestep == 0)
+    for (int v = 0; v < c->cfg.n_wind; v++) d = fmin(d, 0.1 * c->cfg.cfl * c->g.dx / (c->cfg.wind[v].vinf * 1.0e5));
   if (t_dyn) *t_dyn = d;
   if (t_mp) {
     *t_mp = 1.0e99;  // calc_microphysics_dt without MP / without a limit (calc_timestep.cpp:348-357)

@@ -58,6 +58,7 @@ static int bc_code(const std::string& s) {
   if (s == "DMR") return PION_BC_DMACH;
   if (s == "DMR2") return PION_BC_DMACH2;
   if (s == "one-way-outflow") return PION_BC_ONEWAY_OUT;
+  if (s == "stellar-wind") return PION_BC_STWIND;
   return -1;
 }
 
@@ -113,6 +114,23 @@ int main(int argc, char** argv) {
     char key[16];
     snprintf(key, sizeof key, "refvec%d", v);
     p.RefVec[v] = getd(kv, key, 1.0);
+  }
+  // stellar wind sources (ics/get_sim_info.cpp:702-875), constant type only
+  for (int i = 0; i < geti(kv, "WIND_NSRC", 0); i++) {
+    auto key = [&](const char* suffix) { return "WIND_" + std::to_string(i) + "_" + suffix; };
+    if (geti(kv, key("type").c_str(), 0) != 0) { fprintf(stderr, "only constant winds (WIND_%d_type 0)\n", i); return 1; }
+    pion_gpu_wind_source w;
+    memset(&w, 0, sizeof w);
+    for (int a = 0; a < 3; a++) w.dpos[a] = getd(kv, key(("pos" + std::to_string(a)).c_str()).c_str(), 0.0);
+    w.radius = getd(kv, key("radius").c_str(), 0.0);
+    w.mdot = getd(kv, key("mdot").c_str(), 0.0);
+    w.vinf = getd(kv, key("vinf").c_str(), 0.0);
+    w.vrot = getd(kv, key("vrot").c_str(), 0.0);
+    w.temp = getd(kv, key("temp").c_str(), 0.0);
+    w.rstar = getd(kv, key("Rstr").c_str(), 0.0);
+    w.bsrf = getd(kv, key("Bsrf").c_str(), 0.0);
+    for (int t = 0; t < p.ntracer && t < PION_GPU_MAXTR; t++) w.tr[t] = getd(kv, key(("TR" + std::to_string(t)).c_str()).c_str(), 0.0);
+    p.SWP.push_back(w);
   }
   p.starttime = p.simtime = getd(kv, "StartTime", 0.0);
   p.finishtime = getd(kv, "FinishTime", 1e30);

@@ -73,6 +73,8 @@ int sim_control_gpu::Init(int device, const double* P_soa) {
   c.table_C_ffhe = SimPM.table_C_ffhe.data();
   c.table_C_fbdn = SimPM.table_C_fbdn.data();
   c.table_C_cie = SimPM.table_C_cie.data();
+  c.n_wind = (int)SimPM.SWP.size();
+  for (int i = 0; i < c.n_wind && i < 2; i++) c.wind[i] = SimPM.SWP[i];
   c.rank = 0;
   c.nproc = 1;
   Finalise();

@@ -48,6 +48,8 @@ struct SimParamsGPU {
     int cooling = 0, MP_timestep_limit = 0;
     double MinTemperature = 0, MaxTemperature = 1e99;
   } EP;
+  // struct stellarwind_list SWP (sim_params.h:340-380): constant wind sources
+  std::vector<pion_gpu_wind_source> SWP;
   // mp_only_cooling lookup tables (mp_only_cooling.cpp:528-556), 6 columns of n_table values
   std::vector<double> table_T, table_rrhp, table_C_rrh, table_C_ffhe, table_C_fbdn, table_C_cie;
   long Ncell() const { return (long)NG[0] * NG[1] * NG[2]; }

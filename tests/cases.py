@@ -36,3 +36,27 @@ def case_cooling(eqn="euler", solver=8, ndim=3, NG=(12, 10, 8), ntracer=1, mp_li
                    xmax=(NG[0] * dx, NG[1] * dx, NG[2] * dx if ndim > 2 else 1.0), bcs=BCSETS[bcs], ntracer=ntracer, ooa=ooa,
                    cooling=8, mp_timestep_limit=mp_limit, min_temperature=5.0e3, max_temperature=1.0e8,
                    refvec=(2.0e-24, 3.0e-10, 1.0e6, 1.0e6, 1.0e6, 1.0e-6, 1.0e-6, 1.0e-6, 1.0e-6) + (1.0,) * 7)
+
+
+def case_wind(eqn="euler", solver=8, ndim=3, NG=(16, 16, 16), cooling=True, vrot=0.0):
+    """Wind3D-style octant (SURVEY 8d config 5 at test size): constant stellar wind at the origin corner,
+    reflecting N faces / one-way-outflow P faces, 1 tracer, EP_cooling 8 with MP_timestep_limit 1."""
+    import dataclasses
+    base = case_cooling(eqn, solver, ndim=ndim, NG=NG, ntracer=1, mp_limit=1)
+    wind = dict(pos=(0.0, 0.0, 0.0), radius=4.3 * base.dx, mdot=1.0e-7, vinf=1500.0, vrot=vrot, temp=3.0e4, rstar=6.96e11,
+                bsrf=10.0, tr=(1.0, 0.0, 0.0, 0.0))
+    kw = dict(internal_bcs=("stellar-wind",), winds=(wind,), bcs=("reflecting", "one-way-outflow") * 3)
+    if not cooling:
+        kw.update(cooling=0, mp_timestep_limit=0, min_temperature=0.0, max_temperature=1.0e99)
+    return dataclasses.replace(base, **kw)
+
+
+def wind_ambient_state(prob):
+    """Uniform Wind3D ambient medium (params_Wind3D_n0128_l2.txt: rho 2.124e-24, p 2.209e-12, tracer 0)."""
+    import numpy as np
+    P = np.zeros(prob.padded_shape())
+    P[0] = 2.124e-24
+    P[1] = 2.209e-12
+    if prob.eqn != "euler":
+        P[5] = 1.0e-6
+    return P

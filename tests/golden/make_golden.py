@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent))
-from cases import case_1d, case_2d, case_3d, case_cooling  # noqa: E402
+from cases import case_1d, case_2d, case_3d, case_cooling, case_wind, wind_ambient_state  # noqa: E402
 from harness import COOLING_TABLES, TABLE_KEYS, RefSim, cooling_state, random_state  # noqa: E402
 
 CASES = {
@@ -69,10 +69,22 @@ COOLING = {
 }
 CASES.update({k: v[:2] for k, v in COOLING.items()})
 
+# Stellar-wind internal boundary + cooling: the Wind3D configuration at 16^3 / 24^2
+WIND = {
+    "wind3d_euler_hll_cool_n016": (case_wind("euler", 8), 14),
+    "wind3d_glm_hlld_nocool_n012": (case_wind("glm-mhd", 7, NG=(12, 12, 12), cooling=False, vrot=20.0), 6),
+    "wind3d_euler_roe_nocool_n012": (case_wind("euler", 4, NG=(12, 12, 12), cooling=False), 6),
+}
+CASES.update(WIND)
+
 
 def main():
     for name, (prob, nsteps) in CASES.items():
-        if name in COOLING:
+        if name in WIND:
+            r = RefSim(prob)
+            P0 = wind_ambient_state(prob)
+            r.set_state(P0)
+        elif name in COOLING:
             r = RefSim(prob)
             if not COOLING_TABLES.exists() or name == next(iter(COOLING)):
                 tab = r.cooling_tables()

@@ -28,7 +28,7 @@ EQN_NAMES = {"euler": 1, "i-mhd": 2, "glm-mhd": 3}
 EQN_NVAR = {"euler": 5, "i-mhd": 8, "glm-mhd": 9}
 BC_CODES = {
     "periodic": 1, "outflow": 2, "inflow": 3, "reflecting": 4, "fixed": 5,
-    "DMR": 8, "DMR2": 9, "one-way-outflow": 13,
+    "DMR": 8, "DMR2": 9, "one-way-outflow": 13, "stellar-wind": 14,
 }
 PO_MAXVAR = 16
 
@@ -62,6 +62,9 @@ class Problem:
     mp_timestep_limit: int = 0
     min_temperature: float = 0.0
     max_temperature: float = 1.0e99
+    # constant stellar-wind sources (internal boundary "stellar-wind"): dicts with keys
+    # pos (3), radius, mdot [Msun/yr], vinf, vrot [km/s], temp [K], rstar [cm], bsrf [G], tr (tuple)
+    winds: tuple = ()
 
     @property
     def nvar(self):
@@ -116,7 +119,17 @@ class Problem:
             L.append(f"BC_INTERNAL_{i:03d} {b}")
         L += [f"GAMMA {f(self.gamma)}", f"CFL {f(self.cfl)}", f"ArtificialViscosity {self.artviscosity}",
               f"EtaViscosity {f(self.etav)}", "units SI", "rhoval 1.0", "lenval 1.0", "velval 1.0", "magval 1.0",
-              "RT_Nsources 0", "WIND_NSRC 0", "N_JET 0"]
+              "RT_Nsources 0", f"WIND_NSRC {len(self.winds)}", "N_JET 0"]
+        for i, w in enumerate(self.winds):
+            L += [f"WIND_{i}_pos{a} {f(float(w['pos'][a]))}" for a in range(3)]
+            L += [f"WIND_{i}_radius {f(float(w['radius']))}", f"WIND_{i}_type 0", f"WIND_{i}_mdot {f(float(w['mdot']))}",
+                  f"WIND_{i}_vinf {f(float(w['vinf']))}", f"WIND_{i}_vrot {f(float(w.get('vrot', 0.0)))}",
+                  f"WIND_{i}_temp {f(float(w['temp']))}", f"WIND_{i}_Rstr {f(float(w['rstar']))}",
+                  f"WIND_{i}_Bsrf {f(float(w.get('bsrf', 0.0)))}", f"WIND_{i}_evofile NOFILE", f"WIND_{i}_t_offset 0.0",
+                  f"WIND_{i}_t_scalefac 1.0", f"WIND_{i}_updatefreq 1.0", f"WIND_{i}_enhance_mdot 0", f"WIND_{i}_xi 0.0",
+                  f"WIND_{i}_ecentricity_fac 0.0", f"WIND_{i}_orbital_period 0.0", f"WIND_{i}_periastron_vec_x 0.0",
+                  f"WIND_{i}_periastron_vec_y 0.0"]
+            L += [f"WIND_{i}_TR{t} {f(float(w.get('tr', (1.0,) * 4)[t]))}" for t in range(self.ntracer)]
         for v in range(PO_MAXVAR):
             L.append(f"refvec{v} {f(float(self.refvec[v]))}")
         for k, v in self.extra.items():
@@ -291,6 +304,13 @@ class RefSim(_CSim):
         return out
 
 
+class WindSource(C.Structure):
+    """struct po_wind_source == struct pion_gpu_wind_source."""
+    _fields_ = [("dpos", C.c_double * 3), ("radius", C.c_double), ("mdot", C.c_double), ("vinf", C.c_double),
+                ("vrot", C.c_double), ("temp", C.c_double), ("rstar", C.c_double), ("bsrf", C.c_double),
+                ("tr", C.c_double * 4)]
+
+
 class _OracleConfig(C.Structure):
     _fields_ = [
         ("ndim", C.c_int), ("NG", C.c_int * 3), ("nvar", C.c_int), ("ntracer", C.c_int), ("eqntype", C.c_int),
@@ -306,7 +326,21 @@ class _OracleConfig(C.Structure):
         ("n_table", C.c_int),
         ("table_T", C.c_void_p), ("table_rrhp", C.c_void_p), ("table_C_rrh", C.c_void_p),
         ("table_C_ffhe", C.c_void_p), ("table_C_fbdn", C.c_void_p), ("table_C_cie", C.c_void_p),
+        ("n_wind", C.c_int), ("wind", WindSource * 2),
     ]
+
+
+def fill_winds(c, prob):
+    """Problem.winds -> the n_wind / wind[] members shared by the oracle and the GPU config."""
+    c.n_wind = len(prob.winds)
+    for i, w in enumerate(prob.winds):
+        ws = c.wind[i]
+        for a in range(3):
+            ws.dpos[a] = w["pos"][a]
+        ws.radius, ws.mdot, ws.vinf, ws.vrot = w["radius"], w["mdot"], w["vinf"], w.get("vrot", 0.0)
+        ws.temp, ws.rstar, ws.bsrf = w["temp"], w["rstar"], w.get("bsrf", 0.0)
+        for t in range(4):
+            ws.tr[t] = w.get("tr", (1.0,) * 4)[t]
 
 
 def effective_etav(prob: Problem):
@@ -340,6 +374,7 @@ def oracle_config(prob: Problem, tables=None):
     c.op_criterion, c.opfreq_time = prob.op_criterion, prob.opfreq_time
     c.cooling, c.mp_timestep_limit = prob.cooling, prob.mp_timestep_limit
     c.min_temperature, c.max_temperature = prob.min_temperature, prob.max_temperature
+    fill_winds(c, prob)
     keep = []
     if tables is not None:
         c.n_table = len(tables["T"])
@@ -521,6 +556,7 @@ def gpu_config(prob: Problem, device=0, tables=None):
     c.cooling, c.mp_timestep_limit = prob.cooling, prob.mp_timestep_limit
     c.min_temperature, c.max_temperature = prob.min_temperature, prob.max_temperature
     c.rank, c.nproc = 0, 1
+    fill_winds(c, prob)
     keep = []
     if tables is not None:
         c.n_table = len(tables["T"])

@@ -46,7 +46,8 @@ def _load_case(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["tp_BWcrt3D_octant_n016", "tp_DMR_n065_roe", "tp_FieldLoop_64x32_hlld",
-                                  "glm_hlld_fkj_3d_outflow", "cool_euler_hll_3d_dense"])
+                                  "glm_hlld_fkj_3d_outflow", "cool_euler_hll_3d_dense", "wind3d_euler_hll_cool_n016",
+                                  "wind3d_glm_hlld_nocool_n012"])
 def test_cpp_driver_reproduces_reference_golden(name):
     prob, nsteps, z = _load_case(name)
     with tempfile.TemporaryDirectory() as d:

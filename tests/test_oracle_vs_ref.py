@@ -131,3 +131,35 @@ def test_committed_cooling_tables_match_reference():
     r.close()
     for k in TABLE_KEYS:
         assert np.array_equal(tab[k], gold[k]), k
+
+
+# ------------------------------------------------------------------------------------------
+# stellar-wind internal boundary (constant source), with and without cooling
+from cases import case_wind, wind_ambient_state  # noqa: E402
+
+
+@pytest.mark.parametrize("eqn,solver,ndim,NG,cooling,vrot", [
+    ("euler", 8, 3, (16, 16, 16), True, 0.0),
+    ("glm-mhd", 7, 3, (12, 12, 12), False, 20.0),
+    ("i-mhd", 8, 2, (24, 24, 1), True, 20.0),
+    ("euler", 4, 2, (24, 24, 1), False, 0.0),
+])
+def test_stellar_wind_bit_exact(eqn, solver, ndim, NG, cooling, vrot):
+    prob = case_wind(eqn, solver, ndim=ndim, NG=NG, cooling=cooling, vrot=vrot)
+    r = RefSim(prob)
+    o = OracleSim(prob, tables=r.cooling_tables() if cooling else None)
+    try:
+        P = wind_ambient_state(prob)
+        for s in (r, o):
+            s.set_state(P)
+            assert s.init_after_state() == 0
+        assert np.array_equal(r.get_flags(), o.get_flags())  # isbd / isdomain / timestep of the wind cells
+        assert np.array_equal(r.get_state(0), o.get_state(0))
+        assert r.dynamics_dt() == o.dynamics_dt()  # first-step wind limit (calc_timestep.cpp:318-323)
+        dr, do = r.run(5), o.run(5)
+        assert np.array_equal(dr, do)
+        assert np.array_equal(r.get_state(0), o.get_state(0))
+        assert np.array_equal(r.get_state(1), o.get_state(1))
+    finally:
+        r.close()
+        o.close()
