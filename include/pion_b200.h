@@ -65,7 +65,7 @@ typedef struct pion_gpu_config {
   int NG[3];           /* LOCAL interior cells per axis (SimPM.NG / MCMD LocalNG) */
   int nvar, ntracer;   /* SimPM.nvar, SimPM.ntracer (tracers are the last ntracer variables) */
   int eqntype;         /* SimPM.eqntype */
-  int coord_sys;       /* SimPM.coord_sys (only PION_COORD_CRT in this round) */
+  int coord_sys;       /* SimPM.coord_sys: Cartesian 1-3D, cylindrical (z,R) 2-D, spherical 1-D Euler */
   int solver;          /* SimPM.solverType: 4 Roe-CV, 7 HLLD, 8 HLL */
   int artviscosity;    /* SimPM.artviscosity: 0,1,3,4 */
   int spOOA, tmOOA;    /* SimPM.spOOA / tmOOA: (1,1) or (2,2) */

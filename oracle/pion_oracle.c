@@ -881,6 +881,29 @@ static void inter_cell_flux(pion_oracle *s, long cl, long cr, const double *lp, 
 /* ------------------------------------------------------------------ */
 /* coord_sys/VectorOps (Cartesian)                                     */
 /* ------------------------------------------------------------------ */
+/* centre-of-volume radius of a cell: cylindrical VectorOps.h:414-418, spherical
+ * VectorOps_spherical.h:188-197; R3 (spherical, :172-178) */
+static inline double R_com_cyl(const pion_oracle *s, long c) {
+  double R = dpos(s, c, 1);
+  return R + s->dx * s->dx / 12. / R;
+}
+static inline double R_com_sph(const pion_oracle *s, long c) {
+  double R = dpos(s, c, 0);
+  double delta2 = s->dx / R;
+  delta2 *= delta2;
+  return R * (1.0 + 0.25 * delta2) / (1.0 + delta2 / 12.0);
+}
+static inline double R3_sph(const pion_oracle *s, long c) {
+  double R = dpos(s, c, 0);
+  return R + s->dx * s->dx / 12.0 / R;
+}
+/* is `axis` the radial axis of a curvilinear grid?  (Rcyl = YY in 2-D axisymmetry, Rsph = XX) */
+static inline int radial_axis(const pion_oracle *s, int axis) {
+  return (s->cfg.coord_sys == PO_COORD_CYL && axis == 1) || (s->cfg.coord_sys == PO_COORD_SPH && axis == 0);
+}
+static inline double R_com(const pion_oracle *s, long c) {
+  return (s->cfg.coord_sys == PO_COORD_CYL) ? R_com_cyl(s, c) : R_com_sph(s, c);
+}
 /* BaseVectorOps::AvgFalle, AVG_MINMOD variant (VectorOps.cpp:40-59) */
 static inline double avg_falle(double a, double b) {
   if (a * b <= VERY_TINY_VALUE) return 0.0;
@@ -899,6 +922,18 @@ static void set_slope(const pion_oracle *s, long c, int axis, double *dpdx, int 
   if (cn < 0) cn = nextpt(s, cp, 2 * axis);
   const double *Pc = s->Ph + c * nv, *Pn = s->Ph + cn * nv, *Pp = s->Ph + cp * nv;
   double dx = s->dx;
+  if (radial_axis(s, axis)) {
+    /* VectorOps_Cyl::SetSlope case Rcyl (VectorOps.cpp:1158-1182), VectorOps_Sph::SetSlope
+     * (VectorOps_spherical.cpp:372-380): divided differences between centres of volume; a missing
+     * neighbour gives a zero one-sided slope (cyl :1159,:1167) */
+    int noneg = nextpt(s, c, 2 * axis) < 0, nopos = nextpt(s, c, 2 * axis + 1) < 0;
+    for (int v = 0; v < nv; v++) {
+      double slpn = noneg ? 0.0 : (Pc[v] - Pn[v]) / (R_com(s, c) - R_com(s, cn));
+      double slpp = nopos ? 0.0 : (Pp[v] - Pc[v]) / (R_com(s, cp) - R_com(s, c));
+      dpdx[v] = avg_falle(slpn, slpp);
+    }
+    return;
+  }
   for (int v = 0; v < nv; v++) {
     double slpn = (Pc[v] - Pn[v]) / dx;
     double slpp = (Pp[v] - Pc[v]) / dx;
@@ -912,6 +947,11 @@ static void set_edge_state(const pion_oracle *s, long c, int positive, const dou
   double dx = s->dx;
   if (OA == OA1) {
     for (int v = 0; v < nv; v++) edge[v] = Pc[v];
+  } else if (radial_axis(s, s->dir)) {
+    /* VectorOps_Cyl::SetEdgeState RPcyl/RNcyl (VectorOps.cpp:1073-1079), VectorOps_Sph (:312-318) */
+    double R = dpos(s, c, s->dir);
+    double del = positive ? (R + dx * 0.5 - R_com(s, c)) : (R - dx * 0.5 - R_com(s, c));
+    for (int v = 0; v < nv; v++) edge[v] = Pc[v] + dpdx[v] * del;
   } else if (positive) {
     for (int v = 0; v < nv; v++) edge[v] = Pc[v] + dpdx[v] * dx * 0.5;
   } else {
@@ -927,6 +967,11 @@ static double divergence_v(const pion_oracle *s, long c) {
     if (n < 0) n = c;
     if (p < 0) p = c;
     double d = (n == c || p == c) ? s->dx : 2.0 * s->dx;
+    if (s->cfg.coord_sys == PO_COORD_CYL && v == 1) { /* VectorOps_Cyl::Divergence (VectorOps.cpp:948-954) */
+      double rn = R_com_cyl(s, n), rp = R_com_cyl(s, p);
+      divv += 2.0 * (rp * s->Ph[p * nv + VX + v] - rn * s->Ph[n * nv + VX + v]) / (rp * rp - rn * rn);
+      continue;
+    }
     divv += (s->Ph[p * nv + VX + v] - s->Ph[n * nv + VX + v]) / d;
   }
   return divv;
@@ -1017,9 +1062,17 @@ static void mhd_source(pion_oracle *s, long cl, long cr, double dt) {
   pl[s->eBBX] = L[s->eVX]; pl[s->eBBY] = L[s->eVY]; pl[s->eBBZ] = L[s->eVZ];
   pr[s->eMX] = R[s->eBX]; pr[s->eMY] = R[s->eBY]; pr[s->eMZ] = R[s->eBZ]; pr[ERG] = uB_r;
   pr[s->eBBX] = R[s->eVX]; pr[s->eBBY] = R[s->eVY]; pr[s->eBBZ] = R[s->eVZ];
-  for (int v = 0; v < nv; v++) {
-    dUl[v] -= dt * bm * (pl[v]) / dx;
-    dUr[v] += dt * bm * (pr[v]) / dx;
+  if (radial_axis(s, s->dir)) { /* cyl_FV_solver_mhd_ideal_adi::MHDsource case Rcyl (solver_eqn_mhd_adi.cpp:1087-1098) */
+    double rp = dpos(s, cl, 1) + dx * 0.5, rn = rp - dx;
+    for (int v = 0; v < nv; v++) dUl[v] -= dt * bm * (pl[v]) * 2.0 * rp / (rp * rp - rn * rn);
+    rn = rp;
+    rp += dx;
+    for (int v = 0; v < nv; v++) dUr[v] += dt * bm * (pr[v]) * 2.0 * rn / (rp * rp - rn * rn);
+  } else {
+    for (int v = 0; v < nv; v++) {
+      dUl[v] -= dt * bm * (pl[v]) / dx;
+      dUr[v] += dt * bm * (pr[v]) / dx;
+    }
   }
   if (s->cfg.eqntype == PO_EQGLM) {
     for (int v = 0; v < nv; v++) pl[v] = pr[v] = 0.0;
@@ -1036,15 +1089,45 @@ static void mhd_source(pion_oracle *s, long cl, long cr, double dt) {
 /* dU_Cell: Euler uses the dt argument (solver_eqn_hydro_adi.cpp:342-363), MHD
  * uses FV_dt (solver_eqn_mhd_adi.cpp:368-387); DivStateVectorComponent
  * VectorOps.cpp:624-644.  Cartesian: no geometric source. */
-static void dU_cell(pion_oracle *s, long c, const double *fn, const double *fp, double dt) {
+static void dU_cell(pion_oracle *s, long c, const double *fn, const double *fp, const double *dpdx, int OA, double dt) {
   int nv = s->nv;
   double dx = s->dx;
   double mult = (s->cfg.eqntype == PO_EQEUL) ? dt : s->FV_dt;
   double *dU = s->dU + c * nv;
-  for (int v = 0; v < nv; v++) {
-    double u1 = (fn[v] - fp[v]) / dx;
-    dU[v] += mult * u1;
+  double u1[PO_MAXVAR];
+  if (!radial_axis(s, s->dir)) {
+    for (int v = 0; v < nv; v++) u1[v] = (fn[v] - fp[v]) / dx;
+  } else if (s->cfg.coord_sys == PO_COORD_CYL) {
+    /* VectorOps_Cyl::DivStateVectorComponent Rcyl (VectorOps.cpp:1228-1232) */
+    double rp = dpos(s, c, 1) + dx * 0.5, rn = rp - dx;
+    for (int v = 0; v < nv; v++) u1[v] = 2.0 * (rn * fn[v] - rp * fp[v]) / (rp * rp - rn * rn);
+    /* geometric_source: Euler solver_eqn_hydro_adi.cpp:560-590, MHD solver_eqn_mhd_adi.cpp:1001-1036,
+     * GLM :1156-1190 */
+    const double *Ph = s->Ph + c * nv;
+    double R = dpos(s, c, 1);
+    double ptot = Ph[PG], dptot = dpdx[PG];
+    if (s->cfg.eqntype != PO_EQEUL) {
+      ptot += (Ph[s->eBX] * Ph[s->eBX] + Ph[s->eBY] * Ph[s->eBY] + Ph[s->eBZ] * Ph[s->eBZ]) / 2.;
+      dptot = (dpdx[PG] + Ph[s->eBX] * dpdx[s->eBX] + Ph[s->eBY] * dpdx[s->eBY] + Ph[s->eBZ] * dpdx[s->eBZ]);
+    }
+    if (OA == OA1) u1[s->eMX] += ptot / R;
+    else u1[s->eMX] += (ptot + (R - R_com_cyl(s, c)) * dptot) / R;
+    if (s->cfg.eqntype == PO_EQGLM) {
+      if (OA == OA1) u1[s->eBBX] += s->chyp * Ph[SI] / R;
+      else u1[s->eBBX] += s->chyp * (Ph[SI] + (R - R_com_cyl(s, c)) * dpdx[SI]) / R;
+    }
+  } else {
+    /* VectorOps_Sph::DivStateVectorComponent (VectorOps_spherical.cpp:462-467) +
+     * sph_FV_solver_Hydro_Euler::geometric_source (solver_eqn_hydro_adi.cpp:648-668) */
+    double rc = dpos(s, c, 0);
+    double rp = rc + 0.5 * dx, rn = rp - dx;
+    rc = (pow(rp, 3.0) - pow(rn, 3.0)) / 3.0;
+    for (int v = 0; v < nv; v++) u1[v] = (rn * rn * fn[v] - rp * rp * fp[v]) / rc;
+    const double *Ph = s->Ph + c * nv;
+    if (OA == OA1) u1[s->eMX] += 2.0 * Ph[PG] / R3_sph(s, c);
+    else u1[s->eMX] += 2.0 * ((Ph[PG] - dpdx[PG] * R_com_sph(s, c)) / R3_sph(s, c) + dpdx[PG]);
   }
+  for (int v = 0; v < nv; v++) dU[v] += mult * u1[v];
 }
 /* time_integrator::dynamics_dU_column (time_integrator.cpp:645-873) */
 static void dynamics_dU_column(pion_oracle *s, long start, int axis, double dt, int csp) {
@@ -1060,7 +1143,7 @@ static void dynamics_dU_column(pion_oracle *s, long start, int axis, double dt, 
     set_edge_state(s, npt, 0, slope_npt, edgeR, csp);
     inter_cell_flux(s, cpt, npt, edgeL, edgeR, Fr_this);
     mhd_source(s, cpt, npt, dt);
-    dU_cell(s, cpt, Fr_prev, Fr_this, dt);
+    dU_cell(s, cpt, Fr_prev, Fr_this, slope_cpt, csp, dt);
     tmp = Fr_prev; Fr_prev = Fr_this; Fr_this = tmp;
     tmp = slope_cpt; slope_cpt = slope_npt; slope_npt = tmp;
     cpt = npt;
@@ -1072,7 +1155,7 @@ static void dynamics_dU_column(pion_oracle *s, long start, int axis, double dt, 
   set_edge_state(s, npt, 0, slope_npt, edgeR, csp);
   inter_cell_flux(s, cpt, npt, edgeL, edgeR, Fr_this);
   mhd_source(s, cpt, npt, dt);
-  dU_cell(s, cpt, Fr_prev, Fr_this, dt);
+  dU_cell(s, cpt, Fr_prev, Fr_this, slope_cpt, csp, dt);
 }
 /* time_integrator::set_dynamics_dU (time_integrator.cpp:553-636) */
 static void set_dynamics_dU(pion_oracle *s, double dt, int step) {

@@ -34,7 +34,13 @@ __global__ void k_hlld_flags(GridD g, const double* __restrict__ S, unsigned cha
     for (int ax = 0; ax < g.ndim; ax++) {
       long st = axis_stride(g, ax);
       const double* V = S + (2 + ax) * g.vs;
-      divv += (__ldg(V + c + st) - __ldg(V + c - st)) * id2;
+      if (radial_axis(g, ax)) {  // VectorOps_Cyl::Divergence: d(R v_R)/(R dR) between centres of volume (VectorOps.cpp:948-954)
+        const int q = (ax == 0) ? i : j;
+        const double rn = cell_Rcom(g, cell_R(g, ax, q - 1)), rp = cell_Rcom(g, cell_R(g, ax, q + 1));
+        divv += 2.0 * (rp * __ldg(V + c + st) - rn * __ldg(V + c - st)) / (rp * rp - rn * rn);
+      } else {
+        divv += (__ldg(V + c + st) - __ldg(V + c - st)) * id2;
+      }
       double pp = __ldg(S + g.vs + c + st), pn = __ldg(S + g.vs + c - st);
       gradp += fabs(pp - pn) * fast_rcp(fmin(pp, pn));
     }
@@ -67,6 +73,7 @@ __global__ void k_hcorr_eta(GridD g, const double* __restrict__ S, double* __res
         const bool slopeC = (q >= 1), slopeP = (q + 2 < nq);
         Prim M1 = slopeC ? load_prim<EQ>(S, c - st, g.vs, ax, a1, a2) : C;
         Prim P2 = slopeP ? load_prim<EQ>(S, c + 2 * st, g.vs, ax, a1, a2) : P1;
+        if (!radial_axis(g, ax)) {
 #define PION_HE(f)                                                                        \
   {                                                                                       \
     double sc = slopeC ? minmod(C.f - M1.f, P1.f - C.f, tiny2) : 0.0;                      \
@@ -74,9 +81,26 @@ __global__ void k_hcorr_eta(GridD g, const double* __restrict__ S, double* __res
     eL.f = C.f + sc * 0.5;                                                                \
     eR.f = P1.f - sp * 0.5;                                                               \
   }
-        PION_HE(ro) PION_HE(pg) PION_HE(vn)
-        if (EQ != EQ_EULER) { PION_HE(bn) PION_HE(bt1) PION_HE(bt2) }
+          PION_HE(ro) PION_HE(pg) PION_HE(vn)
+          if (EQ != EQ_EULER) { PION_HE(bn) PION_HE(bt1) PION_HE(bt2) }
 #undef PION_HE
+        } else {
+          // curvilinear radial axis: slopes between centres of volume, edge offsets from them
+          double Rq[4], Rcm[4];
+          for (int w = 0; w < 4; w++) { Rq[w] = cell_R(g, ax, q - 1 + w); Rcm[w] = cell_Rcom(g, Rq[w]); }
+          const double i01 = 1.0 / (Rcm[1] - Rcm[0]), i12 = 1.0 / (Rcm[2] - Rcm[1]), i23 = 1.0 / (Rcm[3] - Rcm[2]);
+          const double delL = Rq[1] + 0.5 * g.dx - Rcm[1], delR = Rq[2] - 0.5 * g.dx - Rcm[2];
+#define PION_HER(f)                                                                                              \
+  {                                                                                                              \
+    double sc = slopeC ? minmod((C.f - M1.f) * i01, (P1.f - C.f) * i12, PION_VERY_TINY_VALUE) : 0.0;              \
+    double sp = slopeP ? minmod((P1.f - C.f) * i12, (P2.f - P1.f) * i23, PION_VERY_TINY_VALUE) : 0.0;             \
+    eL.f = C.f + sc * delL;                                                                                      \
+    eR.f = P1.f + sp * delR;                                                                                     \
+  }
+          PION_HER(ro) PION_HER(pg) PION_HER(vn)
+          if (EQ != EQ_EULER) { PION_HER(bn) PION_HER(bt1) PION_HER(bt2) }
+#undef PION_HER
+        }
       }
       double e = 0.5 * (fabs(eR.vn - eL.vn) + fabs(maxspeed<EQ>(eR, gamma) - maxspeed<EQ>(eL, gamma)));
       eta[(long)ax * g.vs + c] = e;

@@ -26,6 +26,10 @@ struct GridD {
   long sy, sz; // element strides of y and z (x stride is 1)
   long vs;     // variable stride
   double dx;
+  // coordinate system (constants.h COORD_*: 1 Cartesian, 2 cylindrical (z,R) 2-D, 3 spherical 1-D) and the
+  // position of the low edge of the first interior cell along the radial axis
+  int coord;
+  double r0;
 };
 
 __host__ __device__ __forceinline__ long gidx(const GridD& g, int i, int j, int k) {
@@ -33,6 +37,22 @@ __host__ __device__ __forceinline__ long gidx(const GridD& g, int i, int j, int 
 }
 __host__ __device__ __forceinline__ long axis_stride(const GridD& g, int ax) {
   return (ax == 0) ? 1L : (ax == 1) ? g.sy : g.sz;
+}
+
+// radial axis of a curvilinear grid: Rcyl = axis 1 of the 2-D (z,R) grid, Rsph = axis 0 in 1-D
+__host__ __device__ __forceinline__ bool radial_axis(const GridD& g, int ax) {
+  return (g.coord == 2 && ax == 1) || (g.coord == 3 && ax == 0);
+}
+// cell-centre radius of padded index q along the radial axis (cell_interface.cpp:506-512)
+__host__ __device__ __forceinline__ double cell_R(const GridD& g, int ax, int q) {
+  return g.r0 + (2 * (q - g.nb[ax]) + 1) * (0.5 * g.dx);
+}
+// centre-of-volume radius: cylindrical VectorOps.h:414-418, spherical VectorOps_spherical.h:188-197
+__host__ __device__ __forceinline__ double cell_Rcom(const GridD& g, double R) {
+  if (g.coord == 2) return R + g.dx * g.dx / 12. / R;
+  double d2 = g.dx / R;
+  d2 *= d2;
+  return R * (1.0 + 0.25 * d2) / (1.0 + d2 / 12.0);
 }
 
 // number of non-tracer variables

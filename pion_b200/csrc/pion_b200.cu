@@ -99,7 +99,11 @@ extern "C" const char* pion_gpu_last_error(void) { return g_last_error.c_str(); 
 static int check_config(const pion_gpu_config& c) {
   if (c.ndim < 1 || c.ndim > 3) { set_error("ndim must be 1..3"); return 1; }
   if (c.eqntype != PION_EQEUL && c.eqntype != PION_EQMHD && c.eqntype != PION_EQGLM) { set_error("unsupported eqntype"); return 1; }
-  if (c.coord_sys != PION_COORD_CRT) { set_error("only Cartesian coordinates in this round"); return 1; }
+  if (c.coord_sys != PION_COORD_CRT && c.coord_sys != PION_COORD_CYL && c.coord_sys != PION_COORD_SPH) { set_error("Bad Geometry in setup_grid()"); return 1; }
+  // setup_fixed_grid.cpp:1133-1190 / solver constructors: axisymmetry is 2-D (z,R), spherical symmetry 1-D Euler
+  if (c.coord_sys == PION_COORD_CYL && c.ndim != 2) { set_error("Cylindrical coordinates only implemented for 2d axial symmetry"); return 1; }
+  if (c.coord_sys == PION_COORD_SPH && (c.ndim != 1 || c.eqntype != PION_EQEUL)) { set_error("Spherical coordinates only implemented for 1D Euler"); return 1; }
+  if (c.coord_sys != PION_COORD_CRT && c.n_wind > 0) { set_error("stellar-wind boundary: only Cartesian grids are built"); return 1; }
   if (c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL) { set_error("solver must be 4 (Roe-CV), 7 (HLLD) or 8 (HLL)"); return 1; }
   if (c.eqntype == PION_EQEUL && c.solver == PION_FLUX_HLLD) { set_error("HLLD needs MHD equations"); return 1; }
   if (c.artviscosity != 0 && c.artviscosity != 1 && c.artviscosity != 3 && c.artviscosity != 4) { set_error("artviscosity must be 0,1,3,4"); return 1; }
@@ -266,6 +270,8 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   g.sz = pitch * g.NGa[1];
   g.vs = ((pitch * g.NGa[1] * g.NGa[2]) + 15) / 16 * 16;
   g.dx = (cfg->xmax[0] - cfg->xmin[0]) / g.NG[0];  // UniformGrid::set_cell_size
+  g.coord = cfg->coord_sys;
+  g.r0 = (cfg->coord_sys == PION_COORD_CYL) ? cfg->xmin[1] : cfg->xmin[0];
   c->nvar = cfg->nvar;
   c->ntr = cfg->ntracer;
   c->nbase_ = cfg->nvar - cfg->ntracer;
@@ -742,7 +748,7 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   }
   // fused 2-D/3-D stages run the flux-once sweep kernel; 1-D grids and the unfused seam
   // call (calc_dynamics_dU) run the per-cell gather kernel
-  const bool sweep = fused && c->g.ndim >= 2 && !c->force_gather;
+  const bool sweep = fused && c->g.ndim >= 2 && c->g.coord == PION_COORD_CRT && !c->force_gather;
   switch (c->cfg.eqntype) {
     case PION_EQEUL: (sweep ? launch_sweep_euler : launch_stage_euler)(c->cfg.solver, fkj, a, c->stream); break;
     case PION_EQMHD: (sweep ? launch_sweep_mhd : launch_stage_mhd)(c->cfg.solver, fkj, a, c->stream); break;

@@ -184,9 +184,18 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
         const Prim P1 = load_prim<EQ>(a.S, c + st, vs, ax, a1, a2);
         // edge states at the low (i-1/2) and high (i+1/2) faces
         Prim lowL = M1, lowR = C, highL = C, highR = P1;
+        // curvilinear radial axis (VectorOps_Cyl / VectorOps_Sph): radii of the cell and its faces,
+        // slope of the centre cell for the geometric source term
+        const bool radial = radial_axis(g, ax);
+        const int qax = (ax == 0) ? i + g.nb[0] : (ax == 1) ? j + g.nb[1] : k + g.nb[2];
+        const double Rc = radial ? cell_R(g, ax, qax) : 0.0;
+        Prim SC;  // slope of cell C (radial axis, second order)
+        SC.ro = SC.pg = SC.vn = SC.vt1 = SC.vt2 = SC.bn = SC.bt1 = SC.bt2 = SC.psi = 0.0;
+        double rdel[4] = {0, 0, 0, 0}, ri[4] = {0, 0, 0, 0};
         if (a.order == 2) {
           const Prim M2 = load_prim<EQ>(a.S, c - 2 * st, vs, ax, a1, a2);
           const Prim P2 = load_prim<EQ>(a.S, c + 2 * st, vs, ax, a1, a2);
+          if (!radial) {
 #define PION_EDGE(f)                                                              \
   {                                                                               \
     double d0 = M1.f - M2.f, d1 = C.f - M1.f, d2 = P1.f - C.f, d3 = P2.f - P1.f;  \
@@ -196,10 +205,41 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
     highL.f = C.f + sc * 0.5;                                                     \
     highR.f = P1.f - sp * 0.5;                                                    \
   }
-          PION_EDGE(ro) PION_EDGE(pg) PION_EDGE(vn) PION_EDGE(vt1) PION_EDGE(vt2)
-          if (EQ != EQ_EULER) { PION_EDGE(bn) PION_EDGE(bt1) PION_EDGE(bt2) }
-          if (EQ == EQ_GLM) { PION_EDGE(psi) }
+            PION_EDGE(ro) PION_EDGE(pg) PION_EDGE(vn) PION_EDGE(vt1) PION_EDGE(vt2)
+            if (EQ != EQ_EULER) { PION_EDGE(bn) PION_EDGE(bt1) PION_EDGE(bt2) }
+            if (EQ == EQ_GLM) { PION_EDGE(psi) }
 #undef PION_EDGE
+          } else {
+            // SetSlope: divided differences between centres of volume; SetEdgeState: distance from the
+            // centre of volume to the face (VectorOps.cpp:1073-1079,1158-1182; VectorOps_spherical.cpp:312-380)
+            double Rq[5], Rcm[5];
+#pragma unroll
+            for (int q = 0; q < 5; q++) {
+              Rq[q] = cell_R(g, ax, qax - 2 + q);
+              Rcm[q] = cell_Rcom(g, Rq[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) ri[q] = 1.0 / (Rcm[q + 1] - Rcm[q]);
+            rdel[0] = Rq[1] + 0.5 * g.dx - Rcm[1];  // M1, + face
+            rdel[1] = Rq[2] - 0.5 * g.dx - Rcm[2];  // C, - face
+            rdel[2] = Rq[2] + 0.5 * g.dx - Rcm[2];  // C, + face
+            rdel[3] = Rq[3] - 0.5 * g.dx - Rcm[3];  // P1, - face
+#define PION_EDGE_R(f)                                                                                   \
+  {                                                                                                      \
+    double s0 = (M1.f - M2.f) * ri[0], s1 = (C.f - M1.f) * ri[1], s2 = (P1.f - C.f) * ri[2], s3 = (P2.f - P1.f) * ri[3]; \
+    double sm = minmod(s0, s1, PION_VERY_TINY_VALUE), sc = minmod(s1, s2, PION_VERY_TINY_VALUE),         \
+           sp = minmod(s2, s3, PION_VERY_TINY_VALUE);                                                    \
+    lowL.f = M1.f + sm * rdel[0];                                                                        \
+    lowR.f = C.f + sc * rdel[1];                                                                         \
+    highL.f = C.f + sc * rdel[2];                                                                        \
+    highR.f = P1.f + sp * rdel[3];                                                                       \
+    SC.f = sc;                                                                                           \
+  }
+            PION_EDGE_R(ro) PION_EDGE_R(pg) PION_EDGE_R(vn) PION_EDGE_R(vt1) PION_EDGE_R(vt2)
+            if (EQ != EQ_EULER) { PION_EDGE_R(bn) PION_EDGE_R(bt1) PION_EDGE_R(bt2) }
+            if (EQ == EQ_GLM) { PION_EDGE_R(psi) }
+#undef PION_EDGE_R
+          }
         }
         // HLLD -> HLL switch (solver_eqn_mhd_adi.cpp:167-177)
         bool hll_low = false, hll_high = false;
@@ -231,39 +271,83 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
         intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(lowL, lowR, a.pp, hll_low, eta_low, Flow);
         intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(highL, highR, a.pp, hll_high, eta_high, Fhigh);
 
+        // geometric weights of this cell along the axis: Cartesian 1/dx everywhere; radial axis:
+        // faces r- = Rc-dx/2, r+ = Rc+dx/2, cyl 2 r/(r+^2 - r-^2), sph r^2/((r+^3 - r-^3)/3)
+        double wlow = idx, whigh = idx, wsrc_low = idx, wsrc_high = idx;
+        if (radial) {
+          const double rp = Rc + g.dx * 0.5, rn = rp - g.dx;
+          if (g.coord == 2) {
+            const double iv = 1.0 / (rp * rp - rn * rn);
+            wlow = 2.0 * rn * iv; whigh = 2.0 * rp * iv;
+            wsrc_low = wlow; wsrc_high = whigh;  // cyl MHDsource (solver_eqn_mhd_adi.cpp:1087-1098)
+          } else {
+            const double iv = 1.0 / ((pow(rp, 3.0) - pow(rn, 3.0)) / 3.0);
+            wlow = rn * rn * iv; whigh = rp * rp * iv;
+          }
+        }
         // Powell + GLM sources from cell-centre states (solver_eqn_mhd_adi.cpp:396-443,782-813):
         // R part of interface (i-1,i) first, then L part of interface (i,i+1)
         if (EQ != EQ_EULER) {
           const double uB = C.bn * C.vn + C.bt1 * C.vt1 + C.bt2 * C.vt2;
           double f = dt * (0.5 * (M1.bn + C.bn));
-          acc.mn += f * C.bn * idx; acc.mt1 += f * C.bt1 * idx; acc.mt2 += f * C.bt2 * idx; acc.erg += f * uB * idx;
-          acc.bbn += f * C.vn * idx; acc.bbt1 += f * C.vt1 * idx; acc.bbt2 += f * C.vt2 * idx;
+          acc.mn += f * C.bn * wsrc_low; acc.mt1 += f * C.bt1 * wsrc_low; acc.mt2 += f * C.bt2 * wsrc_low; acc.erg += f * uB * wsrc_low;
+          acc.bbn += f * C.vn * wsrc_low; acc.bbt1 += f * C.vt1 * wsrc_low; acc.bbt2 += f * C.vt2 * wsrc_low;
           if (EQ == EQ_GLM) {
             double fs = dt * (0.5 * (M1.psi + C.psi));
             acc.erg += fs * (C.vn * C.psi) * idx;
             acc.psi += fs * C.vn * idx;
           }
           f = dt * (0.5 * (C.bn + P1.bn));
-          acc.mn -= f * C.bn * idx; acc.mt1 -= f * C.bt1 * idx; acc.mt2 -= f * C.bt2 * idx; acc.erg -= f * uB * idx;
-          acc.bbn -= f * C.vn * idx; acc.bbt1 -= f * C.vt1 * idx; acc.bbt2 -= f * C.vt2 * idx;
+          acc.mn -= f * C.bn * wsrc_high; acc.mt1 -= f * C.bt1 * wsrc_high; acc.mt2 -= f * C.bt2 * wsrc_high; acc.erg -= f * uB * wsrc_high;
+          acc.bbn -= f * C.vn * wsrc_high; acc.bbt1 -= f * C.vt1 * wsrc_high; acc.bbt2 -= f * C.vt2 * wsrc_high;
           if (EQ == EQ_GLM) {
             double fs = dt * (0.5 * (C.psi + P1.psi));
             acc.erg -= fs * (C.vn * C.psi) * idx;
             acc.psi -= fs * C.vn * idx;
           }
         }
-        // flux difference (dU_Cell + DivStateVectorComponent)
-        acc.rho += dt * ((Flow.rho - Fhigh.rho) * idx);
-        acc.erg += dt * ((Flow.erg - Fhigh.erg) * idx);
-        acc.mn += dt * ((Flow.mn - Fhigh.mn) * idx);
-        acc.mt1 += dt * ((Flow.mt1 - Fhigh.mt1) * idx);
-        acc.mt2 += dt * ((Flow.mt2 - Fhigh.mt2) * idx);
-        if (EQ != EQ_EULER) {
-          acc.bbn += dt * ((Flow.bbn - Fhigh.bbn) * idx);
-          acc.bbt1 += dt * ((Flow.bbt1 - Fhigh.bbt1) * idx);
-          acc.bbt2 += dt * ((Flow.bbt2 - Fhigh.bbt2) * idx);
+        // flux difference (dU_Cell + DivStateVectorComponent) + geometric source term
+        if (!radial) {
+          acc.rho += dt * ((Flow.rho - Fhigh.rho) * idx);
+          acc.erg += dt * ((Flow.erg - Fhigh.erg) * idx);
+          acc.mn += dt * ((Flow.mn - Fhigh.mn) * idx);
+          acc.mt1 += dt * ((Flow.mt1 - Fhigh.mt1) * idx);
+          acc.mt2 += dt * ((Flow.mt2 - Fhigh.mt2) * idx);
+          if (EQ != EQ_EULER) {
+            acc.bbn += dt * ((Flow.bbn - Fhigh.bbn) * idx);
+            acc.bbt1 += dt * ((Flow.bbt1 - Fhigh.bbt1) * idx);
+            acc.bbt2 += dt * ((Flow.bbt2 - Fhigh.bbt2) * idx);
+          }
+          if (EQ == EQ_GLM) acc.psi += dt * ((Flow.psi - Fhigh.psi) * idx);
+        } else {
+          // geometric_source: Euler cyl/sph solver_eqn_hydro_adi.cpp:560-590,648-668; MHD cyl
+          // solver_eqn_mhd_adi.cpp:1001-1036; GLM cyl :1156-1190
+          double gs_mn = 0.0, gs_bbn = 0.0;
+          const double Rcom = cell_Rcom(g, Rc);
+          if (g.coord == 2) {
+            double ptot = C.pg, dptot = SC.pg;
+            if (EQ != EQ_EULER) {
+              ptot += (C.bn * C.bn + C.bt1 * C.bt1 + C.bt2 * C.bt2) / 2.;
+              dptot = SC.pg + C.bn * SC.bn + C.bt1 * SC.bt1 + C.bt2 * SC.bt2;
+            }
+            gs_mn = (a.order == 2) ? (ptot + (Rc - Rcom) * dptot) / Rc : ptot / Rc;
+            if (EQ == EQ_GLM) gs_bbn = (a.order == 2) ? a.pp.chyp * (C.psi + (Rc - Rcom) * SC.psi) / Rc : a.pp.chyp * C.psi / Rc;
+          } else {
+            const double R3 = Rc + g.dx * g.dx / 12.0 / Rc;
+            gs_mn = (a.order == 2) ? 2.0 * ((C.pg - SC.pg * Rcom) / R3 + SC.pg) : 2.0 * C.pg / R3;
+          }
+          acc.rho += dt * (wlow * Flow.rho - whigh * Fhigh.rho);
+          acc.erg += dt * (wlow * Flow.erg - whigh * Fhigh.erg);
+          acc.mn += dt * ((wlow * Flow.mn - whigh * Fhigh.mn) + gs_mn);
+          acc.mt1 += dt * (wlow * Flow.mt1 - whigh * Fhigh.mt1);
+          acc.mt2 += dt * (wlow * Flow.mt2 - whigh * Fhigh.mt2);
+          if (EQ != EQ_EULER) {
+            acc.bbn += dt * ((wlow * Flow.bbn - whigh * Fhigh.bbn) + gs_bbn);
+            acc.bbt1 += dt * (wlow * Flow.bbt1 - whigh * Fhigh.bbt1);
+            acc.bbt2 += dt * (wlow * Flow.bbt2 - whigh * Fhigh.bbt2);
+          }
+          if (EQ == EQ_GLM) acc.psi += dt * (wlow * Flow.psi - whigh * Fhigh.psi);
         }
-        if (EQ == EQ_GLM) acc.psi += dt * ((Flow.psi - Fhigh.psi) * idx);
         // tracers: upwind on the sign of the mass flux (solver_eqn_base.cpp:281-342)
 #pragma unroll
         for (int q = 0; q < PION_MAXTR; q++) {
@@ -273,16 +357,23 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
             double lL = tm1, lR = tc, hL = tc, hR = tp1;
             if (a.order == 2) {
               double tm2 = __ldg(T + c - 2 * st), tp2 = __ldg(T + c + 2 * st);
-              double sm = minmod(tm1 - tm2, tc - tm1, a.tiny2), sc = minmod(tc - tm1, tp1 - tc, a.tiny2),
-                     sp = minmod(tp1 - tc, tp2 - tp1, a.tiny2);
-              lL = tm1 + sm * 0.5; lR = tc - sc * 0.5; hL = tc + sc * 0.5; hR = tp1 - sp * 0.5;
+              if (!radial) {
+                double sm = minmod(tm1 - tm2, tc - tm1, a.tiny2), sc = minmod(tc - tm1, tp1 - tc, a.tiny2),
+                       sp = minmod(tp1 - tc, tp2 - tp1, a.tiny2);
+                lL = tm1 + sm * 0.5; lR = tc - sc * 0.5; hL = tc + sc * 0.5; hR = tp1 - sp * 0.5;
+              } else {
+                double s0 = (tm1 - tm2) * ri[0], s1 = (tc - tm1) * ri[1], s2 = (tp1 - tc) * ri[2], s3 = (tp2 - tp1) * ri[3];
+                double sm = minmod(s0, s1, PION_VERY_TINY_VALUE), sc = minmod(s1, s2, PION_VERY_TINY_VALUE),
+                       sp = minmod(s2, s3, PION_VERY_TINY_VALUE);
+                lL = tm1 + sm * rdel[0]; lR = tc + sc * rdel[1]; hL = tc + sc * rdel[2]; hR = tp1 + sp * rdel[3];
+              }
             }
             double fl = 0.0, fh = 0.0;
             if (Flow.rho > 0.0) fl = lL * Flow.rho * (a.pp.have_mp ? scma_corr(lL) : 1.0);
             else if (Flow.rho < 0.0) fl = lR * Flow.rho * (a.pp.have_mp ? scma_corr(lR) : 1.0);
             if (Fhigh.rho > 0.0) fh = hL * Fhigh.rho * (a.pp.have_mp ? scma_corr(hL) : 1.0);
             else if (Fhigh.rho < 0.0) fh = hR * Fhigh.rho * (a.pp.have_mp ? scma_corr(hR) : 1.0);
-            acctr[q] += dt * ((fl - fh) * idx);
+            acctr[q] += radial ? dt * (wlow * fl - whigh * fh) : dt * ((fl - fh) * idx);
           }
         }
         // rotate the centre state and the accumulators into the next axis' frame

@@ -60,3 +60,16 @@ def wind_ambient_state(prob):
     if prob.eqn != "euler":
         P[5] = 1.0e-6
     return P
+
+
+def case_cyl(eqn, solver, av, NG=(24, 16, 1), bcs=("outflow", "outflow", "reflecting", "outflow"), ntracer=0, ooa=2):
+    """2-D axisymmetric (z, R) grid, R from 0 with a reflecting axis (as the reference's cylindrical test problems)."""
+    return Problem(ndim=2, NG=NG, eqn=eqn, solver=solver, artviscosity=av, xmax=(NG[0] * DX, NG[1] * DX, 1.0),
+                   bcs=tuple(bcs) + ("periodic",) * 2, ntracer=ntracer, ooa=ooa, coords="cylindrical")
+
+
+def case_sph(solver, av, N=64, rmin=0.0, bcs=("reflecting", "outflow"), ntracer=0, ooa=2):
+    """1-D spherically symmetric Euler grid."""
+    return Problem(ndim=1, NG=(N, 1, 1), eqn="euler", solver=solver, artviscosity=av, xmin=(rmin, 0.0, 0.0),
+                   xmax=(rmin + N * DX / 4, 1.0, 1.0), bcs=tuple(bcs) + ("periodic",) * 4, ntracer=ntracer, ooa=ooa,
+                   coords="spherical")

@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent))
-from cases import case_1d, case_2d, case_3d, case_cooling, case_wind, wind_ambient_state  # noqa: E402
+from cases import case_1d, case_2d, case_3d, case_cooling, case_cyl, case_sph, case_wind, wind_ambient_state  # noqa: E402
 from harness import COOLING_TABLES, TABLE_KEYS, RefSim, cooling_state, random_state  # noqa: E402
 
 CASES = {
@@ -24,6 +24,10 @@ CASES = {
     "imhd_hll_2d_reflect": (case_2d("i-mhd", 8, 1, bcs="reflect-outflow"), 4),
     "euler_roe_fkj_3d_mixed": (case_3d("euler", 4, 1, bcs="mixed1", ntracer=1, NG=(10, 8, 6)), 4),
     "euler_hll_1d_reflect_inflow": (case_1d("euler", 8, 1, bcs=("reflecting", "inflow")), 6),
+    # curvilinear grids: 2-D axisymmetric (z,R) and 1-D spherical
+    "cyl_glm_hlld_fkj_2d": (case_cyl("glm-mhd", 7, 1), 4),
+    "cyl_euler_roe_hcorr_2d_tracer": (case_cyl("euler", 4, 4, ntracer=1), 4),
+    "sph_euler_hll_1d": (case_sph(8, 1), 6),
 }
 
 

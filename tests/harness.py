@@ -31,6 +31,7 @@ BC_CODES = {
     "DMR": 8, "DMR2": 9, "one-way-outflow": 13, "stellar-wind": 14,
 }
 PO_MAXVAR = 16
+COORD_CODES = {"cartesian": 1, "cylindrical": 2, "spherical": 3}
 
 
 @dataclass
@@ -65,6 +66,7 @@ class Problem:
     # constant stellar-wind sources (internal boundary "stellar-wind"): dicts with keys
     # pos (3), radius, mdot [Msun/yr], vinf, vrot [km/s], temp [K], rstar [cm], bsrf [G], tr (tuple)
     winds: tuple = ()
+    coords: str = "cartesian"  # "cartesian" | "cylindrical" (2-D z,R) | "spherical" (1-D r)
 
     @property
     def nvar(self):
@@ -91,7 +93,7 @@ class Problem:
     def paramfile_text(self) -> str:
         f = repr  # repr() round-trips through the reference's atof()
         ax = "XYZ"
-        L = [f"ndim {self.ndim}", f"eqn {self.eqn}", "coordinates cartesian", f"solver {self.solver}",
+        L = [f"ndim {self.ndim}", f"eqn {self.eqn}", f"coordinates {self.coords}", f"solver {self.solver}",
              f"OrderOfAccSpace {self.ooa}", f"OrderOfAccTime {self.ooa}", f"ics {self.ics}",
              "OutputFile none", "OutputPath ./", "OutputFileType text",
              f"StartTime {f(self.starttime)}", f"FinishTime {f(self.finishtime)}",
@@ -360,7 +362,7 @@ def oracle_config(prob: Problem, tables=None):
         c.xmin[a] = prob.xmin[a]
         c.xmax[a] = prob.xmax[a]
     c.nvar, c.ntracer, c.eqntype = prob.nvar, prob.ntracer, EQN_NAMES[prob.eqn]
-    c.coord_sys, c.solver, c.artviscosity = 1, prob.solver, prob.artviscosity
+    c.coord_sys, c.solver, c.artviscosity = COORD_CODES[prob.coords], prob.solver, prob.artviscosity
     c.spOOA = c.tmOOA = prob.ooa
     c.gamma, c.cfl, c.etav = prob.gamma, prob.cfl, effective_etav(prob)
     for d in range(6):
@@ -540,7 +542,7 @@ def gpu_config(prob: Problem, device=0, tables=None):
         c.xmax[a] = prob.xmax[a]
         c.sim_xmin[a] = prob.xmin[a]
     c.nvar, c.ntracer, c.eqntype = prob.nvar, prob.ntracer, EQN_NAMES[prob.eqn]
-    c.coord_sys, c.solver, c.artviscosity = 1, prob.solver, prob.artviscosity
+    c.coord_sys, c.solver, c.artviscosity = COORD_CODES[prob.coords], prob.solver, prob.artviscosity
     c.spOOA = c.tmOOA = prob.ooa
     c.gamma, c.cfl, c.etav = prob.gamma, prob.cfl, prob.etav
     for d in range(6):

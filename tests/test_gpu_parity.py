@@ -190,3 +190,21 @@ def test_cooling_source_term(eqn, solver, ndim, NG, ntr, lim, rho0):
     finally:
         o.close()
         g.close()
+
+
+# ------------------------------------------------------------------------------------------
+# curvilinear grids (a12): cylindrical (z,R) and spherical geometric source terms, area-weighted
+# flux divergence, centre-of-volume slopes -- gather kernel path
+from cases import case_cyl, case_sph  # noqa: E402
+
+GEOM_CASES = [
+    case_cyl("euler", 8, 1), case_cyl("euler", 4, 4, ntracer=1), case_cyl("i-mhd", 8, 1), case_cyl("i-mhd", 7, 1),
+    case_cyl("glm-mhd", 7, 1), case_cyl("glm-mhd", 4, 3, ntracer=1), case_cyl("glm-mhd", 7, 1, ooa=1),
+    case_cyl("euler", 8, 0, bcs=("periodic", "periodic", "reflecting", "reflecting")),
+    case_sph(8, 1), case_sph(4, 1, rmin=1.0, bcs=("inflow", "outflow"), ntracer=1), case_sph(8, 0, ooa=1),
+]
+
+
+@pytest.mark.parametrize("prob", GEOM_CASES, ids=lambda p: f"{p.coords[:3]}-{p.eqn}-s{p.solver}-av{p.artviscosity}-oa{p.ooa}")
+def test_curvilinear_geometry(prob):
+    run_pair(prob)
