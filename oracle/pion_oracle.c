@@ -1632,6 +1632,9 @@ static int assign_boundary_data(pion_oracle *s) {
           }
         } while ((c = nextpt(s, c, XP)) >= 0 && (dpos(s, c, 0) <= 1. / 6.));
       } break;
+      case PO_BC_MPI: /* BCMPI (MCMD_boundaries.cpp:57-236): ghost cells are filled by the halo exchange,
+                       * which the caller (tests: torch.distributed/gloo) performs between the seam calls */
+        break;
       case PO_BC_STWIND: /* stellar_wind_boundaries.cpp:29-250 */
         wind_assign(s);
         break;
@@ -1833,6 +1836,8 @@ static int time_update_bcs(pion_oracle *s, int cstep, int maxstep) {
           if (cstep == maxstep)
             for (int v = 0; v < nv; v++) s->P[c * nv + v] = ph[v];
         }
+        break;
+      case PO_BC_MPI:
         break;
       case PO_BC_STWIND: /* updated by TimeUpdateInternalBCs above; skipped here (:238) */
         break;

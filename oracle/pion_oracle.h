@@ -27,7 +27,7 @@ enum { PO_FLUX_ROE = 4, PO_FLUX_HLLD = 7, PO_FLUX_HLL = 8 };
 enum { PO_AV_NONE = 0, PO_AV_FKJ98 = 1, PO_AV_HCORR = 3, PO_AV_HCORR_FKJ98 = 4 };
 enum {
   PO_BC_PERIODIC = 1, PO_BC_OUTFLOW = 2, PO_BC_INFLOW = 3, PO_BC_REFLECTING = 4,
-  PO_BC_FIXED = 5, PO_BC_DMACH = 8, PO_BC_DMACH2 = 9, PO_BC_ONEWAY_OUT = 13, PO_BC_STWIND = 14
+  PO_BC_FIXED = 5, PO_BC_DMACH = 8, PO_BC_DMACH2 = 9, PO_BC_MPI = 10, PO_BC_ONEWAY_OUT = 13, PO_BC_STWIND = 14
 };
 
 /* one constant stellar-wind source: arguments of stellar_wind::add_source
