@@ -138,7 +138,7 @@ __device__ __forceinline__ double tracer_low_face_flux(const StageArgs& a, const
 #define PION_SWEEP_MBAR 1
 #endif
 #ifndef PION_SWEEP_MINBLOCKS
-#define PION_SWEEP_MINBLOCKS 2
+#define PION_SWEEP_MINBLOCKS 1
 #endif
 
 // split-phase block barrier (mbarrier): a thread ARRIVES right after publishing its y flux
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
   extern __shared__ double s_flux[];  // [2][NB + MAXTR][TY][32]
   __shared__ unsigned long long s_bar;
   constexpr int NB = nbase(EQ);
-  constexpr int SLAB = (NB + PION_MAXTR) * TY * 32;
+  constexpr int SLAB = (NB + (TR ? PION_MAXTR : 0)) * TY * 32;  // tracer slabs only in the tracer instantiation
   const GridD& g = a.g;
   const int NX = g.NG[0], NY = g.NG[1], NZ = g.NG[2];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
 template <int EQ, int SOLVER, bool FKJ>
 inline void launch_sweep_t(const StageArgs& a, cudaStream_t s) {
 #ifndef PION_SWEEP_TY
-#define PION_SWEEP_TY 8
+#define PION_SWEEP_TY 12
 #endif
   constexpr int TY = PION_SWEEP_TY;
   constexpr int NB = nbase(EQ);
@@ -376,14 +376,15 @@ inline void launch_sweep_t(const StageArgs& a, cudaStream_t s) {
   }
   const int bz = (NZ + kchunk - 1) / kchunk;
   const size_t smem = (size_t)2 * (NB + PION_MAXTR) * TY * 32 * sizeof(double);
+  const size_t smem_notr = (size_t)2 * NB * TY * 32 * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_notr);
     attr_done = true;
   }
   if (a.ntr > 0) k_stage_sweep<EQ, SOLVER, FKJ, TY, true><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, kchunk);
-  else k_stage_sweep<EQ, SOLVER, FKJ, TY, false><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, kchunk);
+  else k_stage_sweep<EQ, SOLVER, FKJ, TY, false><<<dim3(bx, by, bz), 32 * TY, smem_notr, s>>>(a, kchunk);
 }
 
 }  // namespace pion
