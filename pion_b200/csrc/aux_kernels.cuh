@@ -48,6 +48,35 @@ __global__ void k_hlld_flags(GridD g, const double* __restrict__ S, unsigned cha
   }
 }
 
+// 3-D Cartesian variant: a 32 x 8 tile marches in z keeping p and v_z of the planes k-1, k, k+1 in
+// registers, so every plane of p, v_x, v_y, v_z is pulled from L2 once per tile (the x / y neighbours
+// come from lines the same block has just loaded) instead of three times in the flat sweep above.
+__global__ void __launch_bounds__(256) k_hlld_flags_3d(GridD g, const double* __restrict__ S, unsigned char* __restrict__ flag,
+                                                       int kchunk) {
+  const int ex = g.NGa[0] - 2, ey = g.NGa[1] - 2, ez = g.NGa[2] - 2;
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31) + 1, j = blockIdx.y * 8 + (threadIdx.x >> 5) + 1;
+  if (i > ex || j > ey) return;
+  const int k0 = blockIdx.z * kchunk + 1, k1 = min(k0 + kchunk, ez + 1);
+  const double* Pg = S + g.vs;
+  const double *Vx = S + 2 * g.vs, *Vy = S + 3 * g.vs, *Vz = S + 4 * g.vs;
+  const double id2 = 1.0 / (2.0 * g.dx);
+  long c = gidx(g, i, j, k0);
+  double p_m = __ldg(Pg + c - g.sz), p_c = __ldg(Pg + c), vz_m = __ldg(Vz + c - g.sz), vz_c = __ldg(Vz + c);
+  for (int k = k0; k < k1; k++, c += g.sz) {
+    const double p_p = __ldg(Pg + c + g.sz), vz_p = __ldg(Vz + c + g.sz);
+    const double pxp = __ldg(Pg + c + 1), pxn = __ldg(Pg + c - 1), pyp = __ldg(Pg + c + g.sy), pyn = __ldg(Pg + c - g.sy);
+    // same summation order as the flat kernel: x, y, z
+    double divv = (__ldg(Vx + c + 1) - __ldg(Vx + c - 1)) * id2;
+    double gradp = fabs(pxp - pxn) * fast_rcp(fmin(pxp, pxn));
+    divv += (__ldg(Vy + c + g.sy) - __ldg(Vy + c - g.sy)) * id2;
+    gradp += fabs(pyp - pyn) * fast_rcp(fmin(pyp, pyn));
+    divv += (vz_p - vz_m) * id2;
+    gradp += fabs(p_p - p_m) * fast_rcp(fmin(p_p, p_m));
+    flag[c] = (divv < 0. && gradp > 5.) ? 1 : 0;
+    p_m = p_c; p_c = p_p; vz_m = vz_c; vz_c = vz_p;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // H-correction eta for the interface on the + side of every cell, per axis
 // (calc_Hcorrection / set_Hcorrection, solver_eqn_base.cpp:423-599):

@@ -695,8 +695,16 @@ extern "C" int pion_gpu_get_time(pion_gpu_ctx* c, double* simtime, double* dt, d
 static int launch_preprocess(pion_gpu_ctx* c, const double* S, int order) {
   const GridD& g = c->g;
   if (c->hll) {  // solver_eqn_base.cpp:398-412
-    long n = (long)(g.NGa[0] - 2) * ((g.ndim > 1) ? g.NGa[1] - 2 : 1) * ((g.ndim > 2) ? g.NGa[2] - 2 : 1);
-    k_hlld_flags<<<nblocks(n, 256), 256, 0, c->stream>>>(g, S, c->hll);
+    if (g.ndim == 3 && g.coord == PION_COORD_CRT) {
+      const int ex = g.NGa[0] - 2, ey = g.NGa[1] - 2, ez = g.NGa[2] - 2;
+      int kchunk = 64;
+      const int bx = (ex + 31) / 32, by = (ey + 7) / 8;
+      while (kchunk > 8 && (long)bx * by * ((ez + kchunk - 1) / kchunk) < 148L * 8) kchunk >>= 1;
+      k_hlld_flags_3d<<<dim3(bx, by, (ez + kchunk - 1) / kchunk), 256, 0, c->stream>>>(g, S, c->hll, kchunk);
+    } else {
+      long n = (long)(g.NGa[0] - 2) * ((g.ndim > 1) ? g.NGa[1] - 2 : 1) * ((g.ndim > 2) ? g.NGa[2] - 2 : 1);
+      k_hlld_flags<<<nblocks(n, 256), 256, 0, c->stream>>>(g, S, c->hll);
+    }
     c->launches++;
   }
   if (c->eta) {  // solver_eqn_base.cpp:423-573
