@@ -254,16 +254,22 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
         continue;
       }
 
-      Cons Flow, Fhigh;
-      double Flow_tr[PION_MAXTR], Fhigh_tr[PION_MAXTR];
+      // D = F(low face) - F(high face) of this cell along the axis, formed directly from where the two
+      // fluxes live (registers + shuffle / shared memory / the previous plane's registers)
+      Cons D;
+      double D_tr[PION_MAXTR];
+#define PION_DIFF(LOW, HIGH)                                                                     \
+  D.rho = LOW.rho - HIGH.rho; D.erg = LOW.erg - HIGH.erg; D.mn = LOW.mn - HIGH.mn;               \
+  D.mt1 = LOW.mt1 - HIGH.mt1; D.mt2 = LOW.mt2 - HIGH.mt2;                                        \
+  if (EQ != EQ_EULER) { D.bbn = LOW.bbn - HIGH.bbn; D.bbt1 = LOW.bbt1 - HIGH.bbt1; D.bbt2 = LOW.bbt2 - HIGH.bbt2; } \
+  else { D.bbn = D.bbt1 = D.bbt2 = 0.0; }                                                        \
+  D.psi = (EQ == EQ_GLM) ? LOW.psi - HIGH.psi : 0.0;
       if (step == 1) {
-        Flow = Fnew;
-        Fhigh = cons_shfl_down<EQ>(Fnew);
+        const Cons Fh = cons_shfl_down<EQ>(Fnew);
+        PION_DIFF(Fnew, Fh)
 #pragma unroll
-        for (int q = 0; q < PION_MAXTR; q++) {
-          Flow_tr[q] = Fnew_tr[q];
-          Fhigh_tr[q] = (q < ntr) ? __shfl_down_sync(0xffffffffu, Fnew_tr[q], 1) : 0.0;
-        }
+        for (int q = 0; q < PION_MAXTR; q++)
+          D_tr[q] = (q < ntr) ? Fnew_tr[q] - __shfl_down_sync(0xffffffffu, Fnew_tr[q], 1) : 0.0;
       } else if (step == 2) {
 #if PION_SWEEP_MBAR
         mbar_wait(&s_bar, phase);
@@ -272,24 +278,22 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
         __syncthreads();
 #endif
         const int rn = min(row + 1, TY - 1);
-        Flow = cons_from_smem<EQ, TY>(sbuf, row, lane);
-        Fhigh = cons_from_smem<EQ, TY>(sbuf, rn, lane);
+        const Cons Fl = cons_from_smem<EQ, TY>(sbuf, row, lane);
+        const Cons Fh = cons_from_smem<EQ, TY>(sbuf, rn, lane);
+        PION_DIFF(Fl, Fh)
 #pragma unroll
-        for (int q = 0; q < PION_MAXTR; q++) {
-          Flow_tr[q] = (q < ntr) ? sbuf_tr[(q * TY + row) * 32 + lane] : 0.0;
-          Fhigh_tr[q] = (q < ntr) ? sbuf_tr[(q * TY + rn) * 32 + lane] : 0.0;
-        }
+        for (int q = 0; q < PION_MAXTR; q++)
+          D_tr[q] = (q < ntr) ? sbuf_tr[(q * TY + row) * 32 + lane] - sbuf_tr[(q * TY + rn) * 32 + lane] : 0.0;
       } else {
-        Flow = Fz;
-        Fhigh = Fnew;
+        PION_DIFF(Fz, Fnew)
         Fz = Fnew;
 #pragma unroll
         for (int q = 0; q < PION_MAXTR; q++) {
-          Flow_tr[q] = Fz_tr[q];
-          Fhigh_tr[q] = Fnew_tr[q];
+          D_tr[q] = Fz_tr[q] - Fnew_tr[q];
           Fz_tr[q] = Fnew_tr[q];
         }
       }
+#undef PION_DIFF
 
       if (!warm) {
         // Powell + GLM sources from cell-centre states (solver_eqn_mhd_adi.cpp:396-443,782-813):
@@ -319,20 +323,20 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
           }
         }
         // flux difference (dU_Cell + DivStateVectorComponent)
-        acc.rho += dt * ((Flow.rho - Fhigh.rho) * idx);
-        acc.erg += dt * ((Flow.erg - Fhigh.erg) * idx);
-        acc.mn += dt * ((Flow.mn - Fhigh.mn) * idx);
-        acc.mt1 += dt * ((Flow.mt1 - Fhigh.mt1) * idx);
-        acc.mt2 += dt * ((Flow.mt2 - Fhigh.mt2) * idx);
+        acc.rho += dt * (D.rho * idx);
+        acc.erg += dt * (D.erg * idx);
+        acc.mn += dt * (D.mn * idx);
+        acc.mt1 += dt * (D.mt1 * idx);
+        acc.mt2 += dt * (D.mt2 * idx);
         if (EQ != EQ_EULER) {
-          acc.bbn += dt * ((Flow.bbn - Fhigh.bbn) * idx);
-          acc.bbt1 += dt * ((Flow.bbt1 - Fhigh.bbt1) * idx);
-          acc.bbt2 += dt * ((Flow.bbt2 - Fhigh.bbt2) * idx);
+          acc.bbn += dt * (D.bbn * idx);
+          acc.bbt1 += dt * (D.bbt1 * idx);
+          acc.bbt2 += dt * (D.bbt2 * idx);
         }
-        if (EQ == EQ_GLM) acc.psi += dt * ((Flow.psi - Fhigh.psi) * idx);
+        if (EQ == EQ_GLM) acc.psi += dt * (D.psi * idx);
 #pragma unroll
         for (int q = 0; q < PION_MAXTR; q++)
-          if (q < ntr) acctr[q] += dt * ((Flow_tr[q] - Fhigh_tr[q]) * idx);
+          if (q < ntr) acctr[q] += dt * (D_tr[q] * idx);
         // rotate the centre state and the accumulators into the next axis' frame
         rot3(C.vn, C.vt1, C.vt2);
         rot3(acc.mn, acc.mt1, acc.mt2);
