@@ -67,6 +67,9 @@ struct pion_gpu_ctx {
   long long launches = 0;
   // optional per-launch timing of the stage kernel (bench.py roofline leg)
   bool timing = false;
+  bool timing_suspended = false;  // a split stage is timed as a whole by stage_and_bcs
+  bool no_overlap = false;    // PION_B200_NO_OVERLAP=1: halo exchange after the whole stage (A/B tests)
+  bool force_overlap = false; // PION_B200_OVERLAP=1: split the stage even with a single exchanged face
   bool force_gather = false;  // PION_B200_GATHER=1: run the gather kernel on the fused path too (A/B tests)
   std::vector<cudaEvent_t> tev;  // begin/end pairs
   // multi-GPU
@@ -287,10 +290,16 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   pp.mu_tot_over_kB = cfg->cooling ? (0.609 * 1.672621898e-24) / 1.38064852e-16 : 0.0;
   c->simtime = cfg->starttime;
   { const char* e = getenv("PION_B200_GATHER"); c->force_gather = e && e[0] == '1'; }
+  { const char* e = getenv("PION_B200_NO_OVERLAP"); c->no_overlap = e && e[0] == '1'; }
+  { const char* e = getenv("PION_B200_OVERLAP"); c->force_overlap = e && e[0] == '1'; }
 
   bool ok = true;
   ok &= cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
-  ok &= cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) == cudaSuccess;
+  {
+    int plo = 0, phi = 0;  // the comm stream (boundary shell + halo exchange) outranks the interior update
+    cudaDeviceGetStreamPriorityRange(&plo, &phi);
+    ok &= cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, phi) == cudaSuccess;
+  }
   ok &= cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming) == cudaSuccess;
   ok &= cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming) == cudaSuccess;
   ok &= cudaMalloc(&c->P, c->arr_elems * sizeof(double)) == cudaSuccess;
@@ -440,13 +449,14 @@ static long face_cells(const GridD& g, int face) {
   return n;
 }
 
-static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A);
+static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A, cudaStream_t st);
 
 // TimeUpdateInternalBCs + TimeUpdateExternalBCs on the given arrays (A1 may be null)
-static int update_bcs_arrays(pion_gpu_ctx* c, double* A0, double* A1, double simtime) {
+static int update_bcs_arrays(pion_gpu_ctx* c, double* A0, double* A1, double simtime, cudaStream_t st = nullptr) {
   const GridD& g = c->g;
+  if (!st) st = c->stream;
   if (c->wind_n) {  // TimeUpdateInternalBCs: BC_update_STWIND writes P and Ph, before the external faces
-    k_wind_set<<<nblocks(c->wind_n * c->nvar, 256), 256, 0, c->stream>>>(g.vs, c->nvar, c->wind_n, c->d_wind_idx, c->d_wind_val, c->P, c->Ph);
+    k_wind_set<<<nblocks(c->wind_n * c->nvar, 256), 256, 0, st>>>(g.vs, c->nvar, c->wind_n, c->d_wind_idx, c->d_wind_val, c->P, c->Ph);
     c->launches++;
   }
   for (int ax = 0; ax < g.ndim; ax++) {
@@ -457,19 +467,19 @@ static int update_bcs_arrays(pion_gpu_ctx* c, double* A0, double* A1, double sim
       if (type == PION_BC_MPI) { mpi_face = true; continue; }
       BCArgs b;
       fill_bc_args(c, b, face, type, A0, A1, simtime, c->bc_refval[face]);
-      k_bc_face<<<nblocks(face_cells(g, face), 128), 128, 0, c->stream>>>(b);
+      k_bc_face<<<nblocks(face_cells(g, face), 128), 128, 0, st>>>(b);
       c->launches++;
     }
     if (mpi_face) {
-      if (halo_exchange_axis(c, ax, A0)) return 1;
-      if (A1 && halo_exchange_axis(c, ax, A1)) return 1;
+      if (halo_exchange_axis(c, ax, A0, st)) return 1;
+      if (A1 && halo_exchange_axis(c, ax, A1, st)) return 1;
     }
   }
   for (int i = 0; i < c->cfg.n_internal_bc; i++) {
     if (c->cfg.internal_bc[i] == PION_BC_DMACH2) {
       BCArgs b;
       fill_bc_args(c, b, 2, PION_BC_DMACH2, A0, A1, simtime, c->bc_refval[6 + i]);
-      k_bc_dmach2<<<nblocks((long)g.NG[0] * g.nb[1], 128), 128, 0, c->stream>>>(b);
+      k_bc_dmach2<<<nblocks((long)g.NG[0] * g.nb[1], 128), 128, 0, st>>>(b);
       c->launches++;
     }
   }
@@ -721,8 +731,14 @@ static int launch_preprocess(pion_gpu_ctx* c, const double* S, int order) {
   return 0;
 }
 
+struct StageBox { int tx0, tx1, ty0, ty1, k_lo, k_hi; };
+
+// one stage = one launch over the whole grid (box == nullptr), or one launch per box when the stage is
+// split into boundary shell + interior (only the first launch of a stage resets the dt minimum)
 static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double* dU, double dt, int order,
-                        bool fused, bool want_dt) {
+                        bool fused, bool want_dt, const StageBox* box = nullptr, bool first_box = true,
+                        cudaStream_t st = nullptr) {
+  if (!st) st = c->stream;
   StageArgs a;
   a.g = c->g;
   a.pp = c->pp;
@@ -746,24 +762,33 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   a.fused = fused ? 1 : 0;
   const int fkj = (c->cfg.artviscosity == 1 || c->cfg.artviscosity == 4) ? 1 : 0;
   a.fkj = fkj;
-  if (want_dt)
-    CUDA_OK(cudaMemcpyAsync(c->d_dtmin, &DT_INIT_BITS, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  {
+    int cx, cy;
+    sweep_tile_cells(&cx, &cy);
+    a.tx0 = 0; a.tx1 = (c->g.NG[0] + cx - 1) / cx;
+    a.ty0 = 0; a.ty1 = (c->g.NG[1] + cy - 1) / cy;
+    a.k_lo = 0; a.k_hi = c->g.NG[2];
+    if (box) { a.tx0 = box->tx0; a.tx1 = box->tx1; a.ty0 = box->ty0; a.ty1 = box->ty1; a.k_lo = box->k_lo; a.k_hi = box->k_hi; }
+  }
+  if (want_dt && first_box)
+    CUDA_OK(cudaMemcpyAsync(c->d_dtmin, &DT_INIT_BITS, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (c->timing) {
+  const bool timed = c->timing && !c->timing_suspended;
+  if (timed) {
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
-    CUDA_OK(cudaEventRecord(e0, c->stream));
+    CUDA_OK(cudaEventRecord(e0, st));
   }
   // fused 2-D/3-D stages run the flux-once sweep kernel; 1-D grids and the unfused seam
   // call (calc_dynamics_dU) run the per-cell gather kernel
   const bool sweep = fused && c->g.ndim >= 2 && c->g.coord == PION_COORD_CRT && !c->force_gather;
   switch (c->cfg.eqntype) {
-    case PION_EQEUL: (sweep ? launch_sweep_euler : launch_stage_euler)(c->cfg.solver, fkj, a, c->stream); break;
-    case PION_EQMHD: (sweep ? launch_sweep_mhd : launch_stage_mhd)(c->cfg.solver, fkj, a, c->stream); break;
-    default: (sweep ? launch_sweep_glm : launch_stage_glm)(c->cfg.solver, fkj, a, c->stream); break;
+    case PION_EQEUL: (sweep ? launch_sweep_euler : launch_stage_euler)(c->cfg.solver, fkj, a, st); break;
+    case PION_EQMHD: (sweep ? launch_sweep_mhd : launch_stage_mhd)(c->cfg.solver, fkj, a, st); break;
+    default: (sweep ? launch_sweep_glm : launch_stage_glm)(c->cfg.solver, fkj, a, st); break;
   }
-  if (c->timing) {
-    CUDA_OK(cudaEventRecord(e1, c->stream));
+  if (timed) {
+    CUDA_OK(cudaEventRecord(e1, st));
     c->tev.push_back(e0);
     c->tev.push_back(e1);
   }
@@ -841,6 +866,65 @@ extern "C" int pion_gpu_grid_update_state_vector(pion_gpu_ctx* c, double dt, int
   return 0;
 }
 
+// One fused stage followed by its boundary update.  With a communicator (and no internal
+// boundaries) the stage is split: the tiles next to the six faces run first, then the boundary
+// update -- ghost-fill kernels and the NCCL halo exchange, axis by axis -- runs on the comm stream
+// WHILE the interior tiles run on the compute stream; the next stage waits for both.
+static int stage_and_bcs(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double dt, int order, bool want_dt,
+                         double* bcA0, double* bcA1) {
+  int cx, cy;
+  sweep_tile_cells(&cx, &cy);
+  const GridD& g = c->g;
+  const int ntx = (g.NG[0] + cx - 1) / cx, nty = (g.NG[1] + cy - 1) / cy, NZ = g.NG[2];
+  // shell thickness in tiles: the last tile may hold fewer than the 2 cells the halo slab needs
+  const int sxh = (g.NG[0] - (ntx - 1) * cx < 2) ? 2 : 1, syh = (g.NG[1] - (nty - 1) * cy < 2) ? 2 : 1;
+  const int zs = 8;
+  int nmpi = 0;
+  for (int f = 0; f < 6; f++) nmpi += (c->cfg.bc[f] == PION_BC_MPI);
+  // measured at 2 GPUs (one exchanged face): 53.50 ms/step split vs 53.74 ms unsplit.
+  // PION_B200_NO_OVERLAP=1 turns the split off (A/B tests).
+  const bool want = c->force_overlap || nmpi >= 1;
+  const bool overlap = want && c->comm && c->cfg.n_internal_bc == 0 && g.ndim == 3 && g.coord == PION_COORD_CRT && !c->force_gather &&
+                       !c->no_overlap && ntx >= 2 + sxh && nty >= 2 + syh && NZ >= 3 * zs;
+  if (!overlap) {
+    if (launch_stage(c, S, Pb, out, nullptr, dt, order, true, want_dt)) return 1;
+    return update_bcs_arrays(c, bcA0, bcA1, c->simtime);
+  }
+  const StageBox shell[6] = {
+      {0, ntx, 0, nty, 0, zs},                          // z low
+      {0, ntx, 0, nty, NZ - zs, NZ},                    // z high
+      {0, ntx, 0, 1, zs, NZ - zs},                      // y low
+      {0, ntx, nty - syh, nty, zs, NZ - zs},            // y high
+      {0, 1, 1, nty - syh, zs, NZ - zs},                // x low
+      {ntx - sxh, ntx, 1, nty - syh, zs, NZ - zs},      // x high
+  };
+  const StageBox interior = {1, ntx - sxh, 1, nty - syh, zs, NZ - zs};
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->timing) {  // the seven launches of a split stage count as ONE stage launch for the roofline leg
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    CUDA_OK(cudaEventRecord(e0, c->stream));
+    c->timing_suspended = true;
+  }
+  if (want_dt) CUDA_OK(cudaMemcpyAsync(c->d_dtmin, &DT_INIT_BITS, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  // comm stream (high priority): shell tiles, then ghost fill + halo exchange; compute stream: interior
+  CUDA_OK(cudaEventRecord(c->ev_a, c->stream));
+  CUDA_OK(cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
+  for (int b = 0; b < 6; b++)
+    if (launch_stage(c, S, Pb, out, nullptr, dt, order, true, want_dt, &shell[b], false, c->comm_stream)) return 1;
+  if (launch_stage(c, S, Pb, out, nullptr, dt, order, true, want_dt, &interior, false, c->stream)) return 1;
+  if (c->timing) {
+    CUDA_OK(cudaEventRecord(e1, c->stream));
+    c->tev.push_back(e0);
+    c->tev.push_back(e1);
+    c->timing_suspended = false;
+  }
+  if (update_bcs_arrays(c, bcA0, bcA1, c->simtime, c->comm_stream)) return 1;
+  CUDA_OK(cudaEventRecord(c->ev_b, c->comm_stream));
+  CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+  return 0;
+}
+
 // time_integrator::advance_time (time_integrator.cpp:72-142), fused fast path.
 //   predictor : stencil from P (== Ph at the start of a step), writes Ph
 //   corrector : stencil from Ph, base state P, writes P in place and reduces the
@@ -868,16 +952,14 @@ extern "C" int pion_gpu_advance_time(pion_gpu_ctx* c, double* dt_done) {
     c->FV_dt = 0.5 * dt;
     if (c->cfg.cooling && launch_cooling(c, 0.5 * dt, c->mp_dE, nullptr)) return 1;  // calc_microphysics_dU(0.5dt)
     if (launch_preprocess(c, c->P, 1)) return 1;
-    if (launch_stage(c, c->P, c->P, c->Ph, nullptr, 0.5 * dt, 1, true, false)) return 1;
-    // boundaries of Ph (cstep=OA1 != maxstep=OA2), simtime = start of step
-    if (update_bcs_arrays(c, c->Ph, nullptr, c->simtime)) return 1;
+    // ... then boundaries of Ph (cstep=OA1 != maxstep=OA2), simtime = start of step
+    if (stage_and_bcs(c, c->P, c->P, c->Ph, 0.5 * dt, 1, false, c->Ph, nullptr)) return 1;
     // second_order_update(dt, OA2): Setdt(dt), dynamics OA2 from Ph, update P
     c->FV_dt = dt;
     if (c->cfg.cooling && launch_cooling(c, dt, c->mp_dE, nullptr)) return 1;  // from P again (time_integrator.cpp:472)
     if (launch_preprocess(c, c->Ph, 2)) return 1;
-    if (launch_stage(c, c->Ph, c->P, c->P, nullptr, dt, 2, true, true)) return 1;
-    // boundaries of P (and Ph == P): only P is kept current
-    if (update_bcs_arrays(c, c->P, nullptr, c->simtime)) return 1;
+    // ... then boundaries of P (and Ph == P): only P is kept current
+    if (stage_and_bcs(c, c->Ph, c->P, c->P, dt, 2, true, c->P, nullptr)) return 1;
     c->ph_valid = false;
     c->next_dt_valid = true;
   }
@@ -968,7 +1050,7 @@ extern "C" int pion_gpu_nccl_init(pion_gpu_ctx* c, const char* unique_id128) {
 
 // BC_update_BCMPI for both faces of one axis (MCMD_boundaries.cpp:122-236):
 // pack -> grouped ncclSend/ncclRecv -> unpack, all on the compute stream.
-static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A) {
+static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A, cudaStream_t st) {
   if (!c->comm) { set_error("BCMPI face but no NCCL communicator (call pion_gpu_nccl_init)"); return 1; }
   const GridD& g = c->g;
   for (int s = 0; s < 2; s++) {
@@ -976,7 +1058,7 @@ static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A) {
     if (c->cfg.bc[f] != PION_BC_MPI) continue;
     HaloArgs h;
     h.g = g; h.A = A; h.buf = c->sendbuf[f]; h.face = f; h.nvar = c->nvar; h.pack = 1;
-    k_halo<<<nblocks((long)c->halo_elems[f], 256), 256, 0, c->stream>>>(h);
+    k_halo<<<nblocks((long)c->halo_elems[f], 256), 256, 0, st>>>(h);
     c->launches++;
   }
   // Sends go out in face order (N, P) and receives are posted in the opposite order
@@ -988,12 +1070,12 @@ static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A) {
   for (int s = 0; s < 2; s++) {
     const int f = 2 * ax + s;
     if (c->cfg.bc[f] != PION_BC_MPI) continue;
-    NCCL_OK(ncclSend(c->sendbuf[f], c->halo_elems[f], ncclDouble, c->cfg.ngbprocs[f], c->comm, c->stream));
+    NCCL_OK(ncclSend(c->sendbuf[f], c->halo_elems[f], ncclDouble, c->cfg.ngbprocs[f], c->comm, st));
   }
   for (int s = 1; s >= 0; s--) {
     const int f = 2 * ax + s;
     if (c->cfg.bc[f] != PION_BC_MPI) continue;
-    NCCL_OK(ncclRecv(c->recvbuf[f], c->halo_elems[f], ncclDouble, c->cfg.ngbprocs[f], c->comm, c->stream));
+    NCCL_OK(ncclRecv(c->recvbuf[f], c->halo_elems[f], ncclDouble, c->cfg.ngbprocs[f], c->comm, st));
   }
   NCCL_OK(ncclGroupEnd());
   for (int s = 0; s < 2; s++) {
@@ -1001,7 +1083,7 @@ static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A) {
     if (c->cfg.bc[f] != PION_BC_MPI) continue;
     HaloArgs h;
     h.g = g; h.A = A; h.buf = c->recvbuf[f]; h.face = f; h.nvar = c->nvar; h.pack = 0;
-    k_halo<<<nblocks((long)c->halo_elems[f], 256), 256, 0, c->stream>>>(h);
+    k_halo<<<nblocks((long)c->halo_elems[f], 256), 256, 0, st>>>(h);
     c->launches++;
   }
   CUDA_OK(cudaGetLastError());

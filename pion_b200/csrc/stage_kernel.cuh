@@ -45,6 +45,9 @@ struct StageArgs {
   int ntr;            // tracers
   int fused;          // 1: apply CellAdvanceTime and write `out`; 0: dU += ...
   int fkj;            // FKJ98 viscosity on (AV 1 or 4)
+  // sweep kernel only: the box of tiles / planes this launch covers (x tiles of 31 cells, y tiles of
+  // TY-1 rows, z planes); the whole grid unless the stage is split into boundary shell + interior
+  int tx0, tx1, ty0, ty1, k_lo, k_hi;
 };
 
 // sCMA corrector of one tracer value (microphysics_base.cpp:80-126 with no element
@@ -419,6 +422,8 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
 void launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_stage_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+// cells per sweep tile along x / y (stage_sweep.cuh: 32 lanes, TY rows, one of each only produces fluxes)
+void sweep_tile_cells(int* cx, int* cy);
 // flux-once sweep kernel (stage_sweep.cuh), instantiated in sweep_{euler,mhd,glm}.cu
 void launch_sweep_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_sweep_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);

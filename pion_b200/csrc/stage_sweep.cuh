@@ -169,14 +169,14 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
   constexpr int NB = nbase(EQ);
   constexpr int SLAB = (NB + (TR ? PION_MAXTR : 0)) * TY * 32;  // tracer slabs only in the tracer instantiation
   const GridD& g = a.g;
-  const int NX = g.NG[0], NY = g.NG[1], NZ = g.NG[2];
+  const int NX = g.NG[0], NY = g.NG[1];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
-  int i = blockIdx.x * 31 + lane, j = blockIdx.y * (TY - 1) + row;
+  int i = (blockIdx.x + a.tx0) * 31 + lane, j = (blockIdx.y + a.ty0) * (TY - 1) + row;
   const bool row_active = (row < TY - 1) && (j < NY);               // warp-uniform
   const bool upd_xy = row_active && (lane < 31) && (i < NX);
   i = min(i, NX);  // clamped threads recompute a neighbour's (valid) face; their results are never used
   j = min(j, NY);
-  const int k0 = blockIdx.z * kchunk, k1 = min(k0 + kchunk, NZ);
+  const int k0 = a.k_lo + blockIdx.z * kchunk, k1 = min(k0 + kchunk, a.k_hi);
   const bool has_z = g.ndim > 2;
   const long vs = g.vs;
   const double idx = 1.0 / g.dx;
@@ -370,8 +370,8 @@ inline void launch_sweep_t(const StageArgs& a, cudaStream_t s) {
 #endif
   constexpr int TY = PION_SWEEP_TY;
   constexpr int NB = nbase(EQ);
-  const int NX = a.g.NG[0], NY = a.g.NG[1], NZ = a.g.NG[2];
-  const int bx = (NX + 30) / 31, by = (NY + TY - 2) / (TY - 1);
+  const int bx = a.tx1 - a.tx0, by = a.ty1 - a.ty0, NZ = a.k_hi - a.k_lo;
+  if (bx <= 0 || by <= 0 || NZ <= 0) return;
   // z chunks: enough blocks to fill 148 SMs a few times over, long enough to amortise the extra flux plane
   int kchunk = NZ;
   if (a.g.ndim > 2) {
@@ -390,5 +390,8 @@ inline void launch_sweep_t(const StageArgs& a, cudaStream_t s) {
   if (a.ntr > 0) k_stage_sweep<EQ, SOLVER, FKJ, TY, true><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, kchunk);
   else k_stage_sweep<EQ, SOLVER, FKJ, TY, false><<<dim3(bx, by, bz), 32 * TY, smem_notr, s>>>(a, kchunk);
 }
+
+// number of cells a sweep tile updates along x and y (host side: shell / interior boxes)
+inline void sweep_tile_cells_impl(int* cx, int* cy) { *cx = 31; *cy = PION_SWEEP_TY - 1; }
 
 }  // namespace pion
