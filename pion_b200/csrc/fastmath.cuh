@@ -41,7 +41,7 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 #endif
 }
 
-// sqrt(x), x >= 0 (x == 0 returns 0)
+// sqrt(x), x >= 0 (zero, subnormal and negative x return 0)
 __device__ __forceinline__ double fast_sqrt(double x) {
 #ifdef PION_STRICT
   return sqrt(x);
@@ -52,8 +52,20 @@ __device__ __forceinline__ double fast_sqrt(double x) {
   double t = fma(0.375, e, 0.5);
   y = fma(y * e, t, y);
   double g = x * y;                       // sqrt(x) to <= 2 ulp
-  return (x > 0.0) ? g : 0.0;
+  // the MUFU seed flushes subnormal inputs to zero (seed = inf -> NaN): treat x < DBL_MIN as 0, an
+  // absolute error of at most 1.5e-154
+  return (x >= 2.2250738585072014e-308) ? g : 0.0;
 #endif
 }
+
+// a / b and sqrt(x) as the kernels use them: the branch-free sequences above unless PION_STRICT
+__device__ __forceinline__ double pdiv(double a, double b) {
+#ifdef PION_STRICT
+  return a / b;
+#else
+  return a * fast_rcp(b);
+#endif
+}
+__device__ __forceinline__ double psqrt(double x) { return fast_sqrt(x); }
 
 }  // namespace pion

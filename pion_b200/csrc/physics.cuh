@@ -177,7 +177,7 @@ __device__ __forceinline__ int UtoP(const Cons& u, Prim& p, const PhysParams& pp
     st |= ST_NEG_PG;
     if (pp.have_mp) p.pg = p.ro * pp.min_temp / pp.mu_tot_over_kB;  // MP->Set_Temp(p,MinTemp)
     else p.pg = 0.01 * p.ro;
-  } else if (pp.have_mp && (p.pg * pp.mu_tot_over_kB / p.ro < pp.min_temp)) {
+  } else if (pp.have_mp && (p.pg * pp.mu_tot_over_kB < pp.min_temp * p.ro)) {  // T < Tmin, rho > 0 here
     p.pg = p.ro * pp.min_temp / pp.mu_tot_over_kB;
   }
   return st;
@@ -268,12 +268,16 @@ __device__ __forceinline__ void hydro_HLL(const Prim& L, const Prim& R, const Ph
 __device__ __forceinline__ bool equalD(double a, double b) {
   if (a == b) return true;
   if (fabs(a) + fabs(b) < PION_TINYVALUE) return true;
+#ifdef PION_STRICT
   return (fabs(a - b) / (fabs(a) + fabs(b) + PION_TINYVALUE)) < PION_SMALLVALUE;
+#else
+  return fabs(a - b) < PION_SMALLVALUE * (fabs(a) + fabs(b) + PION_TINYVALUE);  // same test, no division
+#endif
 }
 
 // eqns_Euler::UtoFlux (eqns_hydro_adiabatic.cpp:317-333)
 __device__ __forceinline__ void euler_UtoFlux(const Cons& u, Cons& f, double gm1) {
-  double ir = 1.0 / u.rho;
+  double ir = fast_rcp(u.rho);
   double pg = gm1 * (u.erg - (u.mn * u.mn + u.mt1 * u.mt1 + u.mt2 * u.mt2) * 0.5 * ir);
   f.rho = u.mn;
   f.mn = u.mn * u.mn * ir + pg;
@@ -287,17 +291,18 @@ __device__ __forceinline__ void euler_UtoFlux(const Cons& u, Cons& f, double gm1
 __device__ __forceinline__ void hydro_RoeCV(const Prim& L, const Prim& R, const PhysParams& pp, double hc_eta, Cons& flux,
                                             Prim& pstar) {
   const double g = pp.gamma, gm1 = g - 1.0;
-  double rl = sqrt(L.ro), rr = sqrt(R.ro);
-  double lH = 0.5 * (L.vn * L.vn + L.vt1 * L.vt1 + L.vt2 * L.vt2) + g * L.pg / gm1 / L.ro;
-  double rH = 0.5 * (R.vn * R.vn + R.vt1 * R.vt1 + R.vt2 * R.vt2) + g * R.pg / gm1 / R.ro;
-  double denom = 1.0 / (rl + rr);
+  double rl = psqrt(L.ro), rr = psqrt(R.ro);
+  double lH = 0.5 * (L.vn * L.vn + L.vt1 * L.vt1 + L.vt2 * L.vt2) + pdiv(g * L.pg, gm1 * L.ro);
+  double rH = 0.5 * (R.vn * R.vn + R.vt1 * R.vt1 + R.vt2 * R.vt2) + pdiv(g * R.pg, gm1 * R.ro);
+  double denom = fast_rcp(rl + rr);
   double m_ro = rl * rr;
   double m_vn = (rl * L.vn + rr * R.vn) * denom;
   double m_vt1 = (rl * L.vt1 + rr * R.vt1) * denom;
   double m_vt2 = (rl * L.vt2 + rr * R.vt2) * denom;
   double m_H = (rl * lH + rr * rH) * denom;
   double v2 = m_vn * m_vn + m_vt1 * m_vt1 + m_vt2 * m_vt2;
-  double a = sqrt(gm1 * fmax(m_H - 0.5 * v2, 1.0e-12 * v2));
+  double a = psqrt(gm1 * fmax(m_H - 0.5 * v2, 1.0e-12 * v2));
+  const double ia = fast_rcp(a);
   double ev[5] = {m_vn - a, m_vn, m_vn, m_vn, m_vn + a};
 #pragma unroll
   for (int v = 0; v < 5; v++) ev[v] = (ev[v] < 0.0) ? fmin(ev[v], -hc_eta) : fmax(ev[v], hc_eta);
@@ -312,8 +317,8 @@ __device__ __forceinline__ void hydro_RoeCV(const Prim& L, const Prim& R, const 
   double s2 = d_mt1 - m_vt1 * d_rho;
   double s3 = d_mt2 - m_vt2 * d_rho;
   double u5bar = d_erg - s2 * m_vt1 - s3 * m_vt2;
-  double s1 = (d_rho * (m_H - m_vn * m_vn) + m_vn * d_mn - u5bar) * gm1 / a / a;
-  double s0 = 0.5 * (d_rho * (m_vn + a) - d_mn - a * s1) / a;
+  double s1 = (d_rho * (m_H - m_vn * m_vn) + m_vn * d_mn - u5bar) * gm1 * ia * ia;
+  double s0 = 0.5 * (d_rho * (m_vn + a) - d_mn - a * s1) * ia;
   double s4 = d_rho - s0 - s1;
   Cons fl, fr;
   euler_UtoFlux(ul, fl, gm1);
@@ -341,7 +346,7 @@ __device__ __forceinline__ void hydro_RoeCV(const Prim& L, const Prim& R, const 
   flux.rho *= 0.5; flux.mn *= 0.5; flux.mt1 *= 0.5; flux.mt2 *= 0.5; flux.erg *= 0.5;
   flux.bbn = flux.bbt1 = flux.bbt2 = flux.psi = 0.0;
   pstar.ro = m_ro; pstar.vn = m_vn; pstar.vt1 = m_vt1; pstar.vt2 = m_vt2;
-  pstar.pg = m_ro * a * a / g;
+  pstar.pg = pdiv(m_ro * a * a, g);
   pstar.bn = pstar.bt1 = pstar.bt2 = pstar.psi = 0.0;
 }
 
@@ -518,12 +523,12 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
   Cons UL, UR;
   PtoU_mhd_ideal(L, UL, gm1);
   PtoU_mhd_ideal(R, UR, gm1);
-  double rl = sqrt(L.ro), rr = sqrt(R.ro);
-  double lH = (L.ro * (L.vn * L.vn + L.vt1 * L.vt1 + L.vt2 * L.vt2) / 2.0 + (g * L.pg / gm1) +
-               (L.bn * L.bn + L.bt1 * L.bt1 + L.bt2 * L.bt2)) / L.ro;
-  double rH = (R.ro * (R.vn * R.vn + R.vt1 * R.vt1 + R.vt2 * R.vt2) / 2.0 + (g * R.pg / gm1) +
-               (R.bn * R.bn + R.bt1 * R.bt1 + R.bt2 * R.bt2)) / R.ro;
-  double Roe_denom = 1.0 / (rl + rr);
+  double rl = psqrt(L.ro), rr = psqrt(R.ro);
+  double lH = (L.ro * (L.vn * L.vn + L.vt1 * L.vt1 + L.vt2 * L.vt2) / 2.0 + PION_OVER_GM1(g * L.pg, gm1) +
+               (L.bn * L.bn + L.bt1 * L.bt1 + L.bt2 * L.bt2)) * fast_rcp(L.ro);
+  double rH = (R.ro * (R.vn * R.vn + R.vt1 * R.vt1 + R.vt2 * R.vt2) / 2.0 + PION_OVER_GM1(g * R.pg, gm1) +
+               (R.bn * R.bn + R.bt1 * R.bt1 + R.bt2 * R.bt2)) * fast_rcp(R.ro);
+  double Roe_denom = fast_rcp(rl + rr);
   double m_ro = rl * rr;
   double m_vn = (rl * L.vn + rr * R.vn) * Roe_denom;
   double m_vt1 = (rl * L.vt1 + rr * R.vt1) * Roe_denom;
@@ -533,13 +538,14 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
   double m_bn = 0.5 * (L.bn + R.bn);
   double signBX = (m_bn >= 0.0) ? 1.0 : -1.0;
   double m_H = (rl * lH + rr * rH) * Roe_denom;
-  double Roe_V = sqrt(m_vn * m_vn + m_vt1 * m_vt1 + m_vt2 * m_vt2);
-  double Roe_B = sqrt(m_bn * m_bn + m_bt1 * m_bt1 + m_bt2 * m_bt2);
-  double Roe_Bt = sqrt(m_bt1 * m_bt1 + m_bt2 * m_bt2);
+  double Roe_V = psqrt(m_vn * m_vn + m_vt1 * m_vt1 + m_vt2 * m_vt2);
+  double Roe_B = psqrt(m_bn * m_bn + m_bt1 * m_bt1 + m_bt2 * m_bt2);
+  double Roe_Bt = psqrt(m_bt1 * m_bt1 + m_bt2 * m_bt2);
   double betay, betaz;
   if (Roe_Bt >= PION_TINYVALUE) {
-    betay = m_bt1 / Roe_Bt;
-    betaz = m_bt2 / Roe_Bt;
+    const double iBt = fast_rcp(Roe_Bt);
+    betay = m_bt1 * iBt;
+    betaz = m_bt2 * iBt;
   } else {
     betay = 1.0 / sqrt(2.0);
     betaz = 1.0 / sqrt(2.0);
@@ -552,15 +558,16 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
   double pd_pg = ((0.5 * Roe_V * Roe_V - CGX) * pd_ro - (m_vn * ud_mn + m_vt1 * ud_mt1 + m_vt2 * ud_mt2) + ud_erg -
                   (m_bt1 * pd_bt1 + m_bt2 * pd_bt2)) * gm1;
   // wave speeds
-  double b2 = Roe_B * Roe_B / m_ro;
-  double Roe_a = sqrt((2.0 - g) * CGX + gm1 * fmax((m_H - 0.5 * Roe_V * Roe_V - b2), 1.0e-12 * Roe_V * Roe_V));
+  const double im_ro = fast_rcp(m_ro);
+  double b2 = Roe_B * Roe_B * im_ro;
+  double Roe_a = psqrt((2.0 - g) * CGX + gm1 * fmax((m_H - 0.5 * Roe_V * Roe_V - b2), 1.0e-12 * Roe_V * Roe_V));
   double astar2 = Roe_a * Roe_a + b2;
-  double Roe_ca = sqrt(m_bn * m_bn / m_ro);
+  double Roe_ca = psqrt(m_bn * m_bn * im_ro);
   double Roe_cs = astar2 * astar2 - 4.0 * Roe_a * Roe_a * Roe_ca * Roe_ca;
-  Roe_cs = (Roe_cs <= 0.0) ? 0.0 : sqrt(Roe_cs);
-  double Roe_cf = sqrt(0.5 * (astar2 + Roe_cs));
+  Roe_cs = (Roe_cs <= 0.0) ? 0.0 : psqrt(Roe_cs);
+  double Roe_cf = psqrt(0.5 * (astar2 + Roe_cs));
   Roe_cs = astar2 - Roe_cs;
-  Roe_cs = (Roe_cs <= 0.0) ? 0.0 : sqrt(0.5 * Roe_cs);
+  Roe_cs = (Roe_cs <= 0.0) ? 0.0 : psqrt(0.5 * Roe_cs);
   if (Roe_ca > Roe_cf) Roe_ca = Roe_cf;
   if (Roe_cs > Roe_ca) Roe_cs = Roe_ca;
   double cf2diff = Roe_cf * Roe_cf - Roe_cs * Roe_cs, alphaf, alphas;
@@ -569,9 +576,10 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
     if (alphaf < 0.0) alphaf = 0.;
     alphas = Roe_cf * Roe_cf - Roe_a * Roe_a;
     if (alphas < 0.0) alphas = 0.;
-    alphaf = sqrt(alphaf / cf2diff);
+    const double icf2 = fast_rcp(cf2diff);
+    alphaf = psqrt(alphaf * icf2);
     if (alphaf > 1.0) alphaf = 1.0;
-    alphas = sqrt(alphas / cf2diff);
+    alphas = psqrt(alphas * icf2);
     if (alphas > 1.0) alphas = 1.0;
   } else {
     alphaf = alphas = 1.0 / sqrt(2.0);
@@ -582,7 +590,8 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
 #pragma unroll
   for (int v = 0; v < 7; v++) ev[v] = (ev[v] < 0.0) ? fmin(ev[v], -hc_etamax) : fmax(ev[v], hc_etamax);
   // wave strengths
-  double rootrho = sqrt(m_ro);
+  double rootrho = psqrt(m_ro);
+  const double irootrho = fast_rcp(rootrho);
   double str[7];
   {
     double t_p = (CGX * pd_ro + pd_pg);
@@ -596,16 +605,16 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
                      rootrho * alphaf * Roe_a * t_b);
     str[SP] = 0.5 * (alphas * t_p + m_ro * alphaf * Roe_cf * signBX * t_v + m_ro * alphas * Roe_cs * pd_vn -
                      rootrho * alphaf * Roe_a * t_b);
-    str[AN] = 0.5 * (+betay * pd_vt2 - betaz * pd_vt1 + signBX * (betay * pd_bt2 - betaz * pd_bt1) / rootrho);
-    str[AP] = 0.5 * (-betay * pd_vt2 + betaz * pd_vt1 + signBX * (betay * pd_bt2 - betaz * pd_bt1) / rootrho);
+    str[AN] = 0.5 * (+betay * pd_vt2 - betaz * pd_vt1 + signBX * (betay * pd_bt2 - betaz * pd_bt1) * irootrho);
+    str[AP] = 0.5 * (-betay * pd_vt2 + betaz * pd_vt1 + signBX * (betay * pd_bt2 - betaz * pd_bt1) * irootrho);
     str[CT] = (Roe_a * Roe_a - CGX) * pd_ro - pd_pg;
   }
   // right eigenvectors, component order {rho, mn, mt1, mt2, bt1, bt2, e}
   double rev[7][7];
-  double ia2 = 1.0 / (Roe_a * Roe_a);
+  double ia2 = fast_rcp(Roe_a * Roe_a);
   rev[CT][0] = ia2; rev[CT][1] = m_vn * ia2; rev[CT][2] = m_vt1 * ia2; rev[CT][3] = m_vt2 * ia2;
   rev[CT][4] = 0.0; rev[CT][5] = 0.0;
-  rev[CT][6] = (0.5 * Roe_V * Roe_V + CGX * (g - 2) / gm1) * ia2;
+  rev[CT][6] = (0.5 * Roe_V * Roe_V + PION_OVER_GM1(CGX * (g - 2), gm1)) * ia2;
   rev[AN][0] = 0.0; rev[AN][1] = 0.0;
   rev[AN][2] = -m_ro * betaz;
   rev[AN][3] = +m_ro * betay;
@@ -616,9 +625,9 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
   rev[AP][2] = -rev[AN][2]; rev[AP][3] = -rev[AN][3]; rev[AP][4] = rev[AN][4]; rev[AP][5] = rev[AN][5];
   rev[AP][6] = -rev[AN][6];
   double das = m_ro * alphas, daf = m_ro * alphaf;
-  double hb = m_H - Roe_B * Roe_B / m_ro;
+  double hb = m_H - Roe_B * Roe_B * im_ro;
   double vb = (m_vt1 * betay + m_vt2 * betaz);
-  double inorm = 1.0 / (m_ro * Roe_a * Roe_a);
+  double inorm = fast_rcp(m_ro * Roe_a * Roe_a);
   rev[SN][0] = das;
   rev[SN][1] = das * (m_vn - Roe_cs);
   rev[SN][2] = das * m_vt1 - daf * Roe_cf * betay * signBX;
@@ -668,7 +677,7 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
   flux.psi = 0.0;
   pstar.ro = m_ro; pstar.vn = m_vn; pstar.vt1 = m_vt1; pstar.vt2 = m_vt2;
   pstar.bn = m_bn; pstar.bt1 = m_bt1; pstar.bt2 = m_bt2; pstar.psi = 0.0;
-  pstar.pg = m_ro * Roe_a * Roe_a / g;
+  pstar.pg = pdiv(m_ro * Roe_a * Roe_a, g);
 }
 
 // ---------------------------------------------------------------------------
@@ -746,7 +755,7 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
       momvisc = prefactor * (eR.vt2 - eL.vt2);
       flux.mt2 -= momvisc;
       ergvisc += momvisc * pstar.vt2;
-      prefactor *= pp.etav / (pp.etav * pstar.ro);
+      prefactor *= pdiv(pp.etav, pp.etav * pstar.ro);
       momvisc = prefactor * (eR.bt1 - eL.bt1);
       flux.bbt1 -= momvisc;
       ergvisc += momvisc * pstar.bt1;

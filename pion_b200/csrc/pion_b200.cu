@@ -764,7 +764,7 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   a.fkj = fkj;
   {
     int cx, cy;
-    sweep_tile_cells(&cx, &cy);
+    sweep_tile_cells(c->cfg.eqntype, &cx, &cy);
     a.tx0 = 0; a.tx1 = (c->g.NG[0] + cx - 1) / cx;
     a.ty0 = 0; a.ty1 = (c->g.NG[1] + cy - 1) / cy;
     a.k_lo = 0; a.k_hi = c->g.NG[2];
@@ -873,7 +873,7 @@ extern "C" int pion_gpu_grid_update_state_vector(pion_gpu_ctx* c, double dt, int
 static int stage_and_bcs(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double dt, int order, bool want_dt,
                          double* bcA0, double* bcA1) {
   int cx, cy;
-  sweep_tile_cells(&cx, &cy);
+  sweep_tile_cells(c->cfg.eqntype, &cx, &cy);
   const GridD& g = c->g;
   const int ntx = (g.NG[0] + cx - 1) / cx, nty = (g.NG[1] + cy - 1) / cy, NZ = g.NG[2];
   // shell thickness in tiles: the last tile may hold fewer than the 2 cells the halo slab needs

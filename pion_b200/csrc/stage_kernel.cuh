@@ -52,7 +52,7 @@ struct StageArgs {
 
 // sCMA corrector of one tracer value (microphysics_base.cpp:80-126 with no element
 // tracers): the second assignment wins, so only values > 1 are rescaled.
-__device__ __forceinline__ double scma_corr(double tr) { return (tr > 1.0) ? 1.0 / tr : 1.0; }
+__device__ __forceinline__ double scma_corr(double tr) { return (tr > 1.0) ? fast_rcp(tr) : 1.0; }
 
 // CellTimeStep: Euler solver_eqn_hydro_adi.cpp:460-500, MHD solver_eqn_mhd_adi.cpp:516-574
 template <int EQ>
@@ -80,7 +80,7 @@ __device__ __forceinline__ double cell_time_step(const Prim& p, const PhysParams
     }
     temp += cfast_components(p.ro, p.pg, bx, by, bz, pp.gamma);
   }
-  return (dx / temp) * cfl;
+  return pdiv(dx, temp) * cfl;
 }
 
 __device__ __forceinline__ unsigned long long dbl_ordered_bits(double x) {
@@ -106,7 +106,8 @@ __device__ __forceinline__ int cell_advance_time(const StageArgs& a, long c, con
   const int status = UtoP<EQ>(U, Pn, a.pp);
   if (EQ == EQ_GLM) Pn.psi *= a.glm_damp;
   // temperature cap of grid_update_state_vector (time_integrator.cpp:926-932)
-  if (a.pp.have_mp && (Pn.pg * a.pp.mu_tot_over_kB / Pn.ro > a.pp.max_temp))
+  // T > Tmax  <=>  p mu/kB > Tmax rho (rho > 0): no division on the common path
+  if (a.pp.have_mp && (Pn.pg * a.pp.mu_tot_over_kB > a.pp.max_temp * Pn.ro))
     Pn.pg = Pn.ro * a.pp.max_temp / a.pp.mu_tot_over_kB;
   store_prim<EQ>(a.out, c, vs, Pn);
 #pragma unroll
@@ -115,7 +116,7 @@ __device__ __forceinline__ int cell_advance_time(const StageArgs& a, long c, con
       double pb = __ldg(a.Pb + (long)(NB + q) * vs + c);
       if (a.pp.have_mp) pb *= scma_corr(pb);
       double u = pb * Pb.ro + acctr[q];
-      double pn = u / U.rho;
+      double pn = pdiv(u, U.rho);
       if (a.pp.have_mp) pn *= scma_corr(pn);
       a.out[(long)(NB + q) * vs + c] = pn;
     }
@@ -423,7 +424,7 @@ void launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s)
 void launch_stage_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 // cells per sweep tile along x / y (stage_sweep.cuh: 32 lanes, TY rows, one of each only produces fluxes)
-void sweep_tile_cells(int* cx, int* cy);
+void sweep_tile_cells(int eq, int* cx, int* cy);  // eq: EQ_EULER / EQ_MHD / EQ_GLM
 // flux-once sweep kernel (stage_sweep.cuh), instantiated in sweep_{euler,mhd,glm}.cu
 void launch_sweep_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_sweep_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);

@@ -140,6 +140,20 @@ __device__ __forceinline__ double tracer_low_face_flux(const StageArgs& a, const
 #ifndef PION_SWEEP_MINBLOCKS
 #define PION_SWEEP_MINBLOCKS 1
 #endif
+#ifndef PION_SWEEP_TY
+#define PION_SWEEP_TY 12
+#endif
+#ifndef PION_SWEEP_TY_EULER
+#define PION_SWEEP_TY_EULER 8
+#endif
+#ifndef PION_SWEEP_MINBLOCKS_EULER
+#define PION_SWEEP_MINBLOCKS_EULER 2
+#endif
+// Tile shape per equation set.  MHD (HLLD / Roe) needs ~166 registers: one 384-thread block per SM
+// without spills beats two 256-thread blocks at 128 registers with spills.  Euler is lighter and
+// latency-bound (ncu: long-scoreboard 39 %), so it runs more, smaller blocks per SM.
+__host__ __device__ constexpr int sweep_ty(int eq) { return eq == EQ_EULER ? PION_SWEEP_TY_EULER : PION_SWEEP_TY; }
+__host__ __device__ constexpr int sweep_minb(int eq) { return eq == EQ_EULER ? PION_SWEEP_MINBLOCKS_EULER : PION_SWEEP_MINBLOCKS; }
 
 // split-phase block barrier (mbarrier): a thread ARRIVES right after publishing its y flux
 // and only WAITS after it has computed its x flux, so warp skew hides behind useful work.
@@ -160,10 +174,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const double* p) {
+#if PION_SWEEP_PREFETCH == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 
-template <int EQ, int SOLVER, bool FKJ, int TY, bool TR>
-__global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(const __grid_constant__ StageArgs a, const int kchunk) {
+template <int EQ, int SOLVER, bool FKJ, int TY, int MINB, bool TR>
+__global__ void __launch_bounds__(32 * TY, MINB) k_stage_sweep(const __grid_constant__ StageArgs a, const int kchunk) {
   extern __shared__ double s_flux[];  // [2][NB + MAXTR][TY][32]
   __shared__ unsigned long long s_bar;
   constexpr int NB = nbase(EQ);
@@ -205,7 +225,11 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
     if (has_z && k + 1 < k1) {
       const long cn = c + (long)(a.order == 2 ? 3 : 2) * g.sz;
 #pragma unroll
-      for (int v = 0; v < NB; v++) prefetch_l1(a.S + (long)v * vs + cn);
+      for (int v = 0; v < NB + ntr; v++) prefetch_l1(a.S + (long)v * vs + cn);
+      if (a.Pb != a.S) {  // corrector: base state of the next plane
+#pragma unroll
+        for (int v = 0; v < NB + ntr; v++) prefetch_l1(a.Pb + (long)v * vs + c + g.sz);
+      }
     }
 #endif
 
@@ -365,10 +389,7 @@ __global__ void __launch_bounds__(32 * TY, PION_SWEEP_MINBLOCKS) k_stage_sweep(c
 
 template <int EQ, int SOLVER, bool FKJ>
 inline void launch_sweep_t(const StageArgs& a, cudaStream_t s) {
-#ifndef PION_SWEEP_TY
-#define PION_SWEEP_TY 12
-#endif
-  constexpr int TY = PION_SWEEP_TY;
+  constexpr int TY = sweep_ty(EQ), MINB = sweep_minb(EQ);
   constexpr int NB = nbase(EQ);
   const int bx = a.tx1 - a.tx0, by = a.ty1 - a.ty0, NZ = a.k_hi - a.k_lo;
   if (bx <= 0 || by <= 0 || NZ <= 0) return;
@@ -383,15 +404,15 @@ inline void launch_sweep_t(const StageArgs& a, cudaStream_t s) {
   const size_t smem_notr = (size_t)2 * NB * TY * 32 * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_notr);
+    cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_notr);
     attr_done = true;
   }
-  if (a.ntr > 0) k_stage_sweep<EQ, SOLVER, FKJ, TY, true><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, kchunk);
-  else k_stage_sweep<EQ, SOLVER, FKJ, TY, false><<<dim3(bx, by, bz), 32 * TY, smem_notr, s>>>(a, kchunk);
+  if (a.ntr > 0) k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, true><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, kchunk);
+  else k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, false><<<dim3(bx, by, bz), 32 * TY, smem_notr, s>>>(a, kchunk);
 }
 
 // number of cells a sweep tile updates along x and y (host side: shell / interior boxes)
-inline void sweep_tile_cells_impl(int* cx, int* cy) { *cx = 31; *cy = PION_SWEEP_TY - 1; }
+inline void sweep_tile_cells_impl(int eq, int* cx, int* cy) { *cx = 31; *cy = sweep_ty(eq) - 1; }
 
 }  // namespace pion

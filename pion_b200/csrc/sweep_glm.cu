@@ -13,5 +13,5 @@ void launch_sweep_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s) {
     else launch_sweep_t<EQ_GLM, SOLVE_HLL, false>(a, s);
   }
 }
-void sweep_tile_cells(int* cx, int* cy) { sweep_tile_cells_impl(cx, cy); }
+void sweep_tile_cells(int eq, int* cx, int* cy) { sweep_tile_cells_impl(eq, cx, cy); }
 }  // namespace pion
