@@ -131,9 +131,6 @@ __device__ __forceinline__ double tracer_low_face_flux(const StageArgs& a, const
   return f;
 }
 
-#ifndef PION_SWEEP_PREFETCH
-#define PION_SWEEP_PREFETCH 0
-#endif
 #ifndef PION_SWEEP_MBAR
 #define PION_SWEEP_MBAR 1
 #endif
@@ -174,13 +171,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void prefetch_l1(const double* p) {
-#if PION_SWEEP_PREFETCH == 2
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
 
 template <int EQ, int SOLVER, bool FKJ, int TY, int MINB, bool TR>
 __global__ void __launch_bounds__(32 * TY, MINB) k_stage_sweep(const __grid_constant__ StageArgs a, const int kchunk) {
@@ -220,18 +210,6 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_stage_sweep(const __grid_cons
     double* sbuf = s_flux + (size_t)((k - k0) & 1) * SLAB;
     double* sbuf_tr = sbuf + NB * TY * 32;
 
-    // pull the plane the NEXT iteration touches for the first time towards L1
-#if PION_SWEEP_PREFETCH
-    if (has_z && k + 1 < k1) {
-      const long cn = c + (long)(a.order == 2 ? 3 : 2) * g.sz;
-#pragma unroll
-      for (int v = 0; v < NB + ntr; v++) prefetch_l1(a.S + (long)v * vs + cn);
-      if (a.Pb != a.S) {  // corrector: base state of the next plane
-#pragma unroll
-        for (int v = 0; v < NB + ntr; v++) prefetch_l1(a.Pb + (long)v * vs + c + g.sz);
-      }
-    }
-#endif
 
     Cons acc;
     cons_zero<EQ>(acc);
