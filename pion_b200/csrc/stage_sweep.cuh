@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_stage_sweep(const __grid_cons
 #pragma unroll
   for (int q = 0; q < PION_MAXTR; q++) Fz_tr[q] = 0.0;
 
-  for (int k = has_z ? k0 - 1 : k0; k < k1; k++) {
-    const bool warm = k < k0;  // first iteration of a 3-D chunk: only the z flux into plane k0
+  for (int k = k0 - 1; k < k1; k++) {
+    const bool warm = k < k0;  // first iteration of a chunk: only the fluxes INTO plane k0 (z face, y faces)
     const long c = gidx(g, i + g.nb[0], j + g.nb[1], k + g.nb[2]);
     double* sbuf = s_flux + (size_t)((k - k0) & 1) * SLAB;
     double* sbuf_tr = sbuf + NB * TY * 32;
@@ -224,16 +224,20 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_stage_sweep(const __grid_cons
     }
 
     // Schedule of one plane (ONE flux call site, ONE accumulate site):
-    //   step 0: y flux -> shared memory, arrive      step 1: x flux (shfl), accumulate x
-    //   step 2: wait, accumulate y from shared memory step 3: z flux, accumulate z
-    // so dU is still summed in the reference's order x, y, z.
+    //   step 1: x flux (shfl), accumulate x          step 2: wait, accumulate y from shared memory
+    //   step 3: z flux, accumulate z                 step 4: y flux of the NEXT plane -> shared memory, arrive
+    // so dU is still summed in the reference's order x, y, z, and a whole plane of work separates the
+    // arrive (end of the previous iteration) from the wait (step 2): warp skew never reaches the barrier.
+    // The warm-up iteration does steps 3 and 4 only (the fluxes into the chunk's first plane).
 #pragma unroll 1
-    for (int step = warm ? 3 : 0; step < (has_z ? 4 : 3); step++) {
+    for (int step = warm ? 3 : 1; step <= 4; step++) {
+      if ((step == 3 && !has_z) || (step == 4 && k + 1 >= k1)) continue;
       const int ax = (step == 1) ? 0 : (step == 3) ? 2 : 1;
       const int a1 = (ax == 2) ? 0 : ax + 1;
       const int a2 = (a1 == 2) ? 0 : a1 + 1;
       const long st = axis_stride(g, ax);
-      const long X = (ax == 2) ? c + st : c;  // z: the HIGH face of this cell = low face of the cell above
+      // z: the HIGH face of this cell = low face of the cell above; step 4: the y face of the cell above
+      const long X = (step >= 3) ? c + g.sz : c;
       Cons Fnew;
       cons_zero<EQ>(Fnew);
       double Fnew_tr[PION_MAXTR];
@@ -245,11 +249,13 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_stage_sweep(const __grid_cons
         for (int q = 0; q < PION_MAXTR; q++)
           if (q < ntr) Fnew_tr[q] = tracer_low_face_flux(a, a.S + (long)(NB + q) * vs, X, st, Fnew.rho);
       }
-      if (step == 0) {
-        cons_to_smem<EQ, TY>(sbuf, row, lane, Fnew);
+      if (step == 4) {
+        double* nbuf = s_flux + (size_t)((k + 1 - k0) & 1) * SLAB;  // slab of plane k+1
+        double* nbuf_tr = nbuf + NB * TY * 32;
+        cons_to_smem<EQ, TY>(nbuf, row, lane, Fnew);
 #pragma unroll
         for (int q = 0; q < PION_MAXTR; q++)
-          if (q < ntr) sbuf_tr[(q * TY + row) * 32 + lane] = Fnew_tr[q];
+          if (q < ntr) nbuf_tr[(q * TY + row) * 32 + lane] = Fnew_tr[q];
 #if PION_SWEEP_MBAR
         mbar_arrive(&s_bar);
 #endif
