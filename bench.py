@@ -373,7 +373,7 @@ def main():
                        "global_grid": gNG, "decomposition": nsplit, "l2_policy": "working set (>20 GB per GPU) far exceeds the 126 MB L2",
                        "step": "calculate_timestep + advance_time (predictor, BCs, corrector, BCs, CFL reduction)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(S), "peak_source": peak_src, "kernel": "k_stage_sweep<GLM,HLLD,FKJ98,TY=12> (one launch per stage, two per step)",
+                         "traffic": ncu_traffic(S), "peak_source": peak_src, "kernel": "k_stage_sweep_tma<GLM,HLLD,FKJ98,TY=12> (TMA-staged stencil; one launch per stage, two per step)",
                          "alg_bytes_per_cell_update": ALG_BYTES_PER_CELL_UPDATE, "launches_timed": stage_n,
                          # the path is FP64-pipe-bound on B200: ncu counters of the committed
                          # capture next to the HBM figure the contract asks for

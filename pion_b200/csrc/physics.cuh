@@ -223,7 +223,7 @@ __device__ __forceinline__ double cfast2_ir(double ir, double pg, double bx, dou
   double ch2 = g * pg * ir;
   double temp1 = ch2 + (bx * bx + by * by + bz * bz) * ir;
   double temp2 = 4. * ch2 * bx * bx * ir;
-  temp2 = fmax(PION_MACHINEACCURACY, temp1 * temp1 - temp2);
+  temp2 = pmax(temp1 * temp1 - temp2, PION_MACHINEACCURACY);
   return (temp1 + fast_sqrt(temp2)) / 2.;
 }
 __device__ __forceinline__ double cfast_components(double ro, double pg, double bx, double by, double bz, double g) {
@@ -231,7 +231,7 @@ __device__ __forceinline__ double cfast_components(double ro, double pg, double 
   double ch = sqrt(g * pg / ro);
   double temp1 = ch * ch + (bx * bx + by * by + bz * bz) / ro;
   double temp2 = 4. * ch * ch * bx * bx / ro;
-  temp2 = fmax(PION_MACHINEACCURACY, temp1 * temp1 - temp2);
+  temp2 = pmax(temp1 * temp1 - temp2, PION_MACHINEACCURACY);
   return sqrt((temp1 + sqrt(temp2)) / 2.);
 #else
   return fast_sqrt(cfast2_ir(fast_rcp(ro), pg, bx, by, bz, g));
@@ -251,9 +251,9 @@ __device__ __forceinline__ void hydro_HLL(const Prim& L, const Prim& R, const Ph
   PtoU<EQ_EULER>(R, UR, gm1);
   PUtoFlux<EQ_EULER>(L, UL, FL);
   PUtoFlux<EQ_EULER>(R, UR, FR);
-  double cf_max = fmax(chydro(L.ro, L.pg, pp.gamma), chydro(R.ro, R.pg, pp.gamma));
-  double Sl = fmin(L.vn, R.vn) - cf_max;
-  double Sr = fmax(L.vn, R.vn) + cf_max;
+  double cf_max = pmax(chydro(L.ro, L.pg, pp.gamma), chydro(R.ro, R.pg, pp.gamma));
+  double Sl = pmin(L.vn, R.vn) - cf_max;
+  double Sr = pmax(L.vn, R.vn) + cf_max;
   double idS = fast_rcp(Sr - Sl);
 #define PION_HLL_COMP(c)                                                             \
   flux.c = (Sl > 0) ? FL.c : (Sr < 0) ? FR.c : (Sr * FL.c - Sl * FR.c + Sr * Sl * (UR.c - UL.c)) * idS; \
@@ -301,11 +301,11 @@ __device__ __forceinline__ void hydro_RoeCV(const Prim& L, const Prim& R, const 
   double m_vt2 = (rl * L.vt2 + rr * R.vt2) * denom;
   double m_H = (rl * lH + rr * rH) * denom;
   double v2 = m_vn * m_vn + m_vt1 * m_vt1 + m_vt2 * m_vt2;
-  double a = psqrt(gm1 * fmax(m_H - 0.5 * v2, 1.0e-12 * v2));
+  double a = psqrt(gm1 * pmax(m_H - 0.5 * v2, 1.0e-12 * v2));
   const double ia = fast_rcp(a);
   double ev[5] = {m_vn - a, m_vn, m_vn, m_vn, m_vn + a};
 #pragma unroll
-  for (int v = 0; v < 5; v++) ev[v] = (ev[v] < 0.0) ? fmin(ev[v], -hc_eta) : fmax(ev[v], hc_eta);
+  for (int v = 0; v < 5; v++) ev[v] = (ev[v] < 0.0) ? pmin(ev[v], -hc_eta) : pmax(ev[v], hc_eta);
   Cons ul, ur;
   PtoU<EQ_EULER>(L, ul, gm1);
   PtoU<EQ_EULER>(R, ur, gm1);
@@ -357,13 +357,13 @@ __device__ __forceinline__ void hlld_speeds(const Prim& L, const Prim& R, double
 #ifdef PION_STRICT
   double cf_l = cfast_components(L.ro, L.pg, Bx, L.bt1, L.bt2, g);
   double cf_r = cfast_components(R.ro, R.pg, Bx, R.bt1, R.bt2, g);
-  double cf_max = fmax(cf_l, cf_r);
+  double cf_max = pmax(cf_l, cf_r);
 #else
-  double cf_max = fast_sqrt(fmax(cfast2_ir(fast_rcp(L.ro), L.pg, Bx, L.bt1, L.bt2, g),
+  double cf_max = fast_sqrt(pmax(cfast2_ir(fast_rcp(L.ro), L.pg, Bx, L.bt1, L.bt2, g),
                                  cfast2_ir(fast_rcp(R.ro), R.pg, Bx, R.bt1, R.bt2, g)));
 #endif
-  Sl = fmin(L.vn, R.vn) - cf_max;
-  Sr = fmax(L.vn, R.vn) + cf_max;
+  Sl = pmin(L.vn, R.vn) - cf_max;
+  Sr = pmax(L.vn, R.vn) + cf_max;
 }
 
 // HLLD_MHD::MHD_HLL_flux_solver (HLLD_MHD.cpp:377-417)
@@ -409,10 +409,10 @@ __device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const Phy
   const double BX = 0.5 * (L.bn + R.bn);
   const double BX2 = BX * BX;
   // HLLD_signal_speeds (:342-368)
-  const double cf_max = fast_sqrt(fmax(cfast2_ir(fast_rcp(L.ro), L.pg, BX, L.bt1, L.bt2, g),
+  const double cf_max = fast_sqrt(pmax(cfast2_ir(fast_rcp(L.ro), L.pg, BX, L.bt1, L.bt2, g),
                                        cfast2_ir(fast_rcp(R.ro), R.pg, BX, R.bt1, R.bt2, g)));
-  const double lam0 = fmin(L.vn, R.vn) - cf_max;
-  const double lam4 = fmax(L.vn, R.vn) + cf_max;
+  const double lam0 = pmin(L.vn, R.vn) - cf_max;
+  const double lam4 = pmax(L.vn, R.vn) + cf_max;
   const double sl_vl = lam0 - L.vn, sr_vr = lam4 - R.vn;
   const double pm_l = 0.5 * (L.bn * L.bn + L.bt1 * L.bt1 + L.bt2 * L.bt2);
   const double pm_r = 0.5 * (R.bn * R.bn + R.bt1 * R.bt1 + R.bt2 * R.bt2);
@@ -560,7 +560,7 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
   // wave speeds
   const double im_ro = fast_rcp(m_ro);
   double b2 = Roe_B * Roe_B * im_ro;
-  double Roe_a = psqrt((2.0 - g) * CGX + gm1 * fmax((m_H - 0.5 * Roe_V * Roe_V - b2), 1.0e-12 * Roe_V * Roe_V));
+  double Roe_a = psqrt((2.0 - g) * CGX + gm1 * pmax((m_H - 0.5 * Roe_V * Roe_V - b2), 1.0e-12 * Roe_V * Roe_V));
   double astar2 = Roe_a * Roe_a + b2;
   double Roe_ca = psqrt(m_bn * m_bn * im_ro);
   double Roe_cs = astar2 * astar2 - 4.0 * Roe_a * Roe_a * Roe_ca * Roe_ca;
@@ -588,7 +588,7 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
   ev[FN] = m_vn - Roe_cf; ev[AN] = m_vn - Roe_ca; ev[SN] = m_vn - Roe_cs; ev[CT] = m_vn;
   ev[SP] = m_vn + Roe_cs; ev[AP] = m_vn + Roe_ca; ev[FP] = m_vn + Roe_cf;
 #pragma unroll
-  for (int v = 0; v < 7; v++) ev[v] = (ev[v] < 0.0) ? fmin(ev[v], -hc_etamax) : fmax(ev[v], hc_etamax);
+  for (int v = 0; v < 7; v++) ev[v] = (ev[v] < 0.0) ? pmin(ev[v], -hc_etamax) : pmax(ev[v], hc_etamax);
   // wave strengths
   double rootrho = psqrt(m_ro);
   const double irootrho = fast_rcp(rootrho);

@@ -7,7 +7,9 @@
 //   sim_control/sim_init.cpp:215-280         Init after ReadData
 // There is no CPU fallback: every numerical step is a kernel launch on the
 // context's stream; the host only sequences launches and reads back scalars.
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -85,6 +87,9 @@ struct pion_gpu_ctx {
   double* d_wind_val = nullptr;
   double *sendbuf[6] = {nullptr}, *recvbuf[6] = {nullptr};
   size_t halo_elems[6] = {0};
+  // TMA tensor maps over the two state arrays (3-D grids; the TMA sweep kernel, stage_sweep_tma.cuh)
+  alignas(64) CUtensorMap tmapP, tmapPh;
+  bool have_tmap = false;
 };
 
 static inline int nblocks(long n, int block, int cap = 148 * 16) {
@@ -98,6 +103,37 @@ static inline int nblocks(long n, int block, int cap = 148 * 16) {
 // create / destroy
 // ---------------------------------------------------------------------------
 extern "C" const char* pion_gpu_last_error(void) { return g_last_error.c_str(); }
+
+// Tensor map of one state array for the TMA sweep kernel: a 4-D tensor (x, y, z, variable) over the
+// pitched SoA layout of grid.cuh, box = one plane tile [nbase][TY+3][36].  The driver entry point is
+// fetched through the runtime (no link-time dependency on libcuda).
+static int make_state_tmap(const pion_gpu_ctx* c, double* base, CUtensorMap* out) {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return 1;
+    }
+    enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  int cw, rh, nb;
+  sweep_tma_box(c->cfg.eqntype, &cw, &rh, &nb);
+  const GridD& g = c->g;
+  const cuuint64_t dims[4] = {(cuuint64_t)g.sy, (cuuint64_t)g.NGa[1], (cuuint64_t)g.NGa[2], (cuuint64_t)nb};
+  const cuuint64_t strides[3] = {(cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8, (cuuint64_t)g.vs * 8};
+  const cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)rh, 1u, (cuuint32_t)nb};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 1;
+  }
+  return 0;
+}
 
 static int check_config(const pion_gpu_config& c) {
   if (c.ndim < 1 || c.ndim > 3) { set_error("ndim must be 1..3"); return 1; }
@@ -346,6 +382,14 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
     set_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     pion_gpu_destroy(c);
     return nullptr;
+  }
+  {
+    // 3-D Cartesian grids run the TMA sweep kernel (PION_B200_NO_TMA=1: the LDG sweep kernel, for A/B tests)
+    const char* e = getenv("PION_B200_NO_TMA");
+    if (g.ndim == 3 && g.coord == PION_COORD_CRT && !(e && e[0] == '1')) {
+      if (make_state_tmap(c, c->P, &c->tmapP) || make_state_tmap(c, c->Ph, &c->tmapPh)) { pion_gpu_destroy(c); return nullptr; }
+      c->have_tmap = true;
+    }
   }
   cudaMemsetAsync(c->P, 0, c->arr_elems * sizeof(double), c->stream);
   cudaMemsetAsync(c->Ph, 0, c->arr_elems * sizeof(double), c->stream);
@@ -762,6 +806,7 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   a.fused = fused ? 1 : 0;
   const int fkj = (c->cfg.artviscosity == 1 || c->cfg.artviscosity == 4) ? 1 : 0;
   a.fkj = fkj;
+  a.tmap = !c->have_tmap ? nullptr : (S == c->P) ? (const void*)&c->tmapP : (S == c->Ph) ? (const void*)&c->tmapPh : nullptr;
   {
     int cx, cy;
     sweep_tile_cells(c->cfg.eqntype, &cx, &cy);

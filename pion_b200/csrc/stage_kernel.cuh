@@ -48,6 +48,8 @@ struct StageArgs {
   // sweep kernel only: the box of tiles / planes this launch covers (x tiles of 31 cells, y tiles of
   // TY-1 rows, z planes); the whole grid unless the stage is split into boundary shell + interior
   int tx0, tx1, ty0, ty1, k_lo, k_hi;
+  // HOST pointer to the CUtensorMap of array S (TMA sweep kernel; null = not available)
+  const void* tmap;
 };
 
 // sCMA corrector of one tracer value (microphysics_base.cpp:80-126 with no element
@@ -62,11 +64,11 @@ __device__ __forceinline__ double cell_time_step(const Prim& p, const PhysParams
     temp = p.vn * p.vn;
     if (ndim > 1) temp += p.vt1 * p.vt1;
     if (ndim > 2) temp += p.vt2 * p.vt2;
-    temp = sqrt(temp) + chydro(p.ro, p.pg, pp.gamma);
+    temp = psqrt(temp) + chydro(p.ro, p.pg, pp.gamma);
   } else {
     temp = fabs(p.vn);
-    if (ndim > 1) temp = fmax(temp, fabs(p.vt1));
-    if (ndim > 2) temp = fmax(temp, fabs(p.vt2));
+    if (ndim > 1) temp = pmax(fabs(p.vt1), temp);
+    if (ndim > 2) temp = pmax(fabs(p.vt2), temp);
     double bx = p.bn, by = p.bt1, bz = p.bt2;
     if (ndim > 1) {
       // rotate to the axis of smallest |B| component (:541-563)
@@ -93,10 +95,9 @@ __device__ __forceinline__ unsigned long long dbl_ordered_bits(double x) {
 // grid_update_state_vector (time_integrator.cpp:881-958): U = PtoU(Pb) + dU,
 // out = UtoP(U) with floors; optionally the next step's CellTimeStep.
 template <int EQ>
-__device__ __forceinline__ int cell_advance_time(const StageArgs& a, long c, const Cons& acc, const double* acctr, int ntr, double& my_dt) {
+__device__ __forceinline__ int cell_advance_time_pb(const StageArgs& a, long c, const Prim& Pb, const Cons& acc, const double* acctr, int ntr, double& my_dt) {
   constexpr int NB = nbase(EQ);
   const long vs = a.g.vs;
-  Prim Pb = load_prim<EQ>(a.Pb, c, vs, 0, 1, 2);
   Cons U;
   PtoU<EQ>(Pb, U, a.pp.gamma - 1.0);
   U.rho += acc.rho; U.erg += acc.erg; U.mn += acc.mn; U.mt1 += acc.mt1; U.mt2 += acc.mt2;
@@ -121,8 +122,14 @@ __device__ __forceinline__ int cell_advance_time(const StageArgs& a, long c, con
       a.out[(long)(NB + q) * vs + c] = pn;
     }
   }
-  if (a.dtmin) my_dt = fmin(my_dt, cell_time_step<EQ>(Pn, a.pp, a.g.ndim, a.g.dx, a.cfl));
+  if (a.dtmin) my_dt = pmin(cell_time_step<EQ>(Pn, a.pp, a.g.ndim, a.g.dx, a.cfl), my_dt);
   return status;
+}
+// ... with the base state loaded from a.Pb
+template <int EQ>
+__device__ __forceinline__ int cell_advance_time(const StageArgs& a, long c, const Cons& acc, const double* acctr, int ntr, double& my_dt) {
+  const Prim Pb = load_prim<EQ>(a.Pb, c, a.g.vs, 0, 1, 2);
+  return cell_advance_time_pb<EQ>(a, c, Pb, acc, acctr, ntr, my_dt);
 }
 
 // block-level reductions: min dt (warp shuffles + one atomicMin per block) and error counters
@@ -425,6 +432,7 @@ void launch_stage_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 // cells per sweep tile along x / y (stage_sweep.cuh: 32 lanes, TY rows, one of each only produces fluxes)
 void sweep_tile_cells(int eq, int* cx, int* cy);  // eq: EQ_EULER / EQ_MHD / EQ_GLM
+void sweep_tma_box(int eq, int* cw, int* rh, int* nb);  // box of one TMA plane load (stage_sweep_tma.cuh)
 // flux-once sweep kernel (stage_sweep.cuh), instantiated in sweep_{euler,mhd,glm}.cu
 void launch_sweep_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_sweep_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);

@@ -1,13 +1,13 @@
 // euler instantiations of the flux-once sweep stage kernel (stage_sweep.cuh).
-#include "stage_sweep.cuh"
+#include "stage_sweep_tma.cuh"
 namespace pion {
 void launch_sweep_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s) {
   if (solver == SOLVE_ROE) {
-    if (fkj) launch_sweep_t<EQ_EULER, SOLVE_ROE, true>(a, s);
-    else launch_sweep_t<EQ_EULER, SOLVE_ROE, false>(a, s);
+    if (fkj) launch_sweep_any<EQ_EULER, SOLVE_ROE, true>(a, s);
+    else launch_sweep_any<EQ_EULER, SOLVE_ROE, false>(a, s);
   } else {
-    if (fkj) launch_sweep_t<EQ_EULER, SOLVE_HLL, true>(a, s);
-    else launch_sweep_t<EQ_EULER, SOLVE_HLL, false>(a, s);
+    if (fkj) launch_sweep_any<EQ_EULER, SOLVE_HLL, true>(a, s);
+    else launch_sweep_any<EQ_EULER, SOLVE_HLL, false>(a, s);
   }
 }
 }  // namespace pion

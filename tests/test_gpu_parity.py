@@ -48,6 +48,14 @@ def test_3d_periodic_with_tracer(eqn, solver, av):
     run_pair(case_3d(eqn, solver, av, ntracer=1))
 
 
+@pytest.mark.parametrize("eqn,solver", EQ_SOLVERS)
+@pytest.mark.parametrize("av", [0, 1, 4])
+def test_3d_multi_tile_tma_sweep(eqn, solver, av):
+    """3-D grid without tracers = the TMA-staged sweep kernel (stage_sweep_tma.cuh); 40 x 26 x 20 cells
+    span 2 x 3 tiles and 3 z chunks, so tile halos, the plane ring and chunk warm-up planes are all hit."""
+    run_pair(case_3d(eqn, solver, av, bcs="reflect-outflow", NG=(40, 26, 20)))
+
+
 @pytest.mark.parametrize("bcs", ["outflow", "reflect-outflow", "mixed1", "mixed2"])
 @pytest.mark.parametrize("eqn,solver", [("glm-mhd", 7), ("euler", 8), ("i-mhd", 4)])
 def test_boundary_types(bcs, eqn, solver):
