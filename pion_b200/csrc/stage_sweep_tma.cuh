@@ -31,6 +31,12 @@ namespace pion {
 #ifndef PION_TMA_UNROLL
 #define PION_TMA_UNROLL 1
 #endif
+#ifndef PION_TMA_PRODUCER_SLEEP_NS
+#define PION_TMA_PRODUCER_SLEEP_NS 4000
+#endif
+#ifndef PION_TMA_ONEFLUX
+#define PION_TMA_ONEFLUX 1
+#endif
 
 constexpr int TMA_CW = 36;                                            // tile columns
 __host__ __device__ constexpr int tma_rh(int ty) { return ty + 3; }  // tile rows
@@ -52,6 +58,22 @@ __device__ __forceinline__ void mbar_wait_spin(unsigned long long* bar, unsigned
         "}\n"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// same, with a suspend-time hint (ns): the waiting thread sleeps in hardware until the phase completes
+// instead of re-issuing try_wait (the producer lane waits most of a plane time for the consumers)
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity, unsigned hint_ns) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
         : "memory");
   } while (!ok);
 }
@@ -83,12 +105,13 @@ __device__ __forceinline__ Prim lds_prim(const double* p, int ax, int a1, int a2
   return q;
 }
 
-// flux through the face between tile cells pL | pR (pQ0, pQ3: the next cells outwards), as low_face_flux
-template <int EQ, int SOLVER, bool FKJ, int VS>
-__device__ __forceinline__ void face_flux_tile(const StageArgs& a, const double* pQ0, const double* pL, const double* pR,
-                                               const double* pQ3, bool use_hll, int ax, int a1, int a2, Cons& F) {
-  Prim eL = lds_prim<EQ, VS>(pL, ax, a1, a2);
-  Prim eR = lds_prim<EQ, VS>(pR, ax, a1, a2);
+// edge states at the face between tile cells pL | pR (pQ0, pQ3: the next cells outwards), solver frame of
+// axis ax: SetEdgeState / SetSlope (VectorOps.cpp:535-617)
+template <int EQ, int VS>
+__device__ __forceinline__ void edge_states_tile(const StageArgs& a, const double* pQ0, const double* pL, const double* pR,
+                                                 const double* pQ3, int ax, int a1, int a2, Prim& eL, Prim& eR) {
+  eL = lds_prim<EQ, VS>(pL, ax, a1, a2);
+  eR = lds_prim<EQ, VS>(pR, ax, a1, a2);
   if (a.order == 2) {
     const Prim Q0 = lds_prim<EQ, VS>(pQ0, ax, a1, a2);
     const Prim Q3 = lds_prim<EQ, VS>(pQ3, ax, a1, a2);
@@ -103,7 +126,91 @@ __device__ __forceinline__ void face_flux_tile(const StageArgs& a, const double*
     if (EQ == EQ_GLM) { PION_EDGE2(psi) }
 #undef PION_EDGE2
   }
+}
+
+// flux through that face, as low_face_flux
+template <int EQ, int SOLVER, bool FKJ, int VS>
+__device__ __forceinline__ void face_flux_tile(const StageArgs& a, const double* pQ0, const double* pL, const double* pR,
+                                               const double* pQ3, bool use_hll, int ax, int a1, int a2, Cons& F) {
+  Prim eL, eR;
+  edge_states_tile<EQ, VS>(a, pQ0, pL, pR, pQ3, ax, a1, a2, eL, eR);
   intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(eL, eR, a.pp, use_hll, 0.0, F);
+}
+
+// dU accumulators in the GRID frame (x, y, z): with compile-time axes nothing has to be rotated
+struct NatAcc {
+  double rho, erg, m0, m1, m2, b0, b1, b2, psi;
+};
+// component q (0,1,2) of a triple, q known at compile time
+template <int Q>
+__device__ __forceinline__ double& pick3(double& c0, double& c1, double& c2) { return Q == 0 ? c0 : Q == 1 ? c1 : c2; }
+template <int Q>
+__device__ __forceinline__ double pick3c(double c0, double c1, double c2) { return Q == 0 ? c0 : Q == 1 ? c1 : c2; }
+
+// acc += dt (F_low - F_high) / dx for the axis AX, D in that axis' solver frame (dU_Cell + DivStateVectorComponent)
+template <int EQ, int AX>
+__device__ __forceinline__ void acc_flux_diff(NatAcc& A, const Cons& D, double dt, double idx, double dtdx) {
+  constexpr int A1 = (AX + 1) % 3, A2 = (AX + 2) % 3;
+#ifdef PION_STRICT
+#define PION_ACC(dst, src) dst += dt * (src * idx);
+#else
+#define PION_ACC(dst, src) dst = fma(dtdx, src, dst);
+#endif
+  PION_ACC(A.rho, D.rho) PION_ACC(A.erg, D.erg)
+  PION_ACC(pick3<AX>(A.m0, A.m1, A.m2), D.mn) PION_ACC(pick3<A1>(A.m0, A.m1, A.m2), D.mt1) PION_ACC(pick3<A2>(A.m0, A.m1, A.m2), D.mt2)
+  if (EQ != EQ_EULER) {
+    PION_ACC(pick3<AX>(A.b0, A.b1, A.b2), D.bbn) PION_ACC(pick3<A1>(A.b0, A.b1, A.b2), D.bbt1) PION_ACC(pick3<A2>(A.b0, A.b1, A.b2), D.bbt2)
+  }
+  if (EQ == EQ_GLM) { PION_ACC(A.psi, D.psi) }
+#undef PION_ACC
+}
+
+// Powell + GLM sources of the two interfaces of the cell along AX, from cell-centre states
+// (solver_eqn_mhd_adi.cpp:396-443,782-813): R part of interface (i-1,i), then L part of interface (i,i+1).
+// C is the centre state in the grid frame (vn,vt1,vt2 = vx,vy,vz); qm / qp the tile cells at -1 / +1 along AX.
+template <int EQ, int VS, int AX>
+__device__ __forceinline__ void acc_sources(NatAcc& A, const Prim& C, double uB, const double* qm, const double* qp, double dt,
+                                            double idx, double hdtdx) {
+  if (EQ == EQ_EULER) return;
+  const double bm = qm[(5 + AX) * VS], bp = qp[(5 + AX) * VS];
+  const double Bn = pick3c<AX>(C.bn, C.bt1, C.bt2), Vn = pick3c<AX>(C.vn, C.vt1, C.vt2);
+#ifdef PION_STRICT
+  double f = dt * (0.5 * (bm + Bn));
+  A.m0 += f * C.bn * idx; A.m1 += f * C.bt1 * idx; A.m2 += f * C.bt2 * idx; A.erg += f * uB * idx;
+  A.b0 += f * C.vn * idx; A.b1 += f * C.vt1 * idx; A.b2 += f * C.vt2 * idx;
+  double psm = 0.0, psp = 0.0;
+  if (EQ == EQ_GLM) {
+    psm = qm[8 * VS];
+    psp = qp[8 * VS];
+    double fs = dt * (0.5 * (psm + C.psi));
+    A.erg += fs * (Vn * C.psi) * idx;
+    A.psi += fs * Vn * idx;
+  }
+  f = dt * (0.5 * (Bn + bp));
+  A.m0 -= f * C.bn * idx; A.m1 -= f * C.bt1 * idx; A.m2 -= f * C.bt2 * idx; A.erg -= f * uB * idx;
+  A.b0 -= f * C.vn * idx; A.b1 -= f * C.vt1 * idx; A.b2 -= f * C.vt2 * idx;
+  if (EQ == EQ_GLM) {
+    double fs = dt * (0.5 * (C.psi + psp));
+    A.erg -= fs * (Vn * C.psi) * idx;
+    A.psi -= fs * Vn * idx;
+  }
+#else
+  // the two halves regrouped: (dt/2dx)(bm + Bn) X - (dt/2dx)(Bn + bp) X = (dt/2dx)(bm - bp) X
+  const double gB = hdtdx * (bm - bp);
+  A.m0 = fma(gB, C.bn, A.m0); A.m1 = fma(gB, C.bt1, A.m1); A.m2 = fma(gB, C.bt2, A.m2);
+  A.erg = fma(gB, uB, A.erg);
+  A.b0 = fma(gB, C.vn, A.b0); A.b1 = fma(gB, C.vt1, A.b1); A.b2 = fma(gB, C.vt2, A.b2);
+  if (EQ == EQ_GLM) {
+    const double gS = hdtdx * (qm[8 * VS] - qp[8 * VS]);
+    A.erg = fma(gS, Vn * C.psi, A.erg);
+    A.psi = fma(gS, Vn, A.psi);
+  }
+#endif
+}
+
+__device__ __forceinline__ void cons_diff(Cons& D, const Cons& lo, const Cons& hi) {
+  D.rho = lo.rho - hi.rho; D.erg = lo.erg - hi.erg; D.mn = lo.mn - hi.mn; D.mt1 = lo.mt1 - hi.mt1; D.mt2 = lo.mt2 - hi.mt2;
+  D.bbn = lo.bbn - hi.bbn; D.bbt1 = lo.bbt1 - hi.bbt1; D.bbt2 = lo.bbt2 - hi.bbt2; D.psi = lo.psi - hi.psi;
 }
 
 template <int EQ, int SOLVER, bool FKJ, int TY, int MINB>
@@ -206,6 +313,84 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       mbar_wait_spin(&s_full[2], 0);
     }
 
+#if PION_TMA_ONEFLUX
+    // ---- ONE copy of the Riemann solver: a real loop over the three faces (x of plane k, z high face,
+    // y of plane k+1) whose per-face parts -- stencil loads + reconstruction before the solver, flux
+    // exchange + accumulation after it -- are compile-time specialised per axis, so the hot loop stays
+    // inside the instruction cache and still has immediate LDS offsets and no frame rotation.
+    NatAcc acc;
+    acc.rho = acc.erg = acc.m0 = acc.m1 = acc.m2 = acc.b0 = acc.b1 = acc.b2 = acc.psi = 0.0;
+    Prim C;
+    C.ro = C.pg = C.vn = C.vt1 = C.vt2 = C.bn = C.bt1 = C.bt2 = C.psi = 0.0;
+    const bool domain = upd_xy && !warm && (a.mask ? (a.mask[c] != 0) : true);
+    double uB = 0.0;
+    if (!warm) {
+      C = lds_prim<EQ, VS>(p0, 0, 1, 2);
+      if (a.mp_dE && upd_xy) acc.erg = a.mp_dE[c];  // cooling source term (energy only)
+      if (EQ != EQ_EULER) uB = C.bn * C.vn + C.bt1 * C.vt1 + C.bt2 * C.vt2;
+    }
+#ifdef PION_STRICT
+    const double dtdx = 0.0, hdtdx = 0.0;
+#endif
+#pragma unroll 1
+    for (int f = warm ? 1 : 0; f < 3; f++) {
+      if (f == 2 && kk + 1 >= nk) break;
+      Cons Fnew;
+      cons_zero<EQ>(Fnew);
+      if (row_active || f == 2) {
+        Prim eL, eR;
+        bool use_hll = false;
+        if (f == 0) {
+          edge_states_tile<EQ, VS>(a, p0 - 2, p0 - 1, p0, p0 + 1, 0, 1, 2, eL, eR);
+          if (SOLVER == SOLVE_HLLD) use_hll = (f_xm | f_c) != 0;
+        } else if (f == 1) {
+          // plane k+2 (first needed here): fill number (kk+4) >> 2 of buffer kk & 3
+          mbar_wait_spin(&s_full[kk & 3], ((unsigned)(kk + 4) >> 2) & 1u);
+          edge_states_tile<EQ, VS>(a, pm1, p0, pp1, pp2, 2, 0, 1, eL, eR);
+          if (SOLVER == SOLVE_HLLD) use_hll = (f_c | f_zp) != 0;
+        } else {
+          edge_states_tile<EQ, VS>(a, pp1 - 2 * CW, pp1 - CW, pp1, pp1 + CW, 1, 2, 0, eL, eR);
+          if (SOLVER == SOLVE_HLLD) use_hll = (f_ym | f_zp) != 0;
+        }
+        intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(eL, eR, a.pp, use_hll, 0.0, Fnew);
+      } else if (f == 1) {
+        mbar_wait_spin(&s_full[kk & 3], ((unsigned)(kk + 4) >> 2) & 1u);
+      }
+      Cons D;
+      if (f == 0) {
+        const Cons Fh = cons_shfl_down<EQ>(Fnew);
+        cons_diff(D, Fnew, Fh);
+        acc_sources<EQ, VS, 0>(acc, C, uB, p0 - 1, p0 + 1, dt, idx, hdtdx);
+        acc_flux_diff<EQ, 0>(acc, D, dt, idx, dtdx);
+        // y: both faces come from the slab the previous iteration published
+        mbar_wait_spin(&s_bar, phase);
+        phase ^= 1u;
+        const int rn = min(row + 1, TY - 1);
+        const Cons Fl = cons_from_smem<EQ, TY>(sbuf, row, lane);
+        const Cons Fhy = cons_from_smem<EQ, TY>(sbuf, rn, lane);
+        cons_diff(D, Fl, Fhy);
+        acc_sources<EQ, VS, 1>(acc, C, uB, p0 - CW, p0 + CW, dt, idx, hdtdx);
+        acc_flux_diff<EQ, 1>(acc, D, dt, idx, dtdx);
+      } else if (f == 1) {
+        cons_diff(D, Fz, Fnew);
+        Fz = Fnew;
+        if (!warm) {
+          acc_sources<EQ, VS, 2>(acc, C, uB, pm1, pp1, dt, idx, hdtdx);
+          acc_flux_diff<EQ, 2>(acc, D, dt, idx, dtdx);
+        }
+        // plane k-1 (z flux Q0, z sources) has been read for the last time by this warp
+        __syncwarp();
+        if (lane == 0 && row < TY - 1) mbar_arrive(&s_empty);
+      } else {
+        double* nbuf = s_flux + (size_t)((kk + 1) & 1) * SLAB;  // slab of plane k+1
+        cons_to_smem<EQ, TY>(nbuf, row, lane, Fnew);
+        mbar_arrive(&s_bar);
+      }
+    }
+    Cons accx;  // grid frame == solver frame of x
+    accx.rho = acc.rho; accx.erg = acc.erg; accx.mn = acc.m0; accx.mt1 = acc.m1; accx.mt2 = acc.m2;
+    accx.bbn = acc.b0; accx.bbt1 = acc.b1; accx.bbt2 = acc.b2; accx.psi = acc.psi;
+#else
     Cons acc;
     cons_zero<EQ>(acc);
     Prim C;
@@ -348,9 +533,10 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         if (lane == 0 && row < TY - 1) mbar_arrive(&s_empty);
       }
     }
+#endif
     // the producer refills the buffer of plane k-1 with plane k+3 (needed by the next iteration's z flux)
     if (producer && kk + 1 < nk) {
-      mbar_wait_spin(&s_empty, (unsigned)(kk + 1) & 1u);
+      mbar_wait_sleep(&s_empty, (unsigned)(kk + 1) & 1u, PION_TMA_PRODUCER_SLEEP_NS);
       unsigned long long* fb = &s_full[(kk + 1) & 3];
       mbar_expect_tx(fb, PLANE_BYTES);
       tma_load_plane(s_tile + ((kk + 1) & 3) * PS, &tmap, fb, bx, by, bz + kk + 5);
@@ -362,8 +548,13 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     if (warm) continue;
 
     if (domain) {
+#if PION_TMA_ONEFLUX
+      if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, C, accx, nullptr, 0, my_dt);
+      else status |= cell_advance_time<EQ>(a, c, accx, nullptr, 0, my_dt);
+#else
       if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, C, acc, nullptr, 0, my_dt);
       else status |= cell_advance_time<EQ>(a, c, acc, nullptr, 0, my_dt);
+#endif
     } else if (upd_xy && a.out != a.S) {
       // cell cut out of the domain (time_integrator.cpp:905-908): state untouched
       for (int v = 0; v < NB; v++) a.out[(long)v * vs + c] = a.S[(long)v * vs + c];
