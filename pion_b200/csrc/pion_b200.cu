@@ -119,8 +119,12 @@ static int make_state_tmap(const pion_gpu_ctx* c, double* base, CUtensorMap* out
     }
     enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   }
-  int cw, rh, nb;
-  sweep_tma_box(c->cfg.eqntype, &cw, &rh, &nb);
+  int cw, rh, nb, tx;
+  sweep_tma_box(c->cfg.eqntype, &cw, &rh, &nb, &tx);
+  if ((c->g.xoff + c->g.nb[0]) % 2 || tx % 2) {  // every box must start on a 16-byte boundary in x
+    set_error("TMA sweep: tile boxes would start on odd x offsets");
+    return 1;
+  }
   const GridD& g = c->g;
   const cuuint64_t dims[4] = {(cuuint64_t)g.sy, (cuuint64_t)g.NGa[1], (cuuint64_t)g.NGa[2], (cuuint64_t)nb};
   const cuuint64_t strides[3] = {(cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8, (cuuint64_t)g.vs * 8};
@@ -777,6 +781,15 @@ static int launch_preprocess(pion_gpu_ctx* c, const double* S, int order) {
 
 struct StageBox { int tx0, tx1, ty0, ty1, k_lo, k_hi; };
 
+// cells per tile of the sweep kernel that a fused stage of this context runs (launch_sweep_any's choice)
+static void stage_tile_cells(const pion_gpu_ctx* c, int* cx, int* cy) {
+  sweep_tile_cells(c->cfg.eqntype, cx, cy);
+  if (c->have_tmap && c->ntr == 0 && !c->eta) {
+    int cw, rh, nb;
+    sweep_tma_box(c->cfg.eqntype, &cw, &rh, &nb, cx);
+  }
+}
+
 // one stage = one launch over the whole grid (box == nullptr), or one launch per box when the stage is
 // split into boundary shell + interior (only the first launch of a stage resets the dt minimum)
 static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double* dU, double dt, int order,
@@ -809,7 +822,7 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   a.tmap = !c->have_tmap ? nullptr : (S == c->P) ? (const void*)&c->tmapP : (S == c->Ph) ? (const void*)&c->tmapPh : nullptr;
   {
     int cx, cy;
-    sweep_tile_cells(c->cfg.eqntype, &cx, &cy);
+    stage_tile_cells(c, &cx, &cy);
     a.tx0 = 0; a.tx1 = (c->g.NG[0] + cx - 1) / cx;
     a.ty0 = 0; a.ty1 = (c->g.NG[1] + cy - 1) / cy;
     a.k_lo = 0; a.k_hi = c->g.NG[2];
@@ -918,7 +931,7 @@ extern "C" int pion_gpu_grid_update_state_vector(pion_gpu_ctx* c, double dt, int
 static int stage_and_bcs(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double dt, int order, bool want_dt,
                          double* bcA0, double* bcA1) {
   int cx, cy;
-  sweep_tile_cells(c->cfg.eqntype, &cx, &cy);
+  stage_tile_cells(c, &cx, &cy);
   const GridD& g = c->g;
   const int ntx = (g.NG[0] + cx - 1) / cx, nty = (g.NG[1] + cy - 1) / cy, NZ = g.NG[2];
   // shell thickness in tiles: the last tile may hold fewer than the 2 cells the halo slab needs

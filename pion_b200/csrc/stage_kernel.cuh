@@ -432,7 +432,7 @@ void launch_stage_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 // cells per sweep tile along x / y (stage_sweep.cuh: 32 lanes, TY rows, one of each only produces fluxes)
 void sweep_tile_cells(int eq, int* cx, int* cy);  // eq: EQ_EULER / EQ_MHD / EQ_GLM
-void sweep_tma_box(int eq, int* cw, int* rh, int* nb);  // box of one TMA plane load (stage_sweep_tma.cuh)
+void sweep_tma_box(int eq, int* cw, int* rh, int* nb, int* tx);  // box of one TMA plane load, cells per tile in x (stage_sweep_tma.cuh)
 // flux-once sweep kernel (stage_sweep.cuh), instantiated in sweep_{euler,mhd,glm}.cu
 void launch_sweep_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 void launch_sweep_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);

@@ -5,19 +5,24 @@
 // VectorOps.cpp:535-644, solver_eqn_base.cpp:152-342, solver_eqn_mhd_adi.cpp:368-443,782-844);
 // what changes is where the operands come from:
 //
+//   * a block is a 32 x (TY-1) tile of cells marching in z (warp = row, lane = cell) plus one LIGHT
+//     warp that updates no cells: it produces the y fluxes through the tile's top edge and the x
+//     fluxes through the tile's high-x edge (so all 32 lanes of the other rows update a cell);
 //   * the state planes a block needs live in a ring of FOUR shared-memory plane buffers
-//     [var][TY+3 rows][36 columns] (cells i0-2..i0+33 or i0-3..i0+32, j0-2..j0+TY), each filled by ONE
+//     [var][TY+3 rows][36 columns] (cells i0-2..i0+33, j0-2..j0+TY), each filled by ONE
 //     cp.async.bulk.tensor.4d (TMA, tensor map over A[v][k][j][i]) that completes on an
 //     mbarrier; plane k+3 is requested while plane k is being computed, so no thread ever
 //     waits on a global load for the stencil (ncu of the LDG version: long-scoreboard was the
 //     second stall reason) and every stencil operand is an LDS with an IMMEDIATE offset
 //     (the LDG version spent ~4 integer instructions of 64-bit address arithmetic per load);
-//   * the otherwise idle extra row (warp TY-1, which only produces y fluxes) is the TMA
-//     producer: it waits on the `empty` mbarrier (every consumer warp arrives after its z
-//     flux, the last reader of plane k-1) and re-fills that buffer with plane k+3;
-//   * the step loop is unrolled with compile-time axes, so the solver-frame rotation is
-//     register renaming and the variable permutation of eqns_base::SetDirection
-//     (eqns_base.cpp:94-131) is folded into the LDS offsets.
+//   * the LAST warp to finish with plane k-1 (a running count in shared memory) issues the TMA
+//     that refills its buffer with plane k+3: no producer warp, nobody spins on an "empty" barrier;
+//   * ONE copy of the Riemann solver inside a real loop over the three faces, with the per-face
+//     parts (stencil loads + reconstruction before it, flux exchange + accumulation after it)
+//     specialised at compile time: the hot loop fits the instruction cache (the fully unrolled
+//     form stalled on instruction fetch, ncu no_instruction 0.86 warps/issue), the variable
+//     permutation of eqns_base::SetDirection (eqns_base.cpp:94-131) is folded into the LDS
+//     offsets, and dU is accumulated in the grid frame, so nothing is ever rotated.
 //
 // Out-of-range box coordinates (first-order grids have one ghost layer) are zero-filled by
 // the TMA unit; those values only reach threads whose results are discarded.
@@ -28,17 +33,9 @@
 
 namespace pion {
 
-#ifndef PION_TMA_UNROLL
-#define PION_TMA_UNROLL 1
-#endif
-#ifndef PION_TMA_PRODUCER_SLEEP_NS
-#define PION_TMA_PRODUCER_SLEEP_NS 4000
-#endif
-#ifndef PION_TMA_ONEFLUX
-#define PION_TMA_ONEFLUX 1
-#endif
 
-constexpr int TMA_CW = 36;                                            // tile columns
+constexpr int TMA_TX = 32;                                            // cells a tile updates along x
+constexpr int TMA_CW = 36;                                            // tile columns: cells i0-2 .. i0+33
 __host__ __device__ constexpr int tma_rh(int ty) { return ty + 3; }  // tile rows
 __host__ __device__ constexpr int tma_plane_bytes(int nb, int ty) { return nb * tma_rh(ty) * TMA_CW * 8; }
 __host__ __device__ constexpr int tma_plane_stride(int nb, int ty) { return (tma_plane_bytes(nb, ty) + 127) / 128 * 128; }
@@ -58,22 +55,6 @@ __device__ __forceinline__ void mbar_wait_spin(unsigned long long* bar, unsigned
         "}\n"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// same, with a suspend-time hint (ns): the waiting thread sleeps in hardware until the phase completes
-// instead of re-issuing try_wait (the producer lane waits most of a plane time for the consumers)
-__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity, unsigned hint_ns) {
-  unsigned ok;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
         : "memory");
   } while (!ok);
 }
@@ -223,19 +204,25 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   constexpr int PS = tma_plane_stride(NB, TY) / 8;       // doubles between plane buffers
   constexpr unsigned PLANE_BYTES = tma_plane_bytes(NB, TY);
   constexpr int SLAB = NB * TY * 32;
+  constexpr int XSLAB = NB * TY;
   double* const s_tile = reinterpret_cast<double*>(s_raw);              // [4][NB][RH][CW]
-  double* const s_flux = s_tile + 4 * PS;                                // [2][NB][TY][32]
-  __shared__ unsigned long long s_bar;       // y-flux slab published (all threads arrive)
+  double* const s_flux = s_tile + 4 * PS;                                // [2][NB][TY][32]  y fluxes of a plane
+  double* const s_xedge = s_flux + 2 * SLAB;                             // [3][NB][TY]      x flux through the tile's high x edge
+  __shared__ unsigned long long s_bar;       // y-flux slab + x-edge fluxes published (all threads arrive)
   __shared__ unsigned long long s_full[4];   // plane buffer filled (TMA transaction bytes)
-  __shared__ unsigned long long s_empty;     // plane k-1 no longer read (one arrive per consumer warp)
+  __shared__ unsigned s_done;                // consumer warps that have finished reading plane k-1 (running count)
 
   const GridD& g = a.g;
   const int NX = g.NG[0], NY = g.NG[1];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
-  const int i0 = (blockIdx.x + a.tx0) * 31, j0 = (blockIdx.y + a.ty0) * (TY - 1);
+  const int i0 = (blockIdx.x + a.tx0) * TMA_TX, j0 = (blockIdx.y + a.ty0) * (TY - 1);
+  // The LIGHT warp (row TY-1) updates no cells.  It produces the y fluxes through the tile's top edge (all
+  // lanes), the x fluxes through the tile's high-x edge (lane r = row r, so that all 32 lanes of the
+  // consumer rows update a cell), and its lane 0 issues the TMA loads.
+  const bool light = (row == TY - 1);
   int i = i0 + lane, j = j0 + row;
-  const bool row_active = (row < TY - 1) && (j < NY);               // warp-uniform
-  const bool upd_xy = row_active && (lane < 31) && (i < NX);
+  const bool row_active = !light && (j < NY);               // warp-uniform
+  const bool upd_xy = row_active && (i < NX);
   i = min(i, NX);  // global index only feeds the flag loads / Pb load of discarded threads
   j = min(j, NY);
   const int k0 = a.k_lo + blockIdx.z * kchunk, k1 = min(k0 + kchunk, a.k_hi);
@@ -245,21 +232,21 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   const double idx = 1.0 / g.dx;
 #ifndef PION_STRICT
   const double dtdx = dt * idx, hdtdx = 0.5 * dt * idx;
+#else
+  const double dtdx = 0.0, hdtdx = 0.0;
 #endif
   double my_dt = 1.0e100;
   int status = 0;
-  const bool producer = (row == TY - 1) && (lane == 0);
+  const bool producer = light && (lane == 0);
   const bool pb_is_s = (a.Pb == a.S);  // predictor: the base state is the stencil centre already in registers
 
-  // tile coordinates of the box (element units of the tensor map: x, y, z, v)
-  // (the box must start on a 16-byte boundary in x -- an odd element offset faults on B200,
-  // tools/micro/tma_probe.cu -- so odd starts load one column earlier and the threads shift by one)
-  const int bx_cell = g.xoff + g.nb[0] - 2 + i0;
-  const int xshift = bx_cell & 1;
-  const int bx = bx_cell - xshift, by = g.nb[1] - 2 + j0, bz = g.nb[2] + k0 - 2;
+  // tile coordinates of the box (element units of the tensor map: x, y, z, v).  The box must start on a
+  // 16-byte boundary in x -- an odd element offset faults on B200 (tools/micro/tma_probe.cu); with 32-cell
+  // tiles and an even xoff + nb (checked by the host when it builds the tensor maps) it always does.
+  const int bx = g.xoff + g.nb[0] - 2 + i0, by = g.nb[1] - 2 + j0, bz = g.nb[2] + k0 - 2;
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 32 * TY);
-    mbar_init(&s_empty, TY - 1);
+    s_done = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) mbar_init(&s_full[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -277,34 +264,49 @@ __global__ void __launch_bounds__(32 * TY, MINB)
 
   Cons Fz;  // flux through the low z face of the current cell
   cons_zero<EQ>(Fz);
-  const int coff = (row + 2) * CW + lane + 2 + xshift;  // this thread's cell inside a plane buffer
+  const int coff = (row + 2) * CW + lane + 2;  // this thread's cell inside a plane buffer
+  // light warp, lane r: the cell just beyond the tile's high-x edge in row r (x-edge face = its low x face)
+  const int erow = min(lane, TY - 2);
+  const int eoff = (erow + 2) * CW + TMA_TX + 2;
 
   // HLLD->HLL switch flags (solver_eqn_mhd_adi.cpp:167-177) of the cells (i,j,k), (i-1,j,k), (i,j,k+1),
-  // (i,j-1,k+1): loaded ONE PLANE AHEAD so that the flux never waits on them
-  unsigned f_c = 0, f_xm = 0, f_zp = 0, f_ym = 0;
-  const unsigned char* hp = nullptr;  // flag of cell (i,j,k)
+  // (i,j-1,k+1) -- light warp: of the two cells of its x-edge face in plane k+1 -- loaded ONE PLANE AHEAD so
+  // that the flux never waits on them
+  unsigned f_c = 0, f_xm = 0, f_zp = 0, f_ym = 0, e_a = 0, e_b = 0;
+  const unsigned char* hp = nullptr;   // flag of cell (i,j,k)
+  const unsigned char* hpe = nullptr;  // light warp: flag of cell (i0+31, j0+lane, k)
   if (SOLVER == SOLVE_HLLD) {
     hp = a.hll + gidx(g, i + g.nb[0], j + g.nb[1], k0 - 1 + g.nb[2]);
     f_c = hp[0];
     f_zp = hp[g.sz];
     f_ym = hp[g.sz - g.sy];
+    if (light) {
+      hpe = a.hll + gidx(g, min(i0 + TMA_TX - 1, NX) + g.nb[0], min(j0 + erow, NY) + g.nb[1], k0 - 1 + g.nb[2]);
+      e_a = hpe[g.sz];
+      e_b = hpe[g.sz + 1];
+    }
   }
 
   for (int kk = -1; kk < nk; kk++) {
     const int k = k0 + kk;
-    const bool warm = kk < 0;  // first iteration of a chunk: only the fluxes INTO plane k0 (z face, y faces)
+    const bool warm = kk < 0;  // first iteration of a chunk: only the fluxes INTO plane k0 (z face, y faces, x edge)
+    const bool last = kk + 1 >= nk;
     const long c = gidx(g, i + g.nb[0], j + g.nb[1], k + g.nb[2]);
     // plane p lives in buffer (p - k0 + 2) & 3
     const double* const pm1 = s_tile + ((kk + 1) & 3) * PS + coff;  // plane k-1
     const double* const p0 = s_tile + ((kk + 2) & 3) * PS + coff;   // plane k
     const double* const pp1 = s_tile + ((kk + 3) & 3) * PS + coff;  // plane k+1
     const double* const pp2 = s_tile + (kk & 3) * PS + coff;        // plane k+2
-    double* const sbuf = s_flux + (size_t)(kk & 1) * SLAB;
-    unsigned n_xm = 0, n_zp = 0, n_ym = 0;  // next plane's flags
-    if (SOLVER == SOLVE_HLLD && kk + 1 < nk) {
+    const double* const sbuf = s_flux + (size_t)(kk & 1) * SLAB;
+    unsigned n_xm = 0, n_zp = 0, n_ym = 0, n_ea = 0, n_eb = 0;  // next plane's flags
+    if (SOLVER == SOLVE_HLLD && !last) {
       n_xm = hp[g.sz - 1];
       n_zp = hp[2 * g.sz];
       n_ym = hp[2 * g.sz - g.sy];
+      if (light) {
+        n_ea = hpe[2 * g.sz];
+        n_eb = hpe[2 * g.sz + 1];
+      }
     }
 
     if (warm) {  // planes k0-2, k0-1, k0 (plane k0+1 = "k+2" is waited for below like every iteration)
@@ -313,11 +315,12 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       mbar_wait_spin(&s_full[2], 0);
     }
 
-#if PION_TMA_ONEFLUX
     // ---- ONE copy of the Riemann solver: a real loop over the three faces (x of plane k, z high face,
     // y of plane k+1) whose per-face parts -- stencil loads + reconstruction before the solver, flux
     // exchange + accumulation after it -- are compile-time specialised per axis, so the hot loop stays
     // inside the instruction cache and still has immediate LDS offsets and no frame rotation.
+    // Schedule of one plane: x flux, wait for the previous iteration's slab, accumulate x and y; z flux,
+    // accumulate z; y flux (and, light warp, x-edge flux) of the NEXT plane -> shared memory, arrive.
     NatAcc acc;
     acc.rho = acc.erg = acc.m0 = acc.m1 = acc.m2 = acc.b0 = acc.b1 = acc.b2 = acc.psi = 0.0;
     Prim C;
@@ -329,20 +332,20 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       if (a.mp_dE && upd_xy) acc.erg = a.mp_dE[c];  // cooling source term (energy only)
       if (EQ != EQ_EULER) uB = C.bn * C.vn + C.bt1 * C.vt1 + C.bt2 * C.vt2;
     }
-#ifdef PION_STRICT
-    const double dtdx = 0.0, hdtdx = 0.0;
-#endif
 #pragma unroll 1
-    for (int f = warm ? 1 : 0; f < 3; f++) {
-      if (f == 2 && kk + 1 >= nk) break;
+    for (int f = (warm && !light) ? 1 : 0; f < 3; f++) {
+      if (f == 2 && last) break;
       Cons Fnew;
       cons_zero<EQ>(Fnew);
-      if (row_active || f == 2) {
+      // the light warp uses the x slot for the x-edge face of plane k+1
+      const bool do_flux = (f == 0 && light) ? !last : (row_active || f == 2);
+      if (do_flux) {
         Prim eL, eR;
         bool use_hll = false;
         if (f == 0) {
-          edge_states_tile<EQ, VS>(a, p0 - 2, p0 - 1, p0, p0 + 1, 0, 1, 2, eL, eR);
-          if (SOLVER == SOLVE_HLLD) use_hll = (f_xm | f_c) != 0;
+          const double* const px = light ? (pp1 - coff + eoff) : p0;
+          edge_states_tile<EQ, VS>(a, px - 2, px - 1, px, px + 1, 0, 1, 2, eL, eR);
+          if (SOLVER == SOLVE_HLLD) use_hll = light ? ((e_a | e_b) != 0) : ((f_xm | f_c) != 0);
         } else if (f == 1) {
           // plane k+2 (first needed here): fill number (kk+4) >> 2 of buffer kk & 3
           mbar_wait_spin(&s_full[kk & 3], ((unsigned)(kk + 4) >> 2) & 1u);
@@ -358,13 +361,31 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       }
       Cons D;
       if (f == 0) {
-        const Cons Fh = cons_shfl_down<EQ>(Fnew);
+        if (light) {  // publish the x-edge fluxes of plane k+1 (covered by this iteration's arrive on s_bar)
+          if (lane < TY - 1 && !last) {
+            // three buffers: this store runs ahead of the wait below, i.e. possibly while slower warps
+            // still read the x-edge fluxes of plane k
+            double* xe = s_xedge + (size_t)((kk + 3) % 3) * XSLAB + lane;
+            xe[0] = Fnew.rho; xe[TY] = Fnew.erg; xe[2 * TY] = Fnew.mn; xe[3 * TY] = Fnew.mt1; xe[4 * TY] = Fnew.mt2;
+            if (EQ != EQ_EULER) { xe[5 * TY] = Fnew.bbn; xe[6 * TY] = Fnew.bbt1; xe[7 * TY] = Fnew.bbt2; }
+            if (EQ == EQ_GLM) xe[8 * TY] = Fnew.psi;
+          }
+          if (warm) continue;
+        }
+        // the previous iteration published this plane's y fluxes and x-edge fluxes
+        mbar_wait_spin(&s_bar, phase);
+        phase ^= 1u;
+        Cons Fh = cons_shfl_down<EQ>(Fnew);
+        if (lane == 31) {  // high x face of the tile's last column: from the light warp
+          const double* xe = s_xedge + (size_t)((kk + 2) % 3) * XSLAB + min(row, TY - 2);
+          Fh.rho = xe[0]; Fh.erg = xe[TY]; Fh.mn = xe[2 * TY]; Fh.mt1 = xe[3 * TY]; Fh.mt2 = xe[4 * TY];
+          if (EQ != EQ_EULER) { Fh.bbn = xe[5 * TY]; Fh.bbt1 = xe[6 * TY]; Fh.bbt2 = xe[7 * TY]; }
+          if (EQ == EQ_GLM) Fh.psi = xe[8 * TY];
+        }
         cons_diff(D, Fnew, Fh);
         acc_sources<EQ, VS, 0>(acc, C, uB, p0 - 1, p0 + 1, dt, idx, hdtdx);
         acc_flux_diff<EQ, 0>(acc, D, dt, idx, dtdx);
-        // y: both faces come from the slab the previous iteration published
-        mbar_wait_spin(&s_bar, phase);
-        phase ^= 1u;
+        // y: both faces come from the slab
         const int rn = min(row + 1, TY - 1);
         const Cons Fl = cons_from_smem<EQ, TY>(sbuf, row, lane);
         const Cons Fhy = cons_from_smem<EQ, TY>(sbuf, rn, lane);
@@ -378,183 +399,39 @@ __global__ void __launch_bounds__(32 * TY, MINB)
           acc_sources<EQ, VS, 2>(acc, C, uB, pm1, pp1, dt, idx, hdtdx);
           acc_flux_diff<EQ, 2>(acc, D, dt, idx, dtdx);
         }
-        // plane k-1 (z flux Q0, z sources) has been read for the last time by this warp
+        // plane k-1 (z flux Q0, z sources) has been read for the last time by this warp; the LAST consumer
+        // warp to get here refills that buffer with plane k+3 (needed by the next iteration's z flux), so
+        // nobody spins on an "empty" barrier.  A warp cannot be a whole iteration ahead (s_bar), so the
+        // running count identifies the iteration.
         __syncwarp();
-        if (lane == 0 && row < TY - 1) mbar_arrive(&s_empty);
+        if (lane == 0 && !light) {
+          __threadfence_block();
+          const unsigned old = atomicAdd(&s_done, 1u);
+          if (!last && old == (unsigned)(kk + 2) * (TY - 1) - 1u) {
+            unsigned long long* fb = &s_full[(kk + 1) & 3];
+            mbar_expect_tx(fb, PLANE_BYTES);
+            tma_load_plane(s_tile + ((kk + 1) & 3) * PS, &tmap, fb, bx, by, bz + kk + 5);
+          }
+        }
       } else {
         double* nbuf = s_flux + (size_t)((kk + 1) & 1) * SLAB;  // slab of plane k+1
         cons_to_smem<EQ, TY>(nbuf, row, lane, Fnew);
         mbar_arrive(&s_bar);
       }
-    }
-    Cons accx;  // grid frame == solver frame of x
-    accx.rho = acc.rho; accx.erg = acc.erg; accx.mn = acc.m0; accx.mt1 = acc.m1; accx.mt2 = acc.m2;
-    accx.bbn = acc.b0; accx.bbt1 = acc.b1; accx.bbt2 = acc.b2; accx.psi = acc.psi;
-#else
-    Cons acc;
-    cons_zero<EQ>(acc);
-    Prim C;
-    C.ro = C.pg = C.vn = C.vt1 = C.vt2 = C.bn = C.bt1 = C.bt2 = C.psi = 0.0;
-    const bool domain = upd_xy && !warm && (a.mask ? (a.mask[c] != 0) : true);
-    double uB = 0.0;
-    if (!warm) {
-      C = lds_prim<EQ, VS>(p0, 0, 1, 2);
-      if (a.mp_dE && upd_xy) acc.erg = a.mp_dE[c];  // cooling source term (energy only)
-      if (EQ != EQ_EULER) uB = C.bn * C.vn + C.bt1 * C.vt1 + C.bt2 * C.vt2;
-    }
-
-    // Schedule of one plane (as k_stage_sweep):
-    //   step 1: x flux (shfl), accumulate x          step 2: wait, accumulate y from shared memory
-    //   step 3: z flux, accumulate z                 step 4: y flux of the NEXT plane -> shared memory, arrive
-#if PION_TMA_UNROLL
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-    for (int step = 1; step <= 4; step++) {
-      if (warm && step < 3) continue;
-      if (step == 4 && kk + 1 >= nk) continue;
-      const int ax = (step == 1) ? 0 : (step == 3) ? 2 : 1;
-      const int a1 = (ax == 2) ? 0 : ax + 1;
-      const int a2 = (a1 == 2) ? 0 : a1 + 1;
-      Cons Fnew;
-      cons_zero<EQ>(Fnew);
-      if (step == 3) {
-        // plane k+2 (first needed by the z flux): fill number (kk+4) >> 2 of buffer kk & 3
-        mbar_wait_spin(&s_full[kk & 3], ((unsigned)(kk + 4) >> 2) & 1u);
-      }
-      if (step != 2 && (row_active || ax == 1)) {
-        // ONE flux call site: the four stencil cells of the face and its HLLD->HLL switch
-        const double *pQ0, *pL, *pR, *pQ3;
-        bool use_hll = false;
-        if (step == 1) {
-          pQ0 = p0 - 2; pL = p0 - 1; pR = p0; pQ3 = p0 + 1;
-          if (SOLVER == SOLVE_HLLD) use_hll = (f_xm | f_c) != 0;
-        } else if (step == 3) {
-          pQ0 = pm1; pL = p0; pR = pp1; pQ3 = pp2;
-          if (SOLVER == SOLVE_HLLD) use_hll = (f_c | f_zp) != 0;
-        } else {
-          pQ0 = pp1 - 2 * CW; pL = pp1 - CW; pR = pp1; pQ3 = pp1 + CW;
-          if (SOLVER == SOLVE_HLLD) use_hll = (f_ym | f_zp) != 0;
-        }
-        face_flux_tile<EQ, SOLVER, FKJ, VS>(a, pQ0, pL, pR, pQ3, use_hll, ax, a1, a2, Fnew);
-      }
-      if (step == 4) {
-        double* nbuf = s_flux + (size_t)((kk + 1) & 1) * SLAB;  // slab of plane k+1
-        cons_to_smem<EQ, TY>(nbuf, row, lane, Fnew);
-        mbar_arrive(&s_bar);
-        continue;
-      }
-
-      Cons D;
-#define PION_DIFF(LOW, HIGH)                                                                     \
-  D.rho = LOW.rho - HIGH.rho; D.erg = LOW.erg - HIGH.erg; D.mn = LOW.mn - HIGH.mn;               \
-  D.mt1 = LOW.mt1 - HIGH.mt1; D.mt2 = LOW.mt2 - HIGH.mt2;                                        \
-  if (EQ != EQ_EULER) { D.bbn = LOW.bbn - HIGH.bbn; D.bbt1 = LOW.bbt1 - HIGH.bbt1; D.bbt2 = LOW.bbt2 - HIGH.bbt2; } \
-  else { D.bbn = D.bbt1 = D.bbt2 = 0.0; }                                                        \
-  D.psi = (EQ == EQ_GLM) ? LOW.psi - HIGH.psi : 0.0;
-      if (step == 1) {
-        const Cons Fh = cons_shfl_down<EQ>(Fnew);
-        PION_DIFF(Fnew, Fh)
-      } else if (step == 2) {
-        mbar_wait_spin(&s_bar, phase);
-        phase ^= 1u;
-        const int rn = min(row + 1, TY - 1);
-        const Cons Fl = cons_from_smem<EQ, TY>(sbuf, row, lane);
-        const Cons Fh = cons_from_smem<EQ, TY>(sbuf, rn, lane);
-        PION_DIFF(Fl, Fh)
-      } else {
-        PION_DIFF(Fz, Fnew)
-        Fz = Fnew;
-      }
-#undef PION_DIFF
-
-      if (!warm) {
-        // Powell + GLM sources from cell-centre states (solver_eqn_mhd_adi.cpp:396-443,782-813):
-        // R part of interface (i-1,i), then L part of interface (i,i+1)
-        if (EQ != EQ_EULER) {
-          const double* qm = (step == 1) ? p0 - 1 : (step == 2) ? p0 - CW : pm1;
-          const double* qp = (step == 1) ? p0 + 1 : (step == 2) ? p0 + CW : pp1;
-          const double bm = qm[(5 + ax) * VS], bp = qp[(5 + ax) * VS];
-#ifdef PION_STRICT
-          double f = dt * (0.5 * (bm + C.bn));
-          acc.mn += f * C.bn * idx; acc.mt1 += f * C.bt1 * idx; acc.mt2 += f * C.bt2 * idx; acc.erg += f * uB * idx;
-          acc.bbn += f * C.vn * idx; acc.bbt1 += f * C.vt1 * idx; acc.bbt2 += f * C.vt2 * idx;
-          double psm = 0.0, psp = 0.0;
-          if (EQ == EQ_GLM) {
-            psm = qm[8 * VS];
-            psp = qp[8 * VS];
-            double fs = dt * (0.5 * (psm + C.psi));
-            acc.erg += fs * (C.vn * C.psi) * idx;
-            acc.psi += fs * C.vn * idx;
-          }
-          f = dt * (0.5 * (C.bn + bp));
-          acc.mn -= f * C.bn * idx; acc.mt1 -= f * C.bt1 * idx; acc.mt2 -= f * C.bt2 * idx; acc.erg -= f * uB * idx;
-          acc.bbn -= f * C.vn * idx; acc.bbt1 -= f * C.vt1 * idx; acc.bbt2 -= f * C.vt2 * idx;
-          if (EQ == EQ_GLM) {
-            double fs = dt * (0.5 * (C.psi + psp));
-            acc.erg -= fs * (C.vn * C.psi) * idx;
-            acc.psi -= fs * C.vn * idx;
-          }
-#else
-          // the two halves regrouped: (dt/2dx)(bm + Bn) X - (dt/2dx)(Bn + bp) X = (dt/2dx)(bm - bp) X
-          const double gB = hdtdx * (bm - bp);
-          acc.mn = fma(gB, C.bn, acc.mn); acc.mt1 = fma(gB, C.bt1, acc.mt1); acc.mt2 = fma(gB, C.bt2, acc.mt2);
-          acc.erg = fma(gB, uB, acc.erg);
-          acc.bbn = fma(gB, C.vn, acc.bbn); acc.bbt1 = fma(gB, C.vt1, acc.bbt1); acc.bbt2 = fma(gB, C.vt2, acc.bbt2);
-          if (EQ == EQ_GLM) {
-            const double gS = hdtdx * (qm[8 * VS] - qp[8 * VS]);
-            acc.erg = fma(gS, C.vn * C.psi, acc.erg);
-            acc.psi = fma(gS, C.vn, acc.psi);
-          }
-#endif
-        }
-        // flux difference (dU_Cell + DivStateVectorComponent)
-#ifdef PION_STRICT
-#define PION_ACC(f) acc.f += dt * (D.f * idx);
-#else
-#define PION_ACC(f) acc.f = fma(dtdx, D.f, acc.f);
-#endif
-        PION_ACC(rho) PION_ACC(erg) PION_ACC(mn) PION_ACC(mt1) PION_ACC(mt2)
-        if (EQ != EQ_EULER) { PION_ACC(bbn) PION_ACC(bbt1) PION_ACC(bbt2) }
-        if (EQ == EQ_GLM) { PION_ACC(psi) }
-#undef PION_ACC
-        // rotate the centre state and the accumulators into the next axis' frame
-        rot3(C.vn, C.vt1, C.vt2);
-        rot3(acc.mn, acc.mt1, acc.mt2);
-        if (EQ != EQ_EULER) {
-          rot3(C.bn, C.bt1, C.bt2);
-          rot3(acc.bbn, acc.bbt1, acc.bbt2);
-        }
-      }
-      if (step == 3) {
-        // plane k-1 (z flux Q0, z sources) has been read for the last time by this warp
-        __syncwarp();
-        if (lane == 0 && row < TY - 1) mbar_arrive(&s_empty);
-      }
-    }
-#endif
-    // the producer refills the buffer of plane k-1 with plane k+3 (needed by the next iteration's z flux)
-    if (producer && kk + 1 < nk) {
-      mbar_wait_sleep(&s_empty, (unsigned)(kk + 1) & 1u, PION_TMA_PRODUCER_SLEEP_NS);
-      unsigned long long* fb = &s_full[(kk + 1) & 3];
-      mbar_expect_tx(fb, PLANE_BYTES);
-      tma_load_plane(s_tile + ((kk + 1) & 3) * PS, &tmap, fb, bx, by, bz + kk + 5);
     }
     if (SOLVER == SOLVE_HLLD) {
-      f_c = f_zp; f_xm = n_xm; f_zp = n_zp; f_ym = n_ym;
+      f_c = f_zp; f_xm = n_xm; f_zp = n_zp; f_ym = n_ym; e_a = n_ea; e_b = n_eb;
       hp += g.sz;
+      if (light) hpe += g.sz;
     }
     if (warm) continue;
 
     if (domain) {
-#if PION_TMA_ONEFLUX
+      Cons accx;  // grid frame == solver frame of x
+      accx.rho = acc.rho; accx.erg = acc.erg; accx.mn = acc.m0; accx.mt1 = acc.m1; accx.mt2 = acc.m2;
+      accx.bbn = acc.b0; accx.bbt1 = acc.b1; accx.bbt2 = acc.b2; accx.psi = acc.psi;
       if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, C, accx, nullptr, 0, my_dt);
       else status |= cell_advance_time<EQ>(a, c, accx, nullptr, 0, my_dt);
-#else
-      if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, C, acc, nullptr, 0, my_dt);
-      else status |= cell_advance_time<EQ>(a, c, acc, nullptr, 0, my_dt);
-#endif
     } else if (upd_xy && a.out != a.S) {
       // cell cut out of the domain (time_integrator.cpp:905-908): state untouched
       for (int v = 0; v < NB; v++) a.out[(long)v * vs + c] = a.S[(long)v * vs + c];
@@ -573,7 +450,7 @@ inline void launch_sweep_tma_t(const StageArgs& a, cudaStream_t s) {
   int kchunk = 64;
   while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
   const int bz = (NZ + kchunk - 1) / kchunk;
-  const size_t smem = (size_t)4 * tma_plane_stride(NB, TY) + (size_t)2 * NB * TY * 32 * sizeof(double);
+  const size_t smem = (size_t)4 * tma_plane_stride(NB, TY) + (size_t)2 * NB * TY * 32 * sizeof(double) + (size_t)3 * NB * TY * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -590,7 +467,8 @@ inline void launch_sweep_any(const StageArgs& a, cudaStream_t s) {
 }
 
 // box of one TMA plane load for an equation set (host side: tensor-map creation)
-inline void sweep_tma_box_impl(int eq, int* cw, int* rh, int* nb) {
+inline void sweep_tma_box_impl(int eq, int* cw, int* rh, int* nb, int* tx) {
+  *tx = TMA_TX;
   *cw = TMA_CW;
   *rh = tma_rh(sweep_ty(eq));
   *nb = nbase(eq);
