@@ -77,6 +77,20 @@ __global__ void __launch_bounds__(256) k_hlld_flags_3d(GridD g, const double* __
   }
 }
 
+// Face form of the HLLD->HLL switch for the TMA sweep kernel: the flux through the LOW face of a cell along
+// x / y / z runs HLL when either cell of that face is flagged (solver_eqn_mhd_adi.cpp:167-177), so one
+// byte per cell (bit 0: x face, bit 1: y face, bit 2: z face) replaces two flag loads per face.
+__global__ void k_hll_face_flags(GridD g, const unsigned char* __restrict__ flag, unsigned char* __restrict__ face) {
+  const int ex = g.NGa[0] - 1, ey = g.NGa[1] - 1, ez = g.NGa[2] - 1;
+  const long n = (long)ex * ey * ez;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % ex) + 1, j = (int)((t / ex) % ey) + 1, k = (int)(t / ((long)ex * ey)) + 1;
+    const long c = gidx(g, i, j, k);
+    const unsigned f = flag[c];
+    face[c] = (unsigned char)(((f | flag[c - 1]) ? 1u : 0u) | ((f | flag[c - g.sy]) ? 2u : 0u) | ((f | flag[c - g.sz]) ? 4u : 0u));
+  }
+}
+
 // ---------------------------------------------------------------------------
 // H-correction eta for the interface on the + side of every cell, per axis
 // (calc_Hcorrection / set_Hcorrection, solver_eqn_base.cpp:423-599):

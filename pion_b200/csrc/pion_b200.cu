@@ -53,7 +53,7 @@ struct pion_gpu_ctx {
   int nvar, nbase_, ntr;
   size_t arr_elems;  // doubles per state array
   double *P = nullptr, *Ph = nullptr, *dU = nullptr, *eta = nullptr;
-  unsigned char *hll = nullptr, *mask = nullptr;
+  unsigned char *hll = nullptr, *hllf = nullptr, *mask = nullptr;
   unsigned long long* d_dtmin = nullptr;  // [0] running min for the next step, [1] scratch
   long long* d_counters = nullptr;
   unsigned long long* h_pinned = nullptr;  // pinned mirror for scalar read-back
@@ -393,6 +393,11 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
     if (g.ndim == 3 && g.coord == PION_COORD_CRT && !(e && e[0] == '1')) {
       if (make_state_tmap(c, c->P, &c->tmapP) || make_state_tmap(c, c->Ph, &c->tmapPh)) { pion_gpu_destroy(c); return nullptr; }
       c->have_tmap = true;
+      if (c->hll && (cudaMalloc(&c->hllf, (size_t)g.vs) != cudaSuccess || cudaMemset(c->hllf, 0, (size_t)g.vs) != cudaSuccess)) {
+        set_error("device allocation failed (face flags)");
+        pion_gpu_destroy(c);
+        return nullptr;
+      }
     }
   }
   cudaMemsetAsync(c->P, 0, c->arr_elems * sizeof(double), c->stream);
@@ -409,7 +414,7 @@ extern "C" void pion_gpu_destroy(pion_gpu_ctx* c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm) ncclCommDestroy(c->comm);
-  cudaFree(c->P); cudaFree(c->Ph); cudaFree(c->dU); cudaFree(c->eta); cudaFree(c->hll); cudaFree(c->mask);
+  cudaFree(c->P); cudaFree(c->Ph); cudaFree(c->dU); cudaFree(c->eta); cudaFree(c->hll); cudaFree(c->hllf); cudaFree(c->mask);
   cudaFree(c->d_dtmin); cudaFree(c->d_counters); cudaFree(c->d_red); cudaFree(c->d_tables); cudaFree(c->mp_dE); cudaFree(c->d_wind_idx); cudaFree(c->d_wind_val);
   for (int f = 0; f < 6; f++) { cudaFree(c->sendbuf[f]); cudaFree(c->recvbuf[f]); }
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -759,6 +764,11 @@ static int launch_preprocess(pion_gpu_ctx* c, const double* S, int order) {
       const int bx = (ex + 31) / 32, by = (ey + 7) / 8;
       while (kchunk > 8 && (long)bx * by * ((ez + kchunk - 1) / kchunk) < 148L * 8) kchunk >>= 1;
       k_hlld_flags_3d<<<dim3(bx, by, (ez + kchunk - 1) / kchunk), 256, 0, c->stream>>>(g, S, c->hll, kchunk);
+      if (c->hllf) {  // face form for the TMA sweep kernel
+        const long nf = (long)(g.NGa[0] - 1) * (g.NGa[1] - 1) * (g.NGa[2] - 1);
+        k_hll_face_flags<<<nblocks(nf, 256), 256, 0, c->stream>>>(g, c->hll, c->hllf);
+        c->launches++;
+      }
     } else {
       long n = (long)(g.NGa[0] - 2) * ((g.ndim > 1) ? g.NGa[1] - 2 : 1) * ((g.ndim > 2) ? g.NGa[2] - 2 : 1);
       k_hlld_flags<<<nblocks(n, 256), 256, 0, c->stream>>>(g, S, c->hll);
@@ -806,6 +816,7 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   a.dU = dU;
   a.mp_dE = (fused && c->cfg.cooling) ? c->mp_dE : nullptr;
   a.hll = c->hll;
+  a.hllf = c->hllf;
   a.eta = c->eta;
   a.mask = c->mask;
   a.dt = dt;

@@ -33,6 +33,7 @@ struct StageArgs {
   double* dU;         // unfused: accumulated into; unused by the fused path
   const double* mp_dE;  // fused: microphysics energy source per cell (cooling.cuh), null without microphysics
   const unsigned char* hll;  // HLLD->HLL switch flags per cell (null unless solver==HLLD)
+  const unsigned char* hllf; // the same per LOW FACE, bits 0/1/2 = x/y/z (k_hll_face_flags; TMA sweep kernel only)
   const double* eta;         // H-correction eta, 3 planes of vs doubles (null unless AV 3/4)
   const unsigned char* mask; // 1 = cell is updated (isdomain); null = every interior cell
   double dt;          // stage dt == FV_dt

@@ -66,6 +66,13 @@ __device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* map
       : "memory");
 }
 
+// one flag byte, issued HERE (volatile: the compiler may not sink it to its first use, a whole plane later)
+__device__ __forceinline__ unsigned ldg_u8_now(const unsigned char* p) {
+  unsigned v;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 // primitive state of the tile cell `p` points at (p = address of its density), solver frame of axis ax
 template <int EQ, int VS>
 __device__ __forceinline__ Prim lds_prim(const double* p, int ax, int a1, int a2) {
@@ -269,21 +276,20 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   const int erow = min(lane, TY - 2);
   const int eoff = (erow + 2) * CW + TMA_TX + 2;
 
-  // HLLD->HLL switch flags (solver_eqn_mhd_adi.cpp:167-177) of the cells (i,j,k), (i-1,j,k), (i,j,k+1),
-  // (i,j-1,k+1) -- light warp: of the two cells of its x-edge face in plane k+1 -- loaded ONE PLANE AHEAD so
-  // that the flux never waits on them
-  unsigned f_c = 0, f_xm = 0, f_zp = 0, f_ym = 0, e_a = 0, e_b = 0;
-  const unsigned char* hp = nullptr;   // flag of cell (i,j,k)
-  const unsigned char* hpe = nullptr;  // light warp: flag of cell (i0+31, j0+lane, k)
+  // HLLD->HLL switch (solver_eqn_mhd_adi.cpp:167-177) in face form (k_hll_face_flags: bit 0/1/2 = the low
+  // x/y/z face of a cell runs HLL): this iteration needs the byte of the cells (i,j,k) and (i,j,k+1) -- the
+  // light warp that of the cell beyond its x-edge face in plane k+1 -- and plane k+2's byte is requested ONE
+  // PLANE AHEAD, so that the flux never waits on a global load
+  unsigned w_k = 0, w_k1 = 0, we_k1 = 0;
+  const unsigned char* hp = nullptr;   // face byte of cell (i,j,k)
+  const unsigned char* hpe = nullptr;  // light warp: face byte of cell (i0+32, j0+lane, k)
   if (SOLVER == SOLVE_HLLD) {
-    hp = a.hll + gidx(g, i + g.nb[0], j + g.nb[1], k0 - 1 + g.nb[2]);
-    f_c = hp[0];
-    f_zp = hp[g.sz];
-    f_ym = hp[g.sz - g.sy];
+    hp = a.hllf + gidx(g, i + g.nb[0], j + g.nb[1], k0 - 1 + g.nb[2]);
+    w_k = hp[0];
+    w_k1 = hp[g.sz];
     if (light) {
-      hpe = a.hll + gidx(g, min(i0 + TMA_TX - 1, NX) + g.nb[0], min(j0 + erow, NY) + g.nb[1], k0 - 1 + g.nb[2]);
-      e_a = hpe[g.sz];
-      e_b = hpe[g.sz + 1];
+      hpe = a.hllf + gidx(g, min(i0 + TMA_TX, NX + 1) + g.nb[0], min(j0 + erow, NY) + g.nb[1], k0 - 1 + g.nb[2]);
+      we_k1 = hpe[g.sz];
     }
   }
 
@@ -298,15 +304,10 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     const double* const pp1 = s_tile + ((kk + 3) & 3) * PS + coff;  // plane k+1
     const double* const pp2 = s_tile + (kk & 3) * PS + coff;        // plane k+2
     const double* const sbuf = s_flux + (size_t)(kk & 1) * SLAB;
-    unsigned n_xm = 0, n_zp = 0, n_ym = 0, n_ea = 0, n_eb = 0;  // next plane's flags
+    unsigned n_w = 0, n_we = 0;  // plane k+2's face bytes
     if (SOLVER == SOLVE_HLLD && !last) {
-      n_xm = hp[g.sz - 1];
-      n_zp = hp[2 * g.sz];
-      n_ym = hp[2 * g.sz - g.sy];
-      if (light) {
-        n_ea = hpe[2 * g.sz];
-        n_eb = hpe[2 * g.sz + 1];
-      }
+      n_w = ldg_u8_now(hp + 2 * g.sz);
+      if (light) n_we = ldg_u8_now(hpe + 2 * g.sz);
     }
 
     if (warm) {  // planes k0-2, k0-1, k0 (plane k0+1 = "k+2" is waited for below like every iteration)
@@ -323,15 +324,10 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     // accumulate z; y flux (and, light warp, x-edge flux) of the NEXT plane -> shared memory, arrive.
     NatAcc acc;
     acc.rho = acc.erg = acc.m0 = acc.m1 = acc.m2 = acc.b0 = acc.b1 = acc.b2 = acc.psi = 0.0;
-    Prim C;
-    C.ro = C.pg = C.vn = C.vt1 = C.vt2 = C.bn = C.bt1 = C.bt2 = C.psi = 0.0;
+    // the centre state is RE-READ from the tile wherever it is needed (an LDS with an immediate offset is
+    // cheaper than 18 registers held across the Riemann solver)
     const bool domain = upd_xy && !warm && (a.mask ? (a.mask[c] != 0) : true);
-    double uB = 0.0;
-    if (!warm) {
-      C = lds_prim<EQ, VS>(p0, 0, 1, 2);
-      if (a.mp_dE && upd_xy) acc.erg = a.mp_dE[c];  // cooling source term (energy only)
-      if (EQ != EQ_EULER) uB = C.bn * C.vn + C.bt1 * C.vt1 + C.bt2 * C.vt2;
-    }
+    if (!warm && a.mp_dE && upd_xy) acc.erg = a.mp_dE[c];  // cooling source term (energy only)
 #pragma unroll 1
     for (int f = (warm && !light) ? 1 : 0; f < 3; f++) {
       if (f == 2 && last) break;
@@ -345,15 +341,15 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         if (f == 0) {
           const double* const px = light ? (pp1 - coff + eoff) : p0;
           edge_states_tile<EQ, VS>(a, px - 2, px - 1, px, px + 1, 0, 1, 2, eL, eR);
-          if (SOLVER == SOLVE_HLLD) use_hll = light ? ((e_a | e_b) != 0) : ((f_xm | f_c) != 0);
+          if (SOLVER == SOLVE_HLLD) use_hll = ((light ? we_k1 : w_k) & 1u) != 0;
         } else if (f == 1) {
           // plane k+2 (first needed here): fill number (kk+4) >> 2 of buffer kk & 3
           mbar_wait_spin(&s_full[kk & 3], ((unsigned)(kk + 4) >> 2) & 1u);
           edge_states_tile<EQ, VS>(a, pm1, p0, pp1, pp2, 2, 0, 1, eL, eR);
-          if (SOLVER == SOLVE_HLLD) use_hll = (f_c | f_zp) != 0;
+          if (SOLVER == SOLVE_HLLD) use_hll = (w_k1 & 4u) != 0;
         } else {
           edge_states_tile<EQ, VS>(a, pp1 - 2 * CW, pp1 - CW, pp1, pp1 + CW, 1, 2, 0, eL, eR);
-          if (SOLVER == SOLVE_HLLD) use_hll = (f_ym | f_zp) != 0;
+          if (SOLVER == SOLVE_HLLD) use_hll = (w_k1 & 2u) != 0;
         }
         intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(eL, eR, a.pp, use_hll, 0.0, Fnew);
       } else if (f == 1) {
@@ -383,6 +379,8 @@ __global__ void __launch_bounds__(32 * TY, MINB)
           if (EQ == EQ_GLM) Fh.psi = xe[8 * TY];
         }
         cons_diff(D, Fnew, Fh);
+        const Prim C = lds_prim<EQ, VS>(p0, 0, 1, 2);
+        const double uB = (EQ != EQ_EULER) ? C.bn * C.vn + C.bt1 * C.vt1 + C.bt2 * C.vt2 : 0.0;
         acc_sources<EQ, VS, 0>(acc, C, uB, p0 - 1, p0 + 1, dt, idx, hdtdx);
         acc_flux_diff<EQ, 0>(acc, D, dt, idx, dtdx);
         // y: both faces come from the slab
@@ -396,6 +394,8 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         cons_diff(D, Fz, Fnew);
         Fz = Fnew;
         if (!warm) {
+          const Prim C = lds_prim<EQ, VS>(p0, 0, 1, 2);
+          const double uB = (EQ != EQ_EULER) ? C.bn * C.vn + C.bt1 * C.vt1 + C.bt2 * C.vt2 : 0.0;
           acc_sources<EQ, VS, 2>(acc, C, uB, pm1, pp1, dt, idx, hdtdx);
           acc_flux_diff<EQ, 2>(acc, D, dt, idx, dtdx);
         }
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       }
     }
     if (SOLVER == SOLVE_HLLD) {
-      f_c = f_zp; f_xm = n_xm; f_zp = n_zp; f_ym = n_ym; e_a = n_ea; e_b = n_eb;
+      w_k = w_k1; w_k1 = n_w; we_k1 = n_we;
       hp += g.sz;
       if (light) hpe += g.sz;
     }
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       Cons accx;  // grid frame == solver frame of x
       accx.rho = acc.rho; accx.erg = acc.erg; accx.mn = acc.m0; accx.mt1 = acc.m1; accx.mt2 = acc.m2;
       accx.bbn = acc.b0; accx.bbt1 = acc.b1; accx.bbt2 = acc.b2; accx.psi = acc.psi;
-      if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, C, accx, nullptr, 0, my_dt);
+      if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, lds_prim<EQ, VS>(p0, 0, 1, 2), accx, nullptr, 0, my_dt);
       else status |= cell_advance_time<EQ>(a, c, accx, nullptr, 0, my_dt);
     } else if (upd_xy && a.out != a.S) {
       // cell cut out of the domain (time_integrator.cpp:905-908): state untouched
@@ -462,7 +462,7 @@ inline void launch_sweep_tma_t(const StageArgs& a, cudaStream_t s) {
 // 3-D grids without tracers / H-correction run the TMA kernel, everything else the LDG sweep kernel
 template <int EQ, int SOLVER, bool FKJ>
 inline void launch_sweep_any(const StageArgs& a, cudaStream_t s) {
-  if (a.tmap && a.g.ndim == 3 && a.ntr == 0 && !a.eta) launch_sweep_tma_t<EQ, SOLVER, FKJ>(a, s);
+  if (a.tmap && a.g.ndim == 3 && a.ntr == 0 && !a.eta && (SOLVER != SOLVE_HLLD || a.hllf)) launch_sweep_tma_t<EQ, SOLVER, FKJ>(a, s);
   else launch_sweep_t<EQ, SOLVER, FKJ>(a, s);
 }
 
