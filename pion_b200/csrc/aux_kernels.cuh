@@ -81,13 +81,21 @@ __global__ void __launch_bounds__(256) k_hlld_flags_3d(GridD g, const double* __
 // x / y / z runs HLL when either cell of that face is flagged (solver_eqn_mhd_adi.cpp:167-177), so one
 // byte per cell (bit 0: x face, bit 1: y face, bit 2: z face) replaces two flag loads per face.
 __global__ void k_hll_face_flags(GridD g, const unsigned char* __restrict__ flag, unsigned char* __restrict__ face) {
-  const int ex = g.NGa[0] - 1, ey = g.NGa[1] - 1, ez = g.NGa[2] - 1;
-  const long n = (long)ex * ey * ez;
-  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
-    const int i = (int)(t % ex) + 1, j = (int)((t / ex) % ey) + 1, k = (int)(t / ((long)ex * ey)) + 1;
-    const long c = gidx(g, i, j, k);
-    const unsigned f = flag[c];
-    face[c] = (unsigned char)(((f | flag[c - 1]) ? 1u : 0u) | ((f | flag[c - g.sy]) ? 2u : 0u) | ((f | flag[c - g.sz]) ? 4u : 0u));
+  // four cells per thread: rows are pitched to 16 doubles, so every row starts on a 4-byte boundary; the cell
+  // flags are 0/1 bytes, so the per-byte ORs can be done on whole words.  Rows j = 0 / planes k = 0 have no
+  // lower neighbour and no face anybody needs.
+  const unsigned wpr = (unsigned)(g.sy / 4);
+  const unsigned nrow = (unsigned)(g.NGa[1] - 1);
+  const unsigned n = wpr * nrow * (unsigned)(g.NGa[2] - 1);
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const unsigned q = t % wpr, r = t / wpr;
+    const unsigned j = r % nrow + 1, k = r / nrow + 1;
+    const long o = (long)g.sy * j + (long)g.sz * k + 4L * q;
+    const unsigned w = *reinterpret_cast<const unsigned*>(flag + o);
+    const unsigned xw = (w << 8) | flag[o - 1];
+    const unsigned yw = *reinterpret_cast<const unsigned*>(flag + o - g.sy);
+    const unsigned zw = *reinterpret_cast<const unsigned*>(flag + o - g.sz);
+    *reinterpret_cast<unsigned*>(face + o) = (w | xw) | ((w | yw) << 1) | ((w | zw) << 2);
   }
 }
 
@@ -404,6 +412,22 @@ __global__ void k_wind_set(long vs, int nvar, long nw, const long* __restrict__ 
 }
 
 // small utility kernels
+// upload / download staging: one variable between the host's compact rows (NGa[0] doubles) and the device's
+// pitched rows (grid.cuh).  The PCIe copy itself is a FLAT cudaMemcpyAsync of the compact variable (55 GB/s
+// measured; the strided cudaMemcpy2D form reached ~41 GB/s) and this kernel does the re-pitching in HBM.
+__global__ void k_repack_var(GridD g, double* __restrict__ compact, double* __restrict__ pitched, int to_device) {
+  const int nx = g.NGa[0];
+  const long rows = (long)g.NGa[1] * g.NGa[2];
+  for (long r = blockIdx.x; r < rows; r += gridDim.x) {  // one row per block iteration: no index division
+    double* cr = compact + r * nx;
+    double* pr = pitched + r * g.sy + g.xoff;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+      if (to_device) pr[i] = cr[i];
+      else cr[i] = pr[i];
+    }
+  }
+}
+
 __global__ void k_copy_interior(GridD g, const double* __restrict__ src, double* __restrict__ dst, int nvar, int zero_var) {
   const long ncell = (long)g.NG[0] * g.NG[1] * g.NG[2];
   for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < ncell; t += (long)gridDim.x * blockDim.x) {

@@ -87,6 +87,10 @@ struct pion_gpu_ctx {
   double* d_wind_val = nullptr;
   double *sendbuf[6] = {nullptr}, *recvbuf[6] = {nullptr};
   size_t halo_elems[6] = {0};
+  // upload / download staging (two compact variables, allocated on first use) and its copy stream
+  double* stage[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr};
   // TMA tensor maps over the two state arrays (3-D grids; the TMA sweep kernel, stage_sweep_tma.cuh)
   alignas(64) CUtensorMap tmapP, tmapPh;
   bool have_tmap = false;
@@ -417,6 +421,12 @@ extern "C" void pion_gpu_destroy(pion_gpu_ctx* c) {
   cudaFree(c->P); cudaFree(c->Ph); cudaFree(c->dU); cudaFree(c->eta); cudaFree(c->hll); cudaFree(c->hllf); cudaFree(c->mask);
   cudaFree(c->d_dtmin); cudaFree(c->d_counters); cudaFree(c->d_red); cudaFree(c->d_tables); cudaFree(c->mp_dE); cudaFree(c->d_wind_idx); cudaFree(c->d_wind_val);
   for (int f = 0; f < 6; f++) { cudaFree(c->sendbuf[f]); cudaFree(c->recvbuf[f]); }
+  for (int q = 0; q < 2; q++) {
+    cudaFree(c->stage[q]);
+    if (c->ev_copied[q]) cudaEventDestroy(c->ev_copied[q]);
+    if (c->ev_packed[q]) cudaEventDestroy(c->ev_packed[q]);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -435,6 +445,18 @@ static int ensure_dU(pion_gpu_ctx* c) {
 // ---------------------------------------------------------------------------
 // upload / download: compact padded SoA on the host <-> pitched SoA on the device
 // ---------------------------------------------------------------------------
+static int ensure_staging(pion_gpu_ctx* c) {
+  if (c->stage[0]) return 0;
+  const size_t nv = (size_t)c->g.NGa[0] * c->g.NGa[1] * c->g.NGa[2];
+  CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int q = 0; q < 2; q++) {
+    CUDA_OK(cudaMalloc(&c->stage[q], nv * sizeof(double)));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_copied[q], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_packed[q], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
 static double* state_ptr(pion_gpu_ctx* c, int which) {
   if (which == PION_STATE_P) return c->P;
   if (which == PION_STATE_PH) return c->ph_valid ? c->Ph : c->P;  // after a fused full step Ph == P
@@ -451,10 +473,18 @@ extern "C" int pion_gpu_upload(pion_gpu_ctx* c, int which, const double* soa) {
   double* dst = (which == PION_STATE_P) ? c->P : (which == PION_STATE_PH) ? c->Ph : c->dU;
   const GridD& g = c->g;
   const size_t rows = (size_t)g.NGa[1] * g.NGa[2];
+  if (ensure_staging(c)) return 1;
+  const size_t nv = rows * g.NGa[0];
   for (int v = 0; v < c->nvar; v++) {
-    CUDA_OK(cudaMemcpy2DAsync(dst + (size_t)v * g.vs + g.xoff, g.sy * sizeof(double),
-                              soa + (size_t)v * rows * g.NGa[0], g.NGa[0] * sizeof(double), g.NGa[0] * sizeof(double),
-                              rows, cudaMemcpyHostToDevice, c->stream));
+    const int q = v & 1;
+    // flat PCIe copy of variable v into staging buffer q (once the re-pitch of variable v-2 has drained it),
+    // then the re-pitch kernel on the compute stream: the copy of v+1 overlaps the re-pitch of v
+    if (v >= 2) CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_packed[q], 0));
+    CUDA_OK(cudaMemcpyAsync(c->stage[q], soa + (size_t)v * nv, nv * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_OK(cudaEventRecord(c->ev_copied[q], c->copy_stream));
+    CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied[q], 0));
+    k_repack_var<<<nblocks((long)rows, 1, 148 * 32), 256, 0, c->stream>>>(g, c->stage[q], dst + (size_t)v * g.vs, 1);
+    CUDA_OK(cudaEventRecord(c->ev_packed[q], c->stream));
   }
   CUDA_OK(cudaStreamSynchronize(c->stream));
   if (which == PION_STATE_P) c->next_dt_valid = false;
@@ -467,11 +497,19 @@ extern "C" int pion_gpu_download(pion_gpu_ctx* c, int which, double* soa) {
   const double* src = state_ptr(c, which);
   const GridD& g = c->g;
   const size_t rows = (size_t)g.NGa[1] * g.NGa[2];
+  if (ensure_staging(c)) return 1;
+  const size_t nv = rows * g.NGa[0];
   for (int v = 0; v < c->nvar; v++) {
-    CUDA_OK(cudaMemcpy2DAsync(soa + (size_t)v * rows * g.NGa[0], g.NGa[0] * sizeof(double),
-                              src + (size_t)v * g.vs + g.xoff, g.sy * sizeof(double), g.NGa[0] * sizeof(double), rows,
-                              cudaMemcpyDeviceToHost, c->stream));
+    const int q = v & 1;
+    // pack variable v into staging buffer q (once the copy of variable v-2 has left it), flat PCIe copy out
+    if (v >= 2) CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied[q], 0));
+    k_repack_var<<<nblocks((long)rows, 1, 148 * 32), 256, 0, c->stream>>>(g, c->stage[q], const_cast<double*>(src) + (size_t)v * g.vs, 0);
+    CUDA_OK(cudaEventRecord(c->ev_packed[q], c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_packed[q], 0));
+    CUDA_OK(cudaMemcpyAsync(soa + (size_t)v * nv, c->stage[q], nv * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_OK(cudaEventRecord(c->ev_copied[q], c->copy_stream));
   }
+  CUDA_OK(cudaStreamSynchronize(c->copy_stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -765,8 +803,8 @@ static int launch_preprocess(pion_gpu_ctx* c, const double* S, int order) {
       while (kchunk > 8 && (long)bx * by * ((ez + kchunk - 1) / kchunk) < 148L * 8) kchunk >>= 1;
       k_hlld_flags_3d<<<dim3(bx, by, (ez + kchunk - 1) / kchunk), 256, 0, c->stream>>>(g, S, c->hll, kchunk);
       if (c->hllf) {  // face form for the TMA sweep kernel
-        const long nf = (long)(g.NGa[0] - 1) * (g.NGa[1] - 1) * (g.NGa[2] - 1);
-        k_hll_face_flags<<<nblocks(nf, 256), 256, 0, c->stream>>>(g, c->hll, c->hllf);
+        const long nf = (g.sy / 4) * (long)(g.NGa[1] - 1) * (g.NGa[2] - 1);
+        k_hll_face_flags<<<nblocks(nf, 256, 148 * 64), 256, 0, c->stream>>>(g, c->hll, c->hllf);
         c->launches++;
       }
     } else {
