@@ -36,7 +36,7 @@ extern "C" {
 /* integer codes are the reference's (constants.h:166-246, boundaries/boundaries.h:32-52) */
 enum { PION_EQEUL = 1, PION_EQMHD = 2, PION_EQGLM = 3 };
 enum { PION_COORD_CRT = 1, PION_COORD_CYL = 2, PION_COORD_SPH = 3 };
-enum { PION_FLUX_ROE = 4, PION_FLUX_HLLD = 7, PION_FLUX_HLL = 8 };
+enum { PION_FLUX_ROE = 4, PION_FLUX_ROE_PV = 5, PION_FLUX_FVS = 6, PION_FLUX_HLLD = 7, PION_FLUX_HLL = 8 };  /* 5, 6: Euler only */
 enum { PION_AV_NONE = 0, PION_AV_FKJ98 = 1, PION_AV_HCORR = 3, PION_AV_HCORR_FKJ98 = 4 };
 enum {
   PION_BC_PERIODIC = 1, PION_BC_OUTFLOW = 2, PION_BC_INFLOW = 3, PION_BC_REFLECTING = 4, PION_BC_FIXED = 5,

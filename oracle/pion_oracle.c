@@ -762,6 +762,97 @@ static double select_Hcorr_eta(const pion_oracle *s, long cl, long cr) {
   return eta;
 }
 
+/* eqns_Euler::Enthalpy (eqns_hydro_adiabatic.cpp:356-364) */
+static inline double euler_enthalpy(const pion_oracle *s, const double *p) {
+  double g = s->gamma;
+  return (0.5 * (p[s->eVX] * p[s->eVX] + p[s->eVY] * p[s->eVY] + p[s->eVZ] * p[s->eVZ]) + g * p[PG] / (g - 1.0) / p[RO]);
+}
+
+/* Riemann_FVS_Euler::FVS_flux + Roe_average_state (Riemann_FVS_hydro.cpp:84-248): van Leer (1982) flux
+ * vector splitting; pstar = the Roe-average state (for the viscosity) */
+static void hydro_FVS(pion_oracle *s, const double *pl, const double *pr, double *flux, double *pstar) {
+  double g = s->gamma;
+  double fpos[PO_MAXVAR], fneg[PO_MAXVAR], utemp[PO_MAXVAR];
+  for (int v = 0; v < s->nv; v++) fpos[v] = fneg[v] = 0.0;
+  double cl = chydro(s, pl), cr = chydro(s, pr), Ml = pl[s->eVX] / cl, Mr = pr[s->eVX] / cr, f1 = 0.0, f2 = 0.0;
+  if (Ml < -1.0) {
+    /* zero */
+  } else if (Ml > 1.0) {
+    euler_PtoU(s, pl, utemp);
+    euler_PUtoFlux(s, pl, utemp, fpos);
+  } else {
+    f1 = 0.25 * pl[RO] * cl * (1.0 + Ml) * (1.0 + Ml);
+    f2 = cl * ((g - 1.0) * Ml + 2);
+    fpos[RHO] = f1;
+    fpos[s->eMX] = f1 * f2 / g;
+    fpos[s->eMY] = f1 * pl[s->eVY];
+    fpos[s->eMZ] = f1 * pl[s->eVZ];
+    fpos[ERG] = f1 * (f2 * f2 * 0.5 / (g * g - 1.0) + 0.5 * (pl[s->eVY] * pl[s->eVY] + pl[s->eVZ] * pl[s->eVZ]));
+  }
+  if (Mr > 1.0) {
+    /* zero */
+  } else if (Mr < -1.0) {
+    euler_PtoU(s, pr, utemp);
+    euler_PUtoFlux(s, pr, utemp, fneg);
+  } else {
+    f1 = -0.25 * pr[RO] * cr * (1.0 - Mr) * (1.0 - Mr);
+    f2 = cr * ((g - 1.0) * Mr - 2);
+    fneg[RHO] = f1;
+    fneg[s->eMX] = f1 * f2 / g;
+    fneg[s->eMY] = f1 * pr[s->eVY];
+    fneg[s->eMZ] = f1 * pr[s->eVZ];
+    fneg[ERG] = f1 * (f2 * f2 * 0.5 / (g * g - 1) + 0.5 * (pr[s->eVY] * pr[s->eVY] + pr[s->eVZ] * pr[s->eVZ]));
+  }
+  /* only the five hydro components (rs_nvar = 5): tracer entries of flux stay 0 */
+  flux[RHO] = fpos[RHO] + fneg[RHO];
+  flux[ERG] = fpos[ERG] + fneg[ERG];
+  flux[s->eMX] = fpos[s->eMX] + fneg[s->eMX];
+  flux[s->eMY] = fpos[s->eMY] + fneg[s->eMY];
+  flux[s->eMZ] = fpos[s->eMZ] + fneg[s->eMZ];
+  /* Roe_average_state (:205-248) */
+  double rl = sqrt(pl[RO]), rr = sqrt(pr[RO]), denom = 1.0 / (rl + rr);
+  pstar[RO] = rl * rr;
+  pstar[s->eVX] = (rl * pl[s->eVX] + rr * pr[s->eVX]) * denom;
+  pstar[s->eVY] = (rl * pl[s->eVY] + rr * pr[s->eVY]) * denom;
+  pstar[s->eVZ] = (rl * pl[s->eVZ] + rr * pr[s->eVZ]) * denom;
+  pstar[PG] = denom * (rl * euler_enthalpy(s, pl) + rr * euler_enthalpy(s, pr));
+  pstar[PG] = (g - 1.0) * (pstar[PG] - 0.5 * (pstar[s->eVX] * pstar[s->eVX] + pstar[s->eVY] * pstar[s->eVY] +
+                                               pstar[s->eVZ] * pstar[s->eVZ]));
+  pstar[PG] = pstar[RO] * pstar[PG] / g;
+}
+
+/* Riemann_Roe_Hydro_PV::Roe_prim_var_solver (Roe_Hydro_PrimitiveVar_solver.cpp:62-209): linearised
+ * primitive-variable solver about the Roe-average state; returns the interface state */
+static void hydro_RoePV(pion_oracle *s, const double *left, const double *right, double *pstar) {
+  double g = s->gamma;
+  double rl = sqrt(left[RO]), rr = sqrt(right[RO]), lH = euler_enthalpy(s, left), rH = euler_enthalpy(s, right),
+         denom = 1.0 / (rl + rr), a_mean = 0.0, v2_mean = 0.0;
+  double m_ro = rl * rr;
+  double m_vx = (rl * left[s->eVX] + rr * right[s->eVX]) * denom;
+  double m_vy = (rl * left[s->eVY] + rr * right[s->eVY]) * denom;
+  double m_vz = (rl * left[s->eVZ] + rr * right[s->eVZ]) * denom;
+  double m_H = (rl * lH + rr * rH) * denom;
+  v2_mean = m_vx * m_vx + m_vy * m_vy + m_vz * m_vz;
+  a_mean = sqrt((g - 1.0) * (m_H - 0.5 * v2_mean));
+  if (m_vx - a_mean >= 0.) {
+    for (int i = 0; i < 5; i++) pstar[i] = left[i];
+  } else if (m_vx + a_mean <= 0.) {
+    for (int i = 0; i < 5; i++) pstar[i] = right[i];
+  } else {
+    pstar[PG] = 0.5 * (left[PG] + right[PG] - m_ro * a_mean * (right[s->eVX] - left[s->eVX]));
+    pstar[s->eVX] = 0.5 * (left[s->eVX] + right[s->eVX] - (right[PG] - left[PG]) / m_ro / a_mean);
+    if (pstar[s->eVX] > 0.0) {
+      pstar[RO] = left[RO] + m_ro * (left[s->eVX] - pstar[s->eVX]) / a_mean;
+      pstar[s->eVY] = left[s->eVY];
+      pstar[s->eVZ] = left[s->eVZ];
+    } else {
+      pstar[RO] = right[RO] + m_ro * (pstar[s->eVX] - right[s->eVX]) / a_mean;
+      pstar[s->eVY] = right[s->eVY];
+      pstar[s->eVZ] = right[s->eVZ];
+    }
+  }
+}
+
 /* FV_solver_Hydro_Euler::inviscid_flux (solver_eqn_hydro_adi.cpp:94-205) */
 static void euler_inviscid_flux(pion_oracle *s, const double *Pl, const double *Pr, double *flux, double *pstar) {
   double ustar[PO_MAXVAR];
@@ -771,6 +862,13 @@ static void euler_inviscid_flux(pion_oracle *s, const double *Pl, const double *
   } else if (s->cfg.solver == PO_FLUX_HLL) {
     hydro_HLL(s, Pl, Pr, flux, ustar);
     euler_UtoP(s, ustar, pstar);
+  } else if (s->cfg.solver == PO_FLUX_FVS) {
+    hydro_FVS(s, Pl, Pr, flux, pstar);
+  } else if (s->cfg.solver == PO_FLUX_ROE_PV) {
+    /* :178-187: interface state, then PtoFlux = (virtual) PtoU + PUtoFlux (eqns_base.cpp:230-240) */
+    hydro_RoePV(s, Pl, Pr, pstar);
+    euler_PtoU(s, pstar, ustar);
+    euler_PUtoFlux(s, pstar, ustar, flux);
   } else {
     fprintf(stderr, "pion_oracle: Euler solver %d not restated\n", s->cfg.solver);
     abort();

@@ -24,7 +24,7 @@
 namespace pion {
 
 enum : int { EQ_EULER = 1, EQ_MHD = 2, EQ_GLM = 3 };                 // constants.h:166-172
-enum : int { SOLVE_ROE = 4, SOLVE_HLLD = 7, SOLVE_HLL = 8 };         // constants.h:238-246
+enum : int { SOLVE_ROE = 4, SOLVE_ROE_PV = 5, SOLVE_FVS = 6, SOLVE_HLLD = 7, SOLVE_HLL = 8 };  // constants.h:238-246 (5, 6: Euler only)
 enum : int { AV_NONE = 0, AV_FKJ98 = 1, AV_HCORR = 3, AV_HCORR_FKJ98 = 4 };
 
 #define PION_MACHINEACCURACY 5.e-16    // constants.h:151
@@ -284,6 +284,101 @@ __device__ __forceinline__ void euler_UtoFlux(const Cons& u, Cons& f, double gm1
   f.mt1 = u.mn * u.mt1 * ir;
   f.mt2 = u.mn * u.mt2 * ir;
   f.erg = u.mn * (u.erg + pg) * ir;
+}
+
+// Roe-average primitive state of two Euler states (Toro eq. 11.60): Riemann_FVS_Euler::Roe_average_state
+// (Riemann_FVS_hydro.cpp:205-248) and the first part of Roe_prim_var_solver.  Returns the mean sound speed^2.
+__device__ __forceinline__ double hydro_roe_average(const Prim& L, const Prim& R, double g, Prim& m) {
+  const double gm1 = g - 1.0;
+  const double rl = psqrt(L.ro), rr = psqrt(R.ro);
+  const double lH = 0.5 * (L.vn * L.vn + L.vt1 * L.vt1 + L.vt2 * L.vt2) + pdiv(g * L.pg, gm1 * L.ro);
+  const double rH = 0.5 * (R.vn * R.vn + R.vt1 * R.vt1 + R.vt2 * R.vt2) + pdiv(g * R.pg, gm1 * R.ro);
+  const double denom = fast_rcp(rl + rr);
+  m.ro = rl * rr;
+  m.vn = (rl * L.vn + rr * R.vn) * denom;
+  m.vt1 = (rl * L.vt1 + rr * R.vt1) * denom;
+  m.vt2 = (rl * L.vt2 + rr * R.vt2) * denom;
+  const double H = (rl * lH + rr * rH) * denom;
+  const double a2 = gm1 * (H - 0.5 * (m.vn * m.vn + m.vt1 * m.vt1 + m.vt2 * m.vt2));
+  m.pg = pdiv(m.ro * a2, g);
+  m.bn = m.bt1 = m.bt2 = m.psi = 0.0;
+  return a2;
+}
+
+// Riemann_FVS_Euler::FVS_flux (Riemann_FVS_hydro.cpp:84-198): van Leer (1982) flux-vector splitting;
+// pstar = the Roe-average state (only the viscosity reads it)
+template <bool NEED_PSTAR>
+__device__ __forceinline__ void hydro_FVS(const Prim& L, const Prim& R, const PhysParams& pp, Cons& flux, Prim& pstar) {
+  const double g = pp.gamma, gm1 = g - 1.0;
+  const double ig = fast_rcp(g), ig21 = fast_rcp(g * g - 1.0);
+  Cons fp, fn;
+  fp.rho = fp.erg = fp.mn = fp.mt1 = fp.mt2 = 0.0;
+  fn.rho = fn.erg = fn.mn = fn.mt1 = fn.mt2 = 0.0;
+  const double cl = chydro(L.ro, L.pg, g), cr = chydro(R.ro, R.pg, g);
+  const double Ml = pdiv(L.vn, cl), Mr = pdiv(R.vn, cr);
+  if (Ml < -1.0) {
+  } else if (Ml > 1.0) {
+    Cons u;
+    PtoU<EQ_EULER>(L, u, gm1);
+    PUtoFlux<EQ_EULER>(L, u, fp);
+  } else {
+    const double f1 = 0.25 * L.ro * cl * (1.0 + Ml) * (1.0 + Ml);
+    const double f2 = cl * (gm1 * Ml + 2);
+    fp.rho = f1;
+    fp.mn = f1 * f2 * ig;
+    fp.mt1 = f1 * L.vt1;
+    fp.mt2 = f1 * L.vt2;
+    fp.erg = f1 * (f2 * f2 * 0.5 * ig21 + 0.5 * (L.vt1 * L.vt1 + L.vt2 * L.vt2));
+  }
+  if (Mr > 1.0) {
+  } else if (Mr < -1.0) {
+    Cons u;
+    PtoU<EQ_EULER>(R, u, gm1);
+    PUtoFlux<EQ_EULER>(R, u, fn);
+  } else {
+    const double f1 = -0.25 * R.ro * cr * (1.0 - Mr) * (1.0 - Mr);
+    const double f2 = cr * (gm1 * Mr - 2);
+    fn.rho = f1;
+    fn.mn = f1 * f2 * ig;
+    fn.mt1 = f1 * R.vt1;
+    fn.mt2 = f1 * R.vt2;
+    fn.erg = f1 * (f2 * f2 * 0.5 * ig21 + 0.5 * (R.vt1 * R.vt1 + R.vt2 * R.vt2));
+  }
+  flux.rho = fp.rho + fn.rho; flux.erg = fp.erg + fn.erg;
+  flux.mn = fp.mn + fn.mn; flux.mt1 = fp.mt1 + fn.mt1; flux.mt2 = fp.mt2 + fn.mt2;
+  flux.bbn = flux.bbt1 = flux.bbt2 = flux.psi = 0.0;
+  if (NEED_PSTAR) hydro_roe_average(L, R, g, pstar);
+}
+
+// Riemann_Roe_Hydro_PV::Roe_prim_var_solver (Roe_Hydro_PrimitiveVar_solver.cpp:62-209): interface state of
+// the solver linearised about the Roe average; the flux is PtoFlux(pstar) (solver_eqn_hydro_adi.cpp:178-187)
+__device__ __forceinline__ void hydro_RoePV(const Prim& L, const Prim& R, const PhysParams& pp, Cons& flux, Prim& pstar) {
+  const double g = pp.gamma;
+  Prim m;
+  const double a2 = hydro_roe_average(L, R, g, m);
+  const double a_mean = psqrt(a2);
+  if (m.vn - a_mean >= 0.) {
+    pstar = L;
+  } else if (m.vn + a_mean <= 0.) {
+    pstar = R;
+  } else {
+    const double ia = fast_rcp(a_mean);
+    pstar.pg = 0.5 * (L.pg + R.pg - m.ro * a_mean * (R.vn - L.vn));
+    pstar.vn = 0.5 * (L.vn + R.vn - (R.pg - L.pg) * fast_rcp(m.ro) * ia);
+    if (pstar.vn > 0.0) {
+      pstar.ro = L.ro + m.ro * (L.vn - pstar.vn) * ia;
+      pstar.vt1 = L.vt1;
+      pstar.vt2 = L.vt2;
+    } else {
+      pstar.ro = R.ro + m.ro * (pstar.vn - R.vn) * ia;
+      pstar.vt1 = R.vt1;
+      pstar.vt2 = R.vt2;
+    }
+  }
+  pstar.bn = pstar.bt1 = pstar.bt2 = pstar.psi = 0.0;
+  Cons u;
+  PtoU<EQ_EULER>(pstar, u, g - 1.0);
+  PUtoFlux<EQ_EULER>(pstar, u, flux);
 }
 
 // Riemann_Roe_Hydro_CV::Roe_flux_solver_symmetric
@@ -695,6 +790,10 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
   if (EQ == EQ_EULER) {
     if (SOLVER == SOLVE_ROE) {
       hydro_RoeCV(eL, eR, pp, hc_etamax, flux, pstar);
+    } else if (SOLVER == SOLVE_FVS) {
+      hydro_FVS<FKJ>(eL, eR, pp, flux, pstar);
+    } else if (SOLVER == SOLVE_ROE_PV) {
+      hydro_RoePV(eL, eR, pp, flux, pstar);
     } else {
       Cons ustar;
       hydro_HLL(eL, eR, pp, flux, ustar);

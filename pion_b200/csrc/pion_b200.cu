@@ -151,7 +151,10 @@ static int check_config(const pion_gpu_config& c) {
   if (c.coord_sys == PION_COORD_CYL && c.ndim != 2) { set_error("Cylindrical coordinates only implemented for 2d axial symmetry"); return 1; }
   if (c.coord_sys == PION_COORD_SPH && (c.ndim != 1 || c.eqntype != PION_EQEUL)) { set_error("Spherical coordinates only implemented for 1D Euler"); return 1; }
   if (c.coord_sys != PION_COORD_CRT && c.n_wind > 0) { set_error("stellar-wind boundary: only Cartesian grids are built"); return 1; }
-  if (c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL) { set_error("solver must be 4 (Roe-CV), 7 (HLLD) or 8 (HLL)"); return 1; }
+  const bool euler_only = (c.solver == PION_FLUX_ROE_PV || c.solver == PION_FLUX_FVS);
+  if (c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL && !euler_only) { set_error("solver must be 4 (Roe-CV), 5 (Roe-PV), 6 (FVS), 7 (HLLD) or 8 (HLL)"); return 1; }
+  // solver_eqn_mhd_adi.cpp:132-198: the MHD solvers have no Roe-PV / FVS branch ("what sort of flux solver do you mean???")
+  if (euler_only && c.eqntype != PION_EQEUL) { set_error("solver 5 (Roe-PV) and 6 (FVS) exist for the Euler equations only"); return 1; }
   if (c.eqntype == PION_EQEUL && c.solver == PION_FLUX_HLLD) { set_error("HLLD needs MHD equations"); return 1; }
   if (c.artviscosity != 0 && c.artviscosity != 1 && c.artviscosity != 3 && c.artviscosity != 4) { set_error("artviscosity must be 0,1,3,4"); return 1; }
   if (!((c.spOOA == 1 && c.tmOOA == 1) || (c.spOOA == 2 && c.tmOOA == 2))) { set_error("Bad OOA requests; choose (1,1) or (2,2)"); return 1; }

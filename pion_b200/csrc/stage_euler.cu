@@ -5,6 +5,12 @@ void launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s)
   if (solver == SOLVE_ROE) {
     if (fkj) launch_stage_t<EQ_EULER, SOLVE_ROE, true>(a, s);
     else launch_stage_t<EQ_EULER, SOLVE_ROE, false>(a, s);
+  } else if (solver == SOLVE_FVS) {
+    if (fkj) launch_stage_t<EQ_EULER, SOLVE_FVS, true>(a, s);
+    else launch_stage_t<EQ_EULER, SOLVE_FVS, false>(a, s);
+  } else if (solver == SOLVE_ROE_PV) {
+    if (fkj) launch_stage_t<EQ_EULER, SOLVE_ROE_PV, true>(a, s);
+    else launch_stage_t<EQ_EULER, SOLVE_ROE_PV, false>(a, s);
   } else {
     if (fkj) launch_stage_t<EQ_EULER, SOLVE_HLL, true>(a, s);
     else launch_stage_t<EQ_EULER, SOLVE_HLL, false>(a, s);

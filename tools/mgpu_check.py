@@ -25,6 +25,7 @@ def main():
     worst = 0.0
     cases = [
         # big enough for the split stage (boundary shell first, halo exchange overlapped with the interior)
+        Problem(ndim=3, NG=(192, 96, 96), eqn="glm-mhd", solver=7, artviscosity=1, xmax=(2.0, 1.0, 1.0), bcs=("periodic",) * 6),
         Problem(ndim=3, NG=(128, 64, 64), eqn="glm-mhd", solver=7, artviscosity=1, xmax=(2.0, 1.0, 1.0), bcs=("periodic",) * 6),
         Problem(ndim=3, NG=(128, 64, 64), eqn="euler", solver=8, artviscosity=1, xmax=(2.0, 1.0, 1.0), bcs=("reflecting", "outflow") * 3, ntracer=1),
         Problem(ndim=3, NG=(32, 16, 16), eqn="glm-mhd", solver=7, artviscosity=1, xmax=(2.0, 1.0, 1.0), bcs=("periodic",) * 6),
