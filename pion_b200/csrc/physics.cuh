@@ -221,8 +221,10 @@ __device__ __forceinline__ double chydro(double ro, double pg, double g) {
 __device__ __forceinline__ double cfast2_ir(double ir, double pg, double bx, double by, double bz, double g) {
   // one reciprocal instead of a sqrt + three divisions; ch*ch == g*pg/ro to 1 ulp
   double ch2 = g * pg * ir;
-  double temp1 = ch2 + (bx * bx + by * by + bz * bz) * ir;
-  double temp2 = 4. * ch2 * bx * bx * ir;
+  // b_x^2/rho formed once and shared by both terms (two multiplies fewer than the literal form; 1 ulp)
+  const double bxi = (bx * bx) * ir;
+  double temp1 = (ch2 + bxi) + (by * by + bz * bz) * ir;
+  double temp2 = (4. * ch2) * bxi;
   temp2 = pmax(temp1 * temp1 - temp2, PION_MACHINEACCURACY);
   return (temp1 + fast_sqrt(temp2)) / 2.;
 }
@@ -554,14 +556,14 @@ __device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const Phy
   }
 
   // everything below is for side K only
-  const double K_ro = left ? L.ro : R.ro, K_pg = left ? L.pg : R.pg, K_vn = left ? L.vn : R.vn;
-  const double K_vt1 = left ? L.vt1 : R.vt1, K_vt2 = left ? L.vt2 : R.vt2;
-  const double K_bn = left ? L.bn : R.bn, K_bt1 = left ? L.bt1 : R.bt1, K_bt2 = left ? L.bt2 : R.bt2;
-  const double s_v = left ? sl_vl : sr_vr, is_m = left ? isl_sm : isr_sm;
-  const double rho_s = left ? rho_ls : rho_rs, sq_K = left ? -sq_l : sq_r;  // sign of the ** energy jump folded in
-  const double vys = left ? vys_l : vys_r, vzs = left ? vzs_l : vzs_r;
-  const double bys = left ? bys_l : bys_r, bzs = left ? bzs_l : bzs_r;
-  const double pm_K = left ? pm_l : pm_r, tp_K = left ? tp_l : tp_r;
+  const double K_ro = (left ? L.ro : R.ro), K_pg = (left ? L.pg : R.pg), K_vn = (left ? L.vn : R.vn);
+  const double K_vt1 = (left ? L.vt1 : R.vt1), K_vt2 = (left ? L.vt2 : R.vt2);
+  const double K_bn = (left ? L.bn : R.bn), K_bt1 = (left ? L.bt1 : R.bt1), K_bt2 = (left ? L.bt2 : R.bt2);
+  const double s_v = (left ? sl_vl : sr_vr), is_m = (left ? isl_sm : isr_sm);
+  const double rho_s = (left ? rho_ls : rho_rs), sq_K = (left ? -sq_l : sq_r);  // sign of the ** energy jump folded in
+  const double vys = (left ? vys_l : vys_r), vzs = (left ? vzs_l : vzs_r);
+  const double bys = (left ? bys_l : bys_r), bzs = (left ? bzs_l : bzs_r);
+  const double pm_K = (left ? pm_l : pm_r), tp_K = (left ? tp_l : tp_r);
   const double c2 = outer ? 0.0 : (left ? lam0 : lam4);
   const double c1 = (dstar && BX != 0) ? (left ? lam1 : lam3) : 0.0;
 

@@ -34,6 +34,9 @@
 namespace pion {
 
 
+#ifndef PION_TMA_KCHUNK
+#define PION_TMA_KCHUNK 64
+#endif
 constexpr int TMA_TX = 32;                                            // cells a tile updates along x
 constexpr int TMA_CW = 36;                                            // tile columns: cells i0-2 .. i0+33
 __host__ __device__ constexpr int tma_rh(int ty) { return ty + 3; }  // tile rows
@@ -447,7 +450,7 @@ inline void launch_sweep_tma_t(const StageArgs& a, cudaStream_t s) {
   constexpr int NB = nbase(EQ);
   const int bx = a.tx1 - a.tx0, by = a.ty1 - a.ty0, NZ = a.k_hi - a.k_lo;
   if (bx <= 0 || by <= 0 || NZ <= 0) return;
-  int kchunk = 64;
+  int kchunk = PION_TMA_KCHUNK;
   while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
   const int bz = (NZ + kchunk - 1) / kchunk;
   const size_t smem = (size_t)4 * tma_plane_stride(NB, TY) + (size_t)2 * NB * TY * 32 * sizeof(double) + (size_t)3 * NB * TY * sizeof(double);
