@@ -14,7 +14,7 @@ def run(prob, nsteps, no_tma):
     g.run(nsteps); out = g.get_state(0); g.close(); return out
 
 cases = [(e, s, av) for (e, s) in EQ_SOLVERS for av in (0, 1, 4)]
-if len(sys.argv) > 1: cases = [(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]))]
+if len(sys.argv) > 1: cases = [(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]))] * (int(sys.argv[4]) if len(sys.argv) > 4 else 1)
 for eqn, solver, av in cases:
     prob = case_3d(eqn, solver, av, bcs="reflect-outflow", NG=(40, 26, 20))
     for nsteps in (1, 3):
