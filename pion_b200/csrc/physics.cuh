@@ -516,7 +516,12 @@ __device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const Phy
   const double tp_l = L.pg + pm_l, tp_r = R.pg + pm_r;
   const double rsl = L.ro * sl_vl, rsr = R.ro * sr_vr;
   const double itemp = fast_rcp(rsr - rsl);
-  const double lam2 = (sr_vr * (R.ro * R.vn) - sl_vl * (L.ro * L.vn) - tp_r + tp_l) * itemp;
+  // The two momentum terms are rounded SEPARATELY (no FMA contraction): at a reflecting wall L is the mirror
+  // image of R, both products are then the same number and the contact speed is an exact zero, as in the
+  // reference (HLLD_MHD.cpp:159).  The left/right choice below hinges on its sign, and in ideal MHD the two
+  // star fluxes differ at O(B_n B_t) there (each side's F_K carries its own B_n, which flips across the wall),
+  // so a contracted product's rounding residue would pick the other side (measured: 1e-3 relative in v_t, B_t).
+  const double lam2 = ((__dmul_rn(sr_vr, R.ro * R.vn) - __dmul_rn(sl_vl, L.ro * L.vn)) - tp_r + tp_l) * itemp;
   const double tp_s = (rsr * tp_l - rsl * tp_r + L.ro * R.ro * sr_vr * sl_vl * (R.vn - L.vn)) * itemp;
   const double sl_sm = lam0 - lam2, sr_sm = lam4 - lam2;
   const double isl_sm = fast_rcp(sl_sm), isr_sm = fast_rcp(sr_sm);

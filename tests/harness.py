@@ -465,6 +465,18 @@ def random_state(prob: Problem, seed=12345, smooth=True, amp=0.5):
     return out
 
 
+def hot_sphere_state(prob: Problem, seed=7, amp=0.5, fac=100.0):
+    """random_state with the pressure multiplied by `fac` inside a central ellipsoid (30 % of each extent):
+    |grad p|/p >> 5 and converging/diverging flow at its surface, so that a few thousand cells trip the
+    HLLD -> HLL switch (solver_eqn_mhd_adi.cpp:167-177) -- the smooth random state never does."""
+    P = random_state(prob, seed, amp=amp)
+    shp = P.shape[1:]
+    z, y, x = np.meshgrid(*[np.arange(n) - (n - 1) / 2 for n in shp], indexing="ij")
+    r2 = sum((c / (0.3 * n)) ** 2 for c, n in zip((z, y, x), shp) if n > 1)
+    P[1] = np.where(r2 < 1.0, P[1] * fac, P[1])
+    return P
+
+
 MU_TOT_OVER_KB = (0.609 * 1.672621898e-24) / 1.38064852e-16  # mp_only_cooling.cpp:79-81 with constants.h:53,64
 
 

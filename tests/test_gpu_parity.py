@@ -8,16 +8,16 @@ import numpy as np
 import pytest
 
 from cases import AVS, EQ_SOLVERS, case_1d, case_2d, case_3d
-from harness import GpuSim, OracleSim, RefSim, have_ref, random_state, rel_err
+from harness import GpuSim, OracleSim, RefSim, have_ref, hot_sphere_state, random_state, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 5e-12
 
 
-def run_pair(prob, nsteps=3, seed=7, checker=OracleSim, amp=0.5):
+def run_pair(prob, nsteps=3, seed=7, checker=OracleSim, amp=0.5, state=None):
     o, g = checker(prob), GpuSim(prob)
     try:
-        P = random_state(prob, seed, amp=amp)
+        P = state(prob) if state else random_state(prob, seed, amp=amp)
         for s in (o, g):
             s.set_state(P)
             s.init_after_state()
@@ -61,6 +61,23 @@ def test_3d_multi_tile_tma_sweep(eqn, solver, av):
 def test_boundary_types(bcs, eqn, solver):
     run_pair(case_3d(eqn, solver, 1, bcs=bcs, NG=(10, 8, 6)))
     run_pair(case_2d(eqn, solver, 4, bcs=bcs, ntracer=1, NG=(10, 8, 1)))
+
+
+@pytest.mark.parametrize("eqn", ["i-mhd", "glm-mhd"])
+@pytest.mark.parametrize("av", [0, 1])
+def test_hlld_to_hll_switch_hot_sphere(eqn, av):
+    """A x100 pressure ellipsoid flags ~2600 cells (divV < 0 and sum |dp|/min p > 5): the faces next to them run
+    HLL, the rest HLLD -- divergent inside a warp.  3-D multi-tile (TMA sweep, face-form flags) and 2-D (LDG sweep)."""
+    o = OracleSim(case_3d(eqn, 7, av, bcs="reflect-outflow", NG=(40, 26, 20)))
+    try:
+        o.set_state(hot_sphere_state(o.prob if hasattr(o, "prob") else case_3d(eqn, 7, av, bcs="reflect-outflow", NG=(40, 26, 20))))
+        o.init_after_state()
+        o.run(1)
+        assert int(np.sum((o.get_extra(0) < 0) & (o.get_extra(1) > 5))) > 500, "the switch is not exercised"
+    finally:
+        o.close()
+    run_pair(case_3d(eqn, 7, av, bcs="reflect-outflow", NG=(40, 26, 20)), state=hot_sphere_state)
+    run_pair(case_2d(eqn, 7, av, bcs="outflow", NG=(48, 40, 1)), state=hot_sphere_state)
 
 
 @pytest.mark.parametrize("solver", [4, 5, 6, 8])

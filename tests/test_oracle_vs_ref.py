@@ -5,16 +5,16 @@ import numpy as np
 import pytest
 
 from cases import AVS, EQ_SOLVERS, case_1d, case_2d, case_3d
-from harness import OracleSim, RefSim, have_ref, random_state
+from harness import OracleSim, RefSim, have_ref, hot_sphere_state, random_state
 
 pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
 
 
-def run_pair(prob, nsteps=3, seed=1, amp=0.5):
+def run_pair(prob, nsteps=3, seed=1, amp=0.5, state=None):
     r, o = RefSim(prob), OracleSim(prob)
     try:
         assert r.shape() == o.shape() == prob.padded_shape()
-        P = random_state(prob, seed, amp=amp)
+        P = state(prob) if state else random_state(prob, seed, amp=amp)
         for s in (r, o):
             s.set_state(P)
             assert s.init_after_state() == 0
@@ -48,6 +48,13 @@ def test_3d_periodic_bit_exact(eqn, solver, av, ntr):
 def test_boundary_types_bit_exact(bcs, eqn, solver):
     run_pair(case_3d(eqn, solver, 1, bcs=bcs, NG=(10, 8, 6)))
     run_pair(case_2d(eqn, solver, 4, bcs=bcs, ntracer=1, NG=(10, 8, 1)))
+
+
+@pytest.mark.parametrize("eqn", ["i-mhd", "glm-mhd"])
+def test_hlld_to_hll_switch_bit_exact(eqn):
+    """x100 pressure ellipsoid: thousands of cells trip the HLLD -> HLL switch (the smooth random state trips none)."""
+    run_pair(case_3d(eqn, 7, 1, bcs="reflect-outflow", NG=(20, 16, 12)), state=hot_sphere_state)
+    run_pair(case_2d(eqn, 7, 0, bcs="outflow", NG=(48, 40, 1)), state=hot_sphere_state)
 
 
 @pytest.mark.parametrize("solver", [4, 5, 6, 8])
