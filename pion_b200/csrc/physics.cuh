@@ -511,9 +511,11 @@ __device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const Phy
   const double lam0 = pmin(L.vn, R.vn) - cf_max;
   const double lam4 = pmax(L.vn, R.vn) + cf_max;
   const double sl_vl = lam0 - L.vn, sr_vr = lam4 - R.vn;
-  const double pm_l = 0.5 * (L.bn * L.bn + L.bt1 * L.bt1 + L.bt2 * L.bt2);
-  const double pm_r = 0.5 * (R.bn * R.bn + R.bt1 * R.bt1 + R.bt2 * R.bt2);
-  const double tp_l = L.pg + pm_l, tp_r = R.pg + pm_r;
+  // magnetic pressures with the SAME rounding sequence on both sides (explicit, never contracted: the compiler
+  // would otherwise share sub-expressions with the fast speeds on one side only) -- see lam2 below
+  const double pm_l = 0.5 * __dadd_rn(__dadd_rn(__dmul_rn(L.bn, L.bn), __dmul_rn(L.bt1, L.bt1)), __dmul_rn(L.bt2, L.bt2));
+  const double pm_r = 0.5 * __dadd_rn(__dadd_rn(__dmul_rn(R.bn, R.bn), __dmul_rn(R.bt1, R.bt1)), __dmul_rn(R.bt2, R.bt2));
+  const double tp_l = __dadd_rn(L.pg, pm_l), tp_r = __dadd_rn(R.pg, pm_r);
   const double rsl = L.ro * sl_vl, rsr = R.ro * sr_vr;
   const double itemp = fast_rcp(rsr - rsl);
   // The two momentum terms are rounded SEPARATELY (no FMA contraction): at a reflecting wall L is the mirror
@@ -521,7 +523,7 @@ __device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const Phy
   // reference (HLLD_MHD.cpp:159).  The left/right choice below hinges on its sign, and in ideal MHD the two
   // star fluxes differ at O(B_n B_t) there (each side's F_K carries its own B_n, which flips across the wall),
   // so a contracted product's rounding residue would pick the other side (measured: 1e-3 relative in v_t, B_t).
-  const double lam2 = ((__dmul_rn(sr_vr, R.ro * R.vn) - __dmul_rn(sl_vl, L.ro * L.vn)) - tp_r + tp_l) * itemp;
+  const double lam2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sr_vr, __dmul_rn(R.ro, R.vn)), -__dmul_rn(sl_vl, __dmul_rn(L.ro, L.vn))), -tp_r), tp_l) * itemp;
   const double tp_s = (rsr * tp_l - rsl * tp_r + L.ro * R.ro * sr_vr * sl_vl * (R.vn - L.vn)) * itemp;
   const double sl_sm = lam0 - lam2, sr_sm = lam4 - lam2;
   const double isl_sm = fast_rcp(sl_sm), isr_sm = fast_rcp(sr_sm);
