@@ -130,6 +130,7 @@ static int make_state_tmap(const pion_gpu_ctx* c, double* base, CUtensorMap* out
     return 1;
   }
   const GridD& g = c->g;
+  nb += c->ntr;  // tracers ride along as extra tile variables
   const cuuint64_t dims[4] = {(cuuint64_t)g.sy, (cuuint64_t)g.NGa[1], (cuuint64_t)g.NGa[2], (cuuint64_t)nb};
   const cuuint64_t strides[3] = {(cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8, (cuuint64_t)g.vs * 8};
   const cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)rh, 1u, (cuuint32_t)nb};
@@ -397,7 +398,7 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   {
     // 3-D Cartesian grids run the TMA sweep kernel (PION_B200_NO_TMA=1: the LDG sweep kernel, for A/B tests)
     const char* e = getenv("PION_B200_NO_TMA");
-    if (g.ndim == 3 && g.coord == PION_COORD_CRT && !(e && e[0] == '1')) {
+    if (g.ndim == 3 && g.coord == PION_COORD_CRT && !(e && e[0] == '1') && sweep_tma_fits(c->cfg.eqntype, c->ntr)) {
       if (make_state_tmap(c, c->P, &c->tmapP) || make_state_tmap(c, c->Ph, &c->tmapPh)) { pion_gpu_destroy(c); return nullptr; }
       c->have_tmap = true;
       if (c->hll && (cudaMalloc(&c->hllf, (size_t)g.vs) != cudaSuccess || cudaMemset(c->hllf, 0, (size_t)g.vs) != cudaSuccess)) {
@@ -835,7 +836,7 @@ struct StageBox { int tx0, tx1, ty0, ty1, k_lo, k_hi; };
 // cells per tile of the sweep kernel that a fused stage of this context runs (launch_sweep_any's choice)
 static void stage_tile_cells(const pion_gpu_ctx* c, int* cx, int* cy) {
   sweep_tile_cells(c->cfg.eqntype, cx, cy);
-  if (c->have_tmap && c->ntr == 0 && !c->eta) {
+  if (c->have_tmap && !c->eta) {
     int cw, rh, nb;
     sweep_tma_box(c->cfg.eqntype, &cw, &rh, &nb, cx);
   }

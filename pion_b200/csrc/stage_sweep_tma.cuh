@@ -207,17 +207,45 @@ __device__ __forceinline__ void cons_diff(Cons& D, const Cons& lo, const Cons& h
   D.bbn = lo.bbn - hi.bbn; D.bbt1 = lo.bbt1 - hi.bbt1; D.bbt2 = lo.bbt2 - hi.bbt2; D.psi = lo.psi - hi.psi;
 }
 
-template <int EQ, int SOLVER, bool FKJ, int TY, int MINB>
+// tracers ride along as extra tile variables NB .. NB+NTR-1: edge values (SetEdgeState with the same minmod slopes)
+// and the upwinded flux F[tr] = tr_upwind * F[rho] * sCMA corrector (solver_eqn_base.cpp:281-342)
+template <int VS, int NB, int NTR>
+__device__ __forceinline__ void tracer_edges_tile(const StageArgs& a, const double* pQ0, const double* pL, const double* pR,
+                                                  const double* pQ3, double* trL, double* trR) {
+#pragma unroll
+  for (int q = 0; q < NTR; q++) {
+    double L = pL[(NB + q) * VS], R = pR[(NB + q) * VS];
+    if (a.order == 2) {
+      const double q0 = pQ0[(NB + q) * VS], q3 = pQ3[(NB + q) * VS];
+      const double d0 = L - q0, d1 = R - L, d2 = q3 - R;
+      L += minmod(d0, d1, a.tiny2) * 0.5;
+      R -= minmod(d1, d2, a.tiny2) * 0.5;
+    }
+    trL[q] = L;
+    trR[q] = R;
+  }
+}
+__device__ __forceinline__ double tracer_upwind_flux(const StageArgs& a, double L, double R, double Frho) {
+  double f = 0.0;
+  if (Frho > 0.0) f = L * Frho * (a.pp.have_mp ? scma_corr(L) : 1.0);
+  else if (Frho < 0.0) f = R * Frho * (a.pp.have_mp ? scma_corr(R) : 1.0);
+  return f;
+}
+
+template <int EQ, int SOLVER, bool FKJ, int TY, int MINB, int NTR>
 __global__ void __launch_bounds__(32 * TY, MINB)
     k_stage_sweep_tma(const __grid_constant__ StageArgs a, const __grid_constant__ CUtensorMap tmap, const int kchunk) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   constexpr int NB = nbase(EQ);
+  constexpr int NV = NB + NTR;                           // tile variables: the equations' + the tracers
+  constexpr int NTRA = NTR > 0 ? NTR : 1;                // array extent (no zero-length arrays)
   constexpr int RH = tma_rh(TY), CW = TMA_CW;
   constexpr int VS = RH * CW;                            // doubles between variables of one tile
-  constexpr int PS = tma_plane_stride(NB, TY) / 8;       // doubles between plane buffers
-  constexpr unsigned PLANE_BYTES = tma_plane_bytes(NB, TY);
-  constexpr int SLAB = NB * TY * 32;
-  constexpr int XSLAB = NB * TY;
+  constexpr int PS = tma_plane_stride(NV, TY) / 8;       // doubles between plane buffers
+  constexpr unsigned PLANE_BYTES = tma_plane_bytes(NV, TY);
+  constexpr int CS = TY * 32;                            // doubles between components of a flux slab
+  constexpr int SLAB = NV * TY * 32;
+  constexpr int XSLAB = NV * TY;
   double* const s_tile = reinterpret_cast<double*>(s_raw);              // [4][NB][RH][CW]
   double* const s_flux = s_tile + 4 * PS;                                // [NB][TY][32] y fluxes of a plane, then [NB][TY][32] z fluxes
   double* const s_xedge = s_flux + 2 * SLAB;                             // [3][NB][TY]      x flux through the tile's high x edge
@@ -330,6 +358,9 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     // accumulate z; y flux (and, light warp, x-edge flux) of the NEXT plane -> shared memory, arrive.
     NatAcc acc;
     acc.rho = acc.erg = acc.m0 = acc.m1 = acc.m2 = acc.b0 = acc.b1 = acc.b2 = acc.psi = 0.0;
+    double acctr[NTRA];
+#pragma unroll
+    for (int q = 0; q < NTRA; q++) acctr[q] = 0.0;
     // the centre state is RE-READ from the tile wherever it is needed (an LDS with an immediate offset is
     // cheaper than 18 registers held across the Riemann solver)
     const bool domain = upd_xy && !warm && (a.mask ? (a.mask[c] != 0) : true);
@@ -339,25 +370,34 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       if (f == 2 && last) break;
       Cons Fnew;
       cons_zero<EQ>(Fnew);
+      double Ftr[NTRA];
+#pragma unroll
+      for (int q = 0; q < NTRA; q++) Ftr[q] = 0.0;
       // the light warp uses the x slot for the x-edge face of plane k+1
       const bool do_flux = (f == 0 && light) ? !last : (row_active || f == 2);
       if (do_flux) {
         Prim eL, eR;
+        double trL[NTRA], trR[NTRA];
         bool use_hll = false;
         if (f == 0) {
           const double* const px = light ? (pp1 - coff + eoff) : p0;
           edge_states_tile<EQ, VS>(a, px - 2, px - 1, px, px + 1, 0, 1, 2, eL, eR);
+          tracer_edges_tile<VS, NB, NTR>(a, px - 2, px - 1, px, px + 1, trL, trR);
           if (SOLVER == SOLVE_HLLD) use_hll = ((light ? we_k1 : w_k) & 1u) != 0;
         } else if (f == 1) {
           // plane k+2 (first needed here): fill number (kk+4) >> 2 of buffer kk & 3
           mbar_wait_spin(&s_full[kk & 3], ((unsigned)(kk + 4) >> 2) & 1u);
           edge_states_tile<EQ, VS>(a, pm1, p0, pp1, pp2, 2, 0, 1, eL, eR);
+          tracer_edges_tile<VS, NB, NTR>(a, pm1, p0, pp1, pp2, trL, trR);
           if (SOLVER == SOLVE_HLLD) use_hll = (w_k1 & 4u) != 0;
         } else {
           edge_states_tile<EQ, VS>(a, pp1 - 2 * CW, pp1 - CW, pp1, pp1 + CW, 1, 2, 0, eL, eR);
+          tracer_edges_tile<VS, NB, NTR>(a, pp1 - 2 * CW, pp1 - CW, pp1, pp1 + CW, trL, trR);
           if (SOLVER == SOLVE_HLLD) use_hll = (w_k1 & 2u) != 0;
         }
         intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(eL, eR, a.pp, use_hll, 0.0, Fnew);
+#pragma unroll
+        for (int q = 0; q < NTR; q++) Ftr[q] = tracer_upwind_flux(a, trL[q], trR[q], Fnew.rho);
       } else if (f == 1) {
         mbar_wait_spin(&s_full[kk & 3], ((unsigned)(kk + 4) >> 2) & 1u);
       }
@@ -371,6 +411,8 @@ __global__ void __launch_bounds__(32 * TY, MINB)
             xe[0] = Fnew.rho; xe[TY] = Fnew.erg; xe[2 * TY] = Fnew.mn; xe[3 * TY] = Fnew.mt1; xe[4 * TY] = Fnew.mt2;
             if (EQ != EQ_EULER) { xe[5 * TY] = Fnew.bbn; xe[6 * TY] = Fnew.bbt1; xe[7 * TY] = Fnew.bbt2; }
             if (EQ == EQ_GLM) xe[8 * TY] = Fnew.psi;
+#pragma unroll
+            for (int q = 0; q < NTR; q++) xe[(NB + q) * TY] = Ftr[q];
           }
           if (warm) continue;
         }
@@ -378,17 +420,29 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         mbar_wait_spin(&s_bar, phase);
         phase ^= 1u;
         Cons Fh = cons_shfl_down<EQ>(Fnew);
+        double Fhtr[NTRA];
+#pragma unroll
+        for (int q = 0; q < NTR; q++) Fhtr[q] = __shfl_down_sync(0xffffffffu, Ftr[q], 1);
         if (lane == 31) {  // high x face of the tile's last column: from the light warp
           const double* xe = s_xedge + (size_t)((kk + 2) % 3) * XSLAB + min(row, TY - 2);
           Fh.rho = xe[0]; Fh.erg = xe[TY]; Fh.mn = xe[2 * TY]; Fh.mt1 = xe[3 * TY]; Fh.mt2 = xe[4 * TY];
           if (EQ != EQ_EULER) { Fh.bbn = xe[5 * TY]; Fh.bbt1 = xe[6 * TY]; Fh.bbt2 = xe[7 * TY]; }
           if (EQ == EQ_GLM) Fh.psi = xe[8 * TY];
+#pragma unroll
+          for (int q = 0; q < NTR; q++) Fhtr[q] = xe[(NB + q) * TY];
         }
         cons_diff(D, Fnew, Fh);
         const Prim C = lds_prim<EQ, VS>(p0, 0, 1, 2);
         const double uB = (EQ != EQ_EULER) ? C.bn * C.vn + C.bt1 * C.vt1 + C.bt2 * C.vt2 : 0.0;
         acc_sources<EQ, VS, 0>(acc, C, uB, p0 - 1, p0 + 1, dt, idx, hdtdx);
         acc_flux_diff<EQ, 0>(acc, D, dt, idx, dtdx);
+#ifdef PION_STRICT
+#define PION_ACCTR(q, lo, hi) acctr[q] += dt * (((lo) - (hi)) * idx);
+#else
+#define PION_ACCTR(q, lo, hi) acctr[q] = fma(dtdx, (lo) - (hi), acctr[q]);
+#endif
+#pragma unroll
+        for (int q = 0; q < NTR; q++) PION_ACCTR(q, Ftr[q], Fhtr[q])
         // y: both faces come from the slab
         const int rn = min(row + 1, TY - 1);
         const Cons Fl = cons_from_smem<EQ, TY>(sbuf, row, lane);
@@ -397,11 +451,19 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         cons_diff(D, Fl, Fhy);
         acc_sources<EQ, VS, 1>(acc, C, uB, p0 - CW, p0 + CW, dt, idx, hdtdx);
         acc_flux_diff<EQ, 1>(acc, D, dt, idx, dtdx);
+#pragma unroll
+        for (int q = 0; q < NTR; q++) PION_ACCTR(q, sbuf[(NB + q) * CS + row * 32 + lane], sbuf[(NB + q) * CS + rn * 32 + lane])
       } else if (f == 1) {
         {  // the flux through this cell's low z face was computed one plane ago: thread-private slot in shared memory
           const Cons Fz = cons_from_smem<EQ, TY>(s_fz, row, lane);
           cons_diff(D, Fz, Fnew);
           cons_to_smem<EQ, TY>(s_fz, row, lane, Fnew);
+#pragma unroll
+          for (int q = 0; q < NTR; q++) {
+            double* zt = s_fz + (NB + q) * CS + row * 32 + lane;
+            if (!warm) PION_ACCTR(q, *zt, Ftr[q])
+            *zt = Ftr[q];
+          }
         }
         if (!warm) {
           const Prim C = lds_prim<EQ, VS>(p0, 0, 1, 2);
@@ -430,6 +492,8 @@ __global__ void __launch_bounds__(32 * TY, MINB)
           fphase ^= 1u;
         }
         cons_to_smem<EQ, TY>(nbuf, row, lane, Fnew);
+#pragma unroll
+        for (int q = 0; q < NTR; q++) nbuf[(NB + q) * CS + row * 32 + lane] = Ftr[q];
         mbar_arrive(&s_bar);
       }
     }
@@ -444,43 +508,67 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       Cons accx;  // grid frame == solver frame of x
       accx.rho = acc.rho; accx.erg = acc.erg; accx.mn = acc.m0; accx.mt1 = acc.m1; accx.mt2 = acc.m2;
       accx.bbn = acc.b0; accx.bbt1 = acc.b1; accx.bbt2 = acc.b2; accx.psi = acc.psi;
-      if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, lds_prim<EQ, VS>(p0, 0, 1, 2), accx, nullptr, 0, my_dt);
-      else status |= cell_advance_time<EQ>(a, c, accx, nullptr, 0, my_dt);
+      if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, lds_prim<EQ, VS>(p0, 0, 1, 2), accx, acctr, NTR, my_dt);
+      else status |= cell_advance_time<EQ>(a, c, accx, acctr, NTR, my_dt);
     } else if (upd_xy && a.out != a.S) {
       // cell cut out of the domain (time_integrator.cpp:905-908): state untouched
-      for (int v = 0; v < NB; v++) a.out[(long)v * vs + c] = a.S[(long)v * vs + c];
+      for (int v = 0; v < NV; v++) a.out[(long)v * vs + c] = a.S[(long)v * vs + c];
     }
   }
 
+#undef PION_ACCTR
   stage_block_epilogue(a, my_dt, status);
 }
 
-template <int EQ, int SOLVER, bool FKJ>
+// dynamic shared memory of the TMA kernel: plane ring + y-flux slab + z-flux slots + x-edge slabs
+__host__ __device__ constexpr size_t tma_smem_bytes(int nv, int ty) {
+  return (size_t)4 * tma_plane_stride(nv, ty) + (size_t)2 * nv * ty * 32 * sizeof(double) + (size_t)3 * nv * ty * sizeof(double);
+}
+constexpr size_t TMA_SMEM_MAX = 227 * 1024 - 1024;  // per-block opt-in limit minus the static part
+// tracer counts the TMA kernel is instantiated for
+constexpr int TMA_MAXTR = 1;
+__host__ __device__ constexpr bool tma_fits(int eq, int ntr) {
+  return ntr <= TMA_MAXTR && tma_smem_bytes(nbase(eq) + ntr, sweep_ty(eq)) <= TMA_SMEM_MAX;
+}
+
+template <int EQ, int SOLVER, bool FKJ, int NTR>
 inline void launch_sweep_tma_t(const StageArgs& a, cudaStream_t s) {
   constexpr int TY = sweep_ty(EQ), MINB = sweep_minb(EQ);
-  constexpr int NB = nbase(EQ);
+  constexpr int NV = nbase(EQ) + NTR;
   const int bx = a.tx1 - a.tx0, by = a.ty1 - a.ty0, NZ = a.k_hi - a.k_lo;
   if (bx <= 0 || by <= 0 || NZ <= 0) return;
   int kchunk = PION_TMA_KCHUNK;
   while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
   const int bz = (NZ + kchunk - 1) / kchunk;
-  const size_t smem = (size_t)4 * tma_plane_stride(NB, TY) + (size_t)2 * NB * TY * 32 * sizeof(double) + (size_t)3 * NB * TY * sizeof(double);
+  constexpr size_t smem = tma_smem_bytes(NV, TY);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, *reinterpret_cast<const CUtensorMap*>(a.tmap), kchunk);
+  k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, *reinterpret_cast<const CUtensorMap*>(a.tmap), kchunk);
 }
 
-// 3-D grids without tracers / H-correction run the TMA kernel, everything else the LDG sweep kernel
+// 3-D grids with at most TMA_MAXTR tracers and no H-correction run the TMA kernel when its tile fits the
+// shared memory, everything else the LDG sweep kernel
 template <int EQ, int SOLVER, bool FKJ>
 inline void launch_sweep_any(const StageArgs& a, cudaStream_t s) {
-  if (a.tmap && a.g.ndim == 3 && a.ntr == 0 && !a.eta && (SOLVER != SOLVE_HLLD || a.hllf)) launch_sweep_tma_t<EQ, SOLVER, FKJ>(a, s);
-  else launch_sweep_t<EQ, SOLVER, FKJ>(a, s);
+  const bool tma = a.tmap && a.g.ndim == 3 && !a.eta && (SOLVER != SOLVE_HLLD || a.hllf) && tma_fits(EQ, a.ntr);
+  if (tma && a.ntr == 0) {
+    launch_sweep_tma_t<EQ, SOLVER, FKJ, 0>(a, s);
+    return;
+  }
+  if constexpr (tma_fits(EQ, 1)) {
+    if (tma && a.ntr == 1) {
+      launch_sweep_tma_t<EQ, SOLVER, FKJ, 1>(a, s);
+      return;
+    }
+  }
+  launch_sweep_t<EQ, SOLVER, FKJ>(a, s);
 }
 
 // box of one TMA plane load for an equation set (host side: tensor-map creation)
+inline bool sweep_tma_fits_impl(int eq, int ntr) { return tma_fits(eq, ntr); }
 inline void sweep_tma_box_impl(int eq, int* cw, int* rh, int* nb, int* tx) {
   *tx = TMA_TX;
   *cw = TMA_CW;
