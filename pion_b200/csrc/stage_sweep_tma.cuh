@@ -20,6 +20,7 @@
 //   * the y-flux slab is single-buffered (a second split-phase mbarrier says when everybody has read it) and
 //     the shared memory that frees holds the thread-private z flux carried to the next plane: 18 registers
 //     fewer live across the solver (stage 19.4 -> 18.9 ms);
+//   * one tracer can ride along as an extra tile variable (edge values, upwinded flux, the same exchanges);
 //   * ONE copy of the Riemann solver inside a real loop over the three faces, with the per-face
 //     parts (stencil loads + reconstruction before it, flux exchange + accumulation after it)
 //     specialised at compile time: the hot loop fits the instruction cache (the fully unrolled
