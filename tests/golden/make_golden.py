@@ -15,7 +15,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent))
 from cases import case_1d, case_2d, case_3d, case_cooling, case_cyl, case_sph, case_wind, wind_ambient_state  # noqa: E402
-from harness import COOLING_TABLES, TABLE_KEYS, RefSim, cooling_state, random_state  # noqa: E402
+from harness import COOLING_TABLES, TABLE_KEYS, RefSim, cooling_state, hot_sphere_state, random_state  # noqa: E402
 
 CASES = {
     "glm_hlld_fkj_3d_periodic": (case_3d("glm-mhd", 7, 1, NG=(12, 10, 8)), 4),
@@ -28,7 +28,19 @@ CASES = {
     "cyl_glm_hlld_fkj_2d": (case_cyl("glm-mhd", 7, 1), 4),
     "cyl_euler_roe_hcorr_2d_tracer": (case_cyl("euler", 4, 4, ntracer=1), 4),
     "sph_euler_hll_1d": (case_sph(8, 1), 6),
+    # Euler flux options FVS (6, van Leer) and Roe-PV (5)
+    "euler_fvs_fkj_3d_tracer": (case_3d("euler", 6, 1, bcs="reflect-outflow", ntracer=1, NG=(12, 10, 8)), 4),
+    "euler_roepv_fkj_2d_outflow": (case_2d("euler", 5, 1, bcs="outflow"), 4),
 }
+
+# x100 pressure ellipsoid (harness.hot_sphere_state): thousands of cells trip the HLLD -> HLL switch, next to
+# reflecting walls where the ideal-MHD HLLD contact speed is an exact zero; the second case spans 2 x 2 tiles and
+# 2 z chunks of the TMA sweep kernel
+HOT = {
+    "imhd_hlld_3d_hot_sphere_reflect": (case_3d("i-mhd", 7, 0, bcs="reflect-outflow", NG=(20, 16, 12)), 3),
+    "glm_hlld_fkj_3d_hot_sphere_tiles": (case_3d("glm-mhd", 7, 1, bcs="reflect-outflow", NG=(36, 14, 10)), 2),
+}
+CASES.update(HOT)
 
 
 # The reference's own test problems, initial conditions produced by the reference's IC
@@ -83,8 +95,15 @@ CASES.update(WIND)
 
 
 def main():
+    only = set(sys.argv[1:])  # optional: regenerate just these fixtures
     for name, (prob, nsteps) in CASES.items():
-        if name in WIND:
+        if only and name not in only:
+            continue
+        if name in HOT:
+            P0 = hot_sphere_state(prob, seed=2024)
+            r = RefSim(prob)
+            r.set_state(P0)
+        elif name in WIND:
             r = RefSim(prob)
             P0 = wind_ambient_state(prob)
             r.set_state(P0)
