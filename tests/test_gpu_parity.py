@@ -63,6 +63,14 @@ def test_boundary_types(bcs, eqn, solver):
     run_pair(case_2d(eqn, solver, 4, bcs=bcs, ntracer=1, NG=(10, 8, 1)))
 
 
+@pytest.mark.parametrize("NG", [(33, 12, 9), (65, 23, 17), (31, 11, 8), (32, 22, 70), (7, 5, 3)])
+def test_3d_tile_edge_sizes(NG):
+    """Grid extents around the TMA sweep's tile (32 x 11 cells) and chunk (8..64 planes) sizes: one-cell last
+    tiles, exact fits, a chunk boundary inside the grid, a grid smaller than one tile."""
+    run_pair(case_3d("glm-mhd", 7, 1, bcs="reflect-outflow", NG=NG), nsteps=2)
+    run_pair(case_3d("euler", 8, 1, bcs="mixed1", ntracer=1, NG=NG), nsteps=2)
+
+
 @pytest.mark.parametrize("eqn", ["i-mhd", "glm-mhd"])
 @pytest.mark.parametrize("av", [0, 1])
 def test_hlld_to_hll_switch_hot_sphere(eqn, av):
