@@ -27,9 +27,6 @@ enum : int { EQ_EULER = 1, EQ_MHD = 2, EQ_GLM = 3 };                 // constant
 enum : int { SOLVE_ROE = 4, SOLVE_ROE_PV = 5, SOLVE_FVS = 6, SOLVE_HLLD = 7, SOLVE_HLL = 8 };  // constants.h:238-246 (5, 6: Euler only)
 enum : int { AV_NONE = 0, AV_FKJ98 = 1, AV_HCORR = 3, AV_HCORR_FKJ98 = 4 };
 
-#ifndef PION_MINMOD_INT
-#define PION_MINMOD_INT 1
-#endif
 #define PION_MACHINEACCURACY 5.e-16    // constants.h:151
 #define PION_TINYVALUE 1.0e-100        // constants.h:152
 #define PION_SMALLVALUE 1.0e-12        // constants.h:150
@@ -74,24 +71,18 @@ __device__ __forceinline__ double sq(double x) { return x * x; }
 // the reference's exact expression.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double minmod(double a, double b, double tiny) {
-  double ab = a * b;
 #ifdef PION_STRICT
+  const double ab = a * b;
   if (ab <= tiny) return 0.0;
   double r = a / b;
   return (r > 0.0) ? fmin(r, 1.0) * b : 0.0;
 #else
-#if PION_MINMOD_INT
-  // sign test on the high words (integer pipe) instead of a DMUL + DSETP on the FP64 pipe; a zero operand
-  // still returns zero (it is the smaller magnitude); products below `tiny` = 1e-200 dx^2 are no longer
-  // flushed, an absolute difference far below any variable's rounding
-  (void)ab;
+  // Opposite signs are tested on the sign bits (integer pipe) instead of a DMUL + DSETP on the FP64 pipe; a
+  // zero operand still returns zero (it is the smaller magnitude).  Products below `tiny` = 1e-200 dx^2 are
+  // not flushed to zero as in the reference: an absolute difference far below any variable's rounding.
+  (void)tiny;
   const double m = (fabs(a) < fabs(b)) ? a : b;
   return ((__double2hiint(a) ^ __double2hiint(b)) < 0) ? 0.0 : m;
-#else
-  // a*b > tiny  =>  same sign, both non-zero
-  double m = (fabs(a) < fabs(b)) ? a : b;
-  return (ab <= tiny) ? 0.0 : m;
-#endif
 #endif
 }
 
