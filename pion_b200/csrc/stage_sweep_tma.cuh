@@ -247,12 +247,12 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   constexpr int CS = TY * 32;                            // doubles between components of a flux slab
   constexpr int SLAB = NV * TY * 32;
   constexpr int XSLAB = NV * TY;
-  double* const s_tile = reinterpret_cast<double*>(s_raw);              // [4][NB][RH][CW]
-  double* const s_flux = s_tile + 4 * PS;                                // [NB][TY][32] y fluxes of a plane, then [NB][TY][32] z fluxes
-  double* const s_xedge = s_flux + 2 * SLAB;                             // [3][NB][TY]      x flux through the tile's high x edge
+  double* const s_tile = reinterpret_cast<double*>(s_raw);              // [4][NV][RH][CW]
+  double* const s_flux = s_tile + 4 * PS;                                // [NV][TY][32] y fluxes of a plane, then [NV][TY][32] z fluxes
+  double* const s_xedge = s_flux + 2 * SLAB;                             // [3][NV][TY] x flux through the tile's high x edge
   __shared__ unsigned long long s_bar;       // y-flux slab + x-edge fluxes published (all threads arrive)
   __shared__ unsigned long long s_free;      // y-flux slab read by everybody (the slab is single-buffered)
-  double* const s_fz = s_flux + SLAB;        // [NB][TY][32] thread-private: the z flux carried to the next plane
+  double* const s_fz = s_flux + SLAB;        // [NV][TY][32] thread-private: the z flux carried to the next plane
   __shared__ unsigned long long s_full[4];   // plane buffer filled (TMA transaction bytes)
   __shared__ unsigned s_done;                // consumer warps that have finished reading plane k-1 (running count)
 
@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   const int i0 = (blockIdx.x + a.tx0) * TMA_TX, j0 = (blockIdx.y + a.ty0) * (TY - 1);
   // The LIGHT warp (row TY-1) updates no cells.  It produces the y fluxes through the tile's top edge (all
   // lanes), the x fluxes through the tile's high-x edge (lane r = row r, so that all 32 lanes of the
-  // consumer rows update a cell), and its lane 0 issues the TMA loads.
+  // consumer rows update a cell), and its lane 0 issues the four TMA loads of the prologue (the refills are
+  // issued by whichever consumer warp finishes with a plane last).
   const bool light = (row == TY - 1);
   int i = i0 + lane, j = j0 + row;
   const bool row_active = !light && (j < NY);               // warp-uniform
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   double my_dt = 1.0e100;
   int status = 0;
   const bool producer = light && (lane == 0);
-  const bool pb_is_s = (a.Pb == a.S);  // predictor: the base state is the stencil centre already in registers
+  const bool pb_is_s = (a.Pb == a.S);  // predictor: the base state is the stencil centre (re-read from the tile)
 
   // tile coordinates of the box (element units of the tensor map: x, y, z, v).  The box must start on a
   // 16-byte boundary in x -- an odd element offset faults on B200 (tools/micro/tma_probe.cu); with 32-cell
