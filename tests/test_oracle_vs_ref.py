@@ -57,6 +57,15 @@ def test_hlld_to_hll_switch_bit_exact(eqn):
     run_pair(case_2d(eqn, 7, 0, bcs="outflow", NG=(48, 40, 1)), state=hot_sphere_state)
 
 
+@pytest.mark.parametrize("eqn,solver,av", [("euler", 4, 3), ("euler", 8, 1), ("euler", 6, 1), ("i-mhd", 4, 1), ("i-mhd", 8, 0),
+                                           ("glm-mhd", 4, 4), ("glm-mhd", 8, 1)])
+def test_strong_gradients_bit_exact(eqn, solver, av):
+    """The x100 pressure ellipsoid for the other solvers (Roe entropy fix / H-correction, HLL, FVS), second and
+    first order, next to reflecting walls."""
+    run_pair(case_3d(eqn, solver, av, bcs="reflect-outflow", NG=(14, 12, 10)), nsteps=2, state=hot_sphere_state)
+    run_pair(case_3d(eqn, solver, av, bcs="mixed2", NG=(9, 7, 5), ooa=1), nsteps=2, state=hot_sphere_state)
+
+
 @pytest.mark.parametrize("solver", [4, 5, 6, 8])
 def test_euler_supersonic_branches_bit_exact(solver):
     """|v| up to 3 (1.5 for the linearised Roe-PV solver: beyond that the reference itself produces NaNs) with c ~ 1: the one-sided (supersonic) branches of FVS, Roe-PV, HLL and the Roe-CV entropy fix."""
