@@ -270,12 +270,15 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
           // unlike the velocity permutation which is always modulo 3
           if (g.ndim > 1) {
             const double* e1 = a.eta + (long)((ax + 1) % g.ndim) * vs;
-            eta_low = fmax(eta_low, fmax(fmax(e1[c - st], e1[c]), e1[c - 2 * st]));
+            // (the cell two below does not exist next to a one-deep ghost frame: skipped like the reference's NextPt == 0)
+            eta_low = fmax(eta_low, fmax(e1[c - st], e1[c]));
+            if (qax >= 2) eta_low = fmax(eta_low, e1[c - 2 * st]);
             eta_high = fmax(eta_high, fmax(fmax(e1[c], e1[c + st]), e1[c - st]));
           }
           if (g.ndim > 2) {
             const double* e2 = a.eta + (long)((ax + 2) % g.ndim) * vs;
-            eta_low = fmax(eta_low, fmax(fmax(e2[c - st], e2[c]), e2[c - 2 * st]));
+            eta_low = fmax(eta_low, fmax(e2[c - st], e2[c]));
+            if (qax >= 2) eta_low = fmax(eta_low, e2[c - 2 * st]);
             eta_high = fmax(eta_high, fmax(fmax(e2[c], e2[c + st]), e2[c - st]));
           }
         }

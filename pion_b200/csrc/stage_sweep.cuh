@@ -78,7 +78,7 @@ __device__ __forceinline__ Cons cons_from_smem(const double* s, int row, int lan
 // switch (solver_eqn_mhd_adi.cpp:167-177), H-correction eta (solver_eqn_base.cpp:
 // 608-678) and InterCellFlux.
 template <int EQ, int SOLVER, bool FKJ>
-__device__ __forceinline__ void low_face_flux(const StageArgs& a, long X, long st, int ax, int a1, int a2, Cons& F) {
+__device__ __forceinline__ void low_face_flux(const StageArgs& a, long X, long st, int ax, int a1, int a2, bool has_m2, Cons& F) {
   const GridD& g = a.g;
   const long vs = g.vs;
   Prim eL = load_prim<EQ>(a.S, X - st, vs, ax, a1, a2);
@@ -105,11 +105,15 @@ __device__ __forceinline__ void low_face_flux(const StageArgs& a, long X, long s
     eta = en[X - st];
     if (g.ndim > 1) {
       const double* e1 = a.eta + (long)((ax + 1) % g.ndim) * vs;
-      eta = fmax(eta, fmax(fmax(e1[X - st], e1[X]), e1[X - 2 * st]));
+      // the cell two below along the sweep axis does not exist next to a one-deep ghost frame (first-order
+      // grids): the reference skips it (solver_eqn_base.cpp:659-676, NextPt == 0)
+      eta = fmax(eta, fmax(e1[X - st], e1[X]));
+      if (has_m2) eta = fmax(eta, e1[X - 2 * st]);
     }
     if (g.ndim > 2) {
       const double* e2 = a.eta + (long)((ax + 2) % g.ndim) * vs;
-      eta = fmax(eta, fmax(fmax(e2[X - st], e2[X]), e2[X - 2 * st]));
+      eta = fmax(eta, fmax(e2[X - st], e2[X]));
+      if (has_m2) eta = fmax(eta, e2[X - 2 * st]);
     }
   }
   intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(eL, eR, a.pp, use_hll, eta, F);
@@ -244,7 +248,9 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_stage_sweep(const __grid_cons
 #pragma unroll
       for (int q = 0; q < PION_MAXTR; q++) Fnew_tr[q] = 0.0;
       if (step != 2 && (row_active || ax == 1)) {
-        low_face_flux<EQ, SOLVER, FKJ>(a, X, st, ax, a1, a2, Fnew);
+        // padded index of X along the sweep axis (the H-correction stencil reaches two cells below it)
+        const int qX = (step == 1) ? i + g.nb[0] : (step == 3) ? k + 1 + g.nb[2] : j + g.nb[1];
+        low_face_flux<EQ, SOLVER, FKJ>(a, X, st, ax, a1, a2, qX >= 2, Fnew);
 #pragma unroll
         for (int q = 0; q < PION_MAXTR; q++)
           if (q < ntr) Fnew_tr[q] = tracer_low_face_flux(a, a.S + (long)(NB + q) * vs, X, st, Fnew.rho);

@@ -88,6 +88,15 @@ def test_hlld_to_hll_switch_hot_sphere(eqn, av):
     run_pair(case_2d(eqn, 7, av, bcs="outflow", NG=(48, 40, 1)), state=hot_sphere_state)
 
 
+@pytest.mark.parametrize("eqn,solver,av", [("euler", 4, 3), ("euler", 8, 1), ("euler", 6, 1), ("i-mhd", 4, 1), ("i-mhd", 8, 0),
+                                           ("glm-mhd", 4, 4), ("glm-mhd", 8, 1)])
+def test_strong_gradients(eqn, solver, av):
+    """The x100 pressure ellipsoid next to reflecting walls for the other solvers (Roe entropy fix / H-correction,
+    HLL, FVS): 3-D (TMA sweep, or LDG sweep with H-correction) and first order."""
+    run_pair(case_3d(eqn, solver, av, bcs="reflect-outflow", NG=(36, 14, 10)), nsteps=2, state=hot_sphere_state)
+    run_pair(case_3d(eqn, solver, av, bcs="mixed2", NG=(9, 7, 5), ooa=1), nsteps=2, state=hot_sphere_state)
+
+
 @pytest.mark.parametrize("solver", [4, 5, 6, 8])
 def test_euler_supersonic_branches(solver):
     """|v| up to 3 (1.5 for the linearised Roe-PV solver: beyond that the reference itself produces NaNs) with c ~ 1: the one-sided (supersonic) branches of FVS, Roe-PV, HLL and the Roe-CV entropy fix,
