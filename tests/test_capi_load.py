@@ -75,3 +75,26 @@ def test_decompose_domain_matches_mcmd():
     cfg, _ = gpu_config(Problem(ndim=2, NG=(64, 32, 1), xmax=(2.0, 1.0, 1.0)))
     assert lib.pion_gpu_decompose_domain(cfg, 1, 2) == 0
     assert list(cfg.NG)[:2] == [32, 32] and cfg.xmin[0] == 1.0  # longest axis split first
+
+
+@pytest.mark.skipif(not Path("/root/reference/source/constants.h").exists(), reason="reference tree not mounted")
+def test_header_codes_are_the_reference_integers():
+    """The integer codes of include/pion_b200.h are the reference's own (constants.h, boundaries/boundaries.h), so a
+    maintainer can pass SimPM.eqntype / solverType / artviscosity / BC codes straight through."""
+    hdr = (ROOT / "include" / "pion_b200.h").read_text()
+    mine = {k: int(v) for k, v in re.findall(r"\b(PION_[A-Z0-9_]+)\s*=\s*(\d+)", hdr)}
+    consts = Path("/root/reference/source/constants.h").read_text()
+    ref = {k: int(v) for k, v in re.findall(r"#define\s+([A-Za-z0-9_]+)\s+(\d+)\b", consts)}
+    bcs = Path("/root/reference/source/boundaries/boundaries.h").read_text()
+    ref.update({k: int(v) for k, v in re.findall(r"\b([A-Z0-9_]+)\s*=\s*(\d+)\s*,", bcs)})
+    pairs = {"PION_EQEUL": "EQEUL", "PION_EQMHD": "EQMHD", "PION_EQGLM": "EQGLM", "PION_COORD_CRT": "COORD_CRT",
+             "PION_COORD_CYL": "COORD_CYL", "PION_COORD_SPH": "COORD_SPH", "PION_FLUX_ROE": "FLUX_RSroe",
+             "PION_FLUX_ROE_PV": "FLUX_RSroe_pv", "PION_FLUX_FVS": "FLUX_FVS", "PION_FLUX_HLLD": "FLUX_RS_HLLD",
+             "PION_FLUX_HLL": "FLUX_RS_HLL", "PION_AV_NONE": "AV_NONE", "PION_AV_FKJ98": "AV_FKJ98_1D",
+             "PION_AV_HCORR": "AV_HCORRECTION", "PION_AV_HCORR_FKJ98": "AV_HCORR_FKJ98", "PION_BC_PERIODIC": "PERIODIC",
+             "PION_BC_OUTFLOW": "OUTFLOW", "PION_BC_INFLOW": "INFLOW", "PION_BC_REFLECTING": "REFLECTING",
+             "PION_BC_FIXED": "FIXED", "PION_BC_DMACH": "DMACH", "PION_BC_DMACH2": "DMACH2", "PION_BC_MPI": "BCMPI",
+             "PION_BC_ONEWAY_OUT": "ONEWAY_OUT", "PION_BC_STWIND": "STWIND"}
+    for m, r in pairs.items():
+        assert m in mine and r in ref, (m, r)
+        assert mine[m] == ref[r], (m, mine[m], r, ref[r])
