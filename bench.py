@@ -6,13 +6,17 @@ cell-updates/s.  One step = calculate_timestep + advance_time on the resident gr
 (predictor, ghost fill, corrector, ghost fill, CFL reduction), exactly the quantity
 the reference prints (source/sim_control/sim_control.cpp:270-277).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl ours|reference] [--lib other_build.so]
 
 N=1 workload: "DTE3D_MHD-style" 512^3: cube +-3.086e19 cm,
 outflow on all faces, gamma 5/3, CFL 0.2, rho 2.338e-22, p 1.518e-12, B_x = 14.2e-6
 / sqrt(4 pi), central sphere r = L/4 with 200x pressure.  N>1 (launched by torchrun, one
 rank per GPU): weak scaling, 512^3 per GPU, block-decomposed exactly like
-MCMDcontrol::decomposeDomain, halos by NCCL send/recv, dt by NCCL all-reduce.
+MCMDcontrol::decomposeDomain, halos by NCCL send/recv, dt by NCCL all-reduce; the line also
+carries a `strong` block (BASELINE.json config 4 as written: the 512^3 GLOBAL grid split over
+the N GPUs, 256^3 per GPU at N=8) and `parity_mgpu` (a small global grid through the same
+NCCL path against the same grid on one GPU).  `parity` (N=1) is a 64^3 run of the SAME
+initial state against the reference's CPU implementation, done before the timed region.
 
 Prints ONE JSON line on rank 0.  --impl reference times the reference's own CPU
 implementation (oracle/_ref when built, else the plain-C oracle port) on the host cores.
@@ -56,6 +60,24 @@ def ncu_traffic(size):
         d = json.loads(p.read_text())
         return d.get(str(size), {}).get("bytes_per_launch")
     return None
+
+
+def csrc_digest():
+    """sha1 over the kernel sources: ties profiles/ncu_traffic.json to the build it was captured on."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted((ROOT / "pion_b200" / "csrc").glob("*.cu*")):
+        h.update(f.read_bytes())
+    return h.hexdigest()[:12]
+
+
+def ncu_traffic_source():
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return None
+    d = json.loads(p.read_text())
+    return {"capture": d.get("source"), "captured_on_csrc_digest": d.get("csrc_digest"), "this_build_csrc_digest": csrc_digest(),
+            "same_build": d.get("csrc_digest") == csrc_digest()}
 
 
 def fp64_evidence(cell_updates_per_s_per_gpu):
@@ -226,15 +248,153 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------
+def divb_norm(P, prob):
+    """max |div B| dx / max |B| over the interior, div B by central differences (the reference's
+    Divergence(c, 0, {BX,BY,BZ}): coord_sys/VectorOps.cpp:377-439, as dataio_silo.cpp:1556-1590 reports it)."""
+    g = prob.nbc
+    B = P[5:8]
+    c = (slice(g, -g),) * 3
+    d = ((B[0][g:-g, g:-g, g + 1:B.shape[3] - g + 1] - B[0][g:-g, g:-g, g - 1:-g - 1])
+         + (B[1][g:-g, g + 1:B.shape[2] - g + 1, g:-g] - B[1][g:-g, g - 1:-g - 1, g:-g])
+         + (B[2][g + 1:B.shape[1] - g + 1, g:-g, g:-g] - B[2][g - 1:-g - 1, g:-g, g:-g])) * 0.5
+    bmax = float(np.max(np.sqrt(B[0][c] ** 2 + B[1][c] ** 2 + B[2][c] ** 2)))
+    return float(np.max(np.abs(d))) / bmax
+
+
+def parity_small(local_rank, size=64, steps=5):
+    """The benchmarked initial state at size^3 on the GPU (same library, same C-ABI calls) against the
+    reference's CPU implementation (oracle/_ref when built, else the oracle port): run BEFORE the timed
+    region, its result travels in the bench line."""
+    from harness import GpuSim, OracleSim, RefSim, have_ref, rel_err
+    L = 3.086e19
+    prob = dte_problem((size,) * 3, (-L,) * 3, (L,) * 3)
+    P0 = dte_state(prob, (-L,) * 3, (L,) * 3)
+    kind = cpu_kind()
+    ref = RefSim(prob) if kind == "reference" else OracleSim(prob)
+    gpu = GpuSim(prob, device=local_rank)
+    try:
+        for sim in (ref, gpu):
+            sim.set_state(P0)
+            sim.init_after_state()
+        dr, dg = ref.run(steps), gpu.run(steps)
+        Pr, Pg = ref.get_state(0), gpu.get_state(0)
+        err = rel_err(Pg, Pr, nphys=9)
+        return {"grid": [size] * 3, "steps": steps, "max_rel_err": float(err.max()),
+                "max_rel_err_per_variable": [float(e) for e in err],
+                "dt_max_rel_err": float(np.max(np.abs(dr - dg) / dr)),
+                "checker": "oracle/_ref (unmodified reference translation units)" if kind == "reference" else "oracle port (plain C)",
+                "tolerance": 5e-12, "ok": bool(err.max() < 5e-12),
+                "divB_dx_over_B": {"gpu": divb_norm(Pg, prob), "reference": divb_norm(Pr, prob)},
+                "negative_density": int(gpu.error_counts()[0]), "stage_kernel": gpu.ctx.describe()}
+    finally:
+        ref.close()
+        gpu.close()
+
+
+def nccl_attach(ctx, lib, rank, dist, torch):
+    import ctypes as C
+    idbuf = C.create_string_buffer(128)
+    if rank == 0:
+        assert lib.pion_gpu_nccl_unique_id(idbuf) == 0
+    t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
+    dist.broadcast(t, 0)
+    ctx.nccl_init(bytes(t.cpu().numpy().tobytes()))
+
+
+def decomposed_context(gprob, lib, rank, world, local_rank, dist, torch):
+    """Context of this rank's block of the global problem (MCMDcontrol::decomposeDomain) + its local Problem."""
+    from harness import gpu_config
+    from pion_b200.capi import Context
+    cfg, keep = gpu_config(gprob, device=local_rank)
+    if world > 1:
+        err = lib.pion_gpu_decompose_domain(cfg, rank, world)
+        assert err == 0, lib.pion_gpu_last_error()
+    lprob = dte_problem([cfg.NG[q] for q in range(3)], [cfg.xmin[q] for q in range(3)], [cfg.xmax[q] for q in range(3)])
+    ctx = Context(cfg, keep)
+    if world > 1:
+        nccl_attach(ctx, lib, rank, dist, torch)
+    return ctx, cfg, lprob
+
+
+def parity_mgpu(lib, rank, world, local_rank, dist, torch, steps=4):
+    """A small global grid through the REAL multi-rank path (NCCL halo exchange, boundary-shell / interior
+    split, device-side dt all-reduce) against the same grid advanced by ONE rank on one GPU."""
+    from harness import gpu_config, rel_err
+    from pion_b200.capi import Context
+    G = (192, 96, 64)
+    dx = 2 * 3.086e19 / 64
+    gxmin = tuple(-0.5 * G[a] * dx for a in range(3))
+    gxmax = tuple(0.5 * G[a] * dx for a in range(3))
+    gprob = dte_problem(G, gxmin, gxmax)
+    ctx, cfg, lprob = decomposed_context(gprob, lib, rank, world, local_rank, dist, torch)
+    # sphere radius from the SHORTEST extent so that it crosses every internal boundary
+    Pl = dte_state(lprob, tuple(gxmin[2:]) * 3, tuple(gxmax[2:]) * 3)
+    ctx.upload(Pl)
+    ctx.init_after_upload()
+    dts = ctx.run(steps)
+    desc = ctx.describe()
+    out = ctx.download(0)
+    g = lprob.nbc
+    mine = torch.from_numpy(np.ascontiguousarray(out[:, g:-g, g:-g, g:-g])).cuda()
+    off = [int(round((cfg.xmin[a] - gxmin[a]) / dx)) for a in range(3)]
+    meta = torch.tensor(off + [cfg.NG[a] for a in range(3)], dtype=torch.int64).cuda()
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    # blocks have equal shapes (power-of-two decomposition of an even grid)
+    blocks = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(blocks, mine)
+    ctx.close()
+    res = None
+    if rank == 0:
+        cfg1, keep1 = gpu_config(gprob, device=local_rank)
+        one = Context(cfg1, keep1)
+        one.upload(dte_state(gprob, tuple(gxmin[2:]) * 3, tuple(gxmax[2:]) * 3))
+        one.init_after_upload()
+        d1 = one.run(steps)
+        P1 = one.download(0)[:, g:-g, g:-g, g:-g]
+        one.close()
+        full = np.zeros_like(P1)
+        for m, b in zip(metas, blocks):
+            m = m.cpu().numpy()
+            full[:, m[2]:m[2] + m[5], m[1]:m[1] + m[4], m[0]:m[0] + m[3]] = b.cpu().numpy()
+        err = rel_err(full, P1, nphys=9)
+        res = {"global_grid": list(G), "ranks": world, "steps": steps, "max_rel_err": float(err.max()),
+               "dt_max_rel_err": float(np.max(np.abs(dts - d1) / d1)), "tolerance": 1e-12, "ok": bool(err.max() <= 1e-12),
+               "checker": "the same global grid advanced by one rank (no decomposition) through the same library",
+               "multi_rank_path": desc}
+    return res
+
+
+def timed_steps(ctx, stream, torch, dist, world, steps, barrier):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        ctx.calculate_timestep()
+        ctx.advance_time()
+    e1.record(stream)
+    ctx.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tmax = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    return ms
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", type=int, default=512, help="cells per axis PER GPU")
+    ap.add_argument("--size", type=int, default=512, help="cells per axis PER GPU (weak line); the strong block uses it as the GLOBAL size")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lib", default=None, help="another build of libpion_b200.so (kernel A/B experiments); recorded in the line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
 
@@ -243,22 +403,37 @@ def main():
         return
 
     import torch
-    from harness import gpu_config
-    from pion_b200.capi import Context, load_library
+    from pion_b200.capi import load_library
+    import pion_b200.capi as capi
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus or world == 1, (world, args.gpus)
     torch.cuda.set_device(local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    lib = load_library()
+    lib = load_library(args.lib)
     S = args.size
     L = 3.086e19
-    # global grid: weak scaling, S^3 per GPU, decomposed like MCMDcontrol::decomposeDomain
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness evidence first (outside every timed region) ----
+    parity = parity_m = None
+    if not args.no_parity:
+        if rank == 0 and world == 1:
+            parity = parity_small(local_rank)
+        if world > 1:
+            parity_m = parity_mgpu(lib, rank, world, local_rank, dist, torch)
+
+    # ---- weak line: S^3 per GPU, global grid decomposed like MCMDcontrol::decomposeDomain ----
     nsplit = [1, 1, 1]
     n = 1
     a = 0
@@ -270,22 +445,8 @@ def main():
     gxmin = [-L * nsplit[q] for q in range(3)]
     gxmax = [L * nsplit[q] for q in range(3)]
     gprob = dte_problem(gNG, gxmin, gxmax)
-    cfg, keep = gpu_config(gprob, device=local_rank)
-    if world > 1:
-        err = lib.pion_gpu_decompose_domain(cfg, rank, world)
-        assert err == 0, lib.pion_gpu_last_error()
-    lprob = dte_problem([cfg.NG[q] for q in range(3)], [cfg.xmin[q] for q in range(3)], [cfg.xmax[q] for q in range(3)])
+    ctx, cfg, lprob = decomposed_context(gprob, lib, rank, world, local_rank, dist, torch)
     assert list(lprob.NG) == [S, S, S], lprob.NG
-
-    ctx = Context(cfg, keep)
-    if world > 1:
-        import ctypes as C
-        idbuf = C.create_string_buffer(128)
-        if rank == 0:
-            assert lib.pion_gpu_nccl_unique_id(idbuf) == 0
-        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
-        dist.broadcast(t, 0)
-        ctx.nccl_init(bytes(t.cpu().numpy().tobytes()))
 
     # initial state in pinned host memory (also the e2e staging buffer)
     shp = lprob.padded_shape()
@@ -296,11 +457,6 @@ def main():
 
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     ncell_local = S ** 3
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def step():
         ctx.calculate_timestep()
@@ -315,26 +471,15 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    ctx.sync()
-    barrier()
+    ms = timed_steps(ctx, stream, torch, dist, world, args.steps, barrier)
     tw1 = time.time()
-    ms = e0.elapsed_time(e1)
     stage_ms, stage_n = ctx.stage_timing(False)
     launches = ctx.counters()[2] - l0
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
-    if world > 1:
-        tmax = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
     ms_per_step = ms / args.steps
     value = ncell_local * world * args.steps / (ms * 1e-3)
+    described = ctx.describe()
 
     # end-to-end through the C ABI with HOST buffers: every step uploads the state from
     # pinned host memory, advances it, and reads the new state back.
@@ -342,6 +487,7 @@ def main():
     if not args.no_e2e:
         e2e_steps = max(2, min(3, args.steps))
         nbytes = host.numel() * 8
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
         for _ in range(e2e_steps):
@@ -360,6 +506,32 @@ def main():
                "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes), "steps": e2e_steps}
 
     neg = ctx.counters()[:2]
+    ctx.close()
+    del host
+
+    # ---- strong block: the S^3 GLOBAL grid split over the ranks (BASELINE.json config 4 as written) ----
+    strong = None
+    if world > 1 and not args.no_strong:
+        sprob = dte_problem((S,) * 3, (-L,) * 3, (L,) * 3)
+        sctx, scfg, slprob = decomposed_context(sprob, lib, rank, world, local_rank, dist, torch)
+        sctx.upload(dte_state(slprob, (-L,) * 3, (L,) * 3))
+        sctx.init_after_upload()
+        sstream = torch.cuda.ExternalStream(sctx.stream(), device=torch.device("cuda", local_rank))
+        for _ in range(args.warmup):
+            sctx.calculate_timestep()
+            sctx.advance_time()
+        sctx.sync()
+        sctx.stage_timing(True)
+        sl0 = sctx.counters()[2]
+        sms = timed_steps(sctx, sstream, torch, dist, world, args.steps, barrier)
+        sst_ms, sst_n = sctx.stage_timing(False)
+        strong = {"scaling": "strong", "global_grid": [S] * 3, "local_grid": [scfg.NG[q] for q in range(3)],
+                  "value": S ** 3 * args.steps / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms / args.steps,
+                  "steps": args.steps, "warmup": args.warmup, "stage_share_of_step": sst_ms / sms,
+                  "gpu_launches": int(sctx.counters()[2] - sl0), "multi_rank_path": sctx.describe(),
+                  "negative_density": int(sctx.counters()[0])}
+        sctx.close()
+
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         per_launch_bytes = ALG_BYTES_PER_CELL_UPDATE * ncell_local / 2.0  # two stage launches per step
@@ -373,15 +545,24 @@ def main():
                        "global_grid": gNG, "decomposition": nsplit, "l2_policy": "working set (>20 GB per GPU) far exceeds the 126 MB L2",
                        "step": "calculate_timestep + advance_time (predictor, BCs, corrector, BCs, CFL reduction)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(S), "peak_source": peak_src, "kernel": "k_stage_sweep_tma<GLM,HLLD,FKJ98,TY=12> (TMA-staged stencil; one launch per stage, two per step)",
+                         "traffic": ncu_traffic(S), "traffic_source": ncu_traffic_source(), "peak_source": peak_src,
+                         # what the library says it launched (pion_gpu_describe), not a literal
+                         "kernel": described,
                          "alg_bytes_per_cell_update": ALG_BYTES_PER_CELL_UPDATE, "launches_timed": stage_n,
                          # the path is FP64-pipe-bound on B200: ncu counters of the committed
                          # capture next to the HBM figure the contract asks for
                          "fp64": fp64_evidence(value / world),
                          "avg_launch_ms": stage_avg_ms, "stage_share_of_step": stage_ms / ms},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "library": str(capi.LIB_PATH),
             "state_errors": {"negative_density": int(neg[0]), "negative_pressure_fixups": int(neg[1])},
         }
+        if parity is not None:
+            line["parity"] = parity
+        if parity_m is not None:
+            line["parity_mgpu"] = parity_m
+        if strong is not None:
+            line["strong"] = strong
         if not args.no_cpu_baseline and world == 1:
             kind = cpu_kind()
             t0 = time.perf_counter()
@@ -393,7 +574,6 @@ def main():
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

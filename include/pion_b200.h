@@ -92,6 +92,7 @@ typedef struct pion_gpu_config {
    * (boundaries/stellar_wind_boundaries.cpp:29-341) for constant sources */
   int n_wind;
   pion_gpu_wind_source wind[2];
+  double min_timestep; /* SimPM.min_timestep (sim_params.h:227): calculate_timestep fails if dt falls below it */
 } pion_gpu_config;
 
 typedef struct pion_gpu_ctx pion_gpu_ctx;
@@ -141,12 +142,23 @@ int pion_gpu_grid_update_state_vector(pion_gpu_ctx *ctx, double dt, int step, in
  * (boundaries/assign_update_bcs.cpp:134-246); with nproc>1 the BCMPI faces are
  * NCCL halo exchanges (boundaries/MCMD_boundaries.cpp:57-236). */
 int pion_gpu_time_update_bcs(pion_gpu_ctx *ctx, double simtime, int cstep, int maxstep);
+/* ... and the two halves on their own: TimeUpdateInternalBCs (:134-181; of the internal boundaries only
+ * STWIND is updated there) and TimeUpdateExternalBCs (:191-246; the faces in BC_bd order, then DMACH2). */
+int pion_gpu_time_update_internal_bcs(pion_gpu_ctx *ctx, double simtime, int cstep, int maxstep);
+int pion_gpu_time_update_external_bcs(pion_gpu_ctx *ctx, double simtime, int cstep, int maxstep);
 /* time_integrator::advance_time (time_integrator.cpp:72-142): the fused fast
  * path (predictor, BCs, corrector, BCs, next-step CFL reduction); returns dt. */
 int pion_gpu_advance_time(pion_gpu_ctx *ctx, double *dt_done);
 /* nsteps x { calculate_timestep; advance_time } = body of sim_control::Time_Int
  * (sim_control.cpp:220-266); dts[nsteps] (optional) receives each dt. */
 int pion_gpu_run(pion_gpu_ctx *ctx, int nsteps, double *dts);
+
+/* The output-criterion part of sim_init::output_data (sim_init.cpp:711-744): *due = 1 if the current step is
+ * one the caller should save (op_criterion 0: every `opfreq` steps; 1: simtime has reached next_optime, which
+ * is then advanced by opfreq_time exactly where the reference does it -- calculate_timestep limits dt by it).
+ * sim_control::Time_Int calls output_data after every step (sim_control.cpp:252); pion_gpu_run does this
+ * bookkeeping itself. */
+int pion_gpu_output_due(pion_gpu_ctx *ctx, int opfreq, int *due);
 
 /* error / diagnostic counters accumulated on the device:
  * [0] negative-density events (fatal in the reference), [1] negative-pressure
@@ -164,6 +176,10 @@ void *pion_gpu_stream(pion_gpu_ctx *ctx);
  * events on the context's stream; the call returns the summed duration and count of
  * the launches recorded since the previous call and resets the record. */
 int pion_gpu_stage_timing(pion_gpu_ctx *ctx, int enable, double *total_ms, long long *nlaunch);
+
+/* one line saying what this context launches: the stage-kernel variant of its most recent stage
+ * (template arguments included), tensor maps, halo-overlap mode, environment switches in effect, build flags */
+int pion_gpu_describe(pion_gpu_ctx *ctx, char *buf, int n);
 
 /* multi-GPU: NCCL communicator for the BCMPI faces and the dt all-reduce
  * (replaces comms/comm_mpi.cpp).  `unique_id` is the 128-byte ncclUniqueId

@@ -2132,12 +2132,27 @@ double po_calc_timestep(pion_oracle *s) { return calculate_timestep(s); }
 double po_advance(pion_oracle *s) { return advance_time(s); }
 double po_dynamics_dt(pion_oracle *s) { return calc_dynamics_dt(s); }
 double po_microphysics_dt(pion_oracle *s) { return calc_microphysics_dt(s); }
+/* constants::equalD (constants.cpp:48-69) */
+static int po_equalD(double a, double b) {
+  if (a == b) return 1;
+  if (fabs(a) + fabs(b) < 1.0e-100) return 1;
+  return (fabs(a - b) / (fabs(a) + fabs(b) + 1.0e-100)) < 1.0e-12;
+}
+/* the output-criterion bookkeeping of sim_init::output_data (sim_init.cpp:733-742), called by
+ * sim_control::Time_Int after every step (sim_control.cpp:252): with op_criterion == 1 an output time that
+ * has been reached is consumed, next_optime += opfreq_time */
+static void output_bookkeeping(pion_oracle *s) {
+  if (s->cfg.op_criterion != 1 || s->timestep == 0) return;
+  const int maxtime = s->simtime >= s->cfg.finishtime;
+  if (po_equalD(s->simtime, s->next_optime) || maxtime) s->next_optime += s->cfg.opfreq_time;
+}
 int po_run(pion_oracle *s, int nsteps, double *dts) {
   for (int i = 0; i < nsteps; i++) {
     double dt = calculate_timestep(s);
     if (!(dt > 0)) return i;
     advance_time(s);
     if (dts) dts[i] = dt;
+    output_bookkeeping(s);
   }
   return nsteps;
 }

@@ -175,6 +175,14 @@ class RefSim : public sim_control {
     return SimPM.dt;
   }
   double do_advance() { return advance_time(0, grid[0]); }
+  // Time_Int calls output_data after every step (sim_control.cpp:252).  The harness has no dataio object, so
+  // it cannot call the reference's output_data itself; this is that function's op_criterion == 1 branch
+  // (sim_init.cpp:733-742) with the reference's own equalD: an output time that has been reached is consumed.
+  void output_bookkeeping() {
+    if (SimPM.op_criterion != 1 || SimPM.timestep == 0) return;
+    const bool maxtime = SimPM.simtime >= SimPM.finishtime;
+    if (pconst.equalD(SimPM.simtime, SimPM.next_optime) || maxtime) SimPM.next_optime += SimPM.opfreq_time;
+  }
 
   int do_update_bcs(int cstep, int maxstep) {
     int err = 0;
@@ -335,6 +343,7 @@ int pref_run(void *h, int nsteps, double *dts) {
     if (dt <= 0) return i;
     s->do_advance();
     if (dts) dts[i] = dt;
+    s->output_bookkeeping();
   }
   return nsteps;
 }

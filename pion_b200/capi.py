@@ -6,10 +6,7 @@ from pathlib import Path
 
 import numpy as np
 
-import os
-
-# PION_B200_LIB selects an alternative build of the SAME library (kernel tuning experiments)
-LIB_PATH = Path(os.environ.get("PION_B200_LIB", Path(__file__).resolve().parent / "libpion_b200.so"))
+LIB_PATH = Path(__file__).resolve().parent / "libpion_b200.so"
 MAXVAR = 16
 
 _lib = None
@@ -41,14 +38,21 @@ class GpuConfig(C.Structure):
         ("table_C_ffhe", C.c_void_p), ("table_C_fbdn", C.c_void_p), ("table_C_cie", C.c_void_p),
         ("rank", C.c_int), ("nproc", C.c_int), ("ngbprocs", C.c_int * 6),
         ("n_wind", C.c_int), ("wind", WindSource * 2),
+        ("min_timestep", C.c_double),
     ]
 
 
-def load_library():
-    """Load libpion_b200.so; there is no fallback if it is missing."""
-    global _lib
+def load_library(path=None):
+    """Load libpion_b200.so; there is no fallback if it is missing.  `path` (first call only) selects another
+    build of the SAME library -- kernel tuning experiments pass it explicitly (bench.py --lib); there is no
+    environment switch."""
+    global _lib, LIB_PATH
     if _lib is not None:
+        if path is not None and Path(path).resolve() != LIB_PATH.resolve():
+            raise RuntimeError(f"library already loaded from {LIB_PATH}")
         return _lib
+    if path is not None:
+        LIB_PATH = Path(path)
     if not LIB_PATH.exists():
         raise RuntimeError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -73,13 +77,17 @@ def load_library():
         "pion_gpu_calc_dynamics_dU": (i, [vp, d, i]),
         "pion_gpu_grid_update_state_vector": (i, [vp, d, i, i]),
         "pion_gpu_time_update_bcs": (i, [vp, d, i, i]),
+        "pion_gpu_time_update_internal_bcs": (i, [vp, d, i, i]),
+        "pion_gpu_time_update_external_bcs": (i, [vp, d, i, i]),
         "pion_gpu_advance_time": (i, [vp, pd]),
         "pion_gpu_run": (i, [vp, i, vp]),
+        "pion_gpu_output_due": (i, [vp, i, pi]),
         "pion_gpu_counters": (i, [vp, vp]),
         "pion_gpu_mp_failures": (i, [vp, C.POINTER(C.c_longlong)]),
         "pion_gpu_sync": (i, [vp]),
         "pion_gpu_stream": (vp, [vp]),
         "pion_gpu_stage_timing": (i, [vp, i, pd, C.POINTER(C.c_longlong)]),
+        "pion_gpu_describe": (i, [vp, vp, i]),
         "pion_gpu_nccl_unique_id": (i, [vp]),
         "pion_gpu_nccl_init": (i, [vp, vp]),
         "pion_gpu_decompose_domain": (i, [C.POINTER(GpuConfig), i, i]),
@@ -96,8 +104,10 @@ EXPORTED_SYMBOLS = [
     "pion_gpu_init_after_upload", "pion_gpu_calc_dt", "pion_gpu_calculate_timestep", "pion_gpu_set_dt",
     "pion_gpu_set_glm_speeds", "pion_gpu_set_time", "pion_gpu_get_time", "pion_gpu_calc_microphysics_dU",
     "pion_gpu_calc_dynamics_dU", "pion_gpu_grid_update_state_vector", "pion_gpu_time_update_bcs",
-    "pion_gpu_advance_time", "pion_gpu_run", "pion_gpu_counters", "pion_gpu_mp_failures", "pion_gpu_sync", "pion_gpu_stream",
+    "pion_gpu_time_update_internal_bcs", "pion_gpu_time_update_external_bcs",
+    "pion_gpu_advance_time", "pion_gpu_run", "pion_gpu_output_due", "pion_gpu_counters", "pion_gpu_mp_failures", "pion_gpu_sync", "pion_gpu_stream",
     "pion_gpu_nccl_unique_id", "pion_gpu_nccl_init", "pion_gpu_decompose_domain", "pion_gpu_stage_timing",
+    "pion_gpu_describe",
 ]
 
 
@@ -174,6 +184,12 @@ class Context:
     def time_update_bcs(self, simtime, cstep, maxstep):
         self._ck(self.lib.pion_gpu_time_update_bcs(self.h, simtime, cstep, maxstep), "time_update_bcs")
 
+    def time_update_internal_bcs(self, simtime, cstep, maxstep):
+        self._ck(self.lib.pion_gpu_time_update_internal_bcs(self.h, simtime, cstep, maxstep), "time_update_internal_bcs")
+
+    def time_update_external_bcs(self, simtime, cstep, maxstep):
+        self._ck(self.lib.pion_gpu_time_update_external_bcs(self.h, simtime, cstep, maxstep), "time_update_external_bcs")
+
     def advance_time(self):
         a = C.c_double()
         self._ck(self.lib.pion_gpu_advance_time(self.h, C.byref(a)), "advance_time")
@@ -183,6 +199,11 @@ class Context:
         dts = np.zeros(nsteps)
         self._ck(self.lib.pion_gpu_run(self.h, nsteps, dts.ctypes.data), "run")
         return dts
+
+    def output_due(self, opfreq=0):
+        d = C.c_int()
+        self._ck(self.lib.pion_gpu_output_due(self.h, opfreq, C.byref(d)), "output_due")
+        return bool(d.value)
 
     def counters(self):
         out = (C.c_longlong * 3)()
@@ -204,6 +225,11 @@ class Context:
         ms, n = C.c_double(), C.c_longlong()
         self._ck(self.lib.pion_gpu_stage_timing(self.h, 1 if enable else 0, C.byref(ms), C.byref(n)), "stage_timing")
         return ms.value, n.value
+
+    def describe(self) -> str:
+        buf = C.create_string_buffer(512)
+        self._ck(self.lib.pion_gpu_describe(self.h, buf, 512), "describe")
+        return buf.value.decode()
 
     def nccl_init(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)

@@ -30,6 +30,9 @@ struct CoolParams {
   double inv_Mu2, inv_Mu2_elec_H, Mu_tot_over_kB, MinT, MaxT;
 };
 
+// dynamic shared memory of the cooling kernels: the 11 table columns
+inline size_t cool_smem_bytes(const CoolParams& cp) { return 11 * (size_t)cp.nT * sizeof(double); }
+
 struct CoolArgs {
   GridD g;
   CoolParams cp;

@@ -58,6 +58,24 @@ __device__ __forceinline__ double fast_sqrt(double x) {
 #endif
 }
 
+// sqrt(x) for x known to be >= DBL_MIN (no sub-normal guard: one DSETP + two FSEL fewer).  The wave-speed
+// square roots qualify: their arguments are clamped from below (cfast2_ir: pmax(..., MACHINEACCURACY)) or are
+// a sum with such a square root.  A negative or NaN argument gives NaN, as the reference's sqrt() does.
+__device__ __forceinline__ double fast_sqrt_pos(double x) {
+#if defined(PION_STRICT)
+  return sqrt(x);
+#elif defined(PION_GUARDED_SQRT)
+  return fast_sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  double t = fma(0.375, e, 0.5);
+  y = fma(y * e, t, y);
+  return x * y;
+#endif
+}
+
 // max / min of two doubles.  CUDA's fmax/fmin carry IEEE NaN handling that costs 7 SASS instructions
 // (DSETP.MAX + 2 MOV + FSEL + SEL + LOP3) against 3 for the compare-and-select form; these return the
 // SECOND argument when either operand is NaN, so call sites put the safe value second.

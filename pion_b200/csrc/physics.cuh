@@ -229,7 +229,7 @@ __device__ __forceinline__ double cfast2_ir(double ir, double pg, double bx, dou
   double temp1 = (ch2 + bxi) + (by * by + bz * bz) * ir;
   double temp2 = (4. * ch2) * bxi;
   temp2 = pmax(temp1 * temp1 - temp2, PION_MACHINEACCURACY);
-  return (temp1 + fast_sqrt(temp2)) / 2.;
+  return (temp1 + fast_sqrt_pos(temp2)) / 2.;
 }
 __device__ __forceinline__ double cfast_components(double ro, double pg, double bx, double by, double bz, double g) {
 #ifdef PION_STRICT
@@ -239,7 +239,7 @@ __device__ __forceinline__ double cfast_components(double ro, double pg, double 
   temp2 = pmax(temp1 * temp1 - temp2, PION_MACHINEACCURACY);
   return sqrt((temp1 + sqrt(temp2)) / 2.);
 #else
-  return fast_sqrt(cfast2_ir(fast_rcp(ro), pg, bx, by, bz, g));
+  return fast_sqrt_pos(cfast2_ir(fast_rcp(ro), pg, bx, by, bz, g));
 #endif
 }
 
@@ -459,8 +459,8 @@ __device__ __forceinline__ void hlld_speeds(const Prim& L, const Prim& R, double
   double cf_r = cfast_components(R.ro, R.pg, Bx, R.bt1, R.bt2, g);
   double cf_max = pmax(cf_l, cf_r);
 #else
-  double cf_max = fast_sqrt(pmax(cfast2_ir(fast_rcp(L.ro), L.pg, Bx, L.bt1, L.bt2, g),
-                                 cfast2_ir(fast_rcp(R.ro), R.pg, Bx, R.bt1, R.bt2, g)));
+  double cf_max = fast_sqrt_pos(pmax(cfast2_ir(fast_rcp(L.ro), L.pg, Bx, L.bt1, L.bt2, g),
+                                     cfast2_ir(fast_rcp(R.ro), R.pg, Bx, R.bt1, R.bt2, g)));
 #endif
   Sl = pmin(L.vn, R.vn) - cf_max;
   Sr = pmax(L.vn, R.vn) + cf_max;
@@ -503,14 +503,17 @@ __device__ __forceinline__ void mhd_HLL(const Prim& L, const Prim& R, const Phys
 // selected region's state, i.e. UtoP(ustar) of solver_eqn_mhd_adi.cpp:183 without the
 // round trip through conserved variables (v = (rho v)/rho); only ro, v and B_t are set
 // (all that AVFalle reads, solver_eqn_mhd_adi.cpp:254-284).
-template <bool NEED_PSTAR>
+// SAME_BN: both states carry the same normal field (GLM hands the Dedner star value to both sides,
+// solver_eqn_mhd_adi.cpp:736-738).  0.5 (b + b) == b exactly, so BX is that value itself and the side's own
+// B_n is BX too: identical results, a dozen FP64 instructions fewer per interface.
+template <bool NEED_PSTAR, bool SAME_BN = false>
 __device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const PhysParams& pp, Cons& flux, Prim& pstar) {
   const double g = pp.gamma, gm1 = g - 1.0;
-  const double BX = 0.5 * (L.bn + R.bn);
+  const double BX = SAME_BN ? L.bn : 0.5 * (L.bn + R.bn);
   const double BX2 = BX * BX;
   // HLLD_signal_speeds (:342-368)
-  const double cf_max = fast_sqrt(pmax(cfast2_ir(fast_rcp(L.ro), L.pg, BX, L.bt1, L.bt2, g),
-                                       cfast2_ir(fast_rcp(R.ro), R.pg, BX, R.bt1, R.bt2, g)));
+  const double cf_max = fast_sqrt_pos(pmax(cfast2_ir(fast_rcp(L.ro), L.pg, BX, L.bt1, L.bt2, g),
+                                           cfast2_ir(fast_rcp(R.ro), R.pg, BX, R.bt1, R.bt2, g)));
   const double lam0 = pmin(L.vn, R.vn) - cf_max;
   const double lam4 = pmax(L.vn, R.vn) + cf_max;
   const double sl_vl = lam0 - L.vn, sr_vr = lam4 - R.vn;
@@ -568,7 +571,7 @@ __device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const Phy
   // everything below is for side K only
   const double K_ro = (left ? L.ro : R.ro), K_pg = (left ? L.pg : R.pg), K_vn = (left ? L.vn : R.vn);
   const double K_vt1 = (left ? L.vt1 : R.vt1), K_vt2 = (left ? L.vt2 : R.vt2);
-  const double K_bn = (left ? L.bn : R.bn), K_bt1 = (left ? L.bt1 : R.bt1), K_bt2 = (left ? L.bt2 : R.bt2);
+  const double K_bn = SAME_BN ? BX : (left ? L.bn : R.bn), K_bt1 = (left ? L.bt1 : R.bt1), K_bt2 = (left ? L.bt2 : R.bt2);
   const double s_v = (left ? sl_vl : sr_vr), is_m = (left ? isl_sm : isr_sm);
   const double rho_s = (left ? rho_ls : rho_rs), sq_K = (left ? -sq_l : sq_r);  // sign of the ** energy jump folded in
   const double vys = (left ? vys_l : vys_r), vzs = (left ? vzs_l : vzs_r);
@@ -839,7 +842,11 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
     if (SOLVER == SOLVE_ROE) {
       mhd_RoeCV(l, r, pp, hc_etamax, flux, pstar);
     } else if (SOLVER == SOLVE_HLLD && !use_hll) {
-      mhd_HLLD<FKJ>(l, r, pp, flux, pstar);
+#ifdef PION_NO_SAME_BN
+      mhd_HLLD<FKJ, false>(l, r, pp, flux, pstar);
+#else
+      mhd_HLLD<FKJ, EQ == EQ_GLM>(l, r, pp, flux, pstar);
+#endif
     } else {
       Cons ustar;
       mhd_HLL<FKJ>(l, r, pp, flux, ustar);

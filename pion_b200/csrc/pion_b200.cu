@@ -74,6 +74,8 @@ struct pion_gpu_ctx {
   bool force_overlap = false; // PION_B200_OVERLAP=1: split the stage even with a single exchanged face
   bool force_gather = false;  // PION_B200_GATHER=1: run the gather kernel on the fused path too (A/B tests)
   std::vector<cudaEvent_t> tev;  // begin/end pairs
+  std::vector<cudaEvent_t> tev_pool;  // recycled timing events (no cudaEventCreate inside a timed loop)
+  const char* last_stage_kernel = "(no stage launched yet)";
   // multi-GPU
   ncclComm_t comm = nullptr;
   double* d_red = nullptr;  // 2 doubles for the dt all-reduce
@@ -169,6 +171,10 @@ static int check_config(const pion_gpu_config& c) {
         t != PION_BC_FIXED && t != PION_BC_DMACH && t != PION_BC_ONEWAY_OUT && t != PION_BC_MPI) { set_error("unsupported boundary type"); return 1; }
     if (c.eqntype == PION_EQGLM && c.ndim == 1 && (t == PION_BC_OUTFLOW || t == PION_BC_ONEWAY_OUT)) { set_error("Psi outflow boundary condition doesn't work for 1D! (outflow_boundaries.cpp:57)"); return 1; }
   }
+  // internal_bc[4] / bc_refval[6 + i] / wind[2] are fixed-size: reject counts that would index past them
+  if (c.n_internal_bc < 0 || c.n_internal_bc > 4) { set_error("n_internal_bc must be 0..4"); return 1; }
+  if (c.n_wind < 0 || c.n_wind > 2) { set_error("n_wind must be 0..2"); return 1; }
+  if (c.min_timestep < 0.0) { set_error("min_timestep must be >= 0"); return 1; }
   for (int i = 0; i < c.n_internal_bc; i++) {
     if (c.internal_bc[i] == PION_BC_STWIND) {
       if (c.n_wind < 1 || c.n_wind > 2) { set_error("BC_assign_STWIND() No Sources! (n_wind must be 1 or 2)"); return 1; }
@@ -389,6 +395,7 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   for (int ib = 0; ib < cfg->n_internal_bc; ib++) {
     if (cfg->internal_bc[ib] != PION_BC_STWIND) continue;
     if (build_wind_cells(c)) { pion_gpu_destroy(c); return nullptr; }
+    break;  // one cell list covers every source (a second STWIND entry must not build it again)
   }
   if (!ok) {
     set_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -421,6 +428,8 @@ extern "C" void pion_gpu_destroy(pion_gpu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto e : c->tev) cudaEventDestroy(e);
+  for (auto e : c->tev_pool) cudaEventDestroy(e);
   if (c->comm) ncclCommDestroy(c->comm);
   cudaFree(c->P); cudaFree(c->Ph); cudaFree(c->dU); cudaFree(c->eta); cudaFree(c->hll); cudaFree(c->hllf); cudaFree(c->mask);
   cudaFree(c->d_dtmin); cudaFree(c->d_counters); cudaFree(c->d_red); cudaFree(c->d_tables); cudaFree(c->mp_dE); cudaFree(c->d_wind_idx); cudaFree(c->d_wind_val);
@@ -546,14 +555,20 @@ static long face_cells(const GridD& g, int face) {
 
 static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A, cudaStream_t st);
 
-// TimeUpdateInternalBCs + TimeUpdateExternalBCs on the given arrays (A1 may be null)
-static int update_bcs_arrays(pion_gpu_ctx* c, double* A0, double* A1, double simtime, cudaStream_t st = nullptr) {
-  const GridD& g = c->g;
-  if (!st) st = c->stream;
-  if (c->wind_n) {  // TimeUpdateInternalBCs: BC_update_STWIND writes P and Ph, before the external faces
-    k_wind_set<<<nblocks(c->wind_n * c->nvar, 256), 256, 0, st>>>(g.vs, c->nvar, c->wind_n, c->d_wind_idx, c->d_wind_val, c->P, c->Ph);
+// TimeUpdateInternalBCs (assign_update_bcs.cpp:134-181): of the internal boundaries only STWIND is updated
+// here -- BC_update_STWIND writes P and Ph (stellar_wind_boundaries.cpp:300-341)
+static int update_internal_bcs(pion_gpu_ctx* c, cudaStream_t st) {
+  if (c->wind_n) {
+    k_wind_set<<<nblocks(c->wind_n * c->nvar, 256), 256, 0, st>>>(c->g.vs, c->nvar, c->wind_n, c->d_wind_idx, c->d_wind_val, c->P, c->Ph);
     c->launches++;
   }
+  return 0;
+}
+
+// TimeUpdateExternalBCs (assign_update_bcs.cpp:191-246) on the given arrays (A1 may be null): the six faces in
+// BC_bd order, then DMACH2 (an "internal" boundary by position, but the reference updates it in this call)
+static int update_external_bcs(pion_gpu_ctx* c, double* A0, double* A1, double simtime, cudaStream_t st) {
+  const GridD& g = c->g;
   for (int ax = 0; ax < g.ndim; ax++) {
     bool mpi_face = false;
     for (int s = 0; s < 2; s++) {
@@ -582,13 +597,38 @@ static int update_bcs_arrays(pion_gpu_ctx* c, double* A0, double* A1, double sim
   return 0;
 }
 
-extern "C" int pion_gpu_time_update_bcs(pion_gpu_ctx* c, double simtime, int cstep, int maxstep) {
-  CUDA_OK(cudaSetDevice(c->cfg.device));
+// TimeUpdateInternalBCs + TimeUpdateExternalBCs, as every caller in the reference issues them back to back
+static int update_bcs_arrays(pion_gpu_ctx* c, double* A0, double* A1, double simtime, cudaStream_t st = nullptr) {
+  if (!st) st = c->stream;
+  if (update_internal_bcs(c, st)) return 1;
+  return update_external_bcs(c, A0, A1, simtime, st);
+}
+
+static int ensure_ph_valid(pion_gpu_ctx* c) {
   if (!c->ph_valid) {  // make Ph a true copy before it is used as a separate array again
     CUDA_OK(cudaMemcpyAsync(c->Ph, c->P, c->arr_elems * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     c->ph_valid = true;
   }
+  return 0;
+}
+
+extern "C" int pion_gpu_time_update_bcs(pion_gpu_ctx* c, double simtime, int cstep, int maxstep) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (ensure_ph_valid(c)) return 1;
   return update_bcs_arrays(c, c->Ph, (cstep == maxstep) ? c->P : nullptr, simtime);
+}
+extern "C" int pion_gpu_time_update_internal_bcs(pion_gpu_ctx* c, double simtime, int cstep, int maxstep) {
+  (void)simtime; (void)cstep; (void)maxstep;
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (ensure_ph_valid(c)) return 1;
+  if (update_internal_bcs(c, c->stream)) return 1;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int pion_gpu_time_update_external_bcs(pion_gpu_ctx* c, double simtime, int cstep, int maxstep) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (ensure_ph_valid(c)) return 1;
+  return update_external_bcs(c, c->Ph, (cstep == maxstep) ? c->P : nullptr, simtime, c->stream);
 }
 
 // one device->host read of `n` doubles starting at element `idx` of variable planes of A
@@ -691,65 +731,86 @@ static int launch_calc_dt(pion_gpu_ctx* c) {
   return 0;
 }
 
-static int read_dtmin(pion_gpu_ctx* c, double* out) {
-  CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->d_dtmin, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_OK(cudaStreamSynchronize(c->stream));
-  double d;
-  memcpy(&d, c->h_pinned, sizeof(double));
-  *out = d;
+// Queues the kernels that leave the LOCAL minima in d_dtmin[0] (t_dyn) and d_dtmin[1] (t_mp, 1e99 without a
+// microphysics limit) -- no host synchronisation.  A launch failure is returned, not thrown: the multi-rank
+// caller must still enter the collective.
+static const unsigned long long MP_INIT_BITS = 0x547D42AEA2879F2EULL;  // bits of 1.0e99
+static int queue_local_dt(pion_gpu_ctx* c) {
+  if (!c->next_dt_valid && launch_calc_dt(c)) return 1;
+  // calc_microphysics_dt without MP / without a limit returns 1e99 (calc_timestep.cpp:348-357)
+  CUDA_OK(cudaMemcpyAsync(c->d_dtmin + 1, &MP_INIT_BITS, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  const int lim = c->cfg.mp_timestep_limit;
+  if (c->cfg.cooling && lim >= 1 && lim <= 3) {  // 4 = recombination time only: none for mp_only_cooling
+    CoolArgs a;
+    a.g = c->g; a.cp = c->cool; a.P = c->ph_valid ? c->Ph : c->P;  // timescales(c->Ph)
+    a.dE = nullptr; a.dU = nullptr; a.mask = c->mask; a.dt = 0.0; a.gamma = c->pp.gamma; a.counters = c->d_counters;
+    a.dtmin = c->d_dtmin + 1; a.mp_timestep_limit = lim;
+    const long ncell = (long)c->g.NG[0] * c->g.NG[1] * c->g.NG[2];
+    const size_t smem = cool_smem_bytes(c->cool);
+    switch (c->cfg.eqntype) {
+      case PION_EQEUL: k_mp_dt<EQ_EULER><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
+      case PION_EQMHD: k_mp_dt<EQ_MHD><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
+      default: k_mp_dt<EQ_GLM><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
+    }
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
   return 0;
+}
+
+// One read-back of two doubles from `src` (device) through the pinned mirror.
+static int read_two(pion_gpu_ctx* c, const void* src, double* a, double* b) {
+  CUDA_OK(cudaMemcpyAsync(c->h_pinned, src, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  memcpy(a, c->h_pinned, sizeof(double));
+  memcpy(b, c->h_pinned + 1, sizeof(double));
+  return 0;
+}
+
+// first step with stellar winds: limit dt by the wind speed (calc_timestep.cpp:318-323); the source list is
+// global, so every rank applies the same limit
+static double wind_dt_limit(const pion_gpu_ctx* c, double d) {
+  if (c->timestep == 0)
+    for (int v = 0; v < c->cfg.n_wind; v++) d = fmin(d, 0.1 * c->cfg.cfl * c->g.dx / (c->cfg.wind[v].vinf * 1.0e5));
+  return d;
 }
 
 extern "C" int pion_gpu_calc_dt(pion_gpu_ctx* c, double* t_dyn, double* t_mp) {
   CUDA_OK(cudaSetDevice(c->cfg.device));
-  if (!c->next_dt_valid && launch_calc_dt(c)) return 1;
-  double d;
-  if (read_dtmin(c, &d)) return 1;
-  // first step with stellar winds: limit dt by the wind speed (calc_timestep.cpp:318-323)
-  if (c->timestep == 0)
-    for (int v = 0; v < c->cfg.n_wind; v++) d = fmin(d, 0.1 * c->cfg.cfl * c->g.dx / (c->cfg.wind[v].vinf * 1.0e5));
-  if (t_dyn) *t_dyn = d;
+  if (queue_local_dt(c)) return 1;
+  double d, m;
+  if (read_two(c, c->d_dtmin, &d, &m)) return 1;
+  if (t_dyn) *t_dyn = wind_dt_limit(c, d);
   if (t_mp) {
-    *t_mp = 1.0e99;  // calc_microphysics_dt without MP / without a limit (calc_timestep.cpp:348-357)
-    const int lim = c->cfg.mp_timestep_limit;
-    if (c->cfg.cooling && lim >= 1 && lim <= 3) {  // 4 = recombination time only: none for mp_only_cooling
-      static const unsigned long long MP_INIT_BITS = 0x547D42AEA2879F2EULL;  // bits of 1.0e99
-      CUDA_OK(cudaMemcpyAsync(c->d_dtmin + 1, &MP_INIT_BITS, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
-      CoolArgs a;
-      a.g = c->g; a.cp = c->cool; a.P = c->ph_valid ? c->Ph : c->P;  // timescales(c->Ph)
-      a.dE = nullptr; a.dU = nullptr; a.mask = c->mask; a.dt = 0.0; a.gamma = c->pp.gamma; a.counters = c->d_counters;
-      a.dtmin = c->d_dtmin + 1; a.mp_timestep_limit = lim;
-      const long ncell = (long)c->g.NG[0] * c->g.NG[1] * c->g.NG[2];
-      const size_t smem = 11 * (size_t)c->cool.nT * sizeof(double);
-      switch (c->cfg.eqntype) {
-        case PION_EQEUL: k_mp_dt<EQ_EULER><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
-        case PION_EQMHD: k_mp_dt<EQ_MHD><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
-        default: k_mp_dt<EQ_GLM><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
-      }
-      c->launches++;
-      CUDA_OK(cudaMemcpyAsync(c->h_pinned + 1, c->d_dtmin + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-      CUDA_OK(cudaStreamSynchronize(c->stream));
-      memcpy(t_mp, c->h_pinned + 1, sizeof(double));
-      if (!(*t_mp > 0.0)) { set_error("get_mp_timescales_no_radiation() returned error"); return 1; }
-    }
+    *t_mp = m;
+    if (!(m > 0.0)) { set_error("get_mp_timescales_no_radiation() returned error"); return 1; }
   }
   return 0;
 }
 
 extern "C" int pion_gpu_calculate_timestep(pion_gpu_ctx* c, double* dt_out) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
   double t_dyn, t_mp;
-  if (pion_gpu_calc_dt(c, &t_dyn, &t_mp)) return 1;
-  if (c->comm) {  // sim_control_MPI.cpp:503-504: global MIN of t_dyn and t_mp, one 2-element all-reduce
-    double* hv = reinterpret_cast<double*>(c->h_pinned + 2);
-    hv[0] = t_dyn;
-    hv[1] = t_mp;
-    CUDA_OK(cudaMemcpyAsync(c->d_red, hv, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    NCCL_OK(ncclAllReduce(c->d_red, c->d_red, 2, ncclDouble, ncclMin, c->comm, c->stream));
-    CUDA_OK(cudaMemcpyAsync(hv, c->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-    t_dyn = hv[0];
-    t_mp = hv[1];
+  if (c->comm) {
+    // sim_control_MPI.cpp:503-504: global MIN of t_dyn and t_mp.  The local minima never leave the device: one
+    // 2-element ncclAllReduce(min) straight on the kernels' result words (positive doubles order like their bit
+    // patterns, so the atomicMin words ARE the doubles), then ONE 16-byte read-back.  A rank whose local
+    // kernels failed still enters the collective -- with -1, which wins the MIN -- so that its peers fail with
+    // it instead of blocking in the all-reduce for ever.
+    const int local_err = queue_local_dt(c);
+    if (local_err) {
+      static const double bad[2] = {-1.0, -1.0};
+      cudaMemcpyAsync(c->d_dtmin, bad, sizeof(bad), cudaMemcpyHostToDevice, c->stream);
+    }
+    NCCL_OK(ncclAllReduce(c->d_dtmin, c->d_red, 2, ncclDouble, ncclMin, c->comm, c->stream));
+    if (read_two(c, c->d_red, &t_dyn, &t_mp)) return 1;
+    if (local_err) return 1;
+    if (t_dyn < 0.0) { set_error("calculate_timestep failed on another rank"); return 1; }
+    t_dyn = wind_dt_limit(c, t_dyn);
+  } else {
+    if (pion_gpu_calc_dt(c, &t_dyn, &t_mp)) return 1;
   }
+  if (!(t_mp > 0.0)) { set_error("get_mp_timescales_no_radiation() returned error"); return 1; }
   if (!(t_dyn > 0.0)) { set_error("CellTimeStep function returned failing value"); return 1; }
   c->dt = fmin(t_dyn, t_mp);
   // Set_GLM_Speeds(td, dx, cr): c_h = CFL*dx/t_dyn, c_r = 0.25/dx (calc_timestep.cpp:121-131)
@@ -758,6 +819,7 @@ extern "C" int pion_gpu_calculate_timestep(pion_gpu_ctx* c, double* dt_out) {
     c->cr = 0.25 / c->g.dx;
   }
   // timestep_checking_and_limiting (:219-262)
+  if (c->dt < c->cfg.min_timestep) { set_error("Timestep too short! dt=" + std::to_string(c->dt) + "  min-step=" + std::to_string(c->cfg.min_timestep)); return 1; }
   c->dt = fmin(c->dt, 1.3 * c->last_dt);
   if (c->cfg.op_criterion == 1) {
     c->dt = fmin(c->dt, c->next_optime - c->simtime);
@@ -767,6 +829,35 @@ extern "C" int pion_gpu_calculate_timestep(pion_gpu_ctx* c, double* dt_out) {
   if (c->dt <= 0.0) { set_error("Negative timestep!"); return 1; }
   c->FV_dt = c->dt;
   if (dt_out) *dt_out = c->dt;
+  return 0;
+}
+
+// constants::equalD (constants.cpp:48-69)
+static bool host_equalD(double a, double b) {
+  if (a == b) return true;
+  if (fabs(a) + fabs(b) < 1.0e-100) return true;
+  return (fabs(a - b) / (fabs(a) + fabs(b) + 1.0e-100)) < 1.0e-12;
+}
+
+// The output-criterion part of sim_init::output_data (sim_init.cpp:711-744): is the current step one that the
+// caller should save?  With op_criterion == 1 an output time that has been reached is consumed here
+// (next_optime += opfreq_time), exactly where the reference does it -- without this the dt limiter of
+// calculate_timestep would see next_optime - simtime == 0 on the following step.
+extern "C" int pion_gpu_output_due(pion_gpu_ctx* c, int opfreq, int* due) {
+  int d = 1;
+  const bool maxtime = c->simtime >= c->cfg.finishtime;
+  if (c->timestep == 0) {
+  } else if (c->cfg.op_criterion == 0) {
+    if (opfreq == 0 && !maxtime) d = 0;
+    else if (!maxtime && opfreq != 0 && (c->timestep % opfreq) != 0) d = 0;
+  } else if (c->cfg.op_criterion == 1) {
+    if (!host_equalD(c->simtime, c->next_optime) && !maxtime) d = 0;
+    else c->next_optime += c->cfg.opfreq_time;
+  } else {
+    set_error("op_criterion must be 0 or 1");
+    return 1;
+  }
+  if (due) *due = d;
   return 0;
 }
 
@@ -833,6 +924,17 @@ static int launch_preprocess(pion_gpu_ctx* c, const double* S, int order) {
 
 struct StageBox { int tx0, tx1, ty0, ty1, k_lo, k_hi; };
 
+// a timing event from the context's pool (created on first use, recycled by pion_gpu_stage_timing)
+static int timing_event(pion_gpu_ctx* c, cudaEvent_t* e) {
+  if (!c->tev_pool.empty()) {
+    *e = c->tev_pool.back();
+    c->tev_pool.pop_back();
+    return 0;
+  }
+  CUDA_OK(cudaEventCreate(e));
+  return 0;
+}
+
 // cells per tile of the sweep kernel that a fused stage of this context runs (launch_sweep_any's choice)
 static void stage_tile_cells(const pion_gpu_ctx* c, int* cx, int* cy) {
   sweep_tile_cells(c->cfg.eqntype, cx, cy);
@@ -886,17 +988,16 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool timed = c->timing && !c->timing_suspended;
   if (timed) {
-    CUDA_OK(cudaEventCreate(&e0));
-    CUDA_OK(cudaEventCreate(&e1));
+    if (timing_event(c, &e0) || timing_event(c, &e1)) return 1;
     CUDA_OK(cudaEventRecord(e0, st));
   }
   // fused 2-D/3-D stages run the flux-once sweep kernel; 1-D grids and the unfused seam
   // call (calc_dynamics_dU) run the per-cell gather kernel
   const bool sweep = fused && c->g.ndim >= 2 && c->g.coord == PION_COORD_CRT && !c->force_gather;
   switch (c->cfg.eqntype) {
-    case PION_EQEUL: (sweep ? launch_sweep_euler : launch_stage_euler)(c->cfg.solver, fkj, a, st); break;
-    case PION_EQMHD: (sweep ? launch_sweep_mhd : launch_stage_mhd)(c->cfg.solver, fkj, a, st); break;
-    default: (sweep ? launch_sweep_glm : launch_stage_glm)(c->cfg.solver, fkj, a, st); break;
+    case PION_EQEUL: c->last_stage_kernel = (sweep ? launch_sweep_euler : launch_stage_euler)(c->cfg.solver, fkj, a, st); break;
+    case PION_EQMHD: c->last_stage_kernel = (sweep ? launch_sweep_mhd : launch_stage_mhd)(c->cfg.solver, fkj, a, st); break;
+    default: c->last_stage_kernel = (sweep ? launch_sweep_glm : launch_stage_glm)(c->cfg.solver, fkj, a, st); break;
   }
   if (timed) {
     CUDA_OK(cudaEventRecord(e1, st));
@@ -914,7 +1015,7 @@ static int launch_cooling(pion_gpu_ctx* c, double dt, double* dE, double* dU) {
   a.g = c->g; a.cp = c->cool; a.P = c->P; a.dE = dE; a.dU = dU; a.mask = c->mask; a.dt = dt; a.gamma = c->pp.gamma;
   a.counters = c->d_counters; a.dtmin = nullptr; a.mp_timestep_limit = 0;
   const long ncell = (long)c->g.NG[0] * c->g.NG[1] * c->g.NG[2];
-  const size_t smem = 11 * (size_t)c->cool.nT * sizeof(double);
+  const size_t smem = cool_smem_bytes(c->cool);
   const int blocks = nblocks(ncell, 128, 148 * 32);
   switch (c->cfg.eqntype) {
     case PION_EQEUL: k_cooling_dU<EQ_EULER><<<blocks, 128, smem, c->stream>>>(a); break;
@@ -1011,9 +1112,8 @@ static int stage_and_bcs(pion_gpu_ctx* c, const double* S, const double* Pb, dou
   };
   const StageBox interior = {1, ntx - sxh, 1, nty - syh, zs, NZ - zs};
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (c->timing) {  // the seven launches of a split stage count as ONE stage launch for the roofline leg
-    CUDA_OK(cudaEventCreate(&e0));
-    CUDA_OK(cudaEventCreate(&e1));
+  if (c->timing) {  // the launches of a split stage count as ONE stage launch for the roofline leg
+    if (timing_event(c, &e0) || timing_event(c, &e1)) return 1;
     CUDA_OK(cudaEventRecord(e0, c->stream));
     c->timing_suspended = true;
   }
@@ -1087,6 +1187,8 @@ extern "C" int pion_gpu_run(pion_gpu_ctx* c, int nsteps, double* dts) {
     if (pion_gpu_calculate_timestep(c, &dt)) return 1;
     if (pion_gpu_advance_time(c, nullptr)) return 1;
     if (dts) dts[i] = dt;
+    // Time_Int calls output_data after every step (sim_control.cpp:252); only its next_optime bookkeeping matters here
+    if (c->cfg.op_criterion == 1 && pion_gpu_output_due(c, 0, nullptr)) return 1;
   }
   return 0;
 }
@@ -1127,9 +1229,36 @@ extern "C" int pion_gpu_stage_timing(pion_gpu_ctx* c, int enable, double* total_
   }
   if (total_ms) *total_ms = tot;
   if (nlaunch) *nlaunch = (long long)(c->tev.size() / 2);
-  for (auto e : c->tev) cudaEventDestroy(e);
+  for (auto e : c->tev) c->tev_pool.push_back(e);
   c->tev.clear();
   c->timing = enable != 0;
+  return 0;
+}
+
+// What this context actually launches: the stage-kernel variant of its most recent stage, the options in
+// effect (environment switches included) and the build flags of the library -- so that a bench line or a test
+// log states what ran instead of what was meant to run.
+extern "C" int pion_gpu_describe(pion_gpu_ctx* c, char* buf, int n) {
+  if (!buf || n <= 0) return 1;
+  int nmpi = 0;
+  for (int f = 0; f < 6; f++) nmpi += (c->cfg.bc[f] == PION_BC_MPI);
+  snprintf(buf, (size_t)n,
+           "stage_kernel=%s; tma_tensor_maps=%d; ranks=%d; exchanged_faces=%d; halo_overlap=%s; force_gather=%d; "
+           "build=%s%s%s",
+           c->last_stage_kernel, c->have_tmap ? 1 : 0, c->cfg.nproc > 0 ? c->cfg.nproc : 1, nmpi,
+           c->no_overlap ? "off(PION_B200_NO_OVERLAP)" : c->force_overlap ? "forced(PION_B200_OVERLAP)" : "auto",
+           c->force_gather ? 1 : 0,
+#ifdef PION_STRICT
+           "PION_STRICT",
+#else
+           "default",
+#endif
+#ifdef PION_BUILD_TAG
+           " " PION_BUILD_TAG,
+#else
+           "",
+#endif
+           "");
   return 0;
 }
 

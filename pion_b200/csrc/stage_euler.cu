@@ -1,19 +1,19 @@
 // Euler instantiations of the stage kernel (HLL, Roe-CV; FKJ98 on/off).
 #include "stage_kernel.cuh"
 namespace pion {
-void launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s) {
+const char* launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s) {
   if (solver == SOLVE_ROE) {
-    if (fkj) launch_stage_t<EQ_EULER, SOLVE_ROE, true>(a, s);
-    else launch_stage_t<EQ_EULER, SOLVE_ROE, false>(a, s);
+    if (fkj) return launch_stage_t<EQ_EULER, SOLVE_ROE, true>(a, s);
+    else return launch_stage_t<EQ_EULER, SOLVE_ROE, false>(a, s);
   } else if (solver == SOLVE_FVS) {
-    if (fkj) launch_stage_t<EQ_EULER, SOLVE_FVS, true>(a, s);
-    else launch_stage_t<EQ_EULER, SOLVE_FVS, false>(a, s);
+    if (fkj) return launch_stage_t<EQ_EULER, SOLVE_FVS, true>(a, s);
+    else return launch_stage_t<EQ_EULER, SOLVE_FVS, false>(a, s);
   } else if (solver == SOLVE_ROE_PV) {
-    if (fkj) launch_stage_t<EQ_EULER, SOLVE_ROE_PV, true>(a, s);
-    else launch_stage_t<EQ_EULER, SOLVE_ROE_PV, false>(a, s);
+    if (fkj) return launch_stage_t<EQ_EULER, SOLVE_ROE_PV, true>(a, s);
+    else return launch_stage_t<EQ_EULER, SOLVE_ROE_PV, false>(a, s);
   } else {
-    if (fkj) launch_stage_t<EQ_EULER, SOLVE_HLL, true>(a, s);
-    else launch_stage_t<EQ_EULER, SOLVE_HLL, false>(a, s);
+    if (fkj) return launch_stage_t<EQ_EULER, SOLVE_HLL, true>(a, s);
+    else return launch_stage_t<EQ_EULER, SOLVE_HLL, false>(a, s);
   }
 }
 }  // namespace pion

@@ -1,16 +1,16 @@
 // GLM instantiations of the stage kernel (HLL, HLLD, Roe-CV; FKJ98 on/off).
 #include "stage_kernel.cuh"
 namespace pion {
-void launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s) {
+const char* launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s) {
   if (solver == SOLVE_ROE) {
-    if (fkj) launch_stage_t<EQ_GLM, SOLVE_ROE, true>(a, s);
-    else launch_stage_t<EQ_GLM, SOLVE_ROE, false>(a, s);
+    if (fkj) return launch_stage_t<EQ_GLM, SOLVE_ROE, true>(a, s);
+    else return launch_stage_t<EQ_GLM, SOLVE_ROE, false>(a, s);
   } else if (solver == SOLVE_HLLD) {
-    if (fkj) launch_stage_t<EQ_GLM, SOLVE_HLLD, true>(a, s);
-    else launch_stage_t<EQ_GLM, SOLVE_HLLD, false>(a, s);
+    if (fkj) return launch_stage_t<EQ_GLM, SOLVE_HLLD, true>(a, s);
+    else return launch_stage_t<EQ_GLM, SOLVE_HLLD, false>(a, s);
   } else {
-    if (fkj) launch_stage_t<EQ_GLM, SOLVE_HLL, true>(a, s);
-    else launch_stage_t<EQ_GLM, SOLVE_HLL, false>(a, s);
+    if (fkj) return launch_stage_t<EQ_GLM, SOLVE_HLL, true>(a, s);
+    else return launch_stage_t<EQ_GLM, SOLVE_HLL, false>(a, s);
   }
 }
 }  // namespace pion

@@ -20,6 +20,7 @@
 // and fluxes never touch HBM.  The axis loop is a real loop: the solver frame is
 // rotated in registers between axes, so the Riemann solver is instantiated once.
 #pragma once
+#include <cstdio>
 #include "grid.cuh"
 
 namespace pion {
@@ -431,24 +432,34 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
 }
 
 // host-side launcher implemented per equation set in stage_{euler,mhd,glm}.cu
-void launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
-void launch_stage_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
-void launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+// (every launcher returns the name of the kernel variant it launched: pion_gpu_describe reports it)
+const char* launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+const char* launch_stage_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+const char* launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 // cells per sweep tile along x / y (stage_sweep.cuh: 32 lanes, TY rows, one of each only produces fluxes)
 void sweep_tile_cells(int eq, int* cx, int* cy);  // eq: EQ_EULER / EQ_MHD / EQ_GLM
 bool sweep_tma_fits(int eq, int ntr);  // the TMA sweep kernel exists for this many tracers and its tile fits shared memory
 void sweep_tma_box(int eq, int* cw, int* rh, int* nb, int* tx);  // box of one TMA plane load, cells per tile in x (stage_sweep_tma.cuh)
 // flux-once sweep kernel (stage_sweep.cuh), instantiated in sweep_{euler,mhd,glm}.cu
-void launch_sweep_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
-void launch_sweep_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
-void launch_sweep_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+const char* launch_sweep_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+const char* launch_sweep_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+const char* launch_sweep_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s);
+
+// "k_xxx<EQ=3,SOLVER=7,FKJ=1,...>" built once per instantiation
+inline const char* kernel_variant_name(char* buf, size_t n, const char* kernel, int eq, int solver, bool fkj, const char* extra) {
+  snprintf(buf, n, "%s<EQ=%d,SOLVER=%d,FKJ=%d%s>", kernel, eq, solver, fkj ? 1 : 0, extra);
+  return buf;
+}
 
 template <int EQ, int SOLVER, bool FKJ>
-inline void launch_stage_t(const StageArgs& a, cudaStream_t s) {
+inline const char* launch_stage_t(const StageArgs& a, cudaStream_t s) {
   const long ncell = (long)a.g.NG[0] * a.g.NG[1] * a.g.NG[2];
   const int block = 128;
   const long grid = (ncell + block - 1) / block;
   k_stage<EQ, SOLVER, FKJ><<<(unsigned)grid, block, 0, s>>>(a);
+  static char name[96];
+  static const char* nm = kernel_variant_name(name, sizeof name, "k_stage", EQ, SOLVER, FKJ, " (gather form)");
+  return nm;
 }
 
 }  // namespace pion

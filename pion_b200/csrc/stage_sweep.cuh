@@ -377,12 +377,25 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_stage_sweep(const __grid_cons
   stage_block_epilogue(a, my_dt, status);
 }
 
+// slot of the current device in the per-device "attribute set" flags of the launchers (the last slot is shared
+// by every ordinal >= PION_MAX_DEVICES - 1 and never cached)
+constexpr int PION_MAX_DEVICES = 65;
+inline int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < PION_MAX_DEVICES - 1) ? dev : PION_MAX_DEVICES - 1;
+}
+
 template <int EQ, int SOLVER, bool FKJ>
-inline void launch_sweep_t(const StageArgs& a, cudaStream_t s) {
+inline const char* launch_sweep_t(const StageArgs& a, cudaStream_t s) {
   constexpr int TY = sweep_ty(EQ), MINB = sweep_minb(EQ);
   constexpr int NB = nbase(EQ);
   const int bx = a.tx1 - a.tx0, by = a.ty1 - a.ty0, NZ = a.k_hi - a.k_lo;
-  if (bx <= 0 || by <= 0 || NZ <= 0) return;
+  static char name[2][112];
+  static const char* nm[2] = {
+      kernel_variant_name(name[0], sizeof name[0], "k_stage_sweep", EQ, SOLVER, FKJ, ",TR=0 (LDG stencil)"),
+      kernel_variant_name(name[1], sizeof name[1], "k_stage_sweep", EQ, SOLVER, FKJ, ",TR=1 (LDG stencil)")};
+  if (bx <= 0 || by <= 0 || NZ <= 0) return nm[a.ntr > 0];
   // z chunks: enough blocks to fill 148 SMs a few times over, long enough to amortise the extra flux plane
   int kchunk = NZ;
   if (a.g.ndim > 2) {
@@ -392,14 +405,17 @@ inline void launch_sweep_t(const StageArgs& a, cudaStream_t s) {
   const int bz = (NZ + kchunk - 1) / kchunk;
   const size_t smem = (size_t)2 * (NB + PION_MAXTR) * TY * 32 * sizeof(double);
   const size_t smem_notr = (size_t)2 * NB * TY * 32 * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the opt-in is per DEVICE: one flag per ordinal (a process may hold contexts on several GPUs)
+  static bool attr_done[PION_MAX_DEVICES] = {false};
+  const int dev = current_device_slot();
+  if (!attr_done[dev]) {
     cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_notr);
-    attr_done = true;
+    attr_done[dev] = (dev != PION_MAX_DEVICES - 1);  // the overflow slot is never cached
   }
   if (a.ntr > 0) k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, true><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, kchunk);
   else k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, false><<<dim3(bx, by, bz), 32 * TY, smem_notr, s>>>(a, kchunk);
+  return nm[a.ntr > 0];
 }
 
 // number of cells a sweep tile updates along x and y (host side: shell / interior boxes)

@@ -102,12 +102,12 @@ __device__ __forceinline__ Prim lds_prim(const double* p, int ax, int a1, int a2
 
 // edge states at the face between tile cells pL | pR (pQ0, pQ3: the next cells outwards), solver frame of
 // axis ax: SetEdgeState / SetSlope (VectorOps.cpp:535-617)
-template <int EQ, int VS>
+template <int EQ, int VS, int ORDER>
 __device__ __forceinline__ void edge_states_tile(const StageArgs& a, const double* pQ0, const double* pL, const double* pR,
                                                  const double* pQ3, int ax, int a1, int a2, Prim& eL, Prim& eR) {
   eL = lds_prim<EQ, VS>(pL, ax, a1, a2);
   eR = lds_prim<EQ, VS>(pR, ax, a1, a2);
-  if (a.order == 2) {
+  if (ORDER == 2) {
     const Prim Q0 = lds_prim<EQ, VS>(pQ0, ax, a1, a2);
     const Prim Q3 = lds_prim<EQ, VS>(pQ3, ax, a1, a2);
 #define PION_EDGE2(f)                                                     \
@@ -121,15 +121,6 @@ __device__ __forceinline__ void edge_states_tile(const StageArgs& a, const doubl
     if (EQ == EQ_GLM) { PION_EDGE2(psi) }
 #undef PION_EDGE2
   }
-}
-
-// flux through that face, as low_face_flux
-template <int EQ, int SOLVER, bool FKJ, int VS>
-__device__ __forceinline__ void face_flux_tile(const StageArgs& a, const double* pQ0, const double* pL, const double* pR,
-                                               const double* pQ3, bool use_hll, int ax, int a1, int a2, Cons& F) {
-  Prim eL, eR;
-  edge_states_tile<EQ, VS>(a, pQ0, pL, pR, pQ3, ax, a1, a2, eL, eR);
-  intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(eL, eR, a.pp, use_hll, 0.0, F);
 }
 
 // dU accumulators in the GRID frame (x, y, z): with compile-time axes nothing has to be rotated
@@ -210,13 +201,13 @@ __device__ __forceinline__ void cons_diff(Cons& D, const Cons& lo, const Cons& h
 
 // tracers ride along as extra tile variables NB .. NB+NTR-1: edge values (SetEdgeState with the same minmod slopes)
 // and the upwinded flux F[tr] = tr_upwind * F[rho] * sCMA corrector (solver_eqn_base.cpp:281-342)
-template <int VS, int NB, int NTR>
+template <int VS, int NB, int NTR, int ORDER>
 __device__ __forceinline__ void tracer_edges_tile(const StageArgs& a, const double* pQ0, const double* pL, const double* pR,
                                                   const double* pQ3, double* trL, double* trR) {
 #pragma unroll
   for (int q = 0; q < NTR; q++) {
     double L = pL[(NB + q) * VS], R = pR[(NB + q) * VS];
-    if (a.order == 2) {
+    if (ORDER == 2) {
       const double q0 = pQ0[(NB + q) * VS], q3 = pQ3[(NB + q) * VS];
       const double d0 = L - q0, d1 = R - L, d2 = q3 - R;
       L += minmod(d0, d1, a.tiny2) * 0.5;
@@ -233,7 +224,9 @@ __device__ __forceinline__ double tracer_upwind_flux(const StageArgs& a, double 
   return f;
 }
 
-template <int EQ, int SOLVER, bool FKJ, int TY, int MINB, int NTR>
+// ORDER: spatial order of the stage (1 = predictor of the second-order scheme / first-order runs, 2 = corrector);
+// a template parameter so that the predictor carries no reconstruction code at all
+template <int EQ, int SOLVER, bool FKJ, int TY, int MINB, int NTR, int ORDER>
 __global__ void __launch_bounds__(32 * TY, MINB)
     k_stage_sweep_tma(const __grid_constant__ StageArgs a, const __grid_constant__ CUtensorMap tmap, const int kchunk) {
   extern __shared__ __align__(128) unsigned char s_raw[];
@@ -367,6 +360,15 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     // cheaper than 18 registers held across the Riemann solver)
     const bool domain = upd_xy && !warm && (a.mask ? (a.mask[c] != 0) : true);
     if (!warm && a.mp_dE && upd_xy) acc.erg = a.mp_dE[c];  // cooling source term (energy only)
+#ifdef PION_PB_PREFETCH
+    // corrector: the base state P of this cell is read from HBM at the END of the iteration (cell_advance_time),
+    // three Riemann solves from here; ask for its lines now so that those loads hit L1 (ncu: long-scoreboard
+    // was 14 % of the corrector's stall samples, all on these loads)
+    if (!pb_is_s && domain) {
+#pragma unroll
+      for (int v = 0; v < NV; v++) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Pb + (long)v * vs + c));
+    }
+#endif
 #pragma unroll 1
     for (int f = (warm && !light) ? 1 : 0; f < 3; f++) {
       if (f == 2 && last) break;
@@ -383,18 +385,18 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         bool use_hll = false;
         if (f == 0) {
           const double* const px = light ? (pp1 - coff + eoff) : p0;
-          edge_states_tile<EQ, VS>(a, px - 2, px - 1, px, px + 1, 0, 1, 2, eL, eR);
-          tracer_edges_tile<VS, NB, NTR>(a, px - 2, px - 1, px, px + 1, trL, trR);
+          edge_states_tile<EQ, VS, ORDER>(a, px - 2, px - 1, px, px + 1, 0, 1, 2, eL, eR);
+          tracer_edges_tile<VS, NB, NTR, ORDER>(a, px - 2, px - 1, px, px + 1, trL, trR);
           if (SOLVER == SOLVE_HLLD) use_hll = ((light ? we_k1 : w_k) & 1u) != 0;
         } else if (f == 1) {
           // plane k+2 (first needed here): fill number (kk+4) >> 2 of buffer kk & 3
           mbar_wait_spin(&s_full[kk & 3], ((unsigned)(kk + 4) >> 2) & 1u);
-          edge_states_tile<EQ, VS>(a, pm1, p0, pp1, pp2, 2, 0, 1, eL, eR);
-          tracer_edges_tile<VS, NB, NTR>(a, pm1, p0, pp1, pp2, trL, trR);
+          edge_states_tile<EQ, VS, ORDER>(a, pm1, p0, pp1, pp2, 2, 0, 1, eL, eR);
+          tracer_edges_tile<VS, NB, NTR, ORDER>(a, pm1, p0, pp1, pp2, trL, trR);
           if (SOLVER == SOLVE_HLLD) use_hll = (w_k1 & 4u) != 0;
         } else {
-          edge_states_tile<EQ, VS>(a, pp1 - 2 * CW, pp1 - CW, pp1, pp1 + CW, 1, 2, 0, eL, eR);
-          tracer_edges_tile<VS, NB, NTR>(a, pp1 - 2 * CW, pp1 - CW, pp1, pp1 + CW, trL, trR);
+          edge_states_tile<EQ, VS, ORDER>(a, pp1 - 2 * CW, pp1 - CW, pp1, pp1 + CW, 1, 2, 0, eL, eR);
+          tracer_edges_tile<VS, NB, NTR, ORDER>(a, pp1 - 2 * CW, pp1 - CW, pp1, pp1 + CW, trL, trR);
           if (SOLVER == SOLVE_HLLD) use_hll = (w_k1 & 2u) != 0;
         }
         intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(eL, eR, a.pp, use_hll, 0.0, Fnew);
@@ -533,40 +535,45 @@ __host__ __device__ constexpr bool tma_fits(int eq, int ntr) {
   return ntr <= TMA_MAXTR && tma_smem_bytes(nbase(eq) + ntr, sweep_ty(eq)) <= TMA_SMEM_MAX;
 }
 
-template <int EQ, int SOLVER, bool FKJ, int NTR>
-inline void launch_sweep_tma_t(const StageArgs& a, cudaStream_t s) {
+template <int EQ, int SOLVER, bool FKJ, int NTR, int ORDER>
+inline const char* launch_sweep_tma_o(const StageArgs& a, cudaStream_t s) {
   constexpr int TY = sweep_ty(EQ), MINB = sweep_minb(EQ);
   constexpr int NV = nbase(EQ) + NTR;
+  static char name[128], extra[64];
+  static const char* nm = (snprintf(extra, sizeof extra, ",TY=%d,NTR=%d,ORDER=1|2 (TMA-staged stencil)", TY, NTR),
+                           kernel_variant_name(name, sizeof name, "k_stage_sweep_tma", EQ, SOLVER, FKJ, extra));
   const int bx = a.tx1 - a.tx0, by = a.ty1 - a.ty0, NZ = a.k_hi - a.k_lo;
-  if (bx <= 0 || by <= 0 || NZ <= 0) return;
+  if (bx <= 0 || by <= 0 || NZ <= 0) return nm;
   int kchunk = PION_TMA_KCHUNK;
   while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
   const int bz = (NZ + kchunk - 1) / kchunk;
   constexpr size_t smem = tma_smem_bytes(NV, TY);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
+  // the opt-in is per DEVICE: one flag per ordinal (a process may hold contexts on several GPUs)
+  static bool attr_done[PION_MAX_DEVICES] = {false};
+  const int dev = current_device_slot();
+  if (!attr_done[dev]) {
+    cudaFuncSetAttribute(k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done[dev] = (dev != PION_MAX_DEVICES - 1);  // the overflow slot is never cached
   }
-  k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, *reinterpret_cast<const CUtensorMap*>(a.tmap), kchunk);
+  k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR, ORDER><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, *reinterpret_cast<const CUtensorMap*>(a.tmap), kchunk);
+  return nm;
+}
+template <int EQ, int SOLVER, bool FKJ, int NTR>
+inline const char* launch_sweep_tma_t(const StageArgs& a, cudaStream_t s) {
+  if (a.order == 2) return launch_sweep_tma_o<EQ, SOLVER, FKJ, NTR, 2>(a, s);
+  return launch_sweep_tma_o<EQ, SOLVER, FKJ, NTR, 1>(a, s);
 }
 
 // 3-D grids with at most TMA_MAXTR tracers and no H-correction run the TMA kernel when its tile fits the
 // shared memory, everything else the LDG sweep kernel
 template <int EQ, int SOLVER, bool FKJ>
-inline void launch_sweep_any(const StageArgs& a, cudaStream_t s) {
+inline const char* launch_sweep_any(const StageArgs& a, cudaStream_t s) {
   const bool tma = a.tmap && a.g.ndim == 3 && !a.eta && (SOLVER != SOLVE_HLLD || a.hllf) && tma_fits(EQ, a.ntr);
-  if (tma && a.ntr == 0) {
-    launch_sweep_tma_t<EQ, SOLVER, FKJ, 0>(a, s);
-    return;
-  }
+  if (tma && a.ntr == 0) return launch_sweep_tma_t<EQ, SOLVER, FKJ, 0>(a, s);
   if constexpr (tma_fits(EQ, 1)) {
-    if (tma && a.ntr == 1) {
-      launch_sweep_tma_t<EQ, SOLVER, FKJ, 1>(a, s);
-      return;
-    }
+    if (tma && a.ntr == 1) return launch_sweep_tma_t<EQ, SOLVER, FKJ, 1>(a, s);
   }
-  launch_sweep_t<EQ, SOLVER, FKJ>(a, s);
+  return launch_sweep_t<EQ, SOLVER, FKJ>(a, s);
 }
 
 // box of one TMA plane load for an equation set (host side: tensor-map creation)

@@ -136,6 +136,8 @@ int main(int argc, char** argv) {
   p.finishtime = getd(kv, "FinishTime", 1e30);
   p.op_criterion = geti(kv, "OutputCriterion", 0);
   p.opfreq_time = getd(kv, "OPfreqTime", 0.0);
+  p.opfreq = geti(kv, "OutputFrequency", 0);
+  p.min_timestep = getd(kv, "min_timestep", 0.0);
   p.EP.cooling = geti(kv, "EP_cooling", 0);
   p.EP.MP_timestep_limit = geti(kv, "EP_MP_timestep_limit", 0);
   p.EP.MinTemperature = getd(kv, "EP_Min_Temperature", 0.0);
@@ -181,7 +183,7 @@ int main(int argc, char** argv) {
   if (sim.Init(device, P.data())) { fprintf(stderr, "Init: %s\n", sim.error().c_str()); return 1; }
   if (sim.Time_Int(steps, verbose)) { fprintf(stderr, "Time_Int: %s\n", sim.error().c_str()); return 1; }
   if (out) {
-    if (sim.output_data(P.data())) { fprintf(stderr, "output_data: %s\n", sim.error().c_str()); return 1; }
+    if (sim.download_state(P.data())) { fprintf(stderr, "output_data: %s\n", sim.error().c_str()); return 1; }
     std::ofstream f(out, std::ios::binary);
     f.write(reinterpret_cast<const char*>(P.data()), P.size() * sizeof(double));
   }

@@ -75,6 +75,7 @@ int sim_control_gpu::Init(int device, const double* P_soa) {
   c.table_C_cie = SimPM.table_C_cie.data();
   c.n_wind = (int)SimPM.SWP.size();
   for (int i = 0; i < c.n_wind && i < 2; i++) c.wind[i] = SimPM.SWP[i];
+  c.min_timestep = SimPM.min_timestep;
   c.rank = 0;
   c.nproc = 1;
   Finalise();
@@ -125,15 +126,32 @@ int sim_control_gpu::calc_dynamics_dU(double dt, int step) {
 int sim_control_gpu::grid_update_state_vector(double dt, int step, int ooa) {
   return pion_gpu_grid_update_state_vector(ctx_, dt, step, ooa) ? fail("grid_update_state_vector") : 0;
 }
-// The library updates internal then external boundaries in one call, as every caller in the
-// reference does back to back (time_integrator.cpp:104-107,:128-131); External is the call
-// that performs both, Internal is kept for source compatibility.
-int sim_control_gpu::TimeUpdateInternalBCs(double, int, int) { return 0; }
-int sim_control_gpu::TimeUpdateExternalBCs(double simtime, int cstep, int maxstep) {
-  return pion_gpu_time_update_bcs(ctx_, simtime, cstep, maxstep) ? fail("TimeUpdateExternalBCs") : 0;
+// assign_update_bcs.cpp:134-181 (STWIND cells) and :191-246 (the faces in BC_bd order, then DMACH2)
+int sim_control_gpu::TimeUpdateInternalBCs(double simtime, int cstep, int maxstep) {
+  return pion_gpu_time_update_internal_bcs(ctx_, simtime, cstep, maxstep) ? fail("TimeUpdateInternalBCs") : 0;
 }
-int sim_control_gpu::output_data(double* P_soa) {
-  return pion_gpu_download(ctx_, PION_STATE_P, P_soa) ? fail("output_data") : 0;
+int sim_control_gpu::TimeUpdateExternalBCs(double simtime, int cstep, int maxstep) {
+  return pion_gpu_time_update_external_bcs(ctx_, simtime, cstep, maxstep) ? fail("TimeUpdateExternalBCs") : 0;
+}
+// sim_init::output_data (sim_init.cpp:671-760): the output criteria decide whether this step is saved; an
+// output time that has been reached is consumed (next_optime += opfreq_time).  P_soa may be null (no copy).
+int sim_control_gpu::output_data(double* P_soa, bool* saved) {
+  int due = 0;
+  if (pion_gpu_output_due(ctx_, SimPM.opfreq, &due)) return fail("output_data");
+  if (saved) *saved = due != 0;
+  if (due && P_soa) return pion_gpu_download(ctx_, PION_STATE_P, P_soa) ? fail("output_data") : 0;
+  return 0;
+}
+int sim_control_gpu::download_state(double* P_soa) {
+  return pion_gpu_download(ctx_, PION_STATE_P, P_soa) ? fail("download_state") : 0;
+}
+// the conditions that are fatal inside the reference's per-cell code (rep.error in UtoP / TimeUpdateMP)
+int sim_control_gpu::check_fatal_counters() {
+  long long cnt[3], mpf = 0;
+  if (pion_gpu_counters(ctx_, cnt) || pion_gpu_mp_failures(ctx_, &mpf)) return fail("Time_Int");
+  if (cnt[0]) { err_ = "UtoP: negative density (fatal in the reference, eqns_mhd_adiabatic.cpp:137)"; return 1; }
+  if (mpf) { err_ = "mp_only_cooling integration failed."; return 1; }
+  return 0;
 }
 
 // sim_control::check_eosim (sim_control.cpp:317-392), time criterion
@@ -154,20 +172,20 @@ int sim_control_gpu::Time_Int(long max_steps, bool verbose) {
     if (advance_time() < 0.0) return 1;
     if (verbose) printf("New time: %.10e\t dt=%.10e\t steps: %d\n", SimPM.simtime, SimPM.dt, SimPM.timestep);
     check_eosim();
+    if (output_data(output_buffer_, nullptr)) return 1;  // sim_control.cpp:252
     n++;
+    // the reference aborts inside the step; here the device counters are polled every few steps (one 24-byte
+    // read-back) so that a failed run stops within `fatal_poll_steps` steps instead of running on to the end
+    if (fatal_poll_steps > 0 && (n % fatal_poll_steps) == 0 && check_fatal_counters()) return 1;
   }
   if (pion_gpu_sync(ctx_)) return fail("Time_Int");
-  long long cnt[3], mpf = 0;
-  if (pion_gpu_counters(ctx_, cnt) || pion_gpu_mp_failures(ctx_, &mpf)) return fail("Time_Int");
   wall_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   const int steps = SimPM.timestep - step0;
   // the reference's closing lines (sim_control.cpp:270-277)
   printf("TOTALS ###: Nsteps: %d wall-time: %g time/step: %g\n", steps, wall_, wall_ / (steps > 0 ? steps : 1));
   printf("STEPS: %d\t%.6e\t%.6e\t%.6e\n", steps, wall_, wall_ / (steps > 0 ? steps : 1),
          (double)steps * (double)SimPM.Ncell() / wall_);
-  if (cnt[0]) { err_ = "UtoP: negative density (fatal in the reference, eqns_mhd_adiabatic.cpp:137)"; return 1; }
-  if (mpf) { err_ = "mp_only_cooling integration failed."; return 1; }
-  return 0;
+  return check_fatal_counters();
 }
 
 }  // namespace pion_b200

@@ -40,8 +40,9 @@ struct SimParamsGPU {
   std::vector<int> BC_internal;
   double RefVec[PION_GPU_MAXVAR];
   double starttime = 0, finishtime = 1e30, simtime = 0, dt = 0, last_dt = 1e100;
-  int timestep = 0, op_criterion = 0;
+  int timestep = 0, op_criterion = 0, opfreq = 0;
   double opfreq_time = 0;
+  double min_timestep = 0;  // sim_params.h:227
   bool maxtime = false;
   // struct which_physics EP (sim_params.h:106-160), cooling-only microphysics
   struct {
@@ -88,8 +89,18 @@ class sim_control_gpu {
   int grid_update_state_vector(double dt, int step, int ooa);  // time_integrator.h:179
   int TimeUpdateInternalBCs(double simtime, int cstep, int maxstep);  // assign_update_bcs.h:51
   int TimeUpdateExternalBCs(double simtime, int cstep, int maxstep);  // assign_update_bcs.h:63
-  /// dataio->OutputData side: copy P back to the host array
-  int output_data(double* P_soa);
+  /// sim_init::output_data (sim_init.cpp:671-760): applies the output criteria (op_criterion / opfreq /
+  /// opfreq_time, consuming an output time that has been reached) and, when the step is to be saved, copies
+  /// P back into the host array (null = bookkeeping only).  `saved` reports the decision.
+  int output_data(double* P_soa, bool* saved = nullptr);
+  /// unconditional device -> host copy of P (dataio->OutputData side of the seam)
+  int download_state(double* P_soa);
+  /// host buffer Time_Int hands to output_data after every step (null = bookkeeping only)
+  void set_output_buffer(double* P_soa) { output_buffer_ = P_soa; }
+  /// negative density / failed cooling integrations are fatal in the reference: Time_Int polls the device
+  /// counters every this many steps (0 = only at the end)
+  int fatal_poll_steps = 16;
+  int check_fatal_counters();
   int check_eosim();                                         // sim_control.cpp:317
 
   /// last error text (what the reference would hand to rep.error)
@@ -101,6 +112,7 @@ class sim_control_gpu {
   int fail(const char* where);
   void pull_time();
   pion_gpu_ctx* ctx_ = nullptr;
+  double* output_buffer_ = nullptr;
   std::string err_;
   double wall_ = 0;
 };

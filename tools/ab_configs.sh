@@ -4,5 +4,5 @@ cd "$(dirname "$0")/.."
 for lib in pion_b200/libpion_b200.so pion_b200/variants/*.so; do
   [ -f "$lib" ] || continue
   echo "== $(basename $lib)"
-  PION_B200_LIB=$PWD/$lib python tools/bench_configs.py --no-cpu --only "$1" 2>&1 | grep "^|"
+  python tools/bench_configs.py --lib $PWD/$lib --no-cpu --only "$1" 2>&1 | grep "^|"
 done
