@@ -244,6 +244,10 @@ struct BCArgs {
   double sim_xmin[3];
 };
 
+struct BCRef {
+  double v[PION_MAXVAR];
+};
+
 __device__ __forceinline__ void bc_face_extents(const GridD& g, int face, int* lo, int* hi) {
   const int ax = face >> 1;
   for (int q = 0; q < 3; q++) { lo[q] = 0; hi[q] = g.NGa[q]; }
@@ -256,62 +260,86 @@ __device__ __forceinline__ void bc_face_extents(const GridD& g, int face, int* l
   else { lo[ax] = 0; hi[ax] = g.nb[ax]; }
 }
 
-__global__ void k_bc_face(const __grid_constant__ BCArgs a) {
+// ghost cell number t of face `face` (boundary type `type`, reference values `refval`)
+__device__ __forceinline__ void bc_fill_cell(const BCArgs& a, int face, int type, const double* refval, long t) {
   const GridD& g = a.g;
   int lo[3], hi[3];
-  bc_face_extents(g, a.face, lo, hi);
-  const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
-  const long n = (long)ex * ey * ez;
-  const int ax = a.face >> 1, pos = a.face & 1;
+  bc_face_extents(g, face, lo, hi);
+  const int ex = hi[0] - lo[0], ey = hi[1] - lo[1];
+  const int ax = face >> 1, pos = face & 1;
   const long st = axis_stride(g, ax);
-  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
-    int ijk[3] = {(int)(t % ex) + lo[0], (int)((t / ex) % ey) + lo[1], (int)(t / ((long)ex * ey)) + lo[2]};
-    const long c = gidx(g, ijk[0], ijk[1], ijk[2]);
-    // depth of this ghost cell (1 = adjacent to the grid) and its source cells
-    const int q = ijk[ax];
-    const int edge = pos ? g.NGa[ax] - g.nb[ax] - 1 : g.nb[ax];
-    const int depth = pos ? q - edge : edge - q;
-    const long c_edge = c + (long)(edge - q) * st;
-    const long c_mirror = c_edge + (long)(pos ? -(depth - 1) : (depth - 1)) * st;
-    const long c_per = c + (long)(pos ? -g.NG[ax] : g.NG[ax]) * st;
-    for (int w = 0; w < a.narr; w++) {
-      double* A = a.A[w];
-      switch (a.type) {
-        case 1:  // PERIODIC (periodic_boundaries.cpp:68-88)
-          for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = A[(long)v * g.vs + c_per];
-          break;
-        case 2:   // OUTFLOW (outflow_boundaries.cpp:109-160)
-        case 13:  // ONEWAY_OUT (oneway_out_boundaries.cpp:38-115)
-          for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = A[(long)v * g.vs + c_edge];
-          if (a.type == 13) {
-            const double sgn = pos ? 1.0 : -1.0;
-            const long o = (long)(2 + ax) * g.vs + c;
-            A[o] = sgn * fmax(0.0, A[o] * sgn);
-          }
-          if (a.eq == EQ_GLM) A[8 * g.vs + c] = -A[8 * g.vs + c_mirror];  // GLM_NEGATIVE_BOUNDARY
-          break;
-        case 4:  // REFLECTING (reflecting_boundaries.cpp:123-145): both layers copy the edge cell
-          for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = A[(long)v * g.vs + c_edge] * a.refval[v];
-          break;
-        case 3:  // INFLOW (inflow_boundaries.cpp:83-100)
-        case 5:  // FIXED (fixed_boundaries.cpp:91-107)
-          for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = a.refval[v];
-          break;
-        case 8: {  // DMACH (double_Mach_ref_boundaries.cpp:169-208)
-          const double dxo2 = 0.5 * g.dx;
-          const double xpos = a.sim_xmin[0] + (2 * (ijk[0] - g.nb[0]) + 1) * dxo2;
-          const double ypos = a.sim_xmin[1] + (2 * (ijk[1] - g.nb[1]) + 1) * dxo2;
-          const double bpos = 10.0 * a.simtime / sin(M_PI / 3.0) + 1.0 / 6.0 + ypos / tan(M_PI / 3.0);
-          if (xpos <= bpos) {
-            A[c] = 8.0; A[g.vs + c] = 116.5; A[2 * g.vs + c] = 7.14470958; A[3 * g.vs + c] = -4.125; A[4 * g.vs + c] = 0.0;
-            for (int v = a.ftr; v < a.nvar; v++) A[(long)v * g.vs + c] = 1.0;
-          } else {
-            for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = a.refval[v];
-          }
-        } break;
-        default:
-          break;
-      }
+  int ijk[3] = {(int)(t % ex) + lo[0], (int)((t / ex) % ey) + lo[1], (int)(t / ((long)ex * ey)) + lo[2]};
+  const long c = gidx(g, ijk[0], ijk[1], ijk[2]);
+  // depth of this ghost cell (1 = adjacent to the grid) and its source cells
+  const int q = ijk[ax];
+  const int edge = pos ? g.NGa[ax] - g.nb[ax] - 1 : g.nb[ax];
+  const int depth = pos ? q - edge : edge - q;
+  const long c_edge = c + (long)(edge - q) * st;
+  const long c_mirror = c_edge + (long)(pos ? -(depth - 1) : (depth - 1)) * st;
+  const long c_per = c + (long)(pos ? -g.NG[ax] : g.NG[ax]) * st;
+  for (int w = 0; w < a.narr; w++) {
+    double* A = a.A[w];
+    switch (type) {
+      case 1:  // PERIODIC (periodic_boundaries.cpp:68-88)
+        for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = A[(long)v * g.vs + c_per];
+        break;
+      case 2:   // OUTFLOW (outflow_boundaries.cpp:109-160)
+      case 13:  // ONEWAY_OUT (oneway_out_boundaries.cpp:38-115)
+        for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = A[(long)v * g.vs + c_edge];
+        if (type == 13) {
+          const double sgn = pos ? 1.0 : -1.0;
+          const long o = (long)(2 + ax) * g.vs + c;
+          A[o] = sgn * fmax(0.0, A[o] * sgn);
+        }
+        if (a.eq == EQ_GLM) A[8 * g.vs + c] = -A[8 * g.vs + c_mirror];  // GLM_NEGATIVE_BOUNDARY
+        break;
+      case 4:  // REFLECTING (reflecting_boundaries.cpp:123-145): both layers copy the edge cell
+        for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = A[(long)v * g.vs + c_edge] * refval[v];
+        break;
+      case 3:  // INFLOW (inflow_boundaries.cpp:83-100)
+      case 5:  // FIXED (fixed_boundaries.cpp:91-107)
+        for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = refval[v];
+        break;
+      case 8: {  // DMACH (double_Mach_ref_boundaries.cpp:169-208)
+        const double dxo2 = 0.5 * g.dx;
+        const double xpos = a.sim_xmin[0] + (2 * (ijk[0] - g.nb[0]) + 1) * dxo2;
+        const double ypos = a.sim_xmin[1] + (2 * (ijk[1] - g.nb[1]) + 1) * dxo2;
+        const double bpos = 10.0 * a.simtime / sin(M_PI / 3.0) + 1.0 / 6.0 + ypos / tan(M_PI / 3.0);
+        if (xpos <= bpos) {
+          A[c] = 8.0; A[g.vs + c] = 116.5; A[2 * g.vs + c] = 7.14470958; A[3 * g.vs + c] = -4.125; A[4 * g.vs + c] = 0.0;
+          for (int v = a.ftr; v < a.nvar; v++) A[(long)v * g.vs + c] = 1.0;
+        } else {
+          for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = refval[v];
+        }
+      } break;
+      default:
+        break;
+    }
+  }
+}
+
+__global__ void k_bc_face(const __grid_constant__ BCArgs a) {
+  int lo[3], hi[3];
+  bc_face_extents(a.g, a.face, lo, hi);
+  const long n = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x)
+    bc_fill_cell(a, a.face, a.type, a.refval, t);
+}
+
+// Both faces of ONE axis in one launch (they never read each other's ghost cells -- a periodic face copies
+// from interior cells): three ghost-fill launches per boundary update instead of six.  The order ACROSS axes
+// (x, y, z: edges and corners inherit) stays with the host.  `a.face` is the LOW face; type2 / refval2 describe
+// the high face; a type of 0 (or PION_BC_MPI: filled by the halo exchange) skips that face.
+__global__ void k_bc_axis(const __grid_constant__ BCArgs a, const int type2, const __grid_constant__ BCRef ref2) {
+  int lo[3], hi[3];
+  bc_face_extents(a.g, a.face, lo, hi);
+  const long n = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);  // same count on both faces
+  const bool do_lo = a.type != 0 && a.type != 10, do_hi = type2 != 0 && type2 != 10;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * n; t += (long)gridDim.x * blockDim.x) {
+    if (t < n) {
+      if (do_lo) bc_fill_cell(a, a.face, a.type, a.refval, t);
+    } else if (do_hi) {
+      bc_fill_cell(a, a.face + 1, type2, ref2.v, t - n);
     }
   }
 }
@@ -365,6 +393,33 @@ __global__ void k_halo(const __grid_constant__ HaloArgs a) {
     const long c = (long)v * g.vs + gidx(g, i, j, k);
     if (a.pack) a.buf[t] = a.A[c];
     else a.A[c] = a.buf[t];
+  }
+}
+
+// both exchanged faces of one axis in one launch (buf2 / face + 1 may be absent: null)
+__global__ void k_halo_axis(const __grid_constant__ HaloArgs a, double* const buf2) {
+  const GridD& g = a.g;
+  const int ax = a.face >> 1;
+  for (int s = 0; s < 2; s++) {
+    double* const buf = s ? buf2 : a.buf;
+    if (!buf) continue;
+    int lo[3], hi[3];
+    bc_face_extents(g, 2 * ax + s, lo, hi);
+    if (a.pack) {
+      const int sh = s ? -g.nb[ax] : g.nb[ax];
+      lo[ax] += sh;
+      hi[ax] += sh;
+    }
+    const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+    const long n = (long)ex * ey * ez;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n * a.nvar; t += (long)gridDim.x * blockDim.x) {
+      const int v = (int)(t / n);
+      const long r = t % n;
+      const int i = (int)(r % ex) + lo[0], j = (int)((r / ex) % ey) + lo[1], k = (int)(r / ((long)ex * ey)) + lo[2];
+      const long c = (long)v * g.vs + gidx(g, i, j, k);
+      if (a.pack) buf[t] = a.A[c];
+      else a.A[c] = buf[t];
+    }
   }
 }
 

@@ -76,6 +76,7 @@ struct pion_gpu_ctx {
   std::vector<cudaEvent_t> tev;  // begin/end pairs
   std::vector<cudaEvent_t> tev_pool;  // recycled timing events (no cudaEventCreate inside a timed loop)
   const char* last_stage_kernel = "(no stage launched yet)";
+  bool last_stage_split = false;  // the most recent fused stage ran as boundary shell + interior
   // multi-GPU
   ncclComm_t comm = nullptr;
   double* d_red = nullptr;  // 2 doubles for the dt all-reduce
@@ -570,14 +571,14 @@ static int update_internal_bcs(pion_gpu_ctx* c, cudaStream_t st) {
 static int update_external_bcs(pion_gpu_ctx* c, double* A0, double* A1, double simtime, cudaStream_t st) {
   const GridD& g = c->g;
   for (int ax = 0; ax < g.ndim; ax++) {
-    bool mpi_face = false;
-    for (int s = 0; s < 2; s++) {
-      const int face = 2 * ax + s;
-      const int type = c->cfg.bc[face];
-      if (type == PION_BC_MPI) { mpi_face = true; continue; }
+    const int tlo = c->cfg.bc[2 * ax], thi = c->cfg.bc[2 * ax + 1];
+    const bool mpi_face = (tlo == PION_BC_MPI || thi == PION_BC_MPI);
+    if (tlo != PION_BC_MPI || thi != PION_BC_MPI) {  // at least one physical face: both in ONE launch
       BCArgs b;
-      fill_bc_args(c, b, face, type, A0, A1, simtime, c->bc_refval[face]);
-      k_bc_face<<<nblocks(face_cells(g, face), 128), 128, 0, st>>>(b);
+      fill_bc_args(c, b, 2 * ax, tlo, A0, A1, simtime, c->bc_refval[2 * ax]);
+      BCRef r2;
+      for (int v = 0; v < PION_MAXVAR; v++) r2.v[v] = c->bc_refval[2 * ax + 1][v];
+      k_bc_axis<<<nblocks(2 * face_cells(g, 2 * ax), 128), 128, 0, st>>>(b, thi, r2);
       c->launches++;
     }
     if (mpi_face) {
@@ -947,7 +948,7 @@ static void stage_tile_cells(const pion_gpu_ctx* c, int* cx, int* cy) {
 // one stage = one launch over the whole grid (box == nullptr), or one launch per box when the stage is
 // split into boundary shell + interior (only the first launch of a stage resets the dt minimum)
 static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double* dU, double dt, int order,
-                        bool fused, bool want_dt, const StageBox* box = nullptr, bool first_box = true,
+                        bool fused, bool want_dt, const StageBox* box = nullptr, int nbox = 0, bool first_box = true,
                         cudaStream_t st = nullptr) {
   if (!st) st = c->stream;
   StageArgs a;
@@ -981,7 +982,15 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
     a.tx0 = 0; a.tx1 = (c->g.NG[0] + cx - 1) / cx;
     a.ty0 = 0; a.ty1 = (c->g.NG[1] + cy - 1) / cy;
     a.k_lo = 0; a.k_hi = c->g.NG[2];
-    if (box) { a.tx0 = box->tx0; a.tx1 = box->tx1; a.ty0 = box->ty0; a.ty1 = box->ty1; a.k_lo = box->k_lo; a.k_hi = box->k_hi; }
+    a.nbox = 0;
+    if (box && nbox == 1) { a.tx0 = box->tx0; a.tx1 = box->tx1; a.ty0 = box->ty0; a.ty1 = box->ty1; a.k_lo = box->k_lo; a.k_hi = box->k_hi; }
+    if (box && nbox > 1) {  // several boxes, ONE launch (the sweep kernels decode their box from a table)
+      a.nbox = nbox;
+      for (int q = 0; q < nbox; q++) {
+        a.box[q][0] = box[q].tx0; a.box[q][1] = box[q].tx1; a.box[q][2] = box[q].ty0; a.box[q][3] = box[q].ty1;
+        a.box[q][4] = box[q].k_lo; a.box[q][5] = box[q].k_hi;
+      }
+    }
   }
   if (want_dt && first_box)
     CUDA_OK(cudaMemcpyAsync(c->d_dtmin, &DT_INIT_BITS, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
@@ -1078,12 +1087,14 @@ extern "C" int pion_gpu_grid_update_state_vector(pion_gpu_ctx* c, double dt, int
   return 0;
 }
 
-// One fused stage followed by its boundary update.  With a communicator (and no internal
-// boundaries) the stage is split: the tiles next to the six faces run first, then the boundary
-// update -- ghost-fill kernels and the NCCL halo exchange, axis by axis -- runs on the comm stream
-// WHILE the interior tiles run on the compute stream; the next stage waits for both.
-static int stage_and_bcs(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double dt, int order, bool want_dt,
-                         double* bcA0, double* bcA1) {
+// One fused stage followed by its boundary update.  With a communicator the stage is split: the tiles next
+// to the six faces (ONE launch over a table of six boxes) run first on the high-priority comm stream, then
+// the boundary update -- stellar-wind cells, ghost-fill kernels and the NCCL halo exchange, axis by axis --
+// runs there WHILE the interior tiles run on the compute stream; the next stage waits for both.
+// A stellar-wind internal boundary does not prevent the split: its cells are outside the domain (mask), hold
+// the same constant reference state in P and Ph at all times, and k_wind_set only rewrites those constants.
+static int stage_and_bcs_impl(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double dt, int order, bool want_dt,
+                              double* bcA0, double* bcA1) {
   int cx, cy;
   stage_tile_cells(c, &cx, &cy);
   const GridD& g = c->g;
@@ -1091,13 +1102,13 @@ static int stage_and_bcs(pion_gpu_ctx* c, const double* S, const double* Pb, dou
   // shell thickness in tiles: the last tile may hold fewer than the 2 cells the halo slab needs
   const int sxh = (g.NG[0] - (ntx - 1) * cx < 2) ? 2 : 1, syh = (g.NG[1] - (nty - 1) * cy < 2) ? 2 : 1;
   const int zs = 8;
-  int nmpi = 0;
+  int nmpi = 0, nint_other = 0;
   for (int f = 0; f < 6; f++) nmpi += (c->cfg.bc[f] == PION_BC_MPI);
-  // measured at 2 GPUs (one exchanged face): 53.50 ms/step split vs 53.74 ms unsplit.
-  // PION_B200_NO_OVERLAP=1 turns the split off (A/B tests).
+  for (int i = 0; i < c->cfg.n_internal_bc; i++) nint_other += (c->cfg.internal_bc[i] != PION_BC_STWIND);
   const bool want = c->force_overlap || nmpi >= 1;
-  const bool overlap = want && c->comm && c->cfg.n_internal_bc == 0 && g.ndim == 3 && g.coord == PION_COORD_CRT && !c->force_gather &&
+  const bool overlap = want && c->comm && nint_other == 0 && g.ndim == 3 && g.coord == PION_COORD_CRT && !c->force_gather &&
                        !c->no_overlap && ntx >= 2 + sxh && nty >= 2 + syh && NZ >= 3 * zs;
+  c->last_stage_split = overlap;
   if (!overlap) {
     if (launch_stage(c, S, Pb, out, nullptr, dt, order, true, want_dt)) return 1;
     return update_bcs_arrays(c, bcA0, bcA1, c->simtime);
@@ -1121,19 +1132,23 @@ static int stage_and_bcs(pion_gpu_ctx* c, const double* S, const double* Pb, dou
   // comm stream (high priority): shell tiles, then ghost fill + halo exchange; compute stream: interior
   CUDA_OK(cudaEventRecord(c->ev_a, c->stream));
   CUDA_OK(cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
-  for (int b = 0; b < 6; b++)
-    if (launch_stage(c, S, Pb, out, nullptr, dt, order, true, want_dt, &shell[b], false, c->comm_stream)) return 1;
-  if (launch_stage(c, S, Pb, out, nullptr, dt, order, true, want_dt, &interior, false, c->stream)) return 1;
-  if (c->timing) {
-    CUDA_OK(cudaEventRecord(e1, c->stream));
-    c->tev.push_back(e0);
-    c->tev.push_back(e1);
-    c->timing_suspended = false;
-  }
+  if (launch_stage(c, S, Pb, out, nullptr, dt, order, true, want_dt, shell, 6, false, c->comm_stream)) return 1;
+  if (launch_stage(c, S, Pb, out, nullptr, dt, order, true, want_dt, &interior, 1, false, c->stream)) return 1;
   if (update_bcs_arrays(c, bcA0, bcA1, c->simtime, c->comm_stream)) return 1;
   CUDA_OK(cudaEventRecord(c->ev_b, c->comm_stream));
   CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+  if (c->timing) {  // begin .. join: the whole split stage incl. the exchange it overlaps
+    CUDA_OK(cudaEventRecord(e1, c->stream));
+    c->tev.push_back(e0);
+    c->tev.push_back(e1);
+  }
   return 0;
+}
+static int stage_and_bcs(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double dt, int order, bool want_dt,
+                         double* bcA0, double* bcA1) {
+  const int err = stage_and_bcs_impl(c, S, Pb, out, dt, order, want_dt, bcA0, bcA1);
+  c->timing_suspended = false;  // also on the error paths
+  return err;
 }
 
 // time_integrator::advance_time (time_integrator.cpp:72-142), fused fast path.
@@ -1243,11 +1258,11 @@ extern "C" int pion_gpu_describe(pion_gpu_ctx* c, char* buf, int n) {
   int nmpi = 0;
   for (int f = 0; f < 6; f++) nmpi += (c->cfg.bc[f] == PION_BC_MPI);
   snprintf(buf, (size_t)n,
-           "stage_kernel=%s; tma_tensor_maps=%d; ranks=%d; exchanged_faces=%d; halo_overlap=%s; force_gather=%d; "
+           "stage_kernel=%s; tma_tensor_maps=%d; ranks=%d; exchanged_faces=%d; halo_overlap=%s; split_stage=%d; force_gather=%d; "
            "build=%s%s%s",
            c->last_stage_kernel, c->have_tmap ? 1 : 0, c->cfg.nproc > 0 ? c->cfg.nproc : 1, nmpi,
            c->no_overlap ? "off(PION_B200_NO_OVERLAP)" : c->force_overlap ? "forced(PION_B200_OVERLAP)" : "auto",
-           c->force_gather ? 1 : 0,
+           c->last_stage_split ? 1 : 0, c->force_gather ? 1 : 0,
 #ifdef PION_STRICT
            "PION_STRICT",
 #else
@@ -1293,14 +1308,16 @@ extern "C" int pion_gpu_nccl_init(pion_gpu_ctx* c, const char* unique_id128) {
 static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A, cudaStream_t st) {
   if (!c->comm) { set_error("BCMPI face but no NCCL communicator (call pion_gpu_nccl_init)"); return 1; }
   const GridD& g = c->g;
-  for (int s = 0; s < 2; s++) {
-    const int f = 2 * ax + s;
-    if (c->cfg.bc[f] != PION_BC_MPI) continue;
-    HaloArgs h;
-    h.g = g; h.A = A; h.buf = c->sendbuf[f]; h.face = f; h.nvar = c->nvar; h.pack = 1;
-    k_halo<<<nblocks((long)c->halo_elems[f], 256), 256, 0, st>>>(h);
-    c->launches++;
-  }
+  const int f0 = 2 * ax, f1 = 2 * ax + 1;
+  const bool m0 = c->cfg.bc[f0] == PION_BC_MPI, m1 = c->cfg.bc[f1] == PION_BC_MPI;
+  const size_t nmax = (m0 && m1) ? (c->halo_elems[f0] > c->halo_elems[f1] ? c->halo_elems[f0] : c->halo_elems[f1])
+                                 : (m0 ? c->halo_elems[f0] : c->halo_elems[f1]);
+  HaloArgs h;
+  h.g = g; h.A = A; h.face = f0; h.nvar = c->nvar;
+  // pack the slabs of both exchanged faces in one launch
+  h.buf = m0 ? c->sendbuf[f0] : nullptr; h.pack = 1;
+  k_halo_axis<<<nblocks((long)nmax, 256), 256, 0, st>>>(h, m1 ? c->sendbuf[f1] : nullptr);
+  c->launches++;
   // Sends go out in face order (N, P) and receives are posted in the opposite order
   // (P, N): when both neighbours of this axis are the SAME rank (2 ranks, periodic) NCCL
   // matches operations per peer in order, and the peer's N-side slab must land in our P
@@ -1318,14 +1335,9 @@ static int halo_exchange_axis(pion_gpu_ctx* c, int ax, double* A, cudaStream_t s
     NCCL_OK(ncclRecv(c->recvbuf[f], c->halo_elems[f], ncclDouble, c->cfg.ngbprocs[f], c->comm, st));
   }
   NCCL_OK(ncclGroupEnd());
-  for (int s = 0; s < 2; s++) {
-    const int f = 2 * ax + s;
-    if (c->cfg.bc[f] != PION_BC_MPI) continue;
-    HaloArgs h;
-    h.g = g; h.A = A; h.buf = c->recvbuf[f]; h.face = f; h.nvar = c->nvar; h.pack = 0;
-    k_halo<<<nblocks((long)c->halo_elems[f], 256), 256, 0, st>>>(h);
-    c->launches++;
-  }
+  h.buf = m0 ? c->recvbuf[f0] : nullptr; h.pack = 0;
+  k_halo_axis<<<nblocks((long)nmax, 256), 256, 0, st>>>(h, m1 ? c->recvbuf[f1] : nullptr);
+  c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -50,6 +50,11 @@ struct StageArgs {
   // sweep kernel only: the box of tiles / planes this launch covers (x tiles of 31 cells, y tiles of
   // TY-1 rows, z planes); the whole grid unless the stage is split into boundary shell + interior
   int tx0, tx1, ty0, ty1, k_lo, k_hi;
+  // ... or SEVERAL boxes in one launch (the boundary shell of a split stage: six boxes, one kernel): the grid is
+  // then 1-D, block b belongs to the box q with box_blk0[q] <= b < box_blk0[q+1] and decodes its tile there
+  int nbox;
+  int box[6][6];     // tx0, tx1, ty0, ty1, k_lo, k_hi per box
+  int box_blk0[7];
   // HOST pointer to the CUtensorMap of array S (TMA sweep kernel; null = not available)
   const void* tmap;
 };
@@ -429,6 +434,44 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
   }
 
   stage_block_epilogue(a, my_dt, status);
+}
+
+// The box of tiles / planes a block of the sweep kernels works on, and its tile coordinates inside it
+struct BlockBox {
+  int tx, ty, tz;      // tile coordinates (grid-absolute in x / y; chunk index in z)
+  int k_lo, k_hi;      // plane range of the box
+};
+__device__ __forceinline__ BlockBox sweep_block_box(const StageArgs& a) {
+  BlockBox b;
+  if (a.nbox == 0) {
+    b.tx = blockIdx.x + a.tx0; b.ty = blockIdx.y + a.ty0; b.tz = blockIdx.z; b.k_lo = a.k_lo; b.k_hi = a.k_hi;
+    return b;
+  }
+  int q = 0;
+  while (q + 1 < a.nbox && (int)blockIdx.x >= a.box_blk0[q + 1]) q++;
+  const int r = blockIdx.x - a.box_blk0[q];
+  const int nx = a.box[q][1] - a.box[q][0], ny = a.box[q][3] - a.box[q][2];
+  b.tx = a.box[q][0] + r % nx;
+  b.ty = a.box[q][2] + (r / nx) % ny;
+  b.tz = r / (nx * ny);
+  b.k_lo = a.box[q][4];
+  b.k_hi = a.box[q][5];
+  return b;
+}
+// host side: blocks of one box / fill box_blk0 and return the 1-D grid size
+inline int sweep_box_blocks(const int* bx, int kchunk) {
+  const int nx = bx[1] - bx[0], ny = bx[3] - bx[2], nz = bx[5] - bx[4];
+  if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
+  return nx * ny * ((nz + kchunk - 1) / kchunk);
+}
+inline int sweep_fill_box_table(StageArgs& a, int kchunk) {
+  int tot = 0;
+  for (int q = 0; q < a.nbox; q++) {
+    a.box_blk0[q] = tot;
+    tot += sweep_box_blocks(a.box[q], kchunk);
+  }
+  for (int q = a.nbox; q < 7; q++) a.box_blk0[q] = tot;
+  return tot;
 }
 
 // host-side launcher implemented per equation set in stage_{euler,mhd,glm}.cu

@@ -185,12 +185,13 @@ __global__ void __launch_bounds__(32 * TY, MINB) k_stage_sweep(const __grid_cons
   const GridD& g = a.g;
   const int NX = g.NG[0], NY = g.NG[1];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
-  int i = (blockIdx.x + a.tx0) * 31 + lane, j = (blockIdx.y + a.ty0) * (TY - 1) + row;
+  const BlockBox bb = sweep_block_box(a);
+  int i = bb.tx * 31 + lane, j = bb.ty * (TY - 1) + row;
   const bool row_active = (row < TY - 1) && (j < NY);               // warp-uniform
   const bool upd_xy = row_active && (lane < 31) && (i < NX);
   i = min(i, NX);  // clamped threads recompute a neighbour's (valid) face; their results are never used
   j = min(j, NY);
-  const int k0 = a.k_lo + blockIdx.z * kchunk, k1 = min(k0 + kchunk, a.k_hi);
+  const int k0 = bb.k_lo + bb.tz * kchunk, k1 = min(k0 + kchunk, bb.k_hi);
   const bool has_z = g.ndim > 2;
   const long vs = g.vs;
   const double idx = 1.0 / g.dx;
@@ -395,14 +396,24 @@ inline const char* launch_sweep_t(const StageArgs& a, cudaStream_t s) {
   static const char* nm[2] = {
       kernel_variant_name(name[0], sizeof name[0], "k_stage_sweep", EQ, SOLVER, FKJ, ",TR=0 (LDG stencil)"),
       kernel_variant_name(name[1], sizeof name[1], "k_stage_sweep", EQ, SOLVER, FKJ, ",TR=1 (LDG stencil)")};
-  if (bx <= 0 || by <= 0 || NZ <= 0) return nm[a.ntr > 0];
+  if (a.nbox == 0 && (bx <= 0 || by <= 0 || NZ <= 0)) return nm[a.ntr > 0];
   // z chunks: enough blocks to fill 148 SMs a few times over, long enough to amortise the extra flux plane
   int kchunk = NZ;
-  if (a.g.ndim > 2) {
+  dim3 grid;
+  StageArgs ab = a;
+  if (a.nbox > 0) {  // several boxes, one launch (3-D only): 1-D grid
     kchunk = 64;
-    while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
+    int tot = sweep_fill_box_table(ab, kchunk);
+    while (kchunk > 8 && tot < 148 * 4) { kchunk >>= 1; tot = sweep_fill_box_table(ab, kchunk); }
+    if (tot <= 0) return nm[a.ntr > 0];
+    grid = dim3(tot, 1, 1);
+  } else {
+    if (a.g.ndim > 2) {
+      kchunk = 64;
+      while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
+    }
+    grid = dim3(bx, by, (NZ + kchunk - 1) / kchunk);
   }
-  const int bz = (NZ + kchunk - 1) / kchunk;
   const size_t smem = (size_t)2 * (NB + PION_MAXTR) * TY * 32 * sizeof(double);
   const size_t smem_notr = (size_t)2 * NB * TY * 32 * sizeof(double);
   // the opt-in is per DEVICE: one flag per ordinal (a process may hold contexts on several GPUs)
@@ -413,8 +424,8 @@ inline const char* launch_sweep_t(const StageArgs& a, cudaStream_t s) {
     cudaFuncSetAttribute(k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_notr);
     attr_done[dev] = (dev != PION_MAX_DEVICES - 1);  // the overflow slot is never cached
   }
-  if (a.ntr > 0) k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, true><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, kchunk);
-  else k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, false><<<dim3(bx, by, bz), 32 * TY, smem_notr, s>>>(a, kchunk);
+  if (a.ntr > 0) k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, true><<<grid, 32 * TY, smem, s>>>(ab, kchunk);
+  else k_stage_sweep<EQ, SOLVER, FKJ, TY, MINB, false><<<grid, 32 * TY, smem_notr, s>>>(ab, kchunk);
   return nm[a.ntr > 0];
 }
 

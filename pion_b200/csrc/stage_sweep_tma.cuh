@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   const GridD& g = a.g;
   const int NX = g.NG[0], NY = g.NG[1];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
-  const int i0 = (blockIdx.x + a.tx0) * TMA_TX, j0 = (blockIdx.y + a.ty0) * (TY - 1);
+  const BlockBox bb = sweep_block_box(a);
+  const int i0 = bb.tx * TMA_TX, j0 = bb.ty * (TY - 1);
   // The LIGHT warp (row TY-1) updates no cells.  It produces the y fluxes through the tile's top edge (all
   // lanes), the x fluxes through the tile's high-x edge (lane r = row r, so that all 32 lanes of the
   // consumer rows update a cell), and its lane 0 issues the four TMA loads of the prologue (the refills are
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   const bool upd_xy = row_active && (i < NX);
   i = min(i, NX);  // global index only feeds the flag loads / Pb load of discarded threads
   j = min(j, NY);
-  const int k0 = a.k_lo + blockIdx.z * kchunk, k1 = min(k0 + kchunk, a.k_hi);
+  const int k0 = bb.k_lo + bb.tz * kchunk, k1 = min(k0 + kchunk, bb.k_hi);
   const int nk = k1 - k0;
   const long vs = g.vs;
   const double dt = a.dt;
@@ -543,10 +544,19 @@ inline const char* launch_sweep_tma_o(const StageArgs& a, cudaStream_t s) {
   static const char* nm = (snprintf(extra, sizeof extra, ",TY=%d,NTR=%d,ORDER=1|2 (TMA-staged stencil)", TY, NTR),
                            kernel_variant_name(name, sizeof name, "k_stage_sweep_tma", EQ, SOLVER, FKJ, extra));
   const int bx = a.tx1 - a.tx0, by = a.ty1 - a.ty0, NZ = a.k_hi - a.k_lo;
-  if (bx <= 0 || by <= 0 || NZ <= 0) return nm;
+  if (a.nbox == 0 && (bx <= 0 || by <= 0 || NZ <= 0)) return nm;
   int kchunk = PION_TMA_KCHUNK;
-  while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
-  const int bz = (NZ + kchunk - 1) / kchunk;
+  dim3 grid;
+  StageArgs ab = a;
+  if (a.nbox > 0) {  // several boxes, one launch: 1-D grid
+    int tot = sweep_fill_box_table(ab, kchunk);
+    while (kchunk > 8 && tot < 148 * 4) { kchunk >>= 1; tot = sweep_fill_box_table(ab, kchunk); }
+    if (tot <= 0) return nm;
+    grid = dim3(tot, 1, 1);
+  } else {
+    while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
+    grid = dim3(bx, by, (NZ + kchunk - 1) / kchunk);
+  }
   constexpr size_t smem = tma_smem_bytes(NV, TY);
   // the opt-in is per DEVICE: one flag per ordinal (a process may hold contexts on several GPUs)
   static bool attr_done[PION_MAX_DEVICES] = {false};
@@ -555,7 +565,7 @@ inline const char* launch_sweep_tma_o(const StageArgs& a, cudaStream_t s) {
     cudaFuncSetAttribute(k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done[dev] = (dev != PION_MAX_DEVICES - 1);  // the overflow slot is never cached
   }
-  k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR, ORDER><<<dim3(bx, by, bz), 32 * TY, smem, s>>>(a, *reinterpret_cast<const CUtensorMap*>(a.tmap), kchunk);
+  k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR, ORDER><<<grid, 32 * TY, smem, s>>>(ab, *reinterpret_cast<const CUtensorMap*>(a.tmap), kchunk);
   return nm;
 }
 template <int EQ, int SOLVER, bool FKJ, int NTR>

@@ -8,8 +8,17 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 
+def pytest_addoption(parser):
+    parser.addoption("--pion-lib", default=None,
+                     help="run the GPU tests against another build of libpion_b200.so (e.g. the -DPION_STRICT build)")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    lib = config.getoption("--pion-lib")
+    if lib:
+        from pion_b200.capi import load_library
+        load_library(str(Path(lib).resolve()))
 
 
 @pytest.fixture(scope="session", autouse=True)

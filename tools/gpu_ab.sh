@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 for lib in pion_b200/libpion_b200.so pion_b200/variants/*.so; do
   [ -f "$lib" ] || continue
   name=$(basename $lib .so)
-  timeout 600 python bench.py --lib $PWD/$lib --size $SIZE --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_${TAG}_$name.log 2>&1
+  timeout 600 python bench.py --lib $PWD/$lib --size $SIZE --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/ab_${TAG}_$name.log 2>&1
   echo "$name: $(grep -h '^{' gpurun_out/ab_${TAG}_$name.log | python -c "
 import sys, json
 for l in sys.stdin:
@@ -17,5 +17,5 @@ for l in sys.stdin:
 done
 if [ -n "$NCUV" ]; then
   lib=pion_b200/libpion_b200.so; [ "$NCUV" != default ] && lib=pion_b200/variants/$NCUV
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stage_sweep -s 6 -c 2 -o gpurun_out/prof_sweep_$TAG -f python bench.py --lib $PWD/$lib --size $SIZE --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_$TAG.log 2>&1; echo "ncu exit $?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stage_sweep -s 6 -c 2 -o gpurun_out/prof_sweep_$TAG -f python bench.py --lib $PWD/$lib --size $SIZE --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/ncu_$TAG.log 2>&1; echo "ncu exit $?"
 fi
