@@ -71,6 +71,9 @@ struct pion_oracle {
   double *tT, *t_rrhp, *t_Crrh, *t_Cffhe, *t_Cfbdn, *t_Ccie;
   double *s_rrhp, *s_Crrh, *s_Cffhe, *s_Cfbdn, *s_Ccie;
   int nT;
+  /* cooling_function_SD93CIE spline (EP.cooling 4..7): knots, natural-spline coefficients c = y''/2 */
+  int ns;
+  double *sx, *sy, *sc, s_minslope, s_maxslope;
   double mp_rho, mp_gamma; /* integrator "members" */
   /* stellar wind (grid/stellar_wind_BC.cpp): cells of every source in add order */
   long wind_n;
@@ -1281,7 +1284,7 @@ static int calc_dynamics_dU(pion_oracle *s, double dt, int step) {
 /* microphysics source term: mp_only_cooling + adaptive RKCK           */
 /* ------------------------------------------------------------------ */
 /* mp_only_cooling::Edot_WSS09CIE_heat_cool_metallines (mp_only_cooling.cpp:470-521) */
-static double mp_Edot(const pion_oracle *s, double rho, double T) {
+static double mp_Edot_metallines(const pion_oracle *s, double rho, double T) {
   size_t ihi = s->nT - 1, ilo = 0, imid = 0;
   do {
     imid = ilo + floor((ihi - ilo) / 2.0);
@@ -1297,6 +1300,77 @@ static double mp_Edot(const pion_oracle *s, double rho, double T) {
   rate -= (s->t_Cffhe[iT] + dT * s->s_Cffhe[iT]) * rho2 * s->inv_Mu2_elec_H;
   rate += 8.01e-12 * (s->t_rrhp[iT] + dT * s->s_rrhp[iT]) * rho2 * s->inv_Mu2_elec_H;
   return rate;
+}
+/* Natural cubic spline as the reference gets it from GSL's cspline (tools/interpolate.cpp:59-118): second
+ * derivatives c = y''/2 from the symmetric tridiagonal system (Thomas algorithm), evaluation by bisection +
+ * the cubic in (x - x_i).  Same arithmetic as oracle/shims/gsl_shim.c, which stands in for GSL in oracle/_ref. */
+static void spline_init(int n, const double *xa, const double *ya, double *c) {
+  int m = n - 2;
+  double *diag = (double *)malloc(m * sizeof(double)), *off = (double *)malloc(m * sizeof(double)),
+         *g = (double *)malloc(m * sizeof(double));
+  for (int i = 0; i < m; i++) {
+    double h_i = xa[i + 1] - xa[i], h_ip1 = xa[i + 2] - xa[i + 1];
+    double yd_i = ya[i + 1] - ya[i], yd_ip1 = ya[i + 2] - ya[i + 1];
+    off[i] = h_ip1;
+    diag[i] = 2.0 * (h_ip1 + h_i);
+    g[i] = 3.0 * (yd_ip1 / h_ip1 - yd_i / h_i);
+  }
+  for (int i = 1; i < m; i++) {
+    double w = off[i - 1] / diag[i - 1];
+    diag[i] -= w * off[i - 1];
+    g[i] -= w * g[i - 1];
+  }
+  c[0] = 0.0;
+  c[n - 1] = 0.0;
+  if (m > 0) {
+    c[m] = g[m - 1] / diag[m - 1];
+    for (int i = m - 1; i-- > 0;) c[i + 1] = (g[i] - off[i] * c[i + 2]) / diag[i];
+  }
+  free(diag); free(off); free(g);
+}
+static double spline_eval(const pion_oracle *s, double x) {
+  int lo = 0, hi = s->ns - 1;
+  while (hi > lo + 1) {
+    int mid = (lo + hi) / 2;
+    if (s->sx[mid] > x) hi = mid;
+    else lo = mid;
+  }
+  double dx = s->sx[lo + 1] - s->sx[lo], dy = s->sy[lo + 1] - s->sy[lo];
+  double c_i = s->sc[lo], c_ip1 = s->sc[lo + 1];
+  double b_i = dy / dx - dx * (c_ip1 + 2.0 * c_i) / 3.0;
+  double d_i = (c_ip1 - c_i) / (3.0 * dx);
+  double delx = x - s->sx[lo];
+  return s->sy[lo] + delx * (b_i + delx * (c_i + delx * d_i));
+}
+/* cooling_function_SD93CIE::cooling_rate_SD93CIE (cooling_SD93_cie.cpp:666-704) */
+static double mp_rate_SD93CIE(const pion_oracle *s, double T) {
+  if (T < 0.0 || !isfinite(T)) return HUGE_VAL;
+  double rate = 0.0;
+  T = log10(T);
+  const double MinTemp = s->sx[0], MaxTemp = s->sx[s->ns - 1];
+  if (T > MaxTemp) rate = s->sy[s->ns - 1] + s->s_maxslope * (T - MaxTemp);
+  else if (T < MinTemp) rate = s->sy[0] + s->s_minslope * (T - MinTemp);
+  else rate = spline_eval(s, T);
+  return exp(2.3025850929940459 * rate); /* pconst.ln10(), constants.h:44 */
+}
+/* mp_only_cooling::Edot (mp_only_cooling.cpp:383-420) and the Edot_* it dispatches to (:427-521);
+ * KI02: CoolingFn::CoolingRate with WhichFunction 2 (cooling.cpp:325-399, MinTemp 5 K) */
+static double mp_Edot(const pion_oracle *s, double rho, double T) {
+  switch (s->cfg.cooling) {
+    case 2: {
+      const double nH = rho / s->Mu;
+      if (T <= 0.0 || isnan(T) || isinf(T)) return -0.0;
+      double rate = 0.0;
+      if (T > 5.0) rate += nH * nH * (2.0e-19 * exp(-1.184e5 / (T + 1.0e3)) + 2.8e-28 * sqrt(T) * exp(-92.0 / T));
+      rate -= nH * 2.0e-26;
+      return -rate;
+    }
+    case 4: return -(rho * rho / s->Mu_elec / s->Mu_ion) * mp_rate_SD93CIE(s, T);
+    case 5: return (rho * rho) * (2.733e-21 * exp(-0.782991 * log(T)) / s->Mu_elec / s->Mu - mp_rate_SD93CIE(s, T) / s->Mu_elec / s->Mu_ion);
+    case 7: return 2e-26 * rho / s->Mu - (rho * rho / s->Mu / s->Mu) * mp_rate_SD93CIE(s, T);
+    case 6: return (rho * rho) * (2.733e-21 * exp(-0.782991 * log(T)) / s->Mu_elec / s->Mu - mp_rate_SD93CIE(s, T) / s->Mu / s->Mu);
+    default: return mp_Edot_metallines(s, rho, T);
+  }
 }
 /* mp_only_cooling::dPdt (:227-236) */
 static inline double mp_dPdt(const pion_oracle *s, double E) {
@@ -2047,7 +2121,18 @@ pion_oracle *po_create(const pion_oracle_config *cfg) {
     s->MinT = cfg->min_temperature;
     if (s->MinT < 1.0 || s->MinT > 1.0e6) s->MinT = 1.0;
     if (s->MaxT < 1.0e2 || s->MaxT > 3.0e10) s->MaxT = 1.0e8;
-    int nT = cfg->n_table;
+    if (cfg->cooling >= 4 && cfg->cooling <= 7) {
+      s->ns = cfg->n_spline;
+      s->sx = (double *)malloc(s->ns * sizeof(double));
+      s->sy = (double *)malloc(s->ns * sizeof(double));
+      s->sc = (double *)calloc(s->ns, sizeof(double));
+      memcpy(s->sx, cfg->spline_logT, s->ns * sizeof(double));
+      memcpy(s->sy, cfg->spline_logL, s->ns * sizeof(double));
+      s->s_minslope = cfg->spline_min_slope;
+      s->s_maxslope = cfg->spline_max_slope;
+      spline_init(s->ns, s->sx, s->sy, s->sc);
+    }
+    int nT = (cfg->cooling == 8) ? cfg->n_table : 0;
     s->nT = nT;
     double **dst[6] = {&s->tT, &s->t_rrhp, &s->t_Crrh, &s->t_Cffhe, &s->t_Cfbdn, &s->t_Ccie};
     const double *src[6] = {cfg->table_T, cfg->table_rrhp, cfg->table_C_rrh, cfg->table_C_ffhe, cfg->table_C_fbdn, cfg->table_C_cie};
@@ -2073,6 +2158,7 @@ void po_destroy(pion_oracle *s) {
   for (int i = 0; i < s->nbcs; i++) { free(s->bcs[i].cell); free(s->bcs[i].npt); free(s->bcs[i].isedge); }
   free(s->tT); free(s->t_rrhp); free(s->t_Crrh); free(s->t_Cffhe); free(s->t_Cfbdn); free(s->t_Ccie);
   free(s->s_rrhp); free(s->s_Crrh); free(s->s_Cffhe); free(s->s_Cfbdn); free(s->s_Ccie);
+  free(s->sx); free(s->sy); free(s->sc);
   free(s);
 }
 

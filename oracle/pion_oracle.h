@@ -63,7 +63,8 @@ typedef struct pion_oracle_config {
   int op_criterion;   /* 1: limit dt to hit opfreq_time multiples (sim_init.cpp:270) */
   double opfreq_time;
   /* microphysics: mp_only_cooling (cooling>0 && no chemistry) */
-  int cooling;        /* EP.cooling flag, 0 = none, 8 = WSS09_CIE_LINE_HEAT_COOL */
+  int cooling;        /* EP.cooling flag of mp_only_cooling.cpp:42-48: 0 none, 2 KI02, 4 SD93_CIE, 5 SD93_PLUS_HEATING,
+                         6 WSS09_CIE_PLUS_HEATING, 7 WSS09_CIE_ONLY_COOLING, 8 WSS09_CIE_LINE_HEAT_COOL */
   int mp_timestep_limit;
   double min_temperature, max_temperature;
   int n_table;        /* 200 */
@@ -71,6 +72,12 @@ typedef struct pion_oracle_config {
   /* internal boundary PO_BC_STWIND: constant wind sources (SWP, sim_params.h) */
   int n_wind;
   po_wind_source wind[2];
+  /* EP.cooling 4..7: knots of the cooling-curve spline of cooling_function_SD93CIE (log10 T, log10 Lambda:
+   * Tarray / Larray after setup_SD93_cie() [4, 5] or setup_WSS09_CIE() [6, 7]) and its power-law slopes
+   * outside the table (cooling_SD93_cie.cpp:87-200,555-660) */
+  int n_spline;
+  const double *spline_logT, *spline_logL;
+  double spline_min_slope, spline_max_slope;
 } pion_oracle_config;
 
 typedef struct pion_oracle pion_oracle;

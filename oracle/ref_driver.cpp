@@ -28,6 +28,13 @@
 #include <string>
 #include <vector>
 
+// The knots of the reference's cooling-curve spline are private data members of cooling_function_SD93CIE and
+// the class has no accessor; the tree is read-only here, so the harness opens this ONE header up to read them
+// (pref_cooling_spline below).  All standard headers are included above, nothing else is affected.
+#define private public
+#include "microphysics/cooling_SD93_cie.h"
+#undef private
+
 #include "defines/functionality_flags.h"
 #include "defines/testing_flags.h"
 #include "sim_constants.h"
@@ -421,6 +428,23 @@ int pref_cooling_tables(void *h, int n, double *T, double *rrhp, double *C_rrh, 
     C_cie[i] = mp->cooling_rate_SD93CIE(T[i]);
   }
   return 0;
+}
+
+// Knots (log10 T, log10 Lambda) and out-of-table slopes of the cooling-curve spline the reference's MP object
+// set up (cooling_function_SD93CIE: setup_SD93_cie for EP_cooling 2..5, setup_WSS09_CIE for 6, 7,
+// setup_WSS09_CIE_OnlyMetals for 8), so that the oracle port and the GPU library are fed the reference's own
+// table.  slopes[0] = MinSlope, slopes[1] = MaxSlope.  Returns the number of knots (arrays may be null).
+int pref_cooling_spline(void *h, double *logT, double *logL, double *slopes) {
+  (void)h;
+  class cooling_function_SD93CIE *cf = dynamic_cast<class cooling_function_SD93CIE *>(MP);
+  if (!cf) return 0;
+  const int n = cf->Nspl;
+  for (int i = 0; i < n; i++) {
+    if (logT) logT[i] = cf->Tarray[i];
+    if (logL) logL[i] = cf->Larray[i];
+  }
+  if (slopes) { slopes[0] = cf->MinSlope; slopes[1] = cf->MaxSlope; }
+  return n;
 }
 
 }  // extern "C"

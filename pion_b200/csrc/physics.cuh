@@ -829,6 +829,18 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
       flux.erg -= ergvisc;
     }
   } else {
+    // FV_solver_mhd_ideal_adi::AVFalle (solver_eqn_mhd_adi.cpp:209-288) works on the ORIGINAL edge states
+    // (InterCellFlux passes lp, rp) and on pstar.  Everything it needs from the edge states is formed HERE,
+    // before the Riemann solver -- the fast speed of the mean state (one scalar) and the five jumps -- so that
+    // the edge states themselves are dead once the solver has consumed them (ptxas, capped at 128 registers,
+    // spilled 150 bytes per thread to keep them alive across it).
+    double fkj_c = 0.0, dvn = 0.0, dvt1 = 0.0, dvt2 = 0.0, dbt1 = 0.0, dbt2 = 0.0;
+    if (FKJ) {
+      fkj_c = cfast_components(0.5 * (eL.ro + eR.ro), 0.5 * (eL.pg + eR.pg), 0.5 * (eL.bn + eR.bn),
+                               0.5 * (eL.bt1 + eR.bt1), 0.5 * (eL.bt2 + eR.bt2), pp.gamma) * pp.etav;
+      dvn = eR.vn - eL.vn; dvt1 = eR.vt1 - eL.vt1; dvt2 = eR.vt2 - eL.vt2;
+      dbt1 = eR.bt1 - eL.bt1; dbt2 = eR.bt2 - eL.bt2;
+    }
     // GLM: Dedner 2x2 star state, Bx := Bx*, psi := 0 in the states handed to
     // the ideal-MHD solver (solver_eqn_mhd_adi.cpp:726-742)
     Prim l = eL, r = eR;
@@ -859,25 +871,21 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
       flux.psi = pp.chyp * bxstar;
     }
     if (FKJ) {
-      // FV_solver_mhd_ideal_adi::AVFalle (solver_eqn_mhd_adi.cpp:209-288) on the
-      // ORIGINAL edge states (InterCellFlux passes lp,rp)
-      double prefactor = cfast_components(0.5 * (eL.ro + eR.ro), 0.5 * (eL.pg + eR.pg), 0.5 * (eL.bn + eR.bn),
-                                          0.5 * (eL.bt1 + eR.bt1), 0.5 * (eL.bt2 + eR.bt2), pp.gamma) *
-                         pp.etav * pstar.ro;
-      double momvisc = prefactor * (eR.vn - eL.vn);
+      double prefactor = fkj_c * pstar.ro;
+      double momvisc = prefactor * dvn;
       double ergvisc = momvisc * pstar.vn;
       flux.mn -= momvisc;
-      momvisc = prefactor * (eR.vt1 - eL.vt1);
+      momvisc = prefactor * dvt1;
       flux.mt1 -= momvisc;
       ergvisc += momvisc * pstar.vt1;
-      momvisc = prefactor * (eR.vt2 - eL.vt2);
+      momvisc = prefactor * dvt2;
       flux.mt2 -= momvisc;
       ergvisc += momvisc * pstar.vt2;
       prefactor *= pdiv(pp.etav, pp.etav * pstar.ro);
-      momvisc = prefactor * (eR.bt1 - eL.bt1);
+      momvisc = prefactor * dbt1;
       flux.bbt1 -= momvisc;
       ergvisc += momvisc * pstar.bt1;
-      momvisc = prefactor * (eR.bt2 - eL.bt2);
+      momvisc = prefactor * dbt2;
       flux.bbt2 -= momvisc;
       ergvisc += momvisc * pstar.bt2;
       flux.erg -= ergvisc;

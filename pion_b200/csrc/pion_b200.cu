@@ -965,6 +965,9 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   a.eta = c->eta;
   a.mask = c->mask;
   a.dt = dt;
+  a.idx = 1.0 / c->g.dx;
+  a.dtdx = dt * a.idx;
+  a.hdtdx = 0.5 * dt * a.idx;
   a.tiny2 = PION_VERY_TINY_VALUE * c->g.dx * c->g.dx;
   a.glm_damp = exp(-dt * c->chyp * c->cr);  // eqns_mhd_adiabatic.cpp:650-660 with FV_dt
   a.cfl = c->cfg.cfl;

@@ -38,6 +38,7 @@ struct StageArgs {
   const double* eta;         // H-correction eta, 3 planes of vs doubles (null unless AV 3/4)
   const unsigned char* mask; // 1 = cell is updated (isdomain); null = every interior cell
   double dt;          // stage dt == FV_dt
+  double idx, dtdx, hdtdx;  // 1/dx, dt/dx, dt/(2 dx): launch constants (kernel-parameter bank operands, no registers)
   double tiny2;       // VERY_TINY_VALUE * dx^2 (minmod cut-off for undivided differences)
   double glm_damp;    // exp(-FV_dt * c_h * c_r)
   double cfl;

@@ -63,6 +63,11 @@ __device__ __forceinline__ void mbar_wait_spin(unsigned long long* bar, unsigned
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#ifdef PION_SPIN_SLEEP
+    // a failed try costs three issue slots (YIELD, SYNCS, BRA) the other warps of the sub-partition could use:
+    // ncu counted ~70 tries per wait.  Sleep a little between tries instead.
+    if (!ok) __nanosleep(PION_SPIN_SLEEP);
+#endif
   } while (!ok);
 }
 __device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* map, unsigned long long* bar, int x, int y, int z) {
@@ -267,13 +272,11 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   const int k0 = bb.k_lo + bb.tz * kchunk, k1 = min(k0 + kchunk, bb.k_hi);
   const int nk = k1 - k0;
   const long vs = g.vs;
-  const double dt = a.dt;
-  const double idx = 1.0 / g.dx;
-#ifndef PION_STRICT
-  const double dtdx = dt * idx, hdtdx = 0.5 * dt * idx;
-#else
-  const double dtdx = 0.0, hdtdx = 0.0;
-#endif
+  // (dt, 1/dx, dt/dx, dt/2dx are read from the kernel-parameter bank where they are used)
+#define dt (a.dt)
+#define idx (a.idx)
+#define dtdx (a.dtdx)
+#define hdtdx (a.hdtdx)
   double my_dt = 1.0e100;
   int status = 0;
   const bool producer = light && (lane == 0);
@@ -522,6 +525,10 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   }
 
 #undef PION_ACCTR
+#undef dt
+#undef idx
+#undef dtdx
+#undef hdtdx
   stage_block_epilogue(a, my_dt, status);
 }
 

@@ -297,6 +297,17 @@ class RefSim(_CSim):
         assert err == 0, "reference has no mp_only_cooling object"
         return arrs
 
+    def cooling_spline(self):
+        """Knots and out-of-table slopes of the reference MP object's cooling-curve spline
+        (pref_cooling_spline in oracle/ref_driver.cpp)."""
+        self.lib.pref_cooling_spline.restype = C.c_int
+        self.lib.pref_cooling_spline.argtypes = [C.c_void_p] * 4
+        n = self.lib.pref_cooling_spline(self.h, None, None, None)
+        assert n > 2, "reference has no cooling_function_SD93CIE object"
+        x, y, sl = np.zeros(n), np.zeros(n), np.zeros(2)
+        self.lib.pref_cooling_spline(self.h, x.ctypes.data, y.ctypes.data, sl.ctypes.data)
+        return {"spline_logT": x, "spline_logL": y, "spline_slopes": sl}
+
     def intercell_flux(self, axis, Pl, Pr, divv_l=0.0, gradp_l=0.0, divv_r=0.0, gradp_r=0.0):
         Pl = np.ascontiguousarray(Pl, dtype=np.float64)
         Pr = np.ascontiguousarray(Pr, dtype=np.float64)
@@ -329,7 +340,22 @@ class _OracleConfig(C.Structure):
         ("table_T", C.c_void_p), ("table_rrhp", C.c_void_p), ("table_C_rrh", C.c_void_p),
         ("table_C_ffhe", C.c_void_p), ("table_C_fbdn", C.c_void_p), ("table_C_cie", C.c_void_p),
         ("n_wind", C.c_int), ("wind", WindSource * 2),
+        ("n_spline", C.c_int), ("spline_logT", C.c_void_p), ("spline_logL", C.c_void_p),
+        ("spline_min_slope", C.c_double), ("spline_max_slope", C.c_double),
     ]
+
+
+def fill_spline(c, tables, keep):
+    """tables["spline_logT" / "spline_logL" / "spline_slopes"] -> the n_spline / spline_* members shared by the
+    oracle and the GPU config (EP_cooling 4..7)."""
+    if tables is None or "spline_logT" not in tables:
+        return
+    x = np.ascontiguousarray(tables["spline_logT"], dtype=np.float64)
+    y = np.ascontiguousarray(tables["spline_logL"], dtype=np.float64)
+    keep += [x, y]
+    c.n_spline = len(x)
+    c.spline_logT, c.spline_logL = x.ctypes.data, y.ctypes.data
+    c.spline_min_slope, c.spline_max_slope = float(tables["spline_slopes"][0]), float(tables["spline_slopes"][1])
 
 
 def fill_winds(c, prob):
@@ -378,13 +404,14 @@ def oracle_config(prob: Problem, tables=None):
     c.min_temperature, c.max_temperature = prob.min_temperature, prob.max_temperature
     fill_winds(c, prob)
     keep = []
-    if tables is not None:
+    if tables is not None and "T" in tables:
         c.n_table = len(tables["T"])
         for name, key in [("table_T", "T"), ("table_rrhp", "rrhp"), ("table_C_rrh", "C_rrh"),
                           ("table_C_ffhe", "C_ffhe"), ("table_C_fbdn", "C_fbdn"), ("table_C_cie", "C_cie")]:
             arr = np.ascontiguousarray(tables[key], dtype=np.float64)
             keep.append(arr)
             setattr(c, name, arr.ctypes.data)
+    fill_spline(c, tables, keep)
     return c, keep
 
 
@@ -540,6 +567,36 @@ def rel_err(a, b, scale=None, primitive=True, nphys=None):
     return np.array(errs)
 
 
+def ulp_response(prob: Problem, P0, nsteps, seeds=(1, 2, 3), sim=None):
+    """How far the REFERENCE algorithm's own answer moves when its input moves by one unit in the last place:
+    max over `seeds` of rel_err(run(P0 with rho, p, B_x each multiplied by 1 + {-1,0,1} x 1.1e-16), run(P0)) per
+    variable, with the CPU checker (`sim`, default OracleSim -- bit-exact with the compiled reference).  Discrete
+    decisions in the scheme (HLLD fan region, HLLD -> HLL switch, minmod sign tests) make some states --
+    exact symmetries, exact zeros, strong discontinuities -- respond to rounding noise at 1e-11..1e-9 within a few
+    steps; a GPU/CPU difference below that level is not a defect of either."""
+    sim = sim or OracleSim
+
+    def run(P):
+        o = sim(prob)
+        o.set_state(P)
+        o.init_after_state()
+        o.run(nsteps)
+        R = o.get_state(0)
+        o.close()
+        return R
+
+    base = run(P0)
+    nphys = EQN_NVAR[prob.eqn]
+    resp = np.zeros(prob.nvar)
+    for seed in seeds:
+        rng = np.random.default_rng(seed)
+        P1 = np.array(P0, copy=True)
+        for v in (0, 1, 5) if nphys >= 8 else (0, 1):
+            P1[v] *= 1.0 + rng.integers(-1, 2, size=P1[v].shape) * 1.1e-16
+        resp = np.maximum(resp, rel_err(run(P1), base, nphys=nphys))
+    return resp, base
+
+
 # --------------------------------------------------------------------------
 def gpu_config(prob: Problem, device=0, tables=None):
     """Problem -> struct pion_gpu_config of the product library."""
@@ -572,13 +629,14 @@ def gpu_config(prob: Problem, device=0, tables=None):
     c.rank, c.nproc = 0, 1
     fill_winds(c, prob)
     keep = []
-    if tables is not None:
+    if tables is not None and "T" in tables:
         c.n_table = len(tables["T"])
         for name, key in [("table_T", "T"), ("table_rrhp", "rrhp"), ("table_C_rrh", "C_rrh"),
                           ("table_C_ffhe", "C_ffhe"), ("table_C_fbdn", "C_fbdn"), ("table_C_cie", "C_cie")]:
             arr = np.ascontiguousarray(tables[key], dtype=np.float64)
             keep.append(arr)
             setattr(c, name, arr.ctypes.data)
+    fill_spline(c, tables, keep)
     return c, keep
 
 

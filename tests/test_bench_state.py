@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT))
 
 from bench import divb_norm, dte_problem, dte_state  # noqa: E402  (the bench's own generators: the SAME state)
 from cases import case_2d, case_3d  # noqa: E402
-from harness import GpuSim, OracleSim, RefSim, have_ref, random_state, rel_err  # noqa: E402
+from harness import GpuSim, OracleSim, RefSim, have_ref, random_state, rel_err, ulp_response  # noqa: E402
 from test_golden import load  # noqa: E402
 
 L = 3.086e19
@@ -67,30 +67,55 @@ def test_output_time_limiter_runs_across_output_intervals_cpu():
 
 
 # ---------------------------------------------------------------- GPU
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_bench_state_conditioning_is_what_design_md_says():
+    """The state bench.py times is a static, symmetric medium with a x200 pressure discontinuity: the reference's
+    OWN answer moves by ~1e-11..1e-10 (relative, transverse velocity / field) after a handful of steps when its
+    input moves by one ulp -- discrete decisions (HLLD fan region, HLLD -> HLL switch, minmod) acting on
+    rounding noise.  This is why the GPU tests on this state are stated against that response, not against 5e-12."""
+    prob, P0 = dte_case(32)
+    resp, _ = ulp_response(prob, P0, 5, seeds=(1,), sim=RefSim)
+    assert resp[:3].max() < 1e-13  # density, pressure, v_x: well conditioned
+    assert 1e-13 < resp[3:5].max() < 1e-8  # transverse velocities: rounding noise amplified by ~1e5
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [64, 96])
-def test_gpu_matches_reference_on_the_bench_state(n):
-    """64^3 = 2 x 6 tiles x 1 chunk, 96^3 = 3 x 9 tiles x 3 chunks of the TMA sweep kernel; >= 5 steps."""
+@pytest.mark.parametrize("n,nsteps", [(64, 5), (64, 6), (96, 5)])
+def test_gpu_matches_reference_on_the_bench_state(n, nsteps):
+    """64^3 = 2 x 6 tiles x 1 chunk, 96^3 = 3 x 9 tiles x 3 chunks of the TMA sweep kernel; >= 5 steps.
+    Bound per variable: 5e-12 + 5 x (the reference's own response to a one-ulp change of its input, see
+    test_bench_state_conditioning_is_what_design_md_says); dt sequences agree to 1e-13."""
     prob, P0 = dte_case(n)
-    ref = RefSim(prob) if have_ref() else OracleSim(prob)
+    resp, Pr = ulp_response(prob, P0, nsteps)  # oracle: bit-exact with the compiled reference on this state
+    if have_ref():
+        ref = RefSim(prob)
+        ref.set_state(P0)
+        ref.init_after_state()
+        dr = ref.run(nsteps)
+        assert np.array_equal(ref.get_state(0), Pr)
+        ref.close()
+    else:
+        o = OracleSim(prob)
+        o.set_state(P0)
+        o.init_after_state()
+        dr = o.run(nsteps)
+        o.close()
     gpu = GpuSim(prob)
     try:
-        for s in (ref, gpu):
-            s.set_state(P0)
-            s.init_after_state()
-        nsteps = 6 if n == 64 else 5
-        dr, dg = ref.run(nsteps), gpu.run(nsteps)
+        gpu.set_state(P0)
+        gpu.init_after_state()
+        dg = gpu.run(nsteps)
         assert np.allclose(dr, dg, rtol=1e-13, atol=0), (dr, dg)
-        Pr, Pg = ref.get_state(0), gpu.get_state(0)
+        Pg = gpu.get_state(0)
         assert np.max(np.abs(Pr[2:5])) > 0.0  # the sphere has started to expand
         err = rel_err(Pg, Pr, nphys=9)
-        assert err.max() < TOL, err
+        print(f"DTE {n}^3 x {nsteps} steps: GPU-vs-reference {err}, reference 1-ulp response {resp}")
+        assert np.all(err <= TOL + 5.0 * resp), (err, resp)
         assert gpu.error_counts() == [0, 0]
         assert "k_stage_sweep_tma<EQ=3,SOLVER=7,FKJ=1" in gpu.ctx.describe(), gpu.ctx.describe()
         # div B (reported by bench.py): the GPU run's is the reference run's
         assert abs(divb_norm(Pg, prob) - divb_norm(Pr, prob)) < 1e-9
     finally:
-        ref.close()
         gpu.close()
 
 
