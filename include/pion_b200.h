@@ -80,7 +80,8 @@ typedef struct pion_gpu_config {
   int op_criterion;    /* SimPM.op_criterion, 1: dt limited by next_optime */
   double opfreq_time;
   /* microphysics: mp_only_cooling (EP.cooling && !EP.chemistry) */
-  int cooling;         /* EP.cooling (0 none, 8 = WSS09_CIE_LINE_HEAT_COOL) */
+  int cooling;         /* EP.cooling (mp_only_cooling.cpp:42-48): 0 none, 2 KI02, 4 SD93_CIE, 5 SD93_PLUS_HEATING,
+                          6 WSS09_CIE_PLUS_HEATING, 7 WSS09_CIE_ONLY_COOLING, 8 WSS09_CIE_LINE_HEAT_COOL */
   int mp_timestep_limit;
   double min_temperature, max_temperature;
   int n_table;
@@ -93,6 +94,12 @@ typedef struct pion_gpu_config {
   int n_wind;
   pion_gpu_wind_source wind[2];
   double min_timestep; /* SimPM.min_timestep (sim_params.h:227): calculate_timestep fails if dt falls below it */
+  /* EP.cooling 4..7: the knots (log10 T, log10 Lambda) of cooling_function_SD93CIE's cooling-curve spline --
+   * Tarray / Larray after setup_SD93_cie() [4, 5] or setup_WSS09_CIE() [6, 7] -- and its power-law slopes outside
+   * the table (microphysics/cooling_SD93_cie.cpp:87-200,555-704); n_table / table_* are for EP.cooling 8 only */
+  int n_spline;
+  const double *spline_logT, *spline_logL;
+  double spline_min_slope, spline_max_slope;
 } pion_gpu_config;
 
 typedef struct pion_gpu_ctx pion_gpu_ctx;

@@ -39,6 +39,8 @@ class GpuConfig(C.Structure):
         ("rank", C.c_int), ("nproc", C.c_int), ("ngbprocs", C.c_int * 6),
         ("n_wind", C.c_int), ("wind", WindSource * 2),
         ("min_timestep", C.c_double),
+        ("n_spline", C.c_int), ("spline_logT", C.c_void_p), ("spline_logL", C.c_void_p),
+        ("spline_min_slope", C.c_double), ("spline_max_slope", C.c_double),
     ]
 
 

@@ -1,11 +1,16 @@
 // pion_b200/csrc/cooling.cuh -- per-cell radiative cooling source term
-// (microphysics without chemistry: mp_only_cooling with EP_cooling = 8).
+// (microphysics without chemistry: mp_only_cooling, every cooling function its Edot dispatches to).
 //
 // Reference path restated (paths relative to /root/reference/source):
 //   sim_control/time_integrator.cpp:438-489   calc_noRT_microphysics_dU: for every isdomain
 //                                             cell  dU += PtoU(TimeUpdateMP(P, dt)) - PtoU(P)
 //   microphysics/mp_only_cooling.cpp:167-221  TimeUpdateMP (integrates from the UNCLAMPED
 //                                             Eint0; T clamp applied to the result)
+//   microphysics/mp_only_cooling.cpp:383-420  Edot: dispatch on EP_cooling (2, 4, 5, 6, 7, 8)
+//   microphysics/mp_only_cooling.cpp:427-468  Edot_SD93CIE_cool / _heat_cool, Edot_WSS09CIE_cool / _heat_cool
+//   microphysics/cooling_SD93_cie.cpp:666-704 cooling_rate_SD93CIE: natural cubic spline in (log10 T, log10 Lambda),
+//                                             power laws outside the table
+//   microphysics/cooling.cpp:325-399          CoolingFn::CoolingRate, WhichFunction 2 (KI02)
 //   microphysics/mp_only_cooling.cpp:470-521  Edot_WSS09CIE_heat_cool_metallines: binary
 //                                             search in the 200-point T table + linear interp.
 //   microphysics/mp_only_cooling.cpp:333-358  timescales (cooling time)
@@ -25,13 +30,19 @@
 namespace pion {
 
 struct CoolParams {
-  const double* tables;  // device: [11][nT] = T, rrhp, C_rrh, C_ffhe, C_fbdn, C_cie, then the 5 slopes
+  // device tables.  EP_cooling 8: [11][nT] = T, rrhp, C_rrh, C_ffhe, C_fbdn, C_cie, then the 5 slopes;
+  // EP_cooling 4..7: [3][nT] = spline knots x = log10 T, y = log10 Lambda, c = y''/2 (natural spline); 2: none
+  const double* tables;
   int nT;
+  int mode;  // EP_cooling
   double inv_Mu2, inv_Mu2_elec_H, Mu_tot_over_kB, MinT, MaxT;
+  double Mu, Mu_elec, Mu_ion, smin, smax;  // mean masses; spline slopes below / above the table
 };
 
-// dynamic shared memory of the cooling kernels: the 11 table columns
-inline size_t cool_smem_bytes(const CoolParams& cp) { return 11 * (size_t)cp.nT * sizeof(double); }
+// columns of the device table per cooling function
+__host__ __device__ inline int cool_ncol(int mode) { return mode == 8 ? 11 : (mode >= 4 && mode <= 7) ? 3 : 0; }
+// dynamic shared memory of the cooling kernels: the table columns
+inline size_t cool_smem_bytes(const CoolParams& cp) { return (size_t)cool_ncol(cp.mode) * cp.nT * sizeof(double); }
 
 struct CoolArgs {
   GridD g;
@@ -50,10 +61,12 @@ struct CoolTab {
   const double *T, *rrhp, *Crrh, *Cffhe, *Cfbdn, *Ccie, *s_rrhp, *s_Crrh, *s_Cffhe, *s_Cfbdn, *s_Ccie;
   int nT;
   double inv_Mu2, inv_Mu2_elec_H;
+  int mode;
+  double Mu, Mu_elec, Mu_ion, smin, smax;
 };
 
 __device__ __forceinline__ CoolTab cool_tables_to_smem(const CoolParams& cp, double* s) {
-  for (int t = threadIdx.x; t < 11 * cp.nT; t += blockDim.x) s[t] = cp.tables[t];
+  for (int t = threadIdx.x; t < cool_ncol(cp.mode) * cp.nT; t += blockDim.x) s[t] = cp.tables[t];
   __syncthreads();
   CoolTab ct;
   const int n = cp.nT;
@@ -62,11 +75,71 @@ __device__ __forceinline__ CoolTab cool_tables_to_smem(const CoolParams& cp, dou
   ct.nT = n;
   ct.inv_Mu2 = cp.inv_Mu2;
   ct.inv_Mu2_elec_H = cp.inv_Mu2_elec_H;
+  ct.mode = cp.mode;
+  ct.Mu = cp.Mu; ct.Mu_elec = cp.Mu_elec; ct.Mu_ion = cp.Mu_ion; ct.smin = cp.smin; ct.smax = cp.smax;
   return ct;
 }
 
-// mp_only_cooling::Edot_WSS09CIE_heat_cool_metallines (mp_only_cooling.cpp:470-521)
+// cooling_function_SD93CIE::cooling_rate_SD93CIE (cooling_SD93_cie.cpp:666-704): Lambda(T) from the natural cubic
+// spline through (log10 T, log10 Lambda) -- GSL cspline evaluation: bisection for the interval, then the cubic in
+// (x - x_i) with b_i, d_i formed from the second-derivative coefficients (tools/interpolate.cpp:59-118) -- and the
+// power laws beyond the ends of the table.  Columns (CoolTab): T = x, rrhp = y, Crrh = c.
+__device__ __forceinline__ double cool_rate_SD93CIE(const CoolTab& t, double T) {
+  if (T < 0.0 || !isfinite(T)) return HUGE_VAL;
+  const double* x = t.T;
+  const double* y = t.rrhp;
+  const double* c = t.Crrh;
+  const int n = t.nT;
+  double rate;
+  T = log10(T);
+  const double MinTemp = x[0], MaxTemp = x[n - 1];
+  if (T > MaxTemp) rate = y[n - 1] + t.smax * (T - MaxTemp);
+  else if (T < MinTemp) rate = y[0] + t.smin * (T - MinTemp);
+  else {
+    int lo = 0, hi = n - 1;
+    while (hi > lo + 1) {
+      const int mid = (lo + hi) >> 1;
+      if (x[mid] > T) hi = mid;
+      else lo = mid;
+    }
+    const double dx = x[lo + 1] - x[lo], dy = y[lo + 1] - y[lo];
+    const double c_i = c[lo], c_ip1 = c[lo + 1];
+    const double b_i = dy / dx - dx * (c_ip1 + 2.0 * c_i) / 3.0;
+    const double d_i = (c_ip1 - c_i) / (3.0 * dx);
+    const double delx = T - x[lo];
+    rate = y[lo] + delx * (b_i + delx * (c_i + delx * d_i));
+  }
+  return exp(2.3025850929940459 * rate);  // pconst.ln10() (constants.h:44)
+}
+
+__device__ __forceinline__ double cool_Edot_metallines(const CoolTab& t, double rho, double T);
+
+// mp_only_cooling::Edot (mp_only_cooling.cpp:383-420): launch-uniform dispatch on EP_cooling
 __device__ __forceinline__ double cool_Edot(const CoolTab& t, double rho, double T) {
+  switch (t.mode) {
+    case 2: {  // KI02: -CoolingFn::CoolingRate(T, 0, rho/Mu, 0, 0), WhichFunction 2, MinTemp 5 K (cooling.cpp:325-399)
+      const double nH = rho / t.Mu;
+      if (T <= 0.0 || isnan(T) || isinf(T)) return -0.0;
+      double rate = 0.0;
+      if (T > 5.0) rate += nH * nH * (2.0e-19 * exp(-1.184e5 / (T + 1.0e3)) + 2.8e-28 * sqrt(T) * exp(-92.0 / T));
+      rate -= nH * 2.0e-26;
+      return -rate;
+    }
+    case 4:  // Edot_SD93CIE_cool (:427-433)
+      return -(rho * rho / t.Mu_elec / t.Mu_ion) * cool_rate_SD93CIE(t, T);
+    case 5:  // Edot_SD93CIE_heat_cool (:444-451)
+      return (rho * rho) * (2.733e-21 * exp(-0.782991 * log(T)) / t.Mu_elec / t.Mu - cool_rate_SD93CIE(t, T) / t.Mu_elec / t.Mu_ion);
+    case 7:  // Edot_WSS09CIE_cool (:461-467)
+      return 2e-26 * rho / t.Mu - (rho * rho / t.Mu / t.Mu) * cool_rate_SD93CIE(t, T);
+    case 6:  // Edot_WSS09CIE_heat_cool
+      return (rho * rho) * (2.733e-21 * exp(-0.782991 * log(T)) / t.Mu_elec / t.Mu - cool_rate_SD93CIE(t, T) / t.Mu / t.Mu);
+    default:
+      return cool_Edot_metallines(t, rho, T);
+  }
+}
+
+// mp_only_cooling::Edot_WSS09CIE_heat_cool_metallines (mp_only_cooling.cpp:470-521)
+__device__ __forceinline__ double cool_Edot_metallines(const CoolTab& t, double rho, double T) {
   int ihi = t.nT - 1, ilo = 0;
   do {
     const int imid = ilo + ((ihi - ilo) >> 1);  // ilo + floor((ihi-ilo)/2.0)

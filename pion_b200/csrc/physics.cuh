@@ -85,6 +85,16 @@ __device__ __forceinline__ double minmod(double a, double b, double tiny) {
   return ((__double2hiint(a) ^ __double2hiint(b)) < 0) ? 0.0 : m;
 #endif
 }
+// e += minmod(a, b) * h for callers that only ADD the limited slope to something (h = +-0.5: the product is exact,
+// so the fused form is bit-identical): the smaller-magnitude operand goes into ONE PREDICATED DFMA (predicate: the
+// sign bits agree) instead of DMUL + two FSEL (zeroing) + DADD.  Inline PTX because the compiler if-converts the C
+// form into an unconditional DFMA followed by two FSEL.
+__device__ __forceinline__ void add_limited(double& e, double a, double b, double h) {
+  const double m = (fabs(a) < fabs(b)) ? a : b;
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 x;\n\txor.b32 x, %3, %4;\n\tsetp.ge.s32 p, x, 0;\n\t@p fma.rn.f64 %0, %1, %2, %0;\n\t}"
+      : "+d"(e)
+      : "d"(m), "d"(h), "r"(__double2hiint(a)), "r"(__double2hiint(b)));
+}
 
 // ---------------------------------------------------------------------------
 // Equations of state / conversions
@@ -221,15 +231,20 @@ __device__ __forceinline__ double chydro(double ro, double pg, double g) {
 // eqns_mhd_ideal::cfast_components (eqns_mhd_adiabatic.cpp:263-276).
 // cfast2_ir returns the SQUARE of the fast speed given 1/ro, so that callers needing
 // max(cf_l, cf_r) take one square root of the larger square (sqrt is monotonic: same value).
-__device__ __forceinline__ double cfast2_ir(double ir, double pg, double bx, double by, double bz, double g) {
+// irb: the reciprocal the FIELD terms are divided by (== ir unless the caller passes sums of two states, see
+// intercell_flux: pg and B are then twice the mean state's, ir = 1/(2 rho), irb = ir/2)
+__device__ __forceinline__ double cfast2_ir(double ir, double pg, double bx, double by, double bz, double g, double irb) {
   // one reciprocal instead of a sqrt + three divisions; ch*ch == g*pg/ro to 1 ulp
   double ch2 = g * pg * ir;
   // b_x^2/rho formed once and shared by both terms (two multiplies fewer than the literal form; 1 ulp)
-  const double bxi = (bx * bx) * ir;
-  double temp1 = (ch2 + bxi) + (by * by + bz * bz) * ir;
+  const double bxi = (bx * bx) * irb;
+  double temp1 = (ch2 + bxi) + (by * by + bz * bz) * irb;
   double temp2 = (4. * ch2) * bxi;
   temp2 = pmax(temp1 * temp1 - temp2, PION_MACHINEACCURACY);
   return (temp1 + fast_sqrt_pos(temp2)) / 2.;
+}
+__device__ __forceinline__ double cfast2_ir(double ir, double pg, double bx, double by, double bz, double g) {
+  return cfast2_ir(ir, pg, bx, by, bz, g, ir);
 }
 __device__ __forceinline__ double cfast_components(double ro, double pg, double bx, double by, double bz, double g) {
 #ifdef PION_STRICT
@@ -836,8 +851,15 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
     // spilled 150 bytes per thread to keep them alive across it).
     double fkj_c = 0.0, dvn = 0.0, dvt1 = 0.0, dvt2 = 0.0, dbt1 = 0.0, dbt2 = 0.0;
     if (FKJ) {
+#ifdef PION_STRICT
       fkj_c = cfast_components(0.5 * (eL.ro + eR.ro), 0.5 * (eL.pg + eR.pg), 0.5 * (eL.bn + eR.bn),
                                0.5 * (eL.bt1 + eR.bt1), 0.5 * (eL.bt2 + eR.bt2), pp.gamma) * pp.etav;
+#else
+      // fast speed of the MEAN state from the SUMS: every term of cfast is a ratio to rho, so the halves cancel
+      // against 1/(2 rho_mean) -- powers of two throughout, bit-identical to the literal form, five DMUL fewer
+      const double irs = fast_rcp(eL.ro + eR.ro);  // = 1 / (2 rho_mean)
+      fkj_c = fast_sqrt_pos(cfast2_ir(irs, eL.pg + eR.pg, eL.bn + eR.bn, eL.bt1 + eR.bt1, eL.bt2 + eR.bt2, pp.gamma, 0.5 * irs)) * pp.etav;
+#endif
       dvn = eR.vn - eL.vn; dvt1 = eR.vt1 - eL.vt1; dvt2 = eR.vt2 - eL.vt2;
       dbt1 = eR.bt1 - eL.bt1; dbt2 = eR.bt2 - eL.bt2;
     }
@@ -881,7 +903,13 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
       momvisc = prefactor * dvt2;
       flux.mt2 -= momvisc;
       ergvisc += momvisc * pstar.vt2;
+#ifdef PION_STRICT
       prefactor *= pdiv(pp.etav, pp.etav * pstar.ro);
+#else
+      // prefactor * etaB / (etav rho*) with etaB == etav (both are avcoeff, solver_eqn_base.cpp:82) is
+      // cf * etav * rho* / rho*: the reciprocal cancels (2 ulp regrouping)
+      prefactor = fkj_c;
+#endif
       momvisc = prefactor * dbt1;
       flux.bbt1 -= momvisc;
       ergvisc += momvisc * pstar.bt1;

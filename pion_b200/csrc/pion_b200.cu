@@ -182,9 +182,15 @@ static int check_config(const pion_gpu_config& c) {
     } else if (c.internal_bc[i] != PION_BC_DMACH2) { set_error("unsupported internal boundary"); return 1; }
   }
   if (c.cooling) {
-    if (c.cooling != 8) { set_error("only EP_cooling 8 (WSS09_CIE_LINE_HEAT_COOL, mp_only_cooling) is built"); return 1; }
-    if (c.n_table < 2 || !c.table_T || !c.table_rrhp || !c.table_C_rrh || !c.table_C_ffhe || !c.table_C_fbdn || !c.table_C_cie) {
-      set_error("cooling needs the mp_only_cooling lookup tables (n_table, table_*)");
+    // mp_only_cooling::Edot has cases 2, 4, 5, 6, 7, 8 (mp_only_cooling.cpp:383-420); every other flag -- DMcC (3)
+    // included -- ends in rep.error("bad cooling flag") in the reference
+    if (c.cooling != 2 && (c.cooling < 4 || c.cooling > 8)) { set_error("bad cooling flag in mp_only_cooling::Edot (EP_cooling must be 2, 4, 5, 6, 7 or 8)"); return 1; }
+    if (c.cooling == 8 && (c.n_table < 2 || !c.table_T || !c.table_rrhp || !c.table_C_rrh || !c.table_C_ffhe || !c.table_C_fbdn || !c.table_C_cie)) {
+      set_error("EP_cooling 8 needs the mp_only_cooling lookup tables (n_table, table_*)");
+      return 1;
+    }
+    if (c.cooling >= 4 && c.cooling <= 7 && (c.n_spline < 3 || !c.spline_logT || !c.spline_logL)) {
+      set_error("EP_cooling 4..7 need the knots of the cooling-curve spline (n_spline, spline_logT, spline_logL)");
       return 1;
     }
     if (c.mp_timestep_limit < 0 || c.mp_timestep_limit > 4) { set_error("Bad MP_timestep_limit"); return 1; }
@@ -368,9 +374,12 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   if (cfg->cooling) {
     // mp_only_cooling constructor + gen_mpoc_lookup_tables (mp_only_cooling.cpp:51-160, :528-579)
     const double m_p = 1.672621898e-24;  // constants.h:64
-    const double Mu = 1.40 * m_p, Mu_elec = 1.167 * m_p;
+    const double Mu = 1.40 * m_p, Mu_elec = 1.167 * m_p, Mu_ion = 1.273 * m_p;
     CoolParams& cp = c->cool;
-    cp.nT = cfg->n_table;
+    cp.mode = cfg->cooling;
+    cp.nT = (cfg->cooling == 8) ? cfg->n_table : (cfg->cooling >= 4) ? cfg->n_spline : 0;
+    cp.Mu = Mu; cp.Mu_elec = Mu_elec; cp.Mu_ion = Mu_ion;
+    cp.smin = cfg->spline_min_slope; cp.smax = cfg->spline_max_slope;
     cp.inv_Mu2 = 1.0 / (Mu * Mu);
     cp.inv_Mu2_elec_H = 1.0 / (Mu_elec * Mu);
     cp.Mu_tot_over_kB = pp.mu_tot_over_kB;
@@ -379,11 +388,35 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
     if (cp.MinT < 1.0 || cp.MinT > 1.0e6) cp.MinT = 1.0;      // microphysics_base / mp_only_cooling limits
     if (cp.MaxT < 1.0e2 || cp.MaxT > 3.0e10) cp.MaxT = 1.0e8;
     const int n = cp.nT;
-    std::vector<double> h(11 * (size_t)n, 0.0);
-    const double* src[6] = {cfg->table_T, cfg->table_rrhp, cfg->table_C_rrh, cfg->table_C_ffhe, cfg->table_C_fbdn, cfg->table_C_cie};
-    for (int q = 0; q < 6; q++) memcpy(&h[(size_t)q * n], src[q], n * sizeof(double));
-    for (int q = 1; q < 6; q++)
-      for (int i = 0; i < n - 1; i++) h[(size_t)(5 + q) * n + i] = (h[(size_t)q * n + i + 1] - h[(size_t)q * n + i]) / (h[i + 1] - h[i]);
+    std::vector<double> h((size_t)cool_ncol(cp.mode) * n + 1, 0.0);
+    if (cp.mode == 8) {
+      const double* src[6] = {cfg->table_T, cfg->table_rrhp, cfg->table_C_rrh, cfg->table_C_ffhe, cfg->table_C_fbdn, cfg->table_C_cie};
+      for (int q = 0; q < 6; q++) memcpy(&h[(size_t)q * n], src[q], n * sizeof(double));
+      for (int q = 1; q < 6; q++)
+        for (int i = 0; i < n - 1; i++) h[(size_t)(5 + q) * n + i] = (h[(size_t)q * n + i + 1] - h[(size_t)q * n + i]) / (h[i + 1] - h[i]);
+    } else if (cp.mode >= 4) {
+      // natural cubic spline through the knots, as GSL's cspline builds it for the reference (tools/interpolate.cpp:
+      // 59-118): c = y''/2 from the symmetric tridiagonal system, solved by forward elimination + back substitution
+      double *x = &h[0], *y = &h[n], *cc = &h[2 * (size_t)n];
+      memcpy(x, cfg->spline_logT, n * sizeof(double));
+      memcpy(y, cfg->spline_logL, n * sizeof(double));
+      const int m = n - 2;
+      std::vector<double> diag(m), off(m), rhs(m);
+      for (int i = 0; i < m; i++) {
+        const double h_i = x[i + 1] - x[i], h_ip1 = x[i + 2] - x[i + 1];
+        off[i] = h_ip1;
+        diag[i] = 2.0 * (h_ip1 + h_i);
+        rhs[i] = 3.0 * ((y[i + 2] - y[i + 1]) / h_ip1 - (y[i + 1] - y[i]) / h_i);
+      }
+      for (int i = 1; i < m; i++) {
+        const double w = off[i - 1] / diag[i - 1];
+        diag[i] -= w * off[i - 1];
+        rhs[i] -= w * rhs[i - 1];
+      }
+      cc[0] = cc[n - 1] = 0.0;
+      cc[m] = rhs[m - 1] / diag[m - 1];
+      for (int i = m - 1; i-- > 0;) cc[i + 1] = (rhs[i] - off[i] * cc[i + 2]) / diag[i];
+    }
     ok &= cudaMalloc(&c->d_tables, h.size() * sizeof(double)) == cudaSuccess;
     ok &= cudaMalloc(&c->mp_dE, (size_t)g.vs * sizeof(double)) == cudaSuccess;
     if (ok) {
@@ -392,6 +425,7 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
     }
     cp.tables = c->d_tables;
     c->cfg.table_T = c->cfg.table_rrhp = c->cfg.table_C_rrh = c->cfg.table_C_ffhe = c->cfg.table_C_fbdn = c->cfg.table_C_cie = nullptr;
+    c->cfg.spline_logT = c->cfg.spline_logL = nullptr;
   }
   for (int ib = 0; ib < cfg->n_internal_bc; ib++) {
     if (cfg->internal_bc[ib] != PION_BC_STWIND) continue;

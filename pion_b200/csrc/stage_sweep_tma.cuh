@@ -115,12 +115,21 @@ __device__ __forceinline__ void edge_states_tile(const StageArgs& a, const doubl
   if (ORDER == 2) {
     const Prim Q0 = lds_prim<EQ, VS>(pQ0, ax, a1, a2);
     const Prim Q3 = lds_prim<EQ, VS>(pQ3, ax, a1, a2);
+#ifdef PION_STRICT
 #define PION_EDGE2(f)                                                     \
   {                                                                       \
     const double d0 = eL.f - Q0.f, d1 = eR.f - eL.f, d2 = Q3.f - eR.f;    \
     eL.f += minmod(d0, d1, a.tiny2) * 0.5;                                \
     eR.f -= minmod(d1, d2, a.tiny2) * 0.5;                                \
   }
+#else
+#define PION_EDGE2(f)                                                     \
+  {                                                                       \
+    const double d0 = eL.f - Q0.f, d1 = eR.f - eL.f, d2 = Q3.f - eR.f;    \
+    add_limited(eL.f, d0, d1, 0.5);                                       \
+    add_limited(eR.f, d1, d2, -0.5);                                      \
+  }
+#endif
     PION_EDGE2(ro) PION_EDGE2(pg) PION_EDGE2(vn) PION_EDGE2(vt1) PION_EDGE2(vt2)
     if (EQ != EQ_EULER) { PION_EDGE2(bn) PION_EDGE2(bt1) PION_EDGE2(bt2) }
     if (EQ == EQ_GLM) { PION_EDGE2(psi) }
@@ -215,8 +224,13 @@ __device__ __forceinline__ void tracer_edges_tile(const StageArgs& a, const doub
     if (ORDER == 2) {
       const double q0 = pQ0[(NB + q) * VS], q3 = pQ3[(NB + q) * VS];
       const double d0 = L - q0, d1 = R - L, d2 = q3 - R;
+#ifdef PION_STRICT
       L += minmod(d0, d1, a.tiny2) * 0.5;
       R -= minmod(d1, d2, a.tiny2) * 0.5;
+#else
+      add_limited(L, d0, d1, 0.5);
+      add_limited(R, d1, d2, -0.5);
+#endif
     }
     trL[q] = L;
     trR[q] = R;

@@ -15,7 +15,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent))
 from cases import case_1d, case_2d, case_3d, case_cooling, case_cyl, case_sph, case_wind, wind_ambient_state  # noqa: E402
-from harness import COOLING_TABLES, TABLE_KEYS, RefSim, cooling_state, hot_sphere_state, random_state  # noqa: E402
+from harness import COOLING_SPLINES, COOLING_TABLES, TABLE_KEYS, RefSim, cooling_state, hot_sphere_state, random_state  # noqa: E402
 
 CASES = {
     "glm_hlld_fkj_3d_periodic": (case_3d("glm-mhd", 7, 1, NG=(12, 10, 8)), 4),
@@ -83,7 +83,34 @@ COOLING = {
     "cool_euler_hll_3d_dense": (case_cooling("euler", 8, ntracer=1), 4, 2.0e-21),
     "cool_glm_hlld_3d_dense": (case_cooling("glm-mhd", 7, ntracer=0, bcs="periodic"), 3, 2.0e-22),
 }
+
+
+
+def _cool(flag, eqn, solver, Tmin, Tmax, ntracer):
+    import dataclasses
+    return dataclasses.replace(case_cooling(eqn, solver, ntracer=ntracer), cooling=flag, min_temperature=Tmin, max_temperature=Tmax)
+
+
+# the other cooling functions of mp_only_cooling::Edot: (problem, steps, rho0, T range of the seeded state)
+COOLING.update({
+    "cool_ki02_euler_hll_3d": (_cool(2, "euler", 8, 10.0, 1.0e5, 1), 4, 2.0e-22, 20.0, 2.0e4),
+    "cool_sd93_euler_roe_3d": (_cool(4, "euler", 4, 1.0e4, 1.0e8, 0), 4, 2.0e-23, 2.0e4, 5.0e7),
+    "cool_sd93heat_glm_hlld_3d": (_cool(5, "glm-mhd", 7, 5.0e3, 1.0e8, 0), 3, 2.0e-22, 6.0e3, 5.0e7),
+    "cool_wss09heat_euler_hll_3d": (_cool(6, "euler", 8, 5.0e3, 1.0e8, 1), 4, 2.0e-22, 6.0e3, 5.0e7),
+    "cool_wss09_imhd_hll_3d": (_cool(7, "i-mhd", 8, 1.0e4, 1.0e8, 0), 3, 2.0e-23, 2.0e4, 5.0e7),
+})
 CASES.update({k: v[:2] for k, v in COOLING.items()})
+
+
+def make_cooling_splines():
+    """Knots of the reference's cooling-curve splines (SD93-CIE for EP_cooling 2..5, WSS09-CIE for 6, 7)."""
+    out = {}
+    for pre, flag in (("sd93", 4), ("wss09", 6)):
+        r = RefSim(_cool(flag, "euler", 8, 5.0e3, 1.0e8, 0))
+        sp = r.cooling_spline()
+        r.close()
+        out[pre + "_logT"], out[pre + "_logL"], out[pre + "_slopes"] = sp["spline_logT"], sp["spline_logL"], sp["spline_slopes"]
+    np.savez_compressed(COOLING_SPLINES, **out)
 
 # Stellar-wind internal boundary + cooling: the Wind3D configuration at 16^3 / 24^2
 WIND = {
@@ -96,6 +123,8 @@ CASES.update(WIND)
 
 def main():
     only = set(sys.argv[1:])  # optional: regenerate just these fixtures
+    if not COOLING_SPLINES.exists() or "cooling_splines" in only:
+        make_cooling_splines()
     for name, (prob, nsteps) in CASES.items():
         if only and name not in only:
             continue
@@ -109,10 +138,10 @@ def main():
             r.set_state(P0)
         elif name in COOLING:
             r = RefSim(prob)
-            if not COOLING_TABLES.exists() or name == next(iter(COOLING)):
+            if prob.cooling == 8 and (not COOLING_TABLES.exists() or name == next(iter(COOLING))):
                 tab = r.cooling_tables()
                 np.savez_compressed(COOLING_TABLES, **tab)
-            P0 = cooling_state(prob, seed=2024, rho0=COOLING[name][2])
+            P0 = cooling_state(prob, seed=2024, rho0=COOLING[name][2], **(dict(Tlo=COOLING[name][3], Thi=COOLING[name][4]) if len(COOLING[name]) > 3 else {}))
             r.set_state(P0)
         elif name in TEST_PROBLEMS:
             r = RefSim(prob, run_ics=True)

@@ -252,6 +252,27 @@ TABLE_KEYS = ["T", "rrhp", "C_rrh", "C_ffhe", "C_fbdn", "C_cie"]
 COOLING_TABLES = ROOT / "tests" / "golden" / "cooling_tables_wss09_T5e3_1e8.npz"
 
 
+COOLING_SPLINES = ROOT / "tests" / "golden" / "cooling_splines_sd93_wss09.npz"
+
+
+def load_cooling_spline(flag):
+    """Committed fixture: knots and end slopes of the reference's cooling-curve spline for EP_cooling 4, 5
+    (setup_SD93_cie) or 6, 7 (setup_WSS09_CIE), read out of the reference's MP object by
+    tests/golden/make_golden.py (RefSim.cooling_spline)."""
+    z = np.load(COOLING_SPLINES)
+    pre = "sd93" if flag in (4, 5) else "wss09"
+    return {"spline_logT": z[pre + "_logT"], "spline_logL": z[pre + "_logL"], "spline_slopes": z[pre + "_slopes"]}
+
+
+def tables_for(prob):
+    """The committed cooling fixture a problem's EP_cooling flag needs (None without tabulated data)."""
+    if prob.cooling == 8:
+        return load_cooling_tables()
+    if prob.cooling in (4, 5, 6, 7):
+        return load_cooling_spline(prob.cooling)
+    return None
+
+
 def load_cooling_tables():
     """Committed fixture: the reference's EP_cooling=8 lookup tables for T in [5e3, 1e8] K
     (generated by tests/golden/make_golden.py from oracle/_ref)."""
@@ -507,7 +528,7 @@ def hot_sphere_state(prob: Problem, seed=7, amp=0.5, fac=100.0):
 MU_TOT_OVER_KB = (0.609 * 1.672621898e-24) / 1.38064852e-16  # mp_only_cooling.cpp:79-81 with constants.h:53,64
 
 
-def cooling_state(prob: Problem, seed=4242, rho0=2.0e-24):
+def cooling_state(prob: Problem, seed=4242, rho0=2.0e-24, Tlo=6.0e3, Thi=5.0e7):
     """Seeded cgs state for the cooling tests: rho ~ 2e-24 g/cm3 x [0.3,3], T log-uniform in
     [6e3, 5e7] K (both sides of the cooling-curve peak), |v| <~ 3e6 cm/s, weak B, tracers in
     [0,1.1] (exercises the sCMA clamp).  rho0 = 2e-22 makes the cooling time comparable to the
@@ -517,7 +538,7 @@ def cooling_state(prob: Problem, seed=4242, rho0=2.0e-24):
     rng = np.random.Generator(np.random.PCG64(seed + 1))
     nv_phys = EQN_NVAR[prob.eqn]
     rho = rho0 * 10.0 ** (P[0] - 1.0)
-    T = 10.0 ** (np.log10(6.0e3) + (np.log10(5.0e7) - np.log10(6.0e3)) * np.clip((P[1] - 0.5) * 1.6 - 0.3 + 0.4 * rng.random(shp[1:]), 0, 1))
+    T = 10.0 ** (np.log10(Tlo) + (np.log10(Thi) - np.log10(Tlo)) * np.clip((P[1] - 0.5) * 1.6 - 0.3 + 0.4 * rng.random(shp[1:]), 0, 1))
     out = np.zeros(shp)
     out[0] = rho
     out[1] = rho * T / MU_TOT_OVER_KB

@@ -6,7 +6,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from harness import GpuSim, OracleSim, load_cooling_tables, rel_err
+from harness import GpuSim, OracleSim, rel_err, tables_for
 
 GOLD = Path(__file__).resolve().parent / "golden"
 
@@ -20,11 +20,7 @@ def load(name):
     return prob, nsteps, np.load(GOLD / f"{name}.npz")
 
 
-NAMES = sorted(p.stem for p in GOLD.glob("*.npz") if not p.stem.startswith("cooling_tables"))
-
-
-def tables_for(prob):
-    return load_cooling_tables() if prob.cooling else None
+NAMES = sorted(p.stem for p in GOLD.glob("*.npz") if not p.stem.startswith("cooling_"))
 
 
 def test_golden_fixtures_exist():

@@ -242,6 +242,48 @@ def test_cooling_source_term(eqn, solver, ndim, NG, ntr, lim, rho0):
         g.close()
 
 
+# the other cooling functions mp_only_cooling::Edot dispatches to (KI02, SD93-CIE +- heating, WSS09-CIE +- heating):
+# spline knots from the committed, reference-generated fixture; exp / log / log10 are CUDA's (<= 2 ulp)
+from test_oracle_vs_ref import COOLING_FLAG_CASES, cooling_flag_problem  # noqa: E402
+from harness import tables_for  # noqa: E402
+
+
+@pytest.mark.parametrize("flag,eqn,solver,rho0,Tlo,Thi,Tmin,Tmax", COOLING_FLAG_CASES)
+def test_cooling_functions(flag, eqn, solver, rho0, Tlo, Thi, Tmin, Tmax):
+    prob = cooling_flag_problem(flag, eqn, solver, Tmin, Tmax)
+    tab = tables_for(prob)
+    o, g = OracleSim(prob, tables=tab), GpuSim(prob, tables=tab)
+    try:
+        P = cooling_state(prob, seed=23 + flag, rho0=rho0, Tlo=Tlo, Thi=Thi)
+        for s in (o, g):
+            s.set_state(P)
+            s.init_after_state()
+        tmo, tmg = o.microphysics_dt(), g.microphysics_dt()
+        assert abs(tmo - tmg) <= 1e-12 * tmo, (tmo, tmg)
+        do, dg = o.run(3), g.run(3)
+        assert np.allclose(do, dg, rtol=1e-12, atol=0), (do, dg)
+        err = rel_err(g.get_state(0), o.get_state(0), nphys=prob.nvar - prob.ntracer)
+        print(f"EP_cooling {flag}: GPU vs oracle after 3 steps {err}")
+        assert err.max() < TOL, err
+        assert g.error_counts() == [0, 0] and g.ctx.mp_failures() == 0
+    finally:
+        o.close()
+        g.close()
+
+
+def test_bad_cooling_flag_is_rejected_like_the_reference():
+    """DMcC (3) and anything else without a case in mp_only_cooling::Edot ends in rep.error there; create() fails here."""
+    import dataclasses
+    import ctypes
+    from harness import gpu_config
+    from pion_b200.capi import load_library
+    lib = load_library()
+    for flag in (1, 3, 9):
+        cfg, keep = gpu_config(dataclasses.replace(case_cooling(), cooling=flag), tables=load_cooling_tables())
+        assert not lib.pion_gpu_create(ctypes.byref(cfg))
+        assert b"cooling flag" in lib.pion_gpu_last_error()
+
+
 # ------------------------------------------------------------------------------------------
 # curvilinear grids (a12): cylindrical (z,R) and spherical geometric source terms, area-weighted
 # flux divergence, centre-of-volume slopes -- gather kernel path

@@ -147,6 +147,59 @@ def test_cooling_bit_exact(eqn, solver, ndim, NG, ntr, lim, rho0):
         o.close()
 
 
+# the other cooling functions of mp_only_cooling::Edot (mp_only_cooling.cpp:383-420): KI02 (2), SD93_CIE (4),
+# SD93_PLUS_HEATING (5), WSS09_CIE_PLUS_HEATING (6), WSS09_CIE_ONLY_COOLING (7).  (DMcC, 3, has no case in Edot:
+# the reference aborts with "bad cooling flag".)  The spline knots come from the reference's own MP object.
+COOLING_FLAG_CASES = [
+    # flag, eqn, solver, rho0, Tlo, Thi, Tmin, Tmax
+    (2, "euler", 8, 2.0e-22, 20.0, 2.0e4, 10.0, 1.0e5),
+    (4, "euler", 8, 2.0e-23, 2.0e4, 5.0e7, 1.0e4, 1.0e8),
+    (5, "glm-mhd", 7, 2.0e-22, 6.0e3, 5.0e7, 5.0e3, 1.0e8),
+    (6, "euler", 4, 2.0e-22, 6.0e3, 5.0e7, 5.0e3, 1.0e8),
+    (7, "i-mhd", 8, 2.0e-23, 2.0e4, 5.0e7, 1.0e4, 1.0e8),
+]
+
+
+def cooling_flag_problem(flag, eqn, solver, Tmin, Tmax, NG=(12, 10, 8)):
+    import dataclasses
+    return dataclasses.replace(case_cooling(eqn, solver, ndim=3, NG=NG, ntracer=1 if eqn == "euler" else 0, mp_limit=1),
+                               cooling=flag, min_temperature=Tmin, max_temperature=Tmax)
+
+
+@pytest.mark.parametrize("flag,eqn,solver,rho0,Tlo,Thi,Tmin,Tmax", COOLING_FLAG_CASES)
+def test_cooling_functions_bit_exact(flag, eqn, solver, rho0, Tlo, Thi, Tmin, Tmax):
+    prob = cooling_flag_problem(flag, eqn, solver, Tmin, Tmax)
+    r = RefSim(prob)
+    tab = r.cooling_spline() if flag != 2 else None
+    o = OracleSim(prob, tables=tab)
+    try:
+        P = cooling_state(prob, seed=23 + flag, rho0=rho0, Tlo=Tlo, Thi=Thi)
+        for s in (r, o):
+            s.set_state(P)
+            assert s.init_after_state() == 0
+        assert r.microphysics_dt() == o.microphysics_dt()
+        dr, do = r.run(3), o.run(3)
+        assert np.array_equal(dr, do), (dr, do)
+        assert np.array_equal(r.get_state(0), o.get_state(0))
+        assert r.microphysics_dU(0.5 * dr[-1]) == 0 and o.microphysics_dU(0.5 * dr[-1]) == 0
+        dUr, dUo = r.get_state(2), o.get_state(2)
+        assert np.max(np.abs(dUr[1])) > 0  # the source term does something on this state
+        assert np.array_equal(dUr, dUo)
+    finally:
+        r.close()
+        o.close()
+
+
+def test_committed_cooling_splines_match_reference():
+    from harness import load_cooling_spline
+    for flag in (4, 5, 6, 7):
+        r = RefSim(cooling_flag_problem(flag, "euler", 8, 5.0e3, 1.0e8))
+        sp, gold = r.cooling_spline(), load_cooling_spline(flag)
+        r.close()
+        for k in sp:
+            assert np.array_equal(sp[k], gold[k]), (flag, k)
+
+
 def test_committed_cooling_tables_match_reference():
     from harness import TABLE_KEYS, load_cooling_tables
     r = RefSim(case_cooling())
