@@ -856,11 +856,44 @@ static void hydro_RoePV(pion_oracle *s, const double *left, const double *right,
   }
 }
 
+/* eqns_mhd_ideal::UtoFlux (eqns_mhd_adiabatic.cpp:337-355) */
+static void mhd_UtoFlux(const pion_oracle *s, const double *u, double *f) {
+  double pm = (u[s->eBBX] * u[s->eBBX] + u[s->eBBY] * u[s->eBBY] + u[s->eBBZ] * u[s->eBBZ]) / 2.;
+  double pg = (s->gamma - 1.) *
+              (u[ERG] - (u[s->eMX] * u[s->eMX] + u[s->eMY] * u[s->eMY] + u[s->eMZ] * u[s->eMZ]) / (2. * u[RHO]) - pm);
+  f[RHO] = u[s->eMX];
+  f[s->eMX] = u[s->eMX] * u[s->eMX] / u[RHO] + pg + pm - u[s->eBBX] * u[s->eBBX];
+  f[s->eMY] = u[s->eMX] * u[s->eMY] / u[RHO] - u[s->eBBX] * u[s->eBBY];
+  f[s->eMZ] = u[s->eMX] * u[s->eMZ] / u[RHO] - u[s->eBBX] * u[s->eBBZ];
+  f[ERG] = u[s->eMX] * (u[ERG] + pg + pm) / u[RHO] -
+           u[s->eBBX] * (u[s->eMX] * u[s->eBBX] + u[s->eMY] * u[s->eBBY] + u[s->eMZ] * u[s->eBBZ]) / u[RHO];
+  f[s->eBBX] = 0.;
+  f[s->eBBY] = (u[s->eMX] * u[s->eBBY] - u[s->eMY] * u[s->eBBX]) / u[RHO];
+  f[s->eBBZ] = (u[s->eMX] * u[s->eBBZ] - u[s->eMZ] * u[s->eBBX]) / u[RHO];
+}
+/* FV_solver_base::get_LaxFriedrichs_flux (solver_eqn_base.cpp:109-141): the tracer part is overwritten by
+ * set_interface_tracer_flux; for GLM the psi component is overwritten by the Dedner flux (glm_inviscid_flux) */
+static void lax_friedrichs_flux(pion_oracle *s, const double *l, const double *r, double *f) {
+  double u1[PO_MAXVAR], u2[PO_MAXVAR], f1[PO_MAXVAR], f2[PO_MAXVAR];
+  for (int v = 0; v < PO_MAXVAR; v++) u1[v] = u2[v] = f1[v] = f2[v] = 0.0;
+  const int nq = (s->cfg.eqntype == PO_EQEUL) ? 5 : 8;
+  if (s->cfg.eqntype == PO_EQEUL) {
+    euler_PtoU(s, l, u1); euler_PtoU(s, r, u2);
+    euler_UtoFlux(s, u1, f1); euler_UtoFlux(s, u2, f2);
+  } else {
+    mhd_PtoU(s, l, u1); mhd_PtoU(s, r, u2);
+    mhd_UtoFlux(s, u1, f1); mhd_UtoFlux(s, u2, f2);
+  }
+  for (int v = 0; v < nq; v++) f[v] = 0.5 * (f1[v] + f2[v] + s->dx / s->FV_dt * (u1[v] - u2[v]) / s->ndim);
+}
 /* FV_solver_Hydro_Euler::inviscid_flux (solver_eqn_hydro_adi.cpp:94-205) */
 static void euler_inviscid_flux(pion_oracle *s, const double *Pl, const double *Pr, double *flux, double *pstar) {
   double ustar[PO_MAXVAR];
   for (int v = 0; v < s->nv; v++) { ustar[v] = 0.0; flux[v] = 0.0; pstar[v] = 0.0; }
-  if (s->cfg.solver == PO_FLUX_ROE) {
+  if (s->cfg.solver == PO_FLUX_LF) { /* :142-148 */
+    lax_friedrichs_flux(s, Pl, Pr, flux);
+    for (int v = 0; v < 5; v++) pstar[v] = 0.5 * (Pl[v] + Pr[v]);
+  } else if (s->cfg.solver == PO_FLUX_ROE) {
     hydro_RoeCV(s, Pl, Pr, s->HC_etamax, pstar, flux);
   } else if (s->cfg.solver == PO_FLUX_HLL) {
     hydro_HLL(s, Pl, Pr, flux, ustar);
@@ -882,7 +915,10 @@ static void mhd_ideal_inviscid_flux(pion_oracle *s, long cl, long cr, const doub
                                     double *pstar) {
   double ustar[PO_MAXVAR];
   for (int v = 0; v < s->nv; v++) { ustar[v] = 0.0; flux[v] = 0.0; pstar[v] = 0.0; }
-  if (s->cfg.solver == PO_FLUX_ROE) {
+  if (s->cfg.solver == PO_FLUX_LF) { /* :132-136 */
+    lax_friedrichs_flux(s, Pl, Pr, flux);
+    for (int v = 0; v < s->nv; v++) pstar[v] = 0.5 * (Pl[v] + Pr[v]);
+  } else if (s->cfg.solver == PO_FLUX_ROE) {
     mhd_RoeCV(s, Pl, Pr, s->HC_etamax, pstar, flux);
   } else if (s->cfg.solver == PO_FLUX_HLLD) {
     double DivVl = s->divv[cl], DivVr = s->divv[cr], Gradl = s->gradp[cl], Gradr = s->gradp[cr];
@@ -2055,13 +2091,15 @@ static double advance_time(pion_oracle *s) {
 pion_oracle *po_create(const pion_oracle_config *cfg) {
   pion_oracle *s = (pion_oracle *)calloc(1, sizeof(pion_oracle));
   s->cfg = *cfg;
+  /* "Force Nbc=1 if using Lax-Friedrichs flux" (setup_fixed_grid.cpp:188-190) */
+  if (cfg->solver == PO_FLUX_LF) s->cfg.spOOA = s->cfg.tmOOA = OA1;
   s->nv = cfg->nvar;
   s->ndim = cfg->ndim;
   s->ntr = cfg->ntracer;
   s->ftr = cfg->nvar - cfg->ntracer;
   s->gamma = cfg->gamma;
   /* setup_fixed_grid::setup_grid (setup_fixed_grid.cpp:183-186) */
-  s->nbc = (cfg->spOOA == OA2) ? 2 : 1;
+  s->nbc = (s->cfg.spOOA == OA2) ? 2 : 1;
   for (int a = 0; a < 3; a++) {
     s->nb[a] = (a < s->ndim) ? s->nbc : 0;
     s->NGa[a] = (a < s->ndim) ? cfg->NG[a] + 2 * s->nbc : 1;

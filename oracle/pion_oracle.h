@@ -23,7 +23,7 @@ extern "C" {
  * source/boundaries/boundaries.h:32-52) */
 enum { PO_EQEUL = 1, PO_EQMHD = 2, PO_EQGLM = 3 };
 enum { PO_COORD_CRT = 1, PO_COORD_CYL = 2, PO_COORD_SPH = 3 };
-enum { PO_FLUX_ROE = 4, PO_FLUX_ROE_PV = 5, PO_FLUX_FVS = 6, PO_FLUX_HLLD = 7, PO_FLUX_HLL = 8 };  /* 5, 6: Euler only */
+enum { PO_FLUX_LF = 0, PO_FLUX_ROE = 4, PO_FLUX_ROE_PV = 5, PO_FLUX_FVS = 6, PO_FLUX_HLLD = 7, PO_FLUX_HLL = 8 };  /* 5, 6: Euler only */
 enum { PO_AV_NONE = 0, PO_AV_FKJ98 = 1, PO_AV_HCORR = 3, PO_AV_HCORR_FKJ98 = 4 };
 enum {
   PO_BC_PERIODIC = 1, PO_BC_OUTFLOW = 2, PO_BC_INFLOW = 3, PO_BC_REFLECTING = 4,

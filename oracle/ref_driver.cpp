@@ -47,6 +47,7 @@
 #include "ics/icgen.h"
 #include "ics/get_sim_info.h"
 #include "dataIO/readparams.h"
+#include "dataIO/dataio_text.h"
 #include "microphysics/microphysics_base.h"
 #include "microphysics/mp_only_cooling.h"
 #include "spatial_solvers/solver_eqn_base.h"
@@ -445,6 +446,16 @@ int pref_cooling_spline(void *h, double *logT, double *logL, double *slopes) {
   }
   if (slopes) { slopes[0] = cf->MinSlope; slopes[1] = cf->MaxSlope; }
   return n;
+}
+
+// The reference's own ASCII writer (dataio_text::OutputData -> output_ascii_data, dataio_text.cpp:130-146,477-555)
+// on the current state: writes <base>.txt (counter < 0, as icgen writes initial conditions) or
+// <base>.<counter, 8 digits>.txt.  This is the file pion_ugs_gpu --in-text consumes and --out-text reproduces.
+int pref_output_text(void *h, const char *base, long counter) {
+  RefSim *s = static_cast<RefSim *>(h);
+  class dataio_text dio(s->SimPM);
+  dio.SetSolver(s->solver());
+  return dio.OutputData(base, s->grid, s->SimPM, counter);
 }
 
 }  // extern "C"

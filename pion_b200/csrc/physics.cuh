@@ -24,7 +24,7 @@
 namespace pion {
 
 enum : int { EQ_EULER = 1, EQ_MHD = 2, EQ_GLM = 3 };                 // constants.h:166-172
-enum : int { SOLVE_ROE = 4, SOLVE_ROE_PV = 5, SOLVE_FVS = 6, SOLVE_HLLD = 7, SOLVE_HLL = 8 };  // constants.h:238-246 (5, 6: Euler only)
+enum : int { SOLVE_LF = 0, SOLVE_ROE = 4, SOLVE_ROE_PV = 5, SOLVE_FVS = 6, SOLVE_HLLD = 7, SOLVE_HLL = 8 };  // constants.h:238-246 (5, 6: Euler only)
 enum : int { AV_NONE = 0, AV_FKJ98 = 1, AV_HCORR = 3, AV_HCORR_FKJ98 = 4 };
 
 #define PION_MACHINEACCURACY 5.e-16    // constants.h:151
@@ -52,6 +52,8 @@ struct PhysParams {
   double max_temp;     // EP.MaxTemperature
   double mu_tot_over_kB;  // mp_only_cooling::Mu_tot_over_kB (0 if no microphysics)
   int have_mp;
+  double lf_c;         // Lax-Friedrichs only: dx / FV_dt (set per stage launch)
+  double lf_ndim;      // ... and FV_gndim
 };
 
 __device__ __forceinline__ double sq(double x) { return x * x; }
@@ -304,6 +306,47 @@ __device__ __forceinline__ void euler_UtoFlux(const Cons& u, Cons& f, double gm1
   f.mt1 = u.mn * u.mt1 * ir;
   f.mt2 = u.mn * u.mt2 * ir;
   f.erg = u.mn * (u.erg + pg) * ir;
+}
+
+// eqns_mhd_ideal::UtoFlux (eqns_mhd_adiabatic.cpp:337-355)
+__device__ __forceinline__ void mhd_UtoFlux(const Cons& u, Cons& f, double gm1) {
+  const double ir = fast_rcp(u.rho);
+  const double pm = (u.bbn * u.bbn + u.bbt1 * u.bbt1 + u.bbt2 * u.bbt2) / 2.;
+  const double pg = gm1 * (u.erg - (u.mn * u.mn + u.mt1 * u.mt1 + u.mt2 * u.mt2) * 0.5 * ir - pm);
+  f.rho = u.mn;
+  f.mn = u.mn * u.mn * ir + pg + pm - u.bbn * u.bbn;
+  f.mt1 = u.mn * u.mt1 * ir - u.bbn * u.bbt1;
+  f.mt2 = u.mn * u.mt2 * ir - u.bbn * u.bbt2;
+  f.erg = u.mn * (u.erg + pg + pm) * ir - u.bbn * (u.mn * u.bbn + u.mt1 * u.bbt1 + u.mt2 * u.bbt2) * ir;
+  f.bbn = 0.;
+  f.bbt1 = (u.mn * u.bbt1 - u.mt1 * u.bbn) * ir;
+  f.bbt2 = (u.mn * u.bbt2 - u.mt2 * u.bbn) * ir;
+  f.psi = 0.0;
+}
+
+// FV_solver_base::get_LaxFriedrichs_flux (solver_eqn_base.cpp:109-141) + pstar = mean of the edge states
+// (solver_eqn_hydro_adi.cpp:142-148, solver_eqn_mhd_adi.cpp:132-136).  The reference forces first order in space
+// and time with this flux (setup_fixed_grid.cpp:188-190); pion_gpu_create does the same.
+template <int EQ>
+__device__ __forceinline__ void lax_friedrichs(const Prim& L, const Prim& R, const PhysParams& pp, Cons& flux, Prim& pstar) {
+  const double gm1 = pp.gamma - 1.0;
+  Cons u1, u2, f1, f2;
+  if (EQ == EQ_EULER) {
+    PtoU<EQ_EULER>(L, u1, gm1); PtoU<EQ_EULER>(R, u2, gm1);
+    euler_UtoFlux(u1, f1, gm1); euler_UtoFlux(u2, f2, gm1);
+  } else {
+    PtoU_mhd_ideal(L, u1, gm1); PtoU_mhd_ideal(R, u2, gm1);
+    mhd_UtoFlux(u1, f1, gm1); mhd_UtoFlux(u2, f2, gm1);
+  }
+#define PION_LF_COMP(c) flux.c = 0.5 * (f1.c + f2.c + pp.lf_c * (u1.c - u2.c) / pp.lf_ndim);
+  PION_LF_COMP(rho) PION_LF_COMP(erg) PION_LF_COMP(mn) PION_LF_COMP(mt1) PION_LF_COMP(mt2)
+  if (EQ != EQ_EULER) { PION_LF_COMP(bbn) PION_LF_COMP(bbt1) PION_LF_COMP(bbt2) } else { flux.bbn = flux.bbt1 = flux.bbt2 = 0.0; }
+#undef PION_LF_COMP
+  flux.psi = 0.0;
+  pstar.ro = 0.5 * (L.ro + R.ro); pstar.pg = 0.5 * (L.pg + R.pg);
+  pstar.vn = 0.5 * (L.vn + R.vn); pstar.vt1 = 0.5 * (L.vt1 + R.vt1); pstar.vt2 = 0.5 * (L.vt2 + R.vt2);
+  pstar.bn = 0.5 * (L.bn + R.bn); pstar.bt1 = 0.5 * (L.bt1 + R.bt1); pstar.bt2 = 0.5 * (L.bt2 + R.bt2);
+  pstar.psi = 0.5 * (L.psi + R.psi);
 }
 
 // Roe-average primitive state of two Euler states (Toro eq. 11.60): Riemann_FVS_Euler::Roe_average_state
@@ -818,7 +861,9 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
   constexpr bool FKJ = (AV == AV_FKJ98 || AV == AV_HCORR_FKJ98);
   Prim pstar;
   if (EQ == EQ_EULER) {
-    if (SOLVER == SOLVE_ROE) {
+    if (SOLVER == SOLVE_LF) {
+      lax_friedrichs<EQ_EULER>(eL, eR, pp, flux, pstar);
+    } else if (SOLVER == SOLVE_ROE) {
       hydro_RoeCV(eL, eR, pp, hc_etamax, flux, pstar);
     } else if (SOLVER == SOLVE_FVS) {
       hydro_FVS<FKJ>(eL, eR, pp, flux, pstar);
@@ -873,7 +918,9 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
       l.psi = r.psi = 0.0;
       l.bn = r.bn = bxstar;
     }
-    if (SOLVER == SOLVE_ROE) {
+    if (SOLVER == SOLVE_LF) {
+      lax_friedrichs<EQ_MHD>(l, r, pp, flux, pstar);
+    } else if (SOLVER == SOLVE_ROE) {
       mhd_RoeCV(l, r, pp, hc_etamax, flux, pstar);
     } else if (SOLVER == SOLVE_HLLD && !use_hll) {
 #ifdef PION_NO_SAME_BN

@@ -156,7 +156,7 @@ static int check_config(const pion_gpu_config& c) {
   if (c.coord_sys == PION_COORD_SPH && (c.ndim != 1 || c.eqntype != PION_EQEUL)) { set_error("Spherical coordinates only implemented for 1D Euler"); return 1; }
   if (c.coord_sys != PION_COORD_CRT && c.n_wind > 0) { set_error("stellar-wind boundary: only Cartesian grids are built"); return 1; }
   const bool euler_only = (c.solver == PION_FLUX_ROE_PV || c.solver == PION_FLUX_FVS);
-  if (c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL && !euler_only) { set_error("solver must be 4 (Roe-CV), 5 (Roe-PV), 6 (FVS), 7 (HLLD) or 8 (HLL)"); return 1; }
+  if (c.solver != PION_FLUX_LF && c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL && !euler_only) { set_error("solver must be 0 (Lax-Friedrichs), 4 (Roe-CV), 5 (Roe-PV), 6 (FVS), 7 (HLLD) or 8 (HLL)"); return 1; }
   // solver_eqn_mhd_adi.cpp:132-198: the MHD solvers have no Roe-PV / FVS branch ("what sort of flux solver do you mean???")
   if (euler_only && c.eqntype != PION_EQEUL) { set_error("solver 5 (Roe-PV) and 6 (FVS) exist for the Euler equations only"); return 1; }
   if (c.eqntype == PION_EQEUL && c.solver == PION_FLUX_HLLD) { set_error("HLLD needs MHD equations"); return 1; }
@@ -317,12 +317,14 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   if (cudaSetDevice(cfg->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
   pion_gpu_ctx* c = new pion_gpu_ctx();
   c->cfg = *cfg;
+  // "Force Nbc=1 if using Lax-Friedrichs flux" (setup_fixed_grid.cpp:188-190): first order in space and time
+  if (c->cfg.solver == PION_FLUX_LF) c->cfg.spOOA = c->cfg.tmOOA = 1;
   // ics/get_sim_info.cpp:452-468
   if (c->cfg.artviscosity == 0) c->cfg.etav = 0.0;
   if (c->cfg.artviscosity == 3) c->cfg.etav = 0.1;
   GridD& g = c->g;
   g.ndim = cfg->ndim;
-  const int nbc = (cfg->spOOA == 2) ? 2 : 1;  // setup_fixed_grid.cpp:183-184
+  const int nbc = (c->cfg.spOOA == 2) ? 2 : 1;  // setup_fixed_grid.cpp:183-184
   for (int a = 0; a < 3; a++) {
     g.NG[a] = (a < g.ndim) ? cfg->NG[a] : 1;
     g.nb[a] = (a < g.ndim) ? nbc : 0;
@@ -612,7 +614,7 @@ static int update_external_bcs(pion_gpu_ctx* c, double* A0, double* A1, double s
       fill_bc_args(c, b, 2 * ax, tlo, A0, A1, simtime, c->bc_refval[2 * ax]);
       BCRef r2;
       for (int v = 0; v < PION_MAXVAR; v++) r2.v[v] = c->bc_refval[2 * ax + 1][v];
-      k_bc_axis<<<nblocks(2 * face_cells(g, 2 * ax), 128), 128, 0, st>>>(b, thi, r2);
+      k_bc_axis<<<nblocks(2 * face_cells(g, 2 * ax) * c->nvar, 256, 148 * 32), 256, 0, st>>>(b, thi, r2);
       c->launches++;
     }
     if (mpi_face) {
@@ -719,7 +721,7 @@ extern "C" int pion_gpu_init_after_upload(pion_gpu_ctx* c) {
     // BC_assign_ONEWAY_OUT is BC_assign_OUTFLOW: no velocity clamp at assign time
     // (oneway_out_boundaries.cpp:24-32)
     fill_bc_args(c, b, face, (type == PION_BC_ONEWAY_OUT) ? PION_BC_OUTFLOW : type, c->P, c->Ph, c->simtime, rv);
-    k_bc_face<<<nblocks(face_cells(g, face), 128), 128, 0, c->stream>>>(b);
+    k_bc_face<<<nblocks(face_cells(g, face) * c->nvar, 256, 148 * 32), 256, 0, c->stream>>>(b);
     c->launches++;
   }
   for (int i = 0; i < c->cfg.n_internal_bc; i++) {
@@ -989,6 +991,8 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   a.g = c->g;
   a.pp = c->pp;
   a.pp.chyp = c->chyp;
+  a.pp.lf_c = c->g.dx / dt;  // get_LaxFriedrichs_flux: dx / FV_dt
+  a.pp.lf_ndim = (double)c->g.ndim;
   a.S = S;
   a.Pb = Pb;
   a.out = out;
@@ -1039,7 +1043,8 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   }
   // fused 2-D/3-D stages run the flux-once sweep kernel; 1-D grids and the unfused seam
   // call (calc_dynamics_dU) run the per-cell gather kernel
-  const bool sweep = fused && c->g.ndim >= 2 && c->g.coord == PION_COORD_CRT && !c->force_gather;
+  // (Lax-Friedrichs is only instantiated for the gather kernel)
+  const bool sweep = fused && c->g.ndim >= 2 && c->g.coord == PION_COORD_CRT && !c->force_gather && c->cfg.solver != PION_FLUX_LF;
   switch (c->cfg.eqntype) {
     case PION_EQEUL: c->last_stage_kernel = (sweep ? launch_sweep_euler : launch_stage_euler)(c->cfg.solver, fkj, a, st); break;
     case PION_EQMHD: c->last_stage_kernel = (sweep ? launch_sweep_mhd : launch_stage_mhd)(c->cfg.solver, fkj, a, st); break;

@@ -2,6 +2,10 @@
 #include "stage_kernel.cuh"
 namespace pion {
 const char* launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream_t s) {
+  if (solver == SOLVE_LF) {
+    if (fkj) return launch_stage_t<EQ_GLM, SOLVE_LF, true>(a, s);
+    else return launch_stage_t<EQ_GLM, SOLVE_LF, false>(a, s);
+  }
   if (solver == SOLVE_ROE) {
     if (fkj) return launch_stage_t<EQ_GLM, SOLVE_ROE, true>(a, s);
     else return launch_stage_t<EQ_GLM, SOLVE_ROE, false>(a, s);

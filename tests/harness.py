@@ -72,6 +72,11 @@ class Problem:
     def nvar(self):
         return EQN_NVAR[self.eqn] + self.ntracer
 
+    def __post_init__(self):
+        # "Force Nbc=1 if using Lax-Friedrichs flux" (setup_fixed_grid.cpp:188-190): first order in space and time
+        if self.solver == 0:
+            self.ooa = 1
+
     @property
     def nbc(self):
         return 2 if self.ooa == 2 else 1
@@ -317,6 +322,14 @@ class RefSim(_CSim):
         err = self.lib.pref_cooling_tables(self.h, n, *[arrs[k].ctypes.data for k in TABLE_KEYS])
         assert err == 0, "reference has no mp_only_cooling object"
         return arrs
+
+    def output_text(self, base, counter=-1):
+        """The reference's ASCII writer (dataio_text::OutputData) on the current state: <base>.txt or
+        <base>.<counter:08d>.txt."""
+        self.lib.pref_output_text.restype = C.c_int
+        self.lib.pref_output_text.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
+        err = self.lib.pref_output_text(self.h, str(base).encode(), counter)
+        assert err == 0, "dataio_text::OutputData failed"
 
     def cooling_spline(self):
         """Knots and out-of-table slopes of the reference MP object's cooling-curve spline
