@@ -260,10 +260,8 @@ __device__ __forceinline__ void bc_face_extents(const GridD& g, int face, int* l
   else { lo[ax] = 0; hi[ax] = g.nb[ax]; }
 }
 
-// variable `v` of ghost cell number t of face `face` (boundary type `type`, reference values `refval`).  One thread
-// per (cell, variable): every load is independent of every other (a thread that walked the variables of its cell
-// had nvar dependent-latency round trips and, on x faces, 16 useful bytes per 32-byte sector per row anyway).
-__device__ __forceinline__ void bc_fill_cell_var(const BCArgs& a, int face, int type, const double* refval, long t, int v) {
+// ghost cell number t of face `face` (boundary type `type`, reference values `refval`)
+__device__ __forceinline__ void bc_fill_cell(const BCArgs& a, int face, int type, const double* refval, long t) {
   const GridD& g = a.g;
   int lo[3], hi[3];
   bc_face_extents(g, face, lo, hi);
@@ -279,29 +277,28 @@ __device__ __forceinline__ void bc_fill_cell_var(const BCArgs& a, int face, int 
   const long c_edge = c + (long)(edge - q) * st;
   const long c_mirror = c_edge + (long)(pos ? -(depth - 1) : (depth - 1)) * st;
   const long c_per = c + (long)(pos ? -g.NG[ax] : g.NG[ax]) * st;
-  const long o = (long)v * g.vs;
   for (int w = 0; w < a.narr; w++) {
     double* A = a.A[w];
     switch (type) {
       case 1:  // PERIODIC (periodic_boundaries.cpp:68-88)
-        A[o + c] = A[o + c_per];
+        for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = A[(long)v * g.vs + c_per];
         break;
       case 2:   // OUTFLOW (outflow_boundaries.cpp:109-160)
-      case 13: {  // ONEWAY_OUT (oneway_out_boundaries.cpp:38-115)
-        double val = A[o + c_edge];
-        if (type == 13 && v == 2 + ax) {  // no inflow: the normal velocity is clamped
+      case 13:  // ONEWAY_OUT (oneway_out_boundaries.cpp:38-115)
+        for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = A[(long)v * g.vs + c_edge];
+        if (type == 13) {
           const double sgn = pos ? 1.0 : -1.0;
-          val = sgn * fmax(0.0, val * sgn);
+          const long o = (long)(2 + ax) * g.vs + c;
+          A[o] = sgn * fmax(0.0, A[o] * sgn);
         }
-        if (a.eq == EQ_GLM && v == 8) val = -A[o + c_mirror];  // GLM_NEGATIVE_BOUNDARY
-        A[o + c] = val;
-      } break;
+        if (a.eq == EQ_GLM) A[8 * g.vs + c] = -A[8 * g.vs + c_mirror];  // GLM_NEGATIVE_BOUNDARY
+        break;
       case 4:  // REFLECTING (reflecting_boundaries.cpp:123-145): both layers copy the edge cell
-        A[o + c] = A[o + c_edge] * refval[v];
+        for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = A[(long)v * g.vs + c_edge] * refval[v];
         break;
       case 3:  // INFLOW (inflow_boundaries.cpp:83-100)
       case 5:  // FIXED (fixed_boundaries.cpp:91-107)
-        A[o + c] = refval[v];
+        for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = refval[v];
         break;
       case 8: {  // DMACH (double_Mach_ref_boundaries.cpp:169-208)
         const double dxo2 = 0.5 * g.dx;
@@ -309,10 +306,10 @@ __device__ __forceinline__ void bc_fill_cell_var(const BCArgs& a, int face, int 
         const double ypos = a.sim_xmin[1] + (2 * (ijk[1] - g.nb[1]) + 1) * dxo2;
         const double bpos = 10.0 * a.simtime / sin(M_PI / 3.0) + 1.0 / 6.0 + ypos / tan(M_PI / 3.0);
         if (xpos <= bpos) {
-          const double post[5] = {8.0, 116.5, 7.14470958, -4.125, 0.0};
-          A[o + c] = (v < 5) ? post[v] : (v >= a.ftr) ? 1.0 : A[o + c];
+          A[c] = 8.0; A[g.vs + c] = 116.5; A[2 * g.vs + c] = 7.14470958; A[3 * g.vs + c] = -4.125; A[4 * g.vs + c] = 0.0;
+          for (int v = a.ftr; v < a.nvar; v++) A[(long)v * g.vs + c] = 1.0;
         } else {
-          A[o + c] = refval[v];
+          for (int v = 0; v < a.nvar; v++) A[(long)v * g.vs + c] = refval[v];
         }
       } break;
       default:
@@ -321,31 +318,28 @@ __device__ __forceinline__ void bc_fill_cell_var(const BCArgs& a, int face, int 
   }
 }
 
-__global__ void __launch_bounds__(256) k_bc_face(const __grid_constant__ BCArgs a) {
+__global__ void k_bc_face(const __grid_constant__ BCArgs a) {
   int lo[3], hi[3];
   bc_face_extents(a.g, a.face, lo, hi);
   const long n = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
-  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n * a.nvar; t += (long)gridDim.x * blockDim.x)
-    bc_fill_cell_var(a, a.face, a.type, a.refval, t % n, (int)(t / n));
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x)
+    bc_fill_cell(a, a.face, a.type, a.refval, t);
 }
 
 // Both faces of ONE axis in one launch (they never read each other's ghost cells -- a periodic face copies
 // from interior cells): three ghost-fill launches per boundary update instead of six.  The order ACROSS axes
 // (x, y, z: edges and corners inherit) stays with the host.  `a.face` is the LOW face; type2 / refval2 describe
 // the high face; a type of 0 (or PION_BC_MPI: filled by the halo exchange) skips that face.
-__global__ void __launch_bounds__(256) k_bc_axis(const __grid_constant__ BCArgs a, const int type2, const __grid_constant__ BCRef ref2) {
+__global__ void k_bc_axis(const __grid_constant__ BCArgs a, const int type2, const __grid_constant__ BCRef ref2) {
   int lo[3], hi[3];
   bc_face_extents(a.g, a.face, lo, hi);
   const long n = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);  // same count on both faces
   const bool do_lo = a.type != 0 && a.type != 10, do_hi = type2 != 0 && type2 != 10;
-  const long nn = 2 * n;
-  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < nn * a.nvar; t += (long)gridDim.x * blockDim.x) {
-    const int v = (int)(t / nn);
-    const long r = t % nn;
-    if (r < n) {
-      if (do_lo) bc_fill_cell_var(a, a.face, a.type, a.refval, r, v);
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * n; t += (long)gridDim.x * blockDim.x) {
+    if (t < n) {
+      if (do_lo) bc_fill_cell(a, a.face, a.type, a.refval, t);
     } else if (do_hi) {
-      bc_fill_cell_var(a, a.face + 1, type2, ref2.v, r - n, v);
+      bc_fill_cell(a, a.face + 1, type2, ref2.v, t - n);
     }
   }
 }

@@ -614,7 +614,7 @@ static int update_external_bcs(pion_gpu_ctx* c, double* A0, double* A1, double s
       fill_bc_args(c, b, 2 * ax, tlo, A0, A1, simtime, c->bc_refval[2 * ax]);
       BCRef r2;
       for (int v = 0; v < PION_MAXVAR; v++) r2.v[v] = c->bc_refval[2 * ax + 1][v];
-      k_bc_axis<<<nblocks(2 * face_cells(g, 2 * ax) * c->nvar, 256, 148 * 32), 256, 0, st>>>(b, thi, r2);
+      k_bc_axis<<<nblocks(2 * face_cells(g, 2 * ax), 128), 128, 0, st>>>(b, thi, r2);
       c->launches++;
     }
     if (mpi_face) {
@@ -721,7 +721,7 @@ extern "C" int pion_gpu_init_after_upload(pion_gpu_ctx* c) {
     // BC_assign_ONEWAY_OUT is BC_assign_OUTFLOW: no velocity clamp at assign time
     // (oneway_out_boundaries.cpp:24-32)
     fill_bc_args(c, b, face, (type == PION_BC_ONEWAY_OUT) ? PION_BC_OUTFLOW : type, c->P, c->Ph, c->simtime, rv);
-    k_bc_face<<<nblocks(face_cells(g, face) * c->nvar, 256, 148 * 32), 256, 0, c->stream>>>(b);
+    k_bc_face<<<nblocks(face_cells(g, face), 128), 128, 0, c->stream>>>(b);
     c->launches++;
   }
   for (int i = 0; i < c->cfg.n_internal_bc; i++) {

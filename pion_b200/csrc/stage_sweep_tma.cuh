@@ -383,8 +383,16 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     // three Riemann solves from here; ask for its lines now so that those loads hit L1 (ncu: long-scoreboard
     // was 14 % of the corrector's stall samples, all on these loads)
     if (!pb_is_s && domain) {
+#if PION_PB_PREFETCH == 2
+      // into L2 only, by ONE lane per 128-byte line (lanes 0 and 16 of a row)
+      if ((lane & 15) == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Pb + (long)v * vs + c));
+      }
+#else
 #pragma unroll
       for (int v = 0; v < NV; v++) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Pb + (long)v * vs + c));
+#endif
     }
 #endif
 #pragma unroll 1
