@@ -59,6 +59,7 @@ struct pion_oracle {
   /* solver "class" state: eqns_base.cpp:94-131, solver_eqn_base.h */
   int dir, eVX, eVY, eVZ, eBX, eBY, eBZ, eMX, eMY, eMZ, eBBX, eBBY, eBBZ;
   double FV_dt, chyp, cr, HC_etamax, gamma;
+  long nfail_riemann; /* JMs_riemann_solve returned an error (fatal in the reference) */
   /* time: sim_params.cpp:53 */
   double simtime, dt, last_dt, next_optime;
   int timestep;
@@ -886,6 +887,282 @@ static void lax_friedrichs_flux(pion_oracle *s, const double *l, const double *r
   }
   for (int v = 0; v < nq; v++) f[v] = 0.5 * (f1[v] + f2[v] + s->dx / s->FV_dt * (u1[v] - u2[v]) / s->ndim);
 }
+
+/* ------------------------------------------------------------------ */
+/* Euler linear / exact / hybrid Riemann solvers (solverType 1, 2, 3)  */
+/* Riemann_solvers/riemann.cpp + findroot.cpp + eqns_Euler::HydroWave  */
+/* ------------------------------------------------------------------ */
+#define BASEPG 1.e-5 /* constants.h:336 */
+typedef struct {
+  const pion_oracle *s;
+  double left[5], right[5], pstar[5], cl, cr; /* natural order RO, PG, VX, VY, VZ of the SOLVER frame (eVX = sweep axis) */
+} rs_euler;
+/* eqns_Euler::HydroWave (eqns_hydro_adiabatic.cpp:221-262); lr: 0 = XN (left wave), 1 = XP; pre[] = {ro, pg, vx} */
+static double hydro_wave(double gamma, int lr, double pp, const double *pre) {
+  double pratio = pp / pre[1], u;
+  double c0 = sqrt(gamma * pre[1] / pre[0]);
+  if (pratio < 1) {
+    u = 2. * c0 / (gamma - 1.) * (1 - exp((gamma - 1.) / 2. / gamma * log(pratio)));
+    u = (lr == 0) ? pre[2] + u : pre[2] - u;
+  } else if (pratio > 1) {
+    u = c0 * (pratio - 1.) / sqrt(gamma * (gamma - 1.) / 2. * (1. + pratio * (gamma + 1.) / (gamma - 1.)));
+    u = (lr == 0) ? pre[2] - u : pre[2] + u;
+  } else {
+    u = pre[2];
+  }
+  return u;
+}
+/* eqns_Euler::HydroWaveFull (:269-302) */
+static void hydro_wave_full(double gamma, int lr, double pp, const double *pre, double *u, double *rho) {
+  double pratio = pp / pre[1];
+  *u = hydro_wave(gamma, lr, pp, pre);
+  if (pratio < 1) *rho = pre[0] * exp(log(pratio) / gamma);
+  else if (pratio > 1) *rho = pre[0] * (1 + pratio * (gamma + 1) / (gamma - 1.)) / ((gamma + 1.) / (gamma - 1.) + pratio);
+  else *rho = pre[0];
+}
+/* riemann_Euler::FR_root_function (riemann.cpp:99-121) */
+static double rs_root_function(const rs_euler *r, double pp) {
+  double g = r->s->gamma;
+  double L[3] = {r->left[0], r->left[1], r->left[2]}, R[3] = {r->right[0], r->right[1], r->right[2]};
+  return hydro_wave(g, 1, pp, R) - hydro_wave(g, 0, pp, L);
+}
+/* findroot::bracket_root_pos (findroot.cpp:270-310): `factor` is a float in the reference */
+static int rs_bracket_root_pos(const rs_euler *r, double *x1, double *x2) {
+  float factor = 1.6;
+  if (*x1 == *x2) return 1;
+  if (*x1 > *x2) { double t = *x1; *x1 = *x2; *x2 = t; }
+  double f1 = rs_root_function(r, *x1), f2 = rs_root_function(r, *x2);
+  for (int j = 0; j < 50; j++) {
+    if (f1 * f2 < 0) return 0;
+    if (fabs(f1) < fabs(f2)) f1 = rs_root_function(r, *x1 *= 1. / factor);
+    else f2 = rs_root_function(r, *x2 *= factor);
+  }
+  f1 = rs_root_function(r, *x1 = 0.);
+  if (f1 * f2 < 0) return 0;
+  *x1 = *x2 = 0.;
+  return 1;
+}
+/* findroot::find_root_zbrent (findroot.cpp:359-452): NR zbrent with a purely relative tolerance */
+static int rs_zbrent(const rs_euler *r, double x1, double x2, double tol, double *ans) {
+  int ITMAX = 100;
+  double EPS = MACHINEACCURACY;
+  double a = x1, b = x2, c = x2, d, e, min1, min2;
+  double fa = rs_root_function(r, a), fb = rs_root_function(r, b), fc, p, q, rr, sv, tol1, xm;
+  d = 0.; e = 0.;
+  if ((fa > 0.0 && fb > 0.0) || (fa < 0.0 && fb < 0.0)) return 1;
+  fc = fb;
+  for (int iter = 1; iter <= ITMAX; iter++) {
+    if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) { c = a; fc = fa; e = d = b - a; }
+    if (fabs(fc) < fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+    tol1 = 2.0 * EPS * fabs(b) + 0.5 * tol * fabs(b);
+    xm = 0.5 * (c - b);
+    if (fabs(xm) <= tol1 || fb == 0.0) { *ans = b; return 0; }
+    if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
+      sv = fb / fa;
+      if (a == c) { p = 2.0 * xm * sv; q = 1.0 - sv; }
+      else {
+        q = fa / fc;
+        rr = fb / fc;
+        p = sv * (2.0 * xm * q * (q - rr) - (b - a) * (rr - 1.0));
+        q = (q - 1.0) * (rr - 1.0) * (sv - 1.0);
+      }
+      if (p > 0.0) q = -q;
+      p = fabs(p);
+      min1 = 3.0 * xm * q - fabs(tol1 * q);
+      min2 = fabs(e * q);
+      if (2.0 * p < (min1 < min2 ? min1 : min2)) { e = d; d = p / q; }
+      else { d = xm; e = d; }
+    } else { d = xm; e = d; }
+    a = b;
+    fa = fb;
+    if (fabs(d) > tol1) b += d;
+    else b += ((xm) >= 0.0 ? fabs(tol1) : -fabs(tol1));
+    fb = rs_root_function(r, b);
+  }
+  return 1;
+}
+/* riemann_Euler::check_wave_locations (riemann.cpp:471-585) */
+static void rs_check_wave_locations(rs_euler *r) {
+  const double g = r->s->gamma;
+  double *ps = r->pstar;
+  const double *L = r->left, *R = r->right;
+  if (ps[1] < L[1]) {
+    if (L[2] >= r->cl) { ps[1] = L[1]; ps[0] = L[0]; ps[2] = L[2]; return; }
+    else if (ps[2] > 0.) {
+      double cstar = sqrt(g * ps[1] / ps[0]);
+      if (ps[2] > cstar) {
+        ps[2] = (2. * r->cl + L[2] * (g - 1.)) / (g + 1.);
+        ps[0] = L[0] * exp(2. / (g - 1.) * log(ps[2] / r->cl));
+        ps[1] = exp(g * log(ps[0] / L[0])) * L[1];
+        return;
+      }
+    }
+  }
+  if (ps[1] < R[1]) {
+    if (R[2] <= -r->cr) { ps[1] = R[1]; ps[0] = R[0]; ps[2] = R[2]; return; }
+    else if (ps[2] < 0.) {
+      double cstar = sqrt(g * ps[1] / ps[0]);
+      if (ps[2] < -cstar) {
+        ps[2] = (-2. * r->cr + R[2] * (g - 1.)) / (g + 1.);
+        ps[0] = R[0] * exp(2. / (g - 1.) * log(-ps[2] / r->cr));
+        ps[1] = exp(g * log(ps[0] / R[0])) * R[1];
+        return;
+      }
+    }
+  }
+  if (ps[1] > 1.0000001 * R[1]) {
+    double vsh = R[2] + (ps[1] / R[1] - 1.) * r->cr * r->cr / g / (ps[2] - R[2]);
+    if (vsh < 0.) { ps[1] = R[1]; ps[0] = R[0]; ps[2] = R[2]; return; }
+  }
+  if (ps[1] > 1.0000001 * L[1]) {
+    double vsh = L[2] + (ps[1] / L[1] - 1.) * r->cl * r->cl / g / (ps[2] - L[2]);
+    if (vsh > 0.) { ps[1] = L[1]; ps[0] = L[0]; ps[2] = L[2]; return; }
+  }
+}
+/* riemann_Euler::linearOK (riemann.cpp:592-600) */
+static int rs_linearOK(const rs_euler *r) {
+  const double *L = r->left, *R = r->right;
+  if ((fmax(L[1], R[1]) / fmin(L[1], R[1]) < 1.4) && (fmax(L[0], R[0]) / fmin(L[0], R[0]) < 1.4) &&
+      (fabs(R[2] - L[2]) / fmin(r->cl, r->cr) < 0.03)) return 0;
+  return 1;
+}
+/* riemann_Euler::linear_solver (riemann.cpp:674-747) */
+static int rs_linear_solver(rs_euler *r) {
+  const double g = r->s->gamma;
+  double meanp[5];
+  for (int i = 0; i < 5; i++) meanp[i] = (r->left[i] + r->right[i]) / 2.;
+  double mcs = sqrt(g * meanp[1] / meanp[0]);
+  double *ps = r->pstar;
+  const double *L = r->left, *R = r->right;
+  if (meanp[2] - mcs >= 0.) { for (int i = 0; i < 5; i++) ps[i] = L[i]; return 0; }
+  else if (meanp[2] + mcs <= 0.) { for (int i = 0; i < 5; i++) ps[i] = R[i]; return 0; }
+  ps[1] = 0.5 * (L[1] + R[1] - meanp[0] * mcs * (R[2] - L[2]));
+  ps[2] = 0.5 * (L[2] + R[2] - (R[1] - L[1]) / meanp[0] / mcs);
+  if (fabs(ps[2] / mcs) <= 1.e-6) ps[0] = meanp[0] * (2. + (L[2] - R[2]) / mcs) / 2.;
+  else if (ps[2] > 0) ps[0] = L[0] + meanp[0] * (L[2] - ps[2]) / mcs;
+  else if (ps[2] < 0) ps[0] = R[0] + meanp[0] * (ps[2] - R[2]) / mcs;
+  else return 1;
+  return 0;
+}
+/* riemann_Euler::exact_solver (riemann.cpp:754-822) with FR_find_root (:56-92) and findroot::solve_pos */
+static int rs_exact_solver(rs_euler *r) {
+  const double g = r->s->gamma;
+  double *ps = r->pstar;
+  int err = 0;
+  {
+    double x1 = (r->left[1] + r->right[1]) / 6.0, x2 = x1 * 9.0;
+    if (rs_bracket_root_pos(r, &x1, &x2)) { ps[1] = -1.0; err += 1; }
+    else if (rs_zbrent(r, x1, x2, 1.0e-8, &ps[1])) { ps[1] = -1.0; err += 1; }
+  }
+  double L[3] = {r->left[0], r->left[1], r->left[2]}, R[3] = {r->right[0], r->right[1], r->right[2]};
+  hydro_wave_full(g, 0, ps[1], L, &ps[2], &ps[0]);
+  double rhostar, temp;
+  if ((ps[2] > 0) && (fabs(ps[2] / r->cr) > 1.e-6)) hydro_wave_full(g, 0, ps[1], L, &temp, &rhostar);
+  else if ((ps[2] < 0) && (fabs(ps[2] / r->cr) > 1.e-6)) hydro_wave_full(g, 1, ps[1], R, &temp, &rhostar);
+  else if (fabs(ps[2] / r->cr) <= 1.e-6) {
+    hydro_wave_full(g, 0, ps[1], L, &temp, &rhostar);
+    hydro_wave_full(g, 1, ps[1], R, &temp, &ps[0]);
+    rhostar = (rhostar + ps[0]) / 2.0;
+  } else { ps[0] = -1.0; return 1; }
+  ps[0] = rhostar;
+  if (err != 0) { ps[1] = ps[0] = ps[2] = -1.9; return 1; }
+  rs_check_wave_locations(r);
+  return 0;
+}
+/* riemann_Euler::solve_rarerare (riemann.cpp:829-885) */
+static int rs_solve_rarerare(rs_euler *r) {
+  const double g = r->s->gamma, cl = r->cl, cr = r->cr;
+  double *ps = r->pstar;
+  const double *L = r->left, *R = r->right;
+  ps[1] = pow((cl + cr - (g - 1.) / 2. * (R[2] - L[2])) /
+                  ((cl * exp(-(g - 1.) / 2. / g * log(L[1]))) + (cr * exp(-(g - 1.) / 2. / g * log(R[1])))),
+              2. * g / (g - 1.));
+  ps[2] = L[2] + 2. * cl / (g - 1.) * (1. - exp((g - 1.) / 2. / g * log(ps[1] / L[1])));
+  if ((ps[2] > 0) && (fabs(ps[2] / cr) > 1.e-6)) ps[0] = L[0] * exp(log(ps[1] / L[1]) / g);
+  else if ((ps[2] < 0) && (fabs(ps[2] / cr) > 1.e-6)) ps[0] = R[0] * exp(log(ps[1] / R[1]) / g);
+  else if (fabs(ps[2] / cr) <= 1.e-6) ps[0] = ((R[0] * exp(log(ps[1] / R[1]) / g)) + (L[0] * exp(log(ps[1] / L[1]) / g))) / 2.0;
+  else { ps[0] = -1.0; return 1; }
+  rs_check_wave_locations(r);
+  return 0;
+}
+/* riemann_Euler::solve_cavitation (riemann.cpp:892-960) */
+static int rs_solve_cavitation(rs_euler *r) {
+  const double g = r->s->gamma, cl = r->cl, cr = r->cr;
+  double *ps = r->pstar;
+  const double *L = r->left, *R = r->right;
+  if ((L[2] - cl) >= 0.) { for (int i = 0; i < 5; i++) ps[i] = L[i]; return 0; }
+  double temp = 2. / (g - 1.);
+  if ((L[2] + temp * cl) >= 0.) {
+    ps[2] = (2. * cl + L[2] * (g - 1.)) / (g + 1.);
+    ps[0] = L[0] * exp(2. / (g - 1.) * log(ps[2] / cl));
+    ps[1] = exp(g * log(ps[0] / L[0])) * L[1];
+    return 0;
+  }
+  if ((R[2] - temp * cr) >= 0.) {
+    /* eq_refvec[eqRO|eqPG|eqVX]: the solver's direction-rotated velocity index */
+    ps[0] = r->s->cfg.refvec[RO] * BASEPG;
+    ps[1] = r->s->cfg.refvec[PG] * BASEPG;
+    ps[2] = r->s->cfg.refvec[r->s->eVX] * BASEPG;
+    return 0;
+  }
+  if ((R[2] + cr) > 0.) {
+    ps[2] = (-2. * cr + R[2] * (g - 1.)) / (g + 1.);
+    ps[0] = R[0] * exp(2. / (g - 1.) * log(-ps[2] / cr));
+    ps[1] = exp(g * log(ps[0] / R[0])) * R[1];
+    return 0;
+  }
+  if ((R[2] + cr) <= 0.) { for (int i = 0; i < 5; i++) ps[i] = R[i]; return 0; }
+  return 1;
+}
+/* riemann_Euler::JMs_riemann_solve (riemann.cpp:245-463); l, r, ans are grid-frame primitive vectors */
+static int rs_euler_solve(pion_oracle *s, const double *l, const double *rgt, double *ans, int mode) {
+  rs_euler r;
+  r.s = s;
+  const int ix[5] = {RO, PG, s->eVX, s->eVY, s->eVZ};
+  for (int v = 0; v < 5; v++) { r.left[v] = l[ix[v]]; r.right[v] = rgt[ix[v]]; r.pstar[v] = 0.0; }
+  const double g = s->gamma;
+  /* "same state" shortcut: the sum runs over the UNROTATED components with the unrotated reference vector */
+  double diff = 0.;
+  for (int i = 0; i < 5; i++) diff += fabs(rgt[i] - l[i]) / (fabs(s->cfg.refvec[i]) + TINYVALUE);
+  if (diff < 1.e-6) {
+    for (int i = 0; i < 5; i++) ans[i] = (l[i] + rgt[i]) / 2.;
+    return 0;
+  }
+  r.cl = sqrt(g * r.left[1] / r.left[0]);
+  r.cr = sqrt(g * r.right[1] / r.right[0]);
+  int err = 0, fail = 0;
+  if ((r.right[2] - r.left[2]) <= 2. * (r.cl + sqrt((g - 1.) / 2. / g) * r.cr) / (g - 1.)) {
+    if (mode == 1) {
+      err = rs_linear_solver(&r);
+      if (err) { r.pstar[1] = r.pstar[0] = r.pstar[2] = TINYVALUE; fail = 1; }
+    } else if (mode == 2) {
+      err = rs_exact_solver(&r);
+      if (err) { r.pstar[1] = r.pstar[0] = TINYVALUE; fail = 1; }
+    } else {
+      err = rs_linear_solver(&r);
+      if (err) r.pstar[1] = r.pstar[0] = r.pstar[2] = TINYVALUE;
+      if (err != 0 || rs_linearOK(&r) != 0) {
+        err = rs_exact_solver(&r);
+        if (err) { r.pstar[1] = r.pstar[0] = TINYVALUE; fail = 1; }
+      }
+    }
+  } else if ((r.right[2] - r.left[2]) <= 2. * (r.cl + r.cr) / (g - 1.)) {
+    err = rs_solve_rarerare(&r);
+    if (err) { r.pstar[1] = r.pstar[0] = r.pstar[2] = -1.9e99; fail = 1; }
+  } else {
+    err = rs_solve_cavitation(&r);
+    if (err) { r.pstar[1] = r.pstar[0] = r.pstar[2] = -1.9e100; fail = 1; }
+  }
+  if (!fail) {
+    if (r.pstar[2] > 0) { r.pstar[3] = r.left[3]; r.pstar[4] = r.left[4]; }
+    else { r.pstar[3] = r.right[3]; r.pstar[4] = r.right[4]; }
+    if (r.pstar[1] <= TINYVALUE) r.pstar[1] = BASEPG * s->cfg.refvec[PG];
+    if (r.pstar[0] <= TINYVALUE) r.pstar[0] = BASEPG * s->cfg.refvec[RO];
+  }
+  /* the reference copies rs_pstar[i] -> ans[i] by NATURAL index: rs_pstar is indexed with the rotated eq* indices */
+  for (int v = 0; v < 5; v++) ans[ix[v]] = r.pstar[v];
+  return fail;
+}
 /* FV_solver_Hydro_Euler::inviscid_flux (solver_eqn_hydro_adi.cpp:94-205) */
 static void euler_inviscid_flux(pion_oracle *s, const double *Pl, const double *Pr, double *flux, double *pstar) {
   double ustar[PO_MAXVAR];
@@ -893,6 +1170,10 @@ static void euler_inviscid_flux(pion_oracle *s, const double *Pl, const double *
   if (s->cfg.solver == PO_FLUX_LF) { /* :142-148 */
     lax_friedrichs_flux(s, Pl, Pr, flux);
     for (int v = 0; v < 5; v++) pstar[v] = 0.5 * (Pl[v] + Pr[v]);
+  } else if (s->cfg.solver >= 1 && s->cfg.solver <= 3) { /* :160-168: linear / exact / hybrid Riemann solver, then PtoFlux */
+    if (rs_euler_solve(s, Pl, Pr, pstar, s->cfg.solver)) s->nfail_riemann++;
+    euler_PtoU(s, pstar, ustar);
+    euler_PUtoFlux(s, pstar, ustar, flux);
   } else if (s->cfg.solver == PO_FLUX_ROE) {
     hydro_RoeCV(s, Pl, Pr, s->HC_etamax, pstar, flux);
   } else if (s->cfg.solver == PO_FLUX_HLL) {
