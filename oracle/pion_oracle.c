@@ -1085,6 +1085,11 @@ static int rs_solve_rarerare(rs_euler *r) {
   rs_check_wave_locations(r);
   return 0;
 }
+/* eqns_Euler::SetAvgState (eqns_hydro_adiabatic.cpp:439-453, called once by the riemann_Euler constructor,
+ * riemann.cpp:171): the solver's reference velocities are a tenth of the sound speed of RefVec, all three */
+static double rs_refvel(const pion_oracle *s) {
+  return 0.1 * sqrt(s->gamma * s->cfg.refvec[PG] / s->cfg.refvec[RO]);
+}
 /* riemann_Euler::solve_cavitation (riemann.cpp:892-960) */
 static int rs_solve_cavitation(rs_euler *r) {
   const double g = r->s->gamma, cl = r->cl, cr = r->cr;
@@ -1102,7 +1107,7 @@ static int rs_solve_cavitation(rs_euler *r) {
     /* eq_refvec[eqRO|eqPG|eqVX]: the solver's direction-rotated velocity index */
     ps[0] = r->s->cfg.refvec[RO] * BASEPG;
     ps[1] = r->s->cfg.refvec[PG] * BASEPG;
-    ps[2] = r->s->cfg.refvec[r->s->eVX] * BASEPG;
+    ps[2] = rs_refvel(r->s) * BASEPG;
     return 0;
   }
   if ((R[2] + cr) > 0.) {
@@ -1123,7 +1128,8 @@ static int rs_euler_solve(pion_oracle *s, const double *l, const double *rgt, do
   const double g = s->gamma;
   /* "same state" shortcut: the sum runs over the UNROTATED components with the unrotated reference vector */
   double diff = 0.;
-  for (int i = 0; i < 5; i++) diff += fabs(rgt[i] - l[i]) / (fabs(s->cfg.refvec[i]) + TINYVALUE);
+  const double refvel = rs_refvel(s);
+  for (int i = 0; i < 5; i++) diff += fabs(rgt[i] - l[i]) / (fabs(i >= 2 ? refvel : s->cfg.refvec[i]) + TINYVALUE);
   if (diff < 1.e-6) {
     for (int i = 0; i < 5; i++) ans[i] = (l[i] + rgt[i]) / 2.;
     return 0;

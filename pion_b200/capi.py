@@ -86,6 +86,7 @@ def load_library(path=None):
         "pion_gpu_output_due": (i, [vp, i, pi]),
         "pion_gpu_counters": (i, [vp, vp]),
         "pion_gpu_mp_failures": (i, [vp, C.POINTER(C.c_longlong)]),
+        "pion_gpu_riemann_failures": (i, [vp, C.POINTER(C.c_longlong)]),
         "pion_gpu_sync": (i, [vp]),
         "pion_gpu_stream": (vp, [vp]),
         "pion_gpu_stage_timing": (i, [vp, i, pd, C.POINTER(C.c_longlong)]),
@@ -107,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "pion_gpu_set_glm_speeds", "pion_gpu_set_time", "pion_gpu_get_time", "pion_gpu_calc_microphysics_dU",
     "pion_gpu_calc_dynamics_dU", "pion_gpu_grid_update_state_vector", "pion_gpu_time_update_bcs",
     "pion_gpu_time_update_internal_bcs", "pion_gpu_time_update_external_bcs",
-    "pion_gpu_advance_time", "pion_gpu_run", "pion_gpu_output_due", "pion_gpu_counters", "pion_gpu_mp_failures", "pion_gpu_sync", "pion_gpu_stream",
+    "pion_gpu_advance_time", "pion_gpu_run", "pion_gpu_output_due", "pion_gpu_counters", "pion_gpu_mp_failures", "pion_gpu_riemann_failures", "pion_gpu_sync", "pion_gpu_stream",
     "pion_gpu_nccl_unique_id", "pion_gpu_nccl_init", "pion_gpu_decompose_domain", "pion_gpu_stage_timing",
     "pion_gpu_describe",
 ]
@@ -211,6 +212,11 @@ class Context:
         out = (C.c_longlong * 3)()
         self._ck(self.lib.pion_gpu_counters(self.h, out), "counters")
         return list(out)
+
+    def riemann_failures(self):
+        out = C.c_longlong(0)
+        self._ck(self.lib.pion_gpu_riemann_failures(self.h, C.byref(out)), "riemann_failures")
+        return int(out.value)
 
     def mp_failures(self):
         out = C.c_longlong(0)

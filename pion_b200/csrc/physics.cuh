@@ -24,7 +24,7 @@
 namespace pion {
 
 enum : int { EQ_EULER = 1, EQ_MHD = 2, EQ_GLM = 3 };                 // constants.h:166-172
-enum : int { SOLVE_LF = 0, SOLVE_ROE = 4, SOLVE_ROE_PV = 5, SOLVE_FVS = 6, SOLVE_HLLD = 7, SOLVE_HLL = 8 };  // constants.h:238-246 (5, 6: Euler only)
+enum : int { SOLVE_LF = 0, SOLVE_RSLINEAR = 1, SOLVE_RSEXACT = 2, SOLVE_RSHYBRID = 3, SOLVE_ROE = 4, SOLVE_ROE_PV = 5, SOLVE_FVS = 6, SOLVE_HLLD = 7, SOLVE_HLL = 8 };  // constants.h:238-246 (5, 6: Euler only)
 enum : int { AV_NONE = 0, AV_FKJ98 = 1, AV_HCORR = 3, AV_HCORR_FKJ98 = 4 };
 
 #define PION_MACHINEACCURACY 5.e-16    // constants.h:151
@@ -54,6 +54,7 @@ struct PhysParams {
   int have_mp;
   double lf_c;         // Lax-Friedrichs only: dx / FV_dt (set per stage launch)
   double lf_ndim;      // ... and FV_gndim
+  double rs_refvec[5]; // linear / exact / hybrid Riemann solvers: riemann_Euler::eq_refvec = RefVec[RO, PG] and 0.1 c(RefVec) three times (SetAvgState)
 };
 
 __device__ __forceinline__ double sq(double x) { return x * x; }
@@ -131,7 +132,7 @@ __device__ __forceinline__ void PtoU_mhd_ideal(const Prim& p, Cons& u, double gm
 }
 
 // status bits returned by UtoP
-enum : int { ST_NEG_RHO = 1, ST_NEG_PG = 2 };
+enum : int { ST_NEG_RHO = 1, ST_NEG_PG = 2, ST_RS_FAIL = 4 };  // ST_RS_FAIL: JMs_riemann_solve returned an error
 
 // UtoP with the reference's floors (SET_NEGATIVE_PRESSURE_TO_FIXED_TEMPERATURE):
 // Euler eqns_hydro_adiabatic.cpp:117-205, MHD eqns_mhd_adiabatic.cpp:110-224,
@@ -508,6 +509,284 @@ __device__ __forceinline__ void hydro_RoeCV(const Prim& L, const Prim& R, const 
   pstar.bn = pstar.bt1 = pstar.bt2 = pstar.psi = 0.0;
 }
 
+
+// ---------------------------------------------------------------------------
+// Euler linear / exact / hybrid Riemann solvers (solverType 1, 2, 3):
+// riemann_Euler::JMs_riemann_solve (Riemann_solvers/riemann.cpp:245-463) with linear_solver (:674-747), linearOK
+// (:592-600), exact_solver (:754-822: p* from findroot::solve_pos = bracket_root_pos + Brent's zbrent,
+// findroot.cpp:158-183,270-310,359-452, on eqns_Euler::HydroWave, eqns_hydro_adiabatic.cpp:221-302),
+// check_wave_locations (:471-585), solve_rarerare (:829-885), solve_cavitation (:892-960).  States are
+// {ro, pg, vn} (+ vt1, vt2 copied from the upwind side).  Plain IEEE arithmetic (exp / log / pow / sqrt / division as
+// written in the reference): these solvers run on the gather kernel only and are not performance paths.
+// ---------------------------------------------------------------------------
+struct RsEuler {
+  double g;
+  double L[3], R[3], ps[3], cl, cr;  // ro, pg, vn
+};
+__device__ inline double rs_hydro_wave(double gamma, int lr, double pp, const double* pre) {
+  const double pratio = pp / pre[1];
+  const double c0 = sqrt(gamma * pre[1] / pre[0]);
+  double u;
+  if (pratio < 1) {
+    u = 2. * c0 / (gamma - 1.) * (1 - exp((gamma - 1.) / 2. / gamma * log(pratio)));
+    u = (lr == 0) ? pre[2] + u : pre[2] - u;
+  } else if (pratio > 1) {
+    u = c0 * (pratio - 1.) / sqrt(gamma * (gamma - 1.) / 2. * (1. + pratio * (gamma + 1.) / (gamma - 1.)));
+    u = (lr == 0) ? pre[2] - u : pre[2] + u;
+  } else {
+    u = pre[2];
+  }
+  return u;
+}
+__device__ inline void rs_hydro_wave_full(double gamma, int lr, double pp, const double* pre, double* u, double* rho) {
+  const double pratio = pp / pre[1];
+  *u = rs_hydro_wave(gamma, lr, pp, pre);
+  if (pratio < 1) *rho = pre[0] * exp(log(pratio) / gamma);
+  else if (pratio > 1) *rho = pre[0] * (1 + pratio * (gamma + 1) / (gamma - 1.)) / ((gamma + 1.) / (gamma - 1.) + pratio);
+  else *rho = pre[0];
+}
+__device__ inline double rs_root_function(const RsEuler& r, double pp) {
+  return rs_hydro_wave(r.g, 1, pp, r.R) - rs_hydro_wave(r.g, 0, pp, r.L);
+}
+__device__ inline int rs_bracket_root_pos(const RsEuler& r, double* x1, double* x2) {
+  const float factor = 1.6f;  // a float in the reference
+  if (*x1 == *x2) return 1;
+  if (*x1 > *x2) { const double t = *x1; *x1 = *x2; *x2 = t; }
+  double f1 = rs_root_function(r, *x1), f2 = rs_root_function(r, *x2);
+  for (int j = 0; j < 50; j++) {
+    if (f1 * f2 < 0) return 0;
+    if (fabs(f1) < fabs(f2)) { *x1 *= 1. / factor; f1 = rs_root_function(r, *x1); }
+    else { *x2 *= factor; f2 = rs_root_function(r, *x2); }
+  }
+  *x1 = 0.;
+  f1 = rs_root_function(r, *x1);
+  if (f1 * f2 < 0) return 0;
+  *x1 = *x2 = 0.;
+  return 1;
+}
+__device__ inline int rs_zbrent(const RsEuler& r, double x1, double x2, double tol, double* ans) {
+  const double EPS = PION_MACHINEACCURACY;
+  double a = x1, b = x2, c = x2, d = 0., e = 0., min1, min2;
+  double fa = rs_root_function(r, a), fb = rs_root_function(r, b), fc, p, q, rr, sv, tol1, xm;
+  if ((fa > 0.0 && fb > 0.0) || (fa < 0.0 && fb < 0.0)) return 1;
+  fc = fb;
+  for (int iter = 1; iter <= 100; iter++) {
+    if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) { c = a; fc = fa; e = d = b - a; }
+    if (fabs(fc) < fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+    tol1 = 2.0 * EPS * fabs(b) + 0.5 * tol * fabs(b);
+    xm = 0.5 * (c - b);
+    if (fabs(xm) <= tol1 || fb == 0.0) { *ans = b; return 0; }
+    if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
+      sv = fb / fa;
+      if (a == c) { p = 2.0 * xm * sv; q = 1.0 - sv; }
+      else {
+        q = fa / fc;
+        rr = fb / fc;
+        p = sv * (2.0 * xm * q * (q - rr) - (b - a) * (rr - 1.0));
+        q = (q - 1.0) * (rr - 1.0) * (sv - 1.0);
+      }
+      if (p > 0.0) q = -q;
+      p = fabs(p);
+      min1 = 3.0 * xm * q - fabs(tol1 * q);
+      min2 = fabs(e * q);
+      if (2.0 * p < (min1 < min2 ? min1 : min2)) { e = d; d = p / q; }
+      else { d = xm; e = d; }
+    } else { d = xm; e = d; }
+    a = b;
+    fa = fb;
+    if (fabs(d) > tol1) b += d;
+    else b += ((xm) >= 0.0 ? fabs(tol1) : -fabs(tol1));
+    fb = rs_root_function(r, b);
+  }
+  return 1;
+}
+__device__ inline void rs_check_wave_locations(RsEuler& r) {
+  const double g = r.g;
+  double* ps = r.ps;
+  const double *L = r.L, *R = r.R;
+  if (ps[1] < L[1]) {
+    if (L[2] >= r.cl) { ps[1] = L[1]; ps[0] = L[0]; ps[2] = L[2]; return; }
+    else if (ps[2] > 0.) {
+      const double cstar = sqrt(g * ps[1] / ps[0]);
+      if (ps[2] > cstar) {
+        ps[2] = (2. * r.cl + L[2] * (g - 1.)) / (g + 1.);
+        ps[0] = L[0] * exp(2. / (g - 1.) * log(ps[2] / r.cl));
+        ps[1] = exp(g * log(ps[0] / L[0])) * L[1];
+        return;
+      }
+    }
+  }
+  if (ps[1] < R[1]) {
+    if (R[2] <= -r.cr) { ps[1] = R[1]; ps[0] = R[0]; ps[2] = R[2]; return; }
+    else if (ps[2] < 0.) {
+      const double cstar = sqrt(g * ps[1] / ps[0]);
+      if (ps[2] < -cstar) {
+        ps[2] = (-2. * r.cr + R[2] * (g - 1.)) / (g + 1.);
+        ps[0] = R[0] * exp(2. / (g - 1.) * log(-ps[2] / r.cr));
+        ps[1] = exp(g * log(ps[0] / R[0])) * R[1];
+        return;
+      }
+    }
+  }
+  if (ps[1] > 1.0000001 * R[1]) {
+    const double vsh = R[2] + (ps[1] / R[1] - 1.) * r.cr * r.cr / g / (ps[2] - R[2]);
+    if (vsh < 0.) { ps[1] = R[1]; ps[0] = R[0]; ps[2] = R[2]; return; }
+  }
+  if (ps[1] > 1.0000001 * L[1]) {
+    const double vsh = L[2] + (ps[1] / L[1] - 1.) * r.cl * r.cl / g / (ps[2] - L[2]);
+    if (vsh > 0.) { ps[1] = L[1]; ps[0] = L[0]; ps[2] = L[2]; return; }
+  }
+}
+__device__ inline int rs_linear_solver(RsEuler& r) {
+  double m[3];
+  for (int i = 0; i < 3; i++) m[i] = (r.L[i] + r.R[i]) / 2.;
+  const double mcs = sqrt(r.g * m[1] / m[0]);
+  double* ps = r.ps;
+  const double *L = r.L, *R = r.R;
+  if (m[2] - mcs >= 0.) { for (int i = 0; i < 3; i++) ps[i] = L[i]; return 0; }
+  else if (m[2] + mcs <= 0.) { for (int i = 0; i < 3; i++) ps[i] = R[i]; return 0; }
+  ps[1] = 0.5 * (L[1] + R[1] - m[0] * mcs * (R[2] - L[2]));
+  ps[2] = 0.5 * (L[2] + R[2] - (R[1] - L[1]) / m[0] / mcs);
+  if (fabs(ps[2] / mcs) <= 1.e-6) ps[0] = m[0] * (2. + (L[2] - R[2]) / mcs) / 2.;
+  else if (ps[2] > 0) ps[0] = L[0] + m[0] * (L[2] - ps[2]) / mcs;
+  else if (ps[2] < 0) ps[0] = R[0] + m[0] * (ps[2] - R[2]) / mcs;
+  else return 1;
+  return 0;
+}
+__device__ inline int rs_exact_solver(RsEuler& r) {
+  const double g = r.g;
+  double* ps = r.ps;
+  int err = 0;
+  {
+    double x1 = (r.L[1] + r.R[1]) / 6.0, x2 = x1 * 9.0;
+    if (rs_bracket_root_pos(r, &x1, &x2)) { ps[1] = -1.0; err += 1; }
+    else if (rs_zbrent(r, x1, x2, 1.0e-8, &ps[1])) { ps[1] = -1.0; err += 1; }
+  }
+  rs_hydro_wave_full(g, 0, ps[1], r.L, &ps[2], &ps[0]);
+  double rhostar, temp;
+  if ((ps[2] > 0) && (fabs(ps[2] / r.cr) > 1.e-6)) rs_hydro_wave_full(g, 0, ps[1], r.L, &temp, &rhostar);
+  else if ((ps[2] < 0) && (fabs(ps[2] / r.cr) > 1.e-6)) rs_hydro_wave_full(g, 1, ps[1], r.R, &temp, &rhostar);
+  else if (fabs(ps[2] / r.cr) <= 1.e-6) {
+    rs_hydro_wave_full(g, 0, ps[1], r.L, &temp, &rhostar);
+    rs_hydro_wave_full(g, 1, ps[1], r.R, &temp, &ps[0]);
+    rhostar = (rhostar + ps[0]) / 2.0;
+  } else { ps[0] = -1.0; return 1; }
+  ps[0] = rhostar;
+  if (err != 0) { ps[1] = ps[0] = ps[2] = -1.9; return 1; }
+  rs_check_wave_locations(r);
+  return 0;
+}
+__device__ inline int rs_solve_rarerare(RsEuler& r) {
+  const double g = r.g, cl = r.cl, cr = r.cr;
+  double* ps = r.ps;
+  const double *L = r.L, *R = r.R;
+  ps[1] = pow((cl + cr - (g - 1.) / 2. * (R[2] - L[2])) /
+                  ((cl * exp(-(g - 1.) / 2. / g * log(L[1]))) + (cr * exp(-(g - 1.) / 2. / g * log(R[1])))),
+              2. * g / (g - 1.));
+  ps[2] = L[2] + 2. * cl / (g - 1.) * (1. - exp((g - 1.) / 2. / g * log(ps[1] / L[1])));
+  if ((ps[2] > 0) && (fabs(ps[2] / cr) > 1.e-6)) ps[0] = L[0] * exp(log(ps[1] / L[1]) / g);
+  else if ((ps[2] < 0) && (fabs(ps[2] / cr) > 1.e-6)) ps[0] = R[0] * exp(log(ps[1] / R[1]) / g);
+  else if (fabs(ps[2] / cr) <= 1.e-6) ps[0] = ((R[0] * exp(log(ps[1] / R[1]) / g)) + (L[0] * exp(log(ps[1] / L[1]) / g))) / 2.0;
+  else { ps[0] = -1.0; return 1; }
+  rs_check_wave_locations(r);
+  return 0;
+}
+// copy_lr: 0 = the three scalars were set, 1 = pstar := whole left state, 2 = whole right state (their v_t too)
+__device__ inline int rs_solve_cavitation(RsEuler& r, const double* refvec_ro_pg_vn) {
+  const double g = r.g, cl = r.cl, cr = r.cr;
+  double* ps = r.ps;
+  const double *L = r.L, *R = r.R;
+  if ((L[2] - cl) >= 0.) { for (int i = 0; i < 3; i++) ps[i] = L[i]; return 0; }
+  const double temp = 2. / (g - 1.);
+  if ((L[2] + temp * cl) >= 0.) {
+    ps[2] = (2. * cl + L[2] * (g - 1.)) / (g + 1.);
+    ps[0] = L[0] * exp(2. / (g - 1.) * log(ps[2] / cl));
+    ps[1] = exp(g * log(ps[0] / L[0])) * L[1];
+    return 0;
+  }
+  if ((R[2] - temp * cr) >= 0.) {
+    ps[0] = refvec_ro_pg_vn[0] * 1.e-5;  // BASEPG, constants.h:336
+    ps[1] = refvec_ro_pg_vn[1] * 1.e-5;
+    ps[2] = refvec_ro_pg_vn[2] * 1.e-5;
+    return 0;
+  }
+  if ((R[2] + cr) > 0.) {
+    ps[2] = (-2. * cr + R[2] * (g - 1.)) / (g + 1.);
+    ps[0] = R[0] * exp(2. / (g - 1.) * log(-ps[2] / cr));
+    ps[1] = exp(g * log(ps[0] / R[0])) * R[1];
+    return 0;
+  }
+  if ((R[2] + cr) <= 0.) { for (int i = 0; i < 3; i++) ps[i] = R[i]; return 0; }
+  return 1;
+}
+// JMs_riemann_solve + PtoFlux(pstar); ax = sweep axis (maps the solver frame onto RefVec); returns 1 on a solver failure
+template <int MODE>
+__device__ inline int hydro_JMs(const Prim& l, const Prim& rg, const PhysParams& pp, int ax, Cons& flux, Prim& pstar) {
+  const int a1 = (ax + 1) % 3, a2 = (ax + 2) % 3;
+  const double rv[5] = {pp.rs_refvec[0], pp.rs_refvec[1], pp.rs_refvec[2 + ax], pp.rs_refvec[2 + a1], pp.rs_refvec[2 + a2]};
+  pstar.bn = pstar.bt1 = pstar.bt2 = pstar.psi = 0.0;
+  int fail = 0;
+  // "same state" shortcut (:300-311)
+  const double diff = fabs(rg.ro - l.ro) / (fabs(rv[0]) + PION_TINYVALUE) + fabs(rg.pg - l.pg) / (fabs(rv[1]) + PION_TINYVALUE);
+  // the reference sums the five components in grid order RO, PG, VX, VY, VZ
+  double dv[3];
+  dv[ax] = fabs(rg.vn - l.vn) / (fabs(rv[2]) + PION_TINYVALUE);
+  dv[a1] = fabs(rg.vt1 - l.vt1) / (fabs(rv[3]) + PION_TINYVALUE);
+  dv[a2] = fabs(rg.vt2 - l.vt2) / (fabs(rv[4]) + PION_TINYVALUE);
+  if (((diff + dv[0]) + dv[1]) + dv[2] < 1.e-6) {
+    pstar.ro = (l.ro + rg.ro) / 2.; pstar.pg = (l.pg + rg.pg) / 2.; pstar.vn = (l.vn + rg.vn) / 2.;
+    pstar.vt1 = (l.vt1 + rg.vt1) / 2.; pstar.vt2 = (l.vt2 + rg.vt2) / 2.;
+  } else {
+    RsEuler r;
+    r.g = pp.gamma;
+    r.L[0] = l.ro; r.L[1] = l.pg; r.L[2] = l.vn;
+    r.R[0] = rg.ro; r.R[1] = rg.pg; r.R[2] = rg.vn;
+    r.ps[0] = r.ps[1] = r.ps[2] = 0.0;
+    const double g = pp.gamma;
+    r.cl = sqrt(g * l.pg / l.ro);
+    r.cr = sqrt(g * rg.pg / rg.ro);
+    int err = 0;
+    if ((rg.vn - l.vn) <= 2. * (r.cl + sqrt((g - 1.) / 2. / g) * r.cr) / (g - 1.)) {
+      if (MODE == SOLVE_RSLINEAR) {
+        err = rs_linear_solver(r);
+        if (err) { r.ps[1] = r.ps[0] = r.ps[2] = PION_TINYVALUE; fail = 1; }
+      } else if (MODE == SOLVE_RSEXACT) {
+        err = rs_exact_solver(r);
+        if (err) { r.ps[1] = r.ps[0] = PION_TINYVALUE; fail = 1; }
+      } else {
+        err = rs_linear_solver(r);
+        if (err) r.ps[1] = r.ps[0] = r.ps[2] = PION_TINYVALUE;
+        if (err != 0 || !((pmax(l.pg, rg.pg) / pmin(l.pg, rg.pg) < 1.4) && (pmax(l.ro, rg.ro) / pmin(l.ro, rg.ro) < 1.4) &&
+                          (fabs(rg.vn - l.vn) / pmin(r.cl, r.cr) < 0.03))) {
+          err = rs_exact_solver(r);
+          if (err) { r.ps[1] = r.ps[0] = PION_TINYVALUE; fail = 1; }
+        }
+      }
+    } else if ((rg.vn - l.vn) <= 2. * (r.cl + r.cr) / (g - 1.)) {
+      err = rs_solve_rarerare(r);
+      if (err) { r.ps[1] = r.ps[0] = r.ps[2] = -1.9e99; fail = 1; }
+    } else {
+      err = rs_solve_cavitation(r, rv);
+      if (err) { r.ps[1] = r.ps[0] = r.ps[2] = -1.9e100; fail = 1; }
+    }
+    pstar.ro = r.ps[0]; pstar.pg = r.ps[1]; pstar.vn = r.ps[2];
+    if (!fail) {
+      // v_t only changes across the contact (:433-441) -- also after the whole-state copies of the linear /
+      // cavitation branches, which the reference overwrites here in the same way
+      if (pstar.vn > 0) { pstar.vt1 = l.vt1; pstar.vt2 = l.vt2; }
+      else { pstar.vt1 = rg.vt1; pstar.vt2 = rg.vt2; }
+      if (pstar.pg <= PION_TINYVALUE) pstar.pg = 1.e-5 * rv[1];
+      if (pstar.ro <= PION_TINYVALUE) pstar.ro = 1.e-5 * rv[0];
+    } else {
+      pstar.vt1 = pstar.vt2 = 0.0;
+    }
+  }
+  Cons u;
+  PtoU<EQ_EULER>(pstar, u, pp.gamma - 1.0);
+  PUtoFlux<EQ_EULER>(pstar, u, flux);
+  return fail;
+}
+
 // HLLD_MHD::HLLD_signal_speeds (HLLD_MHD.cpp:342-368); Bx is the same on both
 // sides in the GLM case but the formula is kept general.
 __device__ __forceinline__ void hlld_speeds(const Prim& L, const Prim& R, double g, double& Sl, double& Sr) {
@@ -857,12 +1136,15 @@ __device__ __forceinline__ void mhd_RoeCV(const Prim& L, const Prim& R, const Ph
 // ---------------------------------------------------------------------------
 template <int EQ, int SOLVER, int AV>
 __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, const PhysParams& pp, bool use_hll,
-                                               double hc_etamax, Cons& flux) {
+                                               double hc_etamax, Cons& flux, int ax = 0, int* rs_fail = nullptr) {
   constexpr bool FKJ = (AV == AV_FKJ98 || AV == AV_HCORR_FKJ98);
   Prim pstar;
   if (EQ == EQ_EULER) {
     if (SOLVER == SOLVE_LF) {
       lax_friedrichs<EQ_EULER>(eL, eR, pp, flux, pstar);
+    } else if (SOLVER == SOLVE_RSLINEAR || SOLVER == SOLVE_RSEXACT || SOLVER == SOLVE_RSHYBRID) {
+      const int f = hydro_JMs<SOLVER>(eL, eR, pp, ax, flux, pstar);
+      if (rs_fail) *rs_fail |= f;
     } else if (SOLVER == SOLVE_ROE) {
       hydro_RoeCV(eL, eR, pp, hc_etamax, flux, pstar);
     } else if (SOLVER == SOLVE_FVS) {

@@ -155,10 +155,12 @@ static int check_config(const pion_gpu_config& c) {
   if (c.coord_sys == PION_COORD_CYL && c.ndim != 2) { set_error("Cylindrical coordinates only implemented for 2d axial symmetry"); return 1; }
   if (c.coord_sys == PION_COORD_SPH && (c.ndim != 1 || c.eqntype != PION_EQEUL)) { set_error("Spherical coordinates only implemented for 1D Euler"); return 1; }
   if (c.coord_sys != PION_COORD_CRT && c.n_wind > 0) { set_error("stellar-wind boundary: only Cartesian grids are built"); return 1; }
-  const bool euler_only = (c.solver == PION_FLUX_ROE_PV || c.solver == PION_FLUX_FVS);
-  if (c.solver != PION_FLUX_LF && c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL && !euler_only) { set_error("solver must be 0 (Lax-Friedrichs), 4 (Roe-CV), 5 (Roe-PV), 6 (FVS), 7 (HLLD) or 8 (HLL)"); return 1; }
+  // 1, 2, 3: linear / exact / hybrid Riemann solvers -- built for the Euler equations (riemann.cpp); the MHD linear
+  // solver of riemannMHD.cpp is not
+  const bool euler_only = (c.solver == PION_FLUX_ROE_PV || c.solver == PION_FLUX_FVS || (c.solver >= 1 && c.solver <= 3));
+  if (c.solver != PION_FLUX_LF && c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL && !euler_only) { set_error("solver must be 0 (Lax-Friedrichs), 1-3 (linear / exact / hybrid Riemann solver, Euler), 4 (Roe-CV), 5 (Roe-PV), 6 (FVS), 7 (HLLD) or 8 (HLL)"); return 1; }
   // solver_eqn_mhd_adi.cpp:132-198: the MHD solvers have no Roe-PV / FVS branch ("what sort of flux solver do you mean???")
-  if (euler_only && c.eqntype != PION_EQEUL) { set_error("solver 5 (Roe-PV) and 6 (FVS) exist for the Euler equations only"); return 1; }
+  if (euler_only && c.eqntype != PION_EQEUL) { set_error("solvers 1-3 (linear / exact / hybrid; the MHD linear solver is not built), 5 (Roe-PV) and 6 (FVS) are for the Euler equations only"); return 1; }
   if (c.eqntype == PION_EQEUL && c.solver == PION_FLUX_HLLD) { set_error("HLLD needs MHD equations"); return 1; }
   if (c.artviscosity != 0 && c.artviscosity != 1 && c.artviscosity != 3 && c.artviscosity != 4) { set_error("artviscosity must be 0,1,3,4"); return 1; }
   if (!((c.spOOA == 1 && c.tmOOA == 1) || (c.spOOA == 2 && c.tmOOA == 2))) { set_error("Bad OOA requests; choose (1,1) or (2,2)"); return 1; }
@@ -347,6 +349,11 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   pp.etav = c->cfg.etav;
   pp.chyp = 0.0;
   pp.refvec_ro = cfg->refvec[0];
+  // eqns_Euler::SetAvgState (eqns_hydro_adiabatic.cpp:439-453, riemann.cpp:171): the Riemann solver's three reference
+  // velocities are a tenth of the sound speed of RefVec
+  pp.rs_refvec[0] = cfg->refvec[0];
+  pp.rs_refvec[1] = cfg->refvec[1];
+  pp.rs_refvec[2] = pp.rs_refvec[3] = pp.rs_refvec[4] = 0.1 * sqrt(cfg->gamma * cfg->refvec[1] / cfg->refvec[0]);
   pp.min_temp = cfg->min_temperature;
   pp.max_temp = cfg->max_temperature;
   pp.have_mp = cfg->cooling ? 1 : 0;
@@ -1043,8 +1050,8 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   }
   // fused 2-D/3-D stages run the flux-once sweep kernel; 1-D grids and the unfused seam
   // call (calc_dynamics_dU) run the per-cell gather kernel
-  // (Lax-Friedrichs is only instantiated for the gather kernel)
-  const bool sweep = fused && c->g.ndim >= 2 && c->g.coord == PION_COORD_CRT && !c->force_gather && c->cfg.solver != PION_FLUX_LF;
+  // (Lax-Friedrichs and the linear / exact / hybrid Riemann solvers are only instantiated for the gather kernel)
+  const bool sweep = fused && c->g.ndim >= 2 && c->g.coord == PION_COORD_CRT && !c->force_gather && c->cfg.solver >= PION_FLUX_ROE;
   switch (c->cfg.eqntype) {
     case PION_EQEUL: c->last_stage_kernel = (sweep ? launch_sweep_euler : launch_stage_euler)(c->cfg.solver, fkj, a, st); break;
     case PION_EQMHD: c->last_stage_kernel = (sweep ? launch_sweep_mhd : launch_stage_mhd)(c->cfg.solver, fkj, a, st); break;
@@ -1265,6 +1272,14 @@ extern "C" int pion_gpu_mp_failures(pion_gpu_ctx* c, long long* out) {
   long long t[3];
   if (pion_gpu_counters(c, t)) return 1;
   *out = c->mp_failures;
+  return 0;
+}
+extern "C" int pion_gpu_riemann_failures(pion_gpu_ctx* c, long long* out) {
+  CUDA_OK(cudaSetDevice(c->cfg.device));
+  long long h = 0;
+  CUDA_OK(cudaMemcpyAsync(&h, c->d_counters + 3, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  *out = h;
   return 0;
 }
 extern "C" int pion_gpu_sync(pion_gpu_ctx* c) {

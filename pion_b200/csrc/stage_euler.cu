@@ -6,6 +6,18 @@ const char* launch_stage_euler(int solver, int fkj, const StageArgs& a, cudaStre
     if (fkj) return launch_stage_t<EQ_EULER, SOLVE_LF, true>(a, s);
     else return launch_stage_t<EQ_EULER, SOLVE_LF, false>(a, s);
   }
+  if (solver == SOLVE_RSLINEAR) {
+    if (fkj) return launch_stage_t<EQ_EULER, SOLVE_RSLINEAR, true>(a, s);
+    else return launch_stage_t<EQ_EULER, SOLVE_RSLINEAR, false>(a, s);
+  }
+  if (solver == SOLVE_RSEXACT) {
+    if (fkj) return launch_stage_t<EQ_EULER, SOLVE_RSEXACT, true>(a, s);
+    else return launch_stage_t<EQ_EULER, SOLVE_RSEXACT, false>(a, s);
+  }
+  if (solver == SOLVE_RSHYBRID) {
+    if (fkj) return launch_stage_t<EQ_EULER, SOLVE_RSHYBRID, true>(a, s);
+    else return launch_stage_t<EQ_EULER, SOLVE_RSHYBRID, false>(a, s);
+  }
   if (solver == SOLVE_ROE) {
     if (fkj) return launch_stage_t<EQ_EULER, SOLVE_ROE, true>(a, s);
     else return launch_stage_t<EQ_EULER, SOLVE_ROE, false>(a, s);

@@ -158,6 +158,7 @@ __device__ __forceinline__ void stage_block_epilogue(const StageArgs& a, double 
   if (status && a.counters) {
     if (status & ST_NEG_RHO) atomicAdd((unsigned long long*)&a.counters[0], 1ULL);
     if (status & ST_NEG_PG) atomicAdd((unsigned long long*)&a.counters[1], 1ULL);
+    if (status & ST_RS_FAIL) atomicAdd((unsigned long long*)&a.counters[3], 1ULL);  // fatal in the reference
   }
 }
 
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = t < ncell;
   double my_dt = 1.0e100;
-  int status = 0;
+  int status = 0, rs_status = 0;
 
   if (active) {
     const int i = (int)(t % NX), j = (int)((t / NX) % NY), k = (int)(t / ((long)NX * NY));
@@ -290,8 +291,10 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
           }
         }
         Cons Flow, Fhigh;
-        intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(lowL, lowR, a.pp, hll_low, eta_low, Flow);
-        intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(highL, highR, a.pp, hll_high, eta_high, Fhigh);
+        int rs_fail = 0;
+        intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(lowL, lowR, a.pp, hll_low, eta_low, Flow, ax, &rs_fail);
+        intercell_flux<EQ, SOLVER, FKJ ? AV_FKJ98 : AV_NONE>(highL, highR, a.pp, hll_high, eta_high, Fhigh, ax, &rs_fail);
+        if (rs_fail) rs_status = ST_RS_FAIL;
 
         // geometric weights of this cell along the axis: Cartesian 1/dx everywhere; radial axis:
         // faces r- = Rc-dx/2, r+ = Rc+dx/2, cyl 2 r/(r+^2 - r-^2), sph r^2/((r+^3 - r-^3)/3)
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(128, PION_STAGE_MINBLOCKS) k_stage(const __gri
     }
   }
 
-  stage_block_epilogue(a, my_dt, status);
+  stage_block_epilogue(a, my_dt, status | rs_status);
 }
 
 // The box of tiles / planes a block of the sweep kernels works on, and its tile coordinates inside it

@@ -88,7 +88,7 @@ def test_header_codes_are_the_reference_integers():
     bcs = Path("/root/reference/source/boundaries/boundaries.h").read_text()
     ref.update({k: int(v) for k, v in re.findall(r"\b([A-Z0-9_]+)\s*=\s*(\d+)\s*,", bcs)})
     pairs = {"PION_EQEUL": "EQEUL", "PION_EQMHD": "EQMHD", "PION_EQGLM": "EQGLM", "PION_COORD_CRT": "COORD_CRT",
-             "PION_COORD_CYL": "COORD_CYL", "PION_COORD_SPH": "COORD_SPH", "PION_FLUX_LF": "FLUX_LF", "PION_FLUX_ROE": "FLUX_RSroe",
+             "PION_COORD_CYL": "COORD_CYL", "PION_COORD_SPH": "COORD_SPH", "PION_FLUX_LF": "FLUX_LF", "PION_FLUX_RSLINEAR": "FLUX_RSlinear", "PION_FLUX_RSEXACT": "FLUX_RSexact", "PION_FLUX_RSHYBRID": "FLUX_RShybrid", "PION_FLUX_ROE": "FLUX_RSroe",
              "PION_FLUX_ROE_PV": "FLUX_RSroe_pv", "PION_FLUX_FVS": "FLUX_FVS", "PION_FLUX_HLLD": "FLUX_RS_HLLD",
              "PION_FLUX_HLL": "FLUX_RS_HLL", "PION_AV_NONE": "AV_NONE", "PION_AV_FKJ98": "AV_FKJ98_1D",
              "PION_AV_HCORR": "AV_HCORRECTION", "PION_AV_HCORR_FKJ98": "AV_HCORR_FKJ98", "PION_BC_PERIODIC": "PERIODIC",

@@ -97,12 +97,36 @@ def test_strong_gradients(eqn, solver, av):
     run_pair(case_3d(eqn, solver, av, bcs="mixed2", NG=(9, 7, 5), ooa=1), nsteps=2, state=hot_sphere_state)
 
 
-@pytest.mark.parametrize("solver", [4, 5, 6, 8])
+@pytest.mark.parametrize("solver", [4, 5, 6, 8, 1, 2, 3])
 def test_euler_supersonic_branches(solver):
     """|v| up to 3 (1.5 for the linearised Roe-PV solver: beyond that the reference itself produces NaNs) with c ~ 1: the one-sided (supersonic) branches of FVS, Roe-PV, HLL and the Roe-CV entropy fix,
     2-D (LDG sweep) and multi-tile 3-D (TMA sweep)."""
-    run_pair(case_2d("euler", solver, 1, bcs="outflow"), nsteps=2, amp=1.5 if solver == 5 else 3.0)
-    run_pair(case_3d("euler", solver, 0, bcs="outflow", NG=(40, 26, 20)), nsteps=2, amp=1.5 if solver == 5 else 3.0)
+    amp = 1.5 if solver in (5, 1) else 3.0
+    run_pair(case_2d("euler", solver, 1, bcs="outflow"), nsteps=2, amp=amp)
+    run_pair(case_3d("euler", solver, 0, bcs="outflow", NG=(40, 26, 20)), nsteps=2, amp=amp)
+
+
+def test_exact_riemann_solver_rarefaction_and_cavitation_branches():
+    """Strongly diverging flow across one interface: the two-rarefaction and the cavitation branches of
+    riemann_Euler::JMs_riemann_solve (riemann.cpp:322-420), 1-D and along y in 2-D (rotated reference velocity),
+    and no solver failure is counted."""
+    import dataclasses
+    for solver in (2, 3):
+        for ndim in (1, 2):
+            base = case_1d("euler", solver, 0, bcs=("outflow", "outflow")) if ndim == 1 else case_2d("euler", solver, 0, bcs="outflow")
+            prob = dataclasses.replace(base, cfl=0.2)
+            ax = 3 - (ndim - 1)  # array axis of the jump: x in 1-D, y in 2-D
+
+            def diverging(p, amp_v):
+                P = random_state(p, 5, amp=0.2)
+                n = P.shape[ax]
+                sgn = np.sign(np.arange(n) - n / 2 + 0.5)
+                shape = [1, 1, 1]
+                shape[ax - 1] = n
+                P[2 + (ndim - 1)] = amp_v * sgn.reshape(shape)
+                return P
+            run_pair(prob, nsteps=3, state=lambda p: diverging(p, 3.2))
+            run_pair(prob, nsteps=2, state=lambda p: diverging(p, 6.0))
 
 
 def test_1d_and_first_order():

@@ -57,7 +57,8 @@ def test_hlld_to_hll_switch_bit_exact(eqn):
     run_pair(case_2d(eqn, 7, 0, bcs="outflow", NG=(48, 40, 1)), state=hot_sphere_state)
 
 
-@pytest.mark.parametrize("eqn,solver,av", [("euler", 4, 3), ("euler", 8, 1), ("euler", 6, 1), ("i-mhd", 4, 1), ("i-mhd", 8, 0),
+@pytest.mark.parametrize("eqn,solver,av", [("euler", 4, 3), ("euler", 8, 1), ("euler", 6, 1), ("euler", 1, 1), ("euler", 2, 0), ("euler", 3, 1),
+                                           ("euler", 0, 1), ("i-mhd", 0, 1), ("i-mhd", 4, 1), ("i-mhd", 8, 0),
                                            ("glm-mhd", 4, 4), ("glm-mhd", 8, 1)])
 def test_strong_gradients_bit_exact(eqn, solver, av):
     """The x100 pressure ellipsoid for the other solvers (Roe entropy fix / H-correction, HLL, FVS), second and
@@ -66,11 +67,28 @@ def test_strong_gradients_bit_exact(eqn, solver, av):
     run_pair(case_3d(eqn, solver, av, bcs="mixed2", NG=(9, 7, 5), ooa=1), nsteps=2, state=hot_sphere_state)
 
 
-@pytest.mark.parametrize("solver", [4, 5, 6, 8])
+@pytest.mark.parametrize("solver", [4, 5, 6, 8, 1, 2, 3])
 def test_euler_supersonic_branches_bit_exact(solver):
     """|v| up to 3 (1.5 for the linearised Roe-PV solver: beyond that the reference itself produces NaNs) with c ~ 1: the one-sided (supersonic) branches of FVS, Roe-PV, HLL and the Roe-CV entropy fix."""
-    run_pair(case_2d("euler", solver, 1, bcs="outflow"), nsteps=2, amp=1.5 if solver == 5 else 3.0)
-    run_pair(case_3d("euler", solver, 0, ntracer=1), nsteps=2, amp=1.5 if solver == 5 else 3.0)
+    amp = 1.5 if solver in (5, 1) else 3.0  # the linearised solvers produce NaNs in the reference beyond that
+    run_pair(case_2d("euler", solver, 1, bcs="outflow"), nsteps=2, amp=amp)
+    run_pair(case_3d("euler", solver, 0, ntracer=1), nsteps=2, amp=amp)
+
+
+def test_exact_riemann_solver_rarefaction_and_cavitation_branches_bit_exact():
+    """Strongly diverging flow: (u_R - u_L) beyond the two-rarefaction and the cavitation thresholds of
+    riemann_Euler::JMs_riemann_solve (riemann.cpp:322-420), 1-D so that every interface is one of those."""
+    import dataclasses
+    for solver in (2, 3):
+        prob = dataclasses.replace(case_1d("euler", solver, 0, bcs=("outflow", "outflow")), cfl=0.2)
+
+        def diverging(p, amp_v):
+            P = random_state(p, 5, amp=0.2)
+            x = np.arange(P.shape[3]) - P.shape[3] / 2
+            P[2] = amp_v * np.sign(x + 0.5)[None, None, :]  # a jump of 2 amp_v across ONE interface
+            return P
+        run_pair(prob, nsteps=3, state=lambda p: diverging(p, 3.2))   # two rarefactions: 5.6 < du < 7.7 (c ~ 1.3)
+        run_pair(prob, nsteps=2, state=lambda p: diverging(p, 6.0))   # cavitation: du > 3 (c_l + c_r)
 
 
 def test_1d_and_first_order():
