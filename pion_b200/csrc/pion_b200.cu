@@ -95,7 +95,7 @@ struct pion_gpu_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr};
   // TMA tensor maps over the two state arrays (3-D grids; the TMA sweep kernel, stage_sweep_tma.cuh)
-  alignas(64) CUtensorMap tmapP, tmapPh;
+  alignas(64) CUtensorMap tmapP[2], tmapPh[2];  // [stage order - 1]: the predictor and the corrector use different tiles
   bool have_tmap = false;
 };
 
@@ -114,7 +114,7 @@ extern "C" const char* pion_gpu_last_error(void) { return g_last_error.c_str(); 
 // Tensor map of one state array for the TMA sweep kernel: a 4-D tensor (x, y, z, variable) over the
 // pitched SoA layout of grid.cuh, box = one plane tile [nbase][TY+3][36].  The driver entry point is
 // fetched through the runtime (no link-time dependency on libcuda).
-static int make_state_tmap(const pion_gpu_ctx* c, double* base, CUtensorMap* out) {
+static int make_state_tmap(const pion_gpu_ctx* c, double* base, int order, CUtensorMap* out) {
   static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
   if (!enc) {
     void* fn = nullptr;
@@ -126,8 +126,8 @@ static int make_state_tmap(const pion_gpu_ctx* c, double* base, CUtensorMap* out
     }
     enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   }
-  int cw, rh, nb, tx;
-  sweep_tma_box(c->cfg.eqntype, &cw, &rh, &nb, &tx);
+  int cw, rh, nb, tx, ty;
+  sweep_tma_box(c->cfg.eqntype, order, &cw, &rh, &nb, &tx, &ty);
   if ((c->g.xoff + c->g.nb[0]) % 2 || tx % 2) {  // every box must start on a 16-byte boundary in x
     set_error("TMA sweep: tile boxes would start on odd x offsets");
     return 1;
@@ -450,7 +450,8 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
     // 3-D Cartesian grids run the TMA sweep kernel (PION_B200_NO_TMA=1: the LDG sweep kernel, for A/B tests)
     const char* e = getenv("PION_B200_NO_TMA");
     if (g.ndim == 3 && g.coord == PION_COORD_CRT && !(e && e[0] == '1') && sweep_tma_fits(c->cfg.eqntype, c->ntr)) {
-      if (make_state_tmap(c, c->P, &c->tmapP) || make_state_tmap(c, c->Ph, &c->tmapPh)) { pion_gpu_destroy(c); return nullptr; }
+      for (int o = 1; o <= 2; o++)
+        if (make_state_tmap(c, c->P, o, &c->tmapP[o - 1]) || make_state_tmap(c, c->Ph, o, &c->tmapPh[o - 1])) { pion_gpu_destroy(c); return nullptr; }
       c->have_tmap = true;
       if (c->hll && (cudaMalloc(&c->hllf, (size_t)g.vs) != cudaSuccess || cudaMemset(c->hllf, 0, (size_t)g.vs) != cudaSuccess)) {
         set_error("device allocation failed (face flags)");
@@ -980,11 +981,11 @@ static int timing_event(pion_gpu_ctx* c, cudaEvent_t* e) {
 }
 
 // cells per tile of the sweep kernel that a fused stage of this context runs (launch_sweep_any's choice)
-static void stage_tile_cells(const pion_gpu_ctx* c, int* cx, int* cy) {
+static void stage_tile_cells(const pion_gpu_ctx* c, int order, int* cx, int* cy) {
   sweep_tile_cells(c->cfg.eqntype, cx, cy);
   if (c->have_tmap && !c->eta) {
     int cw, rh, nb;
-    sweep_tma_box(c->cfg.eqntype, &cw, &rh, &nb, cx);
+    sweep_tma_box(c->cfg.eqntype, order, &cw, &rh, &nb, cx, cy);
   }
 }
 
@@ -1023,10 +1024,11 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   a.fused = fused ? 1 : 0;
   const int fkj = (c->cfg.artviscosity == 1 || c->cfg.artviscosity == 4) ? 1 : 0;
   a.fkj = fkj;
-  a.tmap = !c->have_tmap ? nullptr : (S == c->P) ? (const void*)&c->tmapP : (S == c->Ph) ? (const void*)&c->tmapPh : nullptr;
+  const int oi = (order == 2) ? 1 : 0;
+  a.tmap = !c->have_tmap ? nullptr : (S == c->P) ? (const void*)&c->tmapP[oi] : (S == c->Ph) ? (const void*)&c->tmapPh[oi] : nullptr;
   {
     int cx, cy;
-    stage_tile_cells(c, &cx, &cy);
+    stage_tile_cells(c, order, &cx, &cy);
     a.tx0 = 0; a.tx1 = (c->g.NG[0] + cx - 1) / cx;
     a.ty0 = 0; a.ty1 = (c->g.NG[1] + cy - 1) / cy;
     a.k_lo = 0; a.k_hi = c->g.NG[2];
@@ -1145,7 +1147,7 @@ extern "C" int pion_gpu_grid_update_state_vector(pion_gpu_ctx* c, double dt, int
 static int stage_and_bcs_impl(pion_gpu_ctx* c, const double* S, const double* Pb, double* out, double dt, int order, bool want_dt,
                               double* bcA0, double* bcA1) {
   int cx, cy;
-  stage_tile_cells(c, &cx, &cy);
+  stage_tile_cells(c, order, &cx, &cy);
   const GridD& g = c->g;
   const int ntx = (g.NG[0] + cx - 1) / cx, nty = (g.NG[1] + cy - 1) / cy, NZ = g.NG[2];
   // shell thickness in tiles: the last tile may hold fewer than the 2 cells the halo slab needs

@@ -486,7 +486,7 @@ const char* launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream
 // cells per sweep tile along x / y (stage_sweep.cuh: 32 lanes, TY rows, one of each only produces fluxes)
 void sweep_tile_cells(int eq, int* cx, int* cy);  // eq: EQ_EULER / EQ_MHD / EQ_GLM
 bool sweep_tma_fits(int eq, int ntr);  // the TMA sweep kernel exists for this many tracers and its tile fits shared memory
-void sweep_tma_box(int eq, int* cw, int* rh, int* nb, int* tx);  // box of one TMA plane load, cells per tile in x (stage_sweep_tma.cuh)
+void sweep_tma_box(int eq, int order, int* cw, int* rh, int* nb, int* tx, int* ty);  // box of one TMA plane load of a stage of that order, cells per tile in x and y (stage_sweep_tma.cuh)
 // flux-once sweep kernel (stage_sweep.cuh), instantiated in sweep_{euler,mhd,glm}.cu
 const char* launch_sweep_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 const char* launch_sweep_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);

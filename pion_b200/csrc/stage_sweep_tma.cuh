@@ -41,6 +41,21 @@ namespace pion {
 #ifndef PION_TMA_KCHUNK
 #define PION_TMA_KCHUNK 64
 #endif
+// Tile rows and plane-ring depth per stage ORDER (MHD / GLM).  The predictor (ORDER 1, no reconstruction) only reads
+// planes k-1 (Powell / GLM sources), k and k+1, so a ring of THREE plane buffers is enough for it, which leaves room
+// for 16-row tiles (16 warps per SM at 128 registers instead of 12 at 168).  MEASURED AND NOT THE DEFAULT (r02o, 512^3
+// GLM-HLLD predictor): 16 rows / ring 3 = 15.96 ms against 15.3 ms for 12 rows / ring 4 -- at 128 registers ptxas spills
+// 16 words of loop state, the 225 KB of shared memory leave ~30 KB of L1, the spill reloads miss it (long-scoreboard
+// 0.28 -> 1.63 warps per issue) and the FP64 pipe stays at 55 %; 15 rows: the same.  Parity is green for both
+// (-DPION_TMA_TY1=16 -DPION_TMA_RING1=3), the knobs stay for that experiment.
+#ifndef PION_TMA_TY1
+#define PION_TMA_TY1 PION_SWEEP_TY
+#endif
+#ifndef PION_TMA_RING1
+#define PION_TMA_RING1 4
+#endif
+__host__ __device__ constexpr int tma_ty(int eq, int order) { return (eq != EQ_EULER && order == 1) ? PION_TMA_TY1 : sweep_ty(eq); }
+__host__ __device__ constexpr int tma_ring(int eq, int order) { return (eq != EQ_EULER && order == 1) ? PION_TMA_RING1 : 4; }
 constexpr int TMA_TX = 32;                                            // cells a tile updates along x
 constexpr int TMA_CW = 36;                                            // tile columns: cells i0-2 .. i0+33
 __host__ __device__ constexpr int tma_rh(int ty) { return ty + 3; }  // tile rows
@@ -245,7 +260,7 @@ __device__ __forceinline__ double tracer_upwind_flux(const StageArgs& a, double 
 
 // ORDER: spatial order of the stage (1 = predictor of the second-order scheme / first-order runs, 2 = corrector);
 // a template parameter so that the predictor carries no reconstruction code at all
-template <int EQ, int SOLVER, bool FKJ, int TY, int MINB, int NTR, int ORDER>
+template <int EQ, int SOLVER, bool FKJ, int TY, int MINB, int NTR, int ORDER, int RING>
 __global__ void __launch_bounds__(32 * TY, MINB)
     k_stage_sweep_tma(const __grid_constant__ StageArgs a, const __grid_constant__ CUtensorMap tmap, const int kchunk) {
   extern __shared__ __align__(128) unsigned char s_raw[];
@@ -259,13 +274,16 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   constexpr int CS = TY * 32;                            // doubles between components of a flux slab
   constexpr int SLAB = NV * TY * 32;
   constexpr int XSLAB = NV * TY;
-  double* const s_tile = reinterpret_cast<double*>(s_raw);              // [4][NV][RH][CW]
-  double* const s_flux = s_tile + 4 * PS;                                // [NV][TY][32] y fluxes of a plane, then [NV][TY][32] z fluxes
+  static_assert(RING == 4 || (RING == 3 && ORDER == 1), "a three-plane ring holds planes k-1 .. k+1: first-order stages only");
+  // plane k+d lives in buffer (kk + d + BASE) mod RING; the ring starts at plane k0-BASE-... (k0-2 | k0-1)
+  constexpr int BASE = RING - 2;
+  double* const s_tile = reinterpret_cast<double*>(s_raw);              // [RING][NV][RH][CW]
+  double* const s_flux = s_tile + RING * PS;                                // [NV][TY][32] y fluxes of a plane, then [NV][TY][32] z fluxes
   double* const s_xedge = s_flux + 2 * SLAB;                             // [3][NV][TY] x flux through the tile's high x edge
   __shared__ unsigned long long s_bar;       // y-flux slab + x-edge fluxes published (all threads arrive)
   __shared__ unsigned long long s_free;      // y-flux slab read by everybody (the slab is single-buffered)
   double* const s_fz = s_flux + SLAB;        // [NV][TY][32] thread-private: the z flux carried to the next plane
-  __shared__ unsigned long long s_full[4];   // plane buffer filled (TMA transaction bytes)
+  __shared__ unsigned long long s_full[RING];   // plane buffer filled (TMA transaction bytes)
   __shared__ unsigned s_done;                // consumer warps that have finished reading plane k-1 (running count)
 
   const GridD& g = a.g;
@@ -305,16 +323,16 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     mbar_init(&s_free, 32 * TY);
     s_done = 0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) mbar_init(&s_full[q], 1);
+    for (int q = 0; q < RING; q++) mbar_init(&s_full[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
   if (producer) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {  // planes k0-2 .. k0+1
+    for (int q = 0; q < RING; q++) {  // planes k0-2 .. k0+1 (three-plane ring: k0-1 .. k0+1)
       mbar_expect_tx(&s_full[q], PLANE_BYTES);
-      tma_load_plane(s_tile + q * PS, &tmap, &s_full[q], bx, by, bz + q);
+      tma_load_plane(s_tile + q * PS, &tmap, &s_full[q], bx, by, bz + (2 - BASE) + q);
     }
   }
   unsigned phase = 0, fphase = 0;  // parities of the y-flux barriers (published / read by everybody)
@@ -345,11 +363,17 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     const bool warm = kk < 0;  // first iteration of a chunk: only the fluxes INTO plane k0 (z face, y faces, x edge)
     const bool last = kk + 1 >= nk;
     const long c = gidx(g, i + g.nb[0], j + g.nb[1], k + g.nb[2]);
-    // plane p lives in buffer (p - k0 + 2) & 3
-    const double* const pm1 = s_tile + ((kk + 1) & 3) * PS + coff;  // plane k-1
-    const double* const p0 = s_tile + ((kk + 2) & 3) * PS + coff;   // plane k
-    const double* const pp1 = s_tile + ((kk + 3) & 3) * PS + coff;  // plane k+1
-    const double* const pp2 = s_tile + (kk & 3) * PS + coff;        // plane k+2
+    // plane k+d lives in buffer (kk + d + BASE) mod RING (+RING: the warm iteration's plane k-1 of the three-plane
+    // ring has no buffer; its pointer is formed but never dereferenced)
+    const double* const pm1 = s_tile + ((unsigned)(kk - 1 + BASE + RING) % RING) * PS + coff;  // plane k-1
+    const double* const p0 = s_tile + ((unsigned)(kk + BASE) % RING) * PS + coff;              // plane k
+    const double* const pp1 = s_tile + ((unsigned)(kk + 1 + BASE) % RING) * PS + coff;         // plane k+1
+    const double* const pp2 = s_tile + ((unsigned)(kk + 2 + BASE) % RING) * PS + coff;         // plane k+2 (four-plane ring only)
+    // the plane this iteration reads for the first time: k+2 (ring of four: first needed by the z reconstruction),
+    // k+1 (ring of three: by the light warp's x-edge flux, then by everybody's z flux)
+    const unsigned m_new = (unsigned)(kk + 2 * BASE);
+    unsigned long long* const bar_new = &s_full[m_new % RING];
+    const unsigned par_new = (m_new / RING) & 1u;
     const double* const sbuf = s_flux;
     unsigned n_w = 0, n_we = 0;  // plane k+2's face bytes
     if (SOLVER == SOLVE_HLLD && !last) {
@@ -359,9 +383,12 @@ __global__ void __launch_bounds__(32 * TY, MINB)
 
     if (warm) {  // planes k0-2, k0-1, k0 (plane k0+1 = "k+2" is waited for below like every iteration)
       mbar_wait_spin(&s_full[0], 0);
-      mbar_wait_spin(&s_full[1], 0);
-      mbar_wait_spin(&s_full[2], 0);
+      if (RING == 4) {
+        mbar_wait_spin(&s_full[1], 0);
+        mbar_wait_spin(&s_full[2], 0);
+      }
     }
+    if (RING == 3 && light) mbar_wait_spin(bar_new, par_new);
 
     // ---- ONE copy of the Riemann solver: a real loop over the three faces (x of plane k, z high face,
     // y of plane k+1) whose per-face parts -- stencil loads + reconstruction before the solver, flux
@@ -415,8 +442,8 @@ __global__ void __launch_bounds__(32 * TY, MINB)
           tracer_edges_tile<VS, NB, NTR, ORDER>(a, px - 2, px - 1, px, px + 1, trL, trR);
           if (SOLVER == SOLVE_HLLD) use_hll = ((light ? we_k1 : w_k) & 1u) != 0;
         } else if (f == 1) {
-          // plane k+2 (first needed here): fill number (kk+4) >> 2 of buffer kk & 3
-          mbar_wait_spin(&s_full[kk & 3], ((unsigned)(kk + 4) >> 2) & 1u);
+          // the new plane (first needed here)
+          mbar_wait_spin(bar_new, par_new);
           edge_states_tile<EQ, VS, ORDER>(a, pm1, p0, pp1, pp2, 2, 0, 1, eL, eR);
           tracer_edges_tile<VS, NB, NTR, ORDER>(a, pm1, p0, pp1, pp2, trL, trR);
           if (SOLVER == SOLVE_HLLD) use_hll = (w_k1 & 4u) != 0;
@@ -429,7 +456,7 @@ __global__ void __launch_bounds__(32 * TY, MINB)
 #pragma unroll
         for (int q = 0; q < NTR; q++) Ftr[q] = tracer_upwind_flux(a, trL[q], trR[q], Fnew.rho);
       } else if (f == 1) {
-        mbar_wait_spin(&s_full[kk & 3], ((unsigned)(kk + 4) >> 2) & 1u);
+        mbar_wait_spin(bar_new, par_new);
       }
       Cons D;
       if (f == 0) {
@@ -509,10 +536,12 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         if (lane == 0 && !light) {
           __threadfence_block();
           const unsigned old = atomicAdd(&s_done, 1u);
-          if (!last && old == (unsigned)(kk + 2) * (TY - 1) - 1u) {
-            unsigned long long* fb = &s_full[(kk + 1) & 3];
+          // (three-plane ring: the warm iteration has no plane k-1 to replace, plane k0+1 came with the prologue)
+          if (!last && (RING == 4 || !warm) && old == (unsigned)(kk + 2) * (TY - 1) - 1u) {
+            const int bdead = (int)((unsigned)(kk - 1 + BASE) % RING);
+            unsigned long long* fb = &s_full[bdead];
             mbar_expect_tx(fb, PLANE_BYTES);
-            tma_load_plane(s_tile + ((kk + 1) & 3) * PS, &tmap, fb, bx, by, bz + kk + 5);
+            tma_load_plane(s_tile + bdead * PS, &tmap, fb, bx, by, bz + kk + RING + 1);
           }
         }
       } else {
@@ -555,22 +584,24 @@ __global__ void __launch_bounds__(32 * TY, MINB)
 }
 
 // dynamic shared memory of the TMA kernel: plane ring + y-flux slab + z-flux slots + x-edge slabs
-__host__ __device__ constexpr size_t tma_smem_bytes(int nv, int ty) {
-  return (size_t)4 * tma_plane_stride(nv, ty) + (size_t)2 * nv * ty * 32 * sizeof(double) + (size_t)3 * nv * ty * sizeof(double);
+__host__ __device__ constexpr size_t tma_smem_bytes(int nv, int ty, int ring) {
+  return (size_t)ring * tma_plane_stride(nv, ty) + (size_t)2 * nv * ty * 32 * sizeof(double) + (size_t)3 * nv * ty * sizeof(double);
 }
 constexpr size_t TMA_SMEM_MAX = 227 * 1024 - 1024;  // per-block opt-in limit minus the static part
 // tracer counts the TMA kernel is instantiated for
 constexpr int TMA_MAXTR = 1;
 __host__ __device__ constexpr bool tma_fits(int eq, int ntr) {
-  return ntr <= TMA_MAXTR && tma_smem_bytes(nbase(eq) + ntr, sweep_ty(eq)) <= TMA_SMEM_MAX;
+  return ntr <= TMA_MAXTR && tma_smem_bytes(nbase(eq) + ntr, tma_ty(eq, 1), tma_ring(eq, 1)) <= TMA_SMEM_MAX &&
+         tma_smem_bytes(nbase(eq) + ntr, tma_ty(eq, 2), tma_ring(eq, 2)) <= TMA_SMEM_MAX;
 }
 
 template <int EQ, int SOLVER, bool FKJ, int NTR, int ORDER>
 inline const char* launch_sweep_tma_o(const StageArgs& a, cudaStream_t s) {
-  constexpr int TY = sweep_ty(EQ), MINB = sweep_minb(EQ);
+  constexpr int TY = tma_ty(EQ, ORDER), RING = tma_ring(EQ, ORDER), MINB = sweep_minb(EQ);
   constexpr int NV = nbase(EQ) + NTR;
-  static char name[128], extra[64];
-  static const char* nm = (snprintf(extra, sizeof extra, ",TY=%d,NTR=%d,ORDER=1|2 (TMA-staged stencil)", TY, NTR),
+  static char name[160], extra[96];
+  static const char* nm = (snprintf(extra, sizeof extra, ",TY=%d|%d,RING=%d|%d,NTR=%d,ORDER=1|2 (TMA-staged stencil)", tma_ty(EQ, 1), tma_ty(EQ, 2),
+                                    tma_ring(EQ, 1), tma_ring(EQ, 2), NTR),
                            kernel_variant_name(name, sizeof name, "k_stage_sweep_tma", EQ, SOLVER, FKJ, extra));
   const int bx = a.tx1 - a.tx0, by = a.ty1 - a.ty0, NZ = a.k_hi - a.k_lo;
   if (a.nbox == 0 && (bx <= 0 || by <= 0 || NZ <= 0)) return nm;
@@ -586,15 +617,15 @@ inline const char* launch_sweep_tma_o(const StageArgs& a, cudaStream_t s) {
     while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
     grid = dim3(bx, by, (NZ + kchunk - 1) / kchunk);
   }
-  constexpr size_t smem = tma_smem_bytes(NV, TY);
+  constexpr size_t smem = tma_smem_bytes(NV, TY, RING);
   // the opt-in is per DEVICE: one flag per ordinal (a process may hold contexts on several GPUs)
   static bool attr_done[PION_MAX_DEVICES] = {false};
   const int dev = current_device_slot();
   if (!attr_done[dev]) {
-    cudaFuncSetAttribute(k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR, ORDER, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done[dev] = (dev != PION_MAX_DEVICES - 1);  // the overflow slot is never cached
   }
-  k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR, ORDER><<<grid, 32 * TY, smem, s>>>(ab, *reinterpret_cast<const CUtensorMap*>(a.tmap), kchunk);
+  k_stage_sweep_tma<EQ, SOLVER, FKJ, TY, MINB, NTR, ORDER, RING><<<grid, 32 * TY, smem, s>>>(ab, *reinterpret_cast<const CUtensorMap*>(a.tmap), kchunk);
   return nm;
 }
 template <int EQ, int SOLVER, bool FKJ, int NTR>
@@ -617,10 +648,11 @@ inline const char* launch_sweep_any(const StageArgs& a, cudaStream_t s) {
 
 // box of one TMA plane load for an equation set (host side: tensor-map creation)
 inline bool sweep_tma_fits_impl(int eq, int ntr) { return tma_fits(eq, ntr); }
-inline void sweep_tma_box_impl(int eq, int* cw, int* rh, int* nb, int* tx) {
+inline void sweep_tma_box_impl(int eq, int order, int* cw, int* rh, int* nb, int* tx, int* ty) {
   *tx = TMA_TX;
+  *ty = tma_ty(eq, order) - 1;
   *cw = TMA_CW;
-  *rh = tma_rh(sweep_ty(eq));
+  *rh = tma_rh(tma_ty(eq, order));
   *nb = nbase(eq);
 }
 
