@@ -61,6 +61,7 @@ def main():
     ap.add_argument("--size", type=int, default=384)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--lib", default=None, help="another build of libpion_b200.so (kernel A/B experiments)")
     args = ap.parse_args()
     import torch
     from bench import timed_steps
@@ -74,7 +75,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = load_library()
+    lib = load_library(args.lib)
     tables = load_cooling_tables()
 
     def barrier():
