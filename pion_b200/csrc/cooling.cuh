@@ -37,6 +37,11 @@ struct CoolParams {
   int mode;  // EP_cooling
   double inv_Mu2, inv_Mu2_elec_H, Mu_tot_over_kB, MinT, MaxT;
   double Mu, Mu_elec, Mu_ion, smin, smax;  // mean masses; spline slopes below / above the table
+  // EP_cooling 8: the T column is log-uniform (mp_only_cooling.cpp:117-160 builds it that way; checked on the host):
+  // the interval of a temperature is GUESSED from a float log2 and then corrected against the table, instead of the
+  // eight dependent shared-memory loads of the reference's binary search -- same interval for every input
+  int guess_ok;
+  float l2T0, inv_l2step;
 };
 
 // columns of the device table per cooling function
@@ -49,6 +54,8 @@ struct CoolArgs {
   CoolParams cp;
   const double* P;            // state the source term is integrated from (start-of-step P)
   double* dE;                 // fused path: energy source per cell (one plane), overwritten
+  double* dE2;                // fused second-order step: the source of the SECOND interval dt2 (the corrector's), or null
+  double dt2;
   double* dU;                 // seam path: full dU array, energy plane accumulated (+=)
   const unsigned char* mask;  // isdomain
   double dt, gamma;
@@ -57,26 +64,28 @@ struct CoolArgs {
   int mp_timestep_limit;
 };
 
+// The table columns in shared memory: ONE base pointer, column q starts at tab + q nT (eleven column pointers held
+// across the integrator cost 22 registers: with them the kernel did not fit the 64 registers that 32 warps per SM allow)
 struct CoolTab {
-  const double *T, *rrhp, *Crrh, *Cffhe, *Cfbdn, *Ccie, *s_rrhp, *s_Crrh, *s_Cffhe, *s_Cfbdn, *s_Ccie;
+  const double* tab;
   int nT;
+  __device__ __forceinline__ const double* col(int q) const { return tab + q * nT; }
   double inv_Mu2, inv_Mu2_elec_H;
-  int mode;
   double Mu, Mu_elec, Mu_ion, smin, smax;
+  int guess_ok;
+  float l2T0, inv_l2step;
 };
 
 __device__ __forceinline__ CoolTab cool_tables_to_smem(const CoolParams& cp, double* s) {
   for (int t = threadIdx.x; t < cool_ncol(cp.mode) * cp.nT; t += blockDim.x) s[t] = cp.tables[t];
   __syncthreads();
   CoolTab ct;
-  const int n = cp.nT;
-  ct.T = s; ct.rrhp = s + n; ct.Crrh = s + 2 * n; ct.Cffhe = s + 3 * n; ct.Cfbdn = s + 4 * n; ct.Ccie = s + 5 * n;
-  ct.s_rrhp = s + 6 * n; ct.s_Crrh = s + 7 * n; ct.s_Cffhe = s + 8 * n; ct.s_Cfbdn = s + 9 * n; ct.s_Ccie = s + 10 * n;
-  ct.nT = n;
+  ct.tab = s;  // EP_cooling 8 columns: 0 T, 1 rrhp, 2 C_rrh, 3 C_ffhe, 4 C_fbdn, 5 C_cie, 6..10 their slopes
+  ct.nT = cp.nT;
   ct.inv_Mu2 = cp.inv_Mu2;
   ct.inv_Mu2_elec_H = cp.inv_Mu2_elec_H;
-  ct.mode = cp.mode;
   ct.Mu = cp.Mu; ct.Mu_elec = cp.Mu_elec; ct.Mu_ion = cp.Mu_ion; ct.smin = cp.smin; ct.smax = cp.smax;
+  ct.guess_ok = cp.guess_ok; ct.l2T0 = cp.l2T0; ct.inv_l2step = cp.inv_l2step;
   return ct;
 }
 
@@ -86,9 +95,9 @@ __device__ __forceinline__ CoolTab cool_tables_to_smem(const CoolParams& cp, dou
 // power laws beyond the ends of the table.  Columns (CoolTab): T = x, rrhp = y, Crrh = c.
 __device__ __forceinline__ double cool_rate_SD93CIE(const CoolTab& t, double T) {
   if (T < 0.0 || !isfinite(T)) return HUGE_VAL;
-  const double* x = t.T;
-  const double* y = t.rrhp;
-  const double* c = t.Crrh;
+  const double* x = t.col(0);
+  const double* y = t.col(1);
+  const double* c = t.col(2);
   const int n = t.nT;
   double rate;
   T = log10(T);
@@ -114,9 +123,12 @@ __device__ __forceinline__ double cool_rate_SD93CIE(const CoolTab& t, double T) 
 
 __device__ __forceinline__ double cool_Edot_metallines(const CoolTab& t, double rho, double T);
 
-// mp_only_cooling::Edot (mp_only_cooling.cpp:383-420): launch-uniform dispatch on EP_cooling
+// mp_only_cooling::Edot (mp_only_cooling.cpp:383-420): the dispatch on EP_cooling is a TEMPLATE parameter -- the
+// integrator inlines Edot seven times, and with every cooling function's code (exp / log10 bodies) in each copy the
+// kernel needed 126 registers whichever function ran
+template <int MODE>
 __device__ __forceinline__ double cool_Edot(const CoolTab& t, double rho, double T) {
-  switch (t.mode) {
+  switch (MODE) {
     case 2: {  // KI02: -CoolingFn::CoolingRate(T, 0, rho/Mu, 0, 0), WhichFunction 2, MinTemp 5 K (cooling.cpp:325-399)
       const double nH = rho / t.Mu;
       if (T <= 0.0 || isnan(T) || isinf(T)) return -0.0;
@@ -140,20 +152,34 @@ __device__ __forceinline__ double cool_Edot(const CoolTab& t, double rho, double
 
 // mp_only_cooling::Edot_WSS09CIE_heat_cool_metallines (mp_only_cooling.cpp:470-521)
 __device__ __forceinline__ double cool_Edot_metallines(const CoolTab& t, double rho, double T) {
-  int ihi = t.nT - 1, ilo = 0;
-  do {
-    const int imid = ilo + ((ihi - ilo) >> 1);  // ilo + floor((ihi-ilo)/2.0)
-    if (t.T[imid] < T) ilo = imid;
-    else ihi = imid;
-  } while (ihi - ilo > 1);
-  const int iT = ilo;
-  const double dT = T - t.T[iT];
+  // The reference's bisection ends at iT = the last entry below T, clamped to [0, nT-2] (0 for T <= T[0], NaN or
+  // negative T; nT-2 for T > T[nT-1]).  Same index here: guess, then walk until both neighbours agree.
+  int iT;
+  if (t.guess_ok) {
+    int gss = (int)((__log2f((float)T) - t.l2T0) * t.inv_l2step);  // (int) of NaN is 0, of +-inf saturates
+    gss = max(0, min(gss, t.nT - 2));
+    const double* tT = t.tab;
+    while (gss > 0 && !(tT[gss] < T)) gss--;
+    while (gss < t.nT - 2 && tT[gss + 1] < T) gss++;
+    iT = gss;
+  } else {
+    int ihi = t.nT - 1, ilo = 0;
+    do {
+      const int imid = ilo + ((ihi - ilo) >> 1);  // ilo + floor((ihi-ilo)/2.0)
+      if (t.tab[imid] < T) ilo = imid;
+      else ihi = imid;
+    } while (ihi - ilo > 1);
+    iT = ilo;
+  }
+  const double* e = t.tab + iT;  // entry iT of column q: e[q nT]
+  const int n = t.nT;
+  const double dT = T - e[0];
   const double rho2 = rho * rho;
-  double rate = -(t.Cfbdn[iT] + dT * t.s_Cfbdn[iT]) * rho2 * t.inv_Mu2_elec_H;
-  rate = fmin(rate, -(t.Ccie[iT] + dT * t.s_Ccie[iT]) * rho2 * t.inv_Mu2);
-  rate -= (t.Crrh[iT] + dT * t.s_Crrh[iT]) * rho2 * t.inv_Mu2_elec_H;
-  rate -= (t.Cffhe[iT] + dT * t.s_Cffhe[iT]) * rho2 * t.inv_Mu2_elec_H;
-  rate += 8.01e-12 * (t.rrhp[iT] + dT * t.s_rrhp[iT]) * rho2 * t.inv_Mu2_elec_H;
+  double rate = -(e[4 * n] + dT * e[9 * n]) * rho2 * t.inv_Mu2_elec_H;   // C_fbdn
+  rate = fmin(rate, -(e[5 * n] + dT * e[10 * n]) * rho2 * t.inv_Mu2);    // C_cie
+  rate -= (e[2 * n] + dT * e[7 * n]) * rho2 * t.inv_Mu2_elec_H;          // C_rrh
+  rate -= (e[3 * n] + dT * e[8 * n]) * rho2 * t.inv_Mu2_elec_H;          // C_ffhe
+  rate += 8.01e-12 * (e[n] + dT * e[6 * n]) * rho2 * t.inv_Mu2_elec_H;   // rrhp
   return rate;
 }
 
@@ -161,19 +187,23 @@ struct CoolCell {
   double rho, gm1, Mu_tot_over_kB;
 };
 // mp_only_cooling::dPdt (:227-236)
+template <int MODE>
 __device__ __forceinline__ double cool_dPdt(const CoolTab& t, const CoolCell& c, double E) {
-  return cool_Edot(t, c.rho, E * c.gm1 * c.Mu_tot_over_kB / c.rho);
+  return cool_Edot<MODE>(t, c.rho, E * c.gm1 * c.Mu_tot_over_kB / c.rho);
 }
 
-// Integrator_Base::Step_RK5CK for one variable (integrator.cpp:285-371)
-__device__ __forceinline__ void cool_step_rk5ck(const CoolTab& t, const CoolCell& c, double p0, double dt, double& pf, double& dp) {
+// Integrator_Base::Step_RK5CK for one variable (integrator.cpp:285-371).  k1 = dPdt(p0) is handed in: it only depends
+// on p0, which the bisection loop of the stepper does not change, so it is evaluated once per stepper call instead of once
+// per trial step -- and once per CELL for the first sub-step of the two intervals (dt/2, dt) a second-order step
+// integrates from the same P (k_cooling_dU2).  Same value, same rounding: bit-identical results.
+template <int MODE>
+__device__ __forceinline__ void cool_step_rk5ck(const CoolTab& t, const CoolCell& c, double p0, double k1, double dt, double& pf, double& dp) {
   const double b21 = 0.2, b31 = 3. / 40., b32 = 9. / 40., b41 = 0.3, b42 = -0.9, b43 = 1.2, b51 = -11. / 54., b52 = 2.5,
                b53 = -70. / 27., b54 = 35. / 27., b61 = 1631. / 55296., b62 = 175. / 512., b63 = 575. / 13824.,
                b64 = 44275. / 110592., b65 = 253. / 4096., c1 = 37. / 378., c3 = 250. / 621., c4 = 125. / 594.,
                c6 = 512. / 1771.;
   const double dc1 = c1 - 2825. / 27648., dc3 = c3 - 18575. / 48384., dc4 = c4 - 13525. / 55296., dc5 = -277. / 14336.,
                dc6 = c6 - 0.25;
-  double k1 = cool_dPdt(t, c, p0);
   double ptemp = 0.0;
   ptemp += fabs(k1) * dt / (p0 + 1.0e-100);
   if (ptemp < 1.e-6) {
@@ -183,27 +213,28 @@ __device__ __forceinline__ void cool_step_rk5ck(const CoolTab& t, const CoolCell
   }
   k1 *= dt;
   ptemp = p0 + b21 * k1;
-  double k2 = cool_dPdt(t, c, ptemp) * dt;
+  double k2 = cool_dPdt<MODE>(t, c, ptemp) * dt;
   ptemp = p0 + b31 * k1 + b32 * k2;
-  double k3 = cool_dPdt(t, c, ptemp) * dt;
+  double k3 = cool_dPdt<MODE>(t, c, ptemp) * dt;
   ptemp = p0 + b41 * k1 + b42 * k2 + b43 * k3;
-  double k4 = cool_dPdt(t, c, ptemp) * dt;
+  double k4 = cool_dPdt<MODE>(t, c, ptemp) * dt;
   ptemp = p0 + b51 * k1 + b52 * k2 + b53 * k3 + b54 * k4;
-  double k5 = cool_dPdt(t, c, ptemp) * dt;
+  double k5 = cool_dPdt<MODE>(t, c, ptemp) * dt;
   ptemp = p0 + b61 * k1 + b62 * k2 + b63 * k3 + b64 * k4 + b65 * k5;
-  double k6 = cool_dPdt(t, c, ptemp) * dt;
+  double k6 = cool_dPdt<MODE>(t, c, ptemp) * dt;
   pf = p0 + c1 * k1 + c3 * k3 + c4 * k4 + c6 * k6;
   dp = dc1 * k1 + dc3 * k3 + dc4 * k4 + dc5 * k5 + dc6 * k6;
 }
 
 // Integrator_Base::Stepper_RKCK, BISECTION_STEPPER variant (integrator.cpp:401-530)
-__device__ __forceinline__ int cool_stepper(const CoolTab& t, const CoolCell& c, double p0, double t0, double htry,
+template <int MODE>
+__device__ __forceinline__ int cool_stepper(const CoolTab& t, const CoolCell& c, double p0, double k1, double t0, double htry,
                                             double errtol, double& p1, double& hdid, double& hnext) {
   int rval = 0, ct = 0;
   double h = htry, maxerr, err = 0.0, ptemp = 0.0;
   if (h < 0) return 1;
   do {
-    cool_step_rk5ck(t, c, p0, h, ptemp, err);
+    cool_step_rk5ck<MODE>(t, c, p0, k1, h, ptemp, err);
     maxerr = 0;
     if (!isfinite(err) || !isfinite(ptemp) || ptemp < 0.0) {
       maxerr = fmax(maxerr, 1000.0);
@@ -224,26 +255,52 @@ __device__ __forceinline__ int cool_stepper(const CoolTab& t, const CoolCell& c,
   return rval;
 }
 
-// Integrator_Base::Int_Adaptive_RKCK (integrator.cpp:540-606)
-__device__ __forceinline__ int cool_integrate(const CoolTab& t, const CoolCell& c, double p0, double dt, double& pf) {
-  double tt = 0.0, p1 = p0, p2 = 0.0;
+// Integrator_Base::Int_Adaptive_RKCK (integrator.cpp:540-606); k1_0 = dPdt(p0) of the first sub-step
+template <int MODE>
+__device__ __forceinline__ int cool_integrate(const CoolTab& t, const CoolCell& c, double p0, double k1_0, double dt, double& pf) {
+  double tt = 0.0, p1 = p0, p2 = 0.0, k1 = k1_0;
   const double tf = 0.0 + dt;
   double h = dt, hdid = 0.0, hnext = 0.0;
   int err = 0, ct = 0;
-  do {
-    err += cool_stepper(t, c, p1, tt, h, 1.0e-2, p2, hdid, hnext);
+  for (;;) {
+    err += cool_stepper<MODE>(t, c, p1, k1, tt, h, 1.0e-2, p2, hdid, hnext);
     tt += hdid;
     h = fmin(hnext, tf - tt);
     ct++;
     p1 = p2;
-  } while (tt < tf && (err == 0) && (ct < 25));
+    if (!(tt < tf && (err == 0) && (ct < 25))) break;
+    k1 = cool_dPdt<MODE>(t, c, p1);
+  }
   pf = p1;
   return err;
 }
+template <int MODE>
+__device__ __forceinline__ int cool_integrate(const CoolTab& t, const CoolCell& c, double p0, double dt, double& pf) {
+  return cool_integrate<MODE>(t, c, p0, cool_dPdt<MODE>(t, c, p0), dt, pf);
+}
 
-// calc_noRT_microphysics_dU: one thread per interior cell.
+// dE = (PtoU(p') - PtoU(P)).erg for the integrated internal energy Eint (calc_noRT_microphysics_dU, time_integrator.cpp:
+// 438-489, with the temperature clamp of TimeUpdateMP, mp_only_cooling.cpp:208-216)
 template <int EQ>
-__global__ void __launch_bounds__(128) k_cooling_dU(const __grid_constant__ CoolArgs a) {
+__device__ __forceinline__ double cool_dE_of(const CoolArgs& a, const Prim& p, const Cons& ui, double Eint) {
+  Prim po = p;
+  po.pg = Eint * (a.gamma - 1);
+  const double Tf = po.pg * a.cp.Mu_tot_over_kB / po.ro;
+  if (Tf > a.cp.MaxT) po.pg *= a.cp.MaxT / Tf;
+  else if (Tf < a.cp.MinT) po.pg *= a.cp.MinT / Tf;
+  Cons uf;
+  PtoU<EQ>(po, uf, a.gamma - 1.0);
+  return uf.erg - ui.erg;
+}
+
+// calc_noRT_microphysics_dU: one thread per interior cell.  A second-order step calls it twice from the same P -- with dt/2
+// before the predictor and with dt before the corrector (time_integrator.cpp:150-250) -- so the fused path integrates both
+// intervals in ONE launch (dE for dt, dE2 for dt2): one read of P, one table set-up, and the first Edot evaluation shared.
+#ifndef PION_COOL_MINB
+#define PION_COOL_MINB 8
+#endif
+template <int EQ, int MODE>
+__global__ void __launch_bounds__(128, PION_COOL_MINB) k_cooling_dU(const __grid_constant__ CoolArgs a) {
   extern __shared__ double s_tab[];
   const CoolTab t = cool_tables_to_smem(a.cp, s_tab);
   const GridD& g = a.g;
@@ -252,35 +309,37 @@ __global__ void __launch_bounds__(128) k_cooling_dU(const __grid_constant__ Cool
   for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += (long)gridDim.x * blockDim.x) {
     const int i = (int)(q % g.NG[0]), j = (int)((q / g.NG[0]) % g.NG[1]), k = (int)(q / ((long)g.NG[0] * g.NG[1]));
     const long c = gidx(g, i + g.nb[0], j + g.nb[1], k + g.nb[2]);
-    double dE = 0.0;
+    double dE = 0.0, dE2 = 0.0;
     if (!a.mask || a.mask[c]) {
-      Prim p = load_prim<EQ>(a.P, c, g.vs, 0, 1, 2);
+      // the integration only needs rho and p; the rest of the state (kinetic / magnetic energy of PtoU) is read AFTER
+      // it, so that it does not occupy registers across the integrator (the memory clobber keeps the loads there)
+      const double ro = __ldg(a.P + c), pg = __ldg(a.P + g.vs + c);
       CoolCell cc;
-      cc.rho = p.ro;
+      cc.rho = ro;
       cc.gm1 = a.gamma - 1.0;
       cc.Mu_tot_over_kB = a.cp.Mu_tot_over_kB;
-      const double Eint0 = p.pg / (a.gamma - 1.0);
-      double Eint;
-      fails += (cool_integrate(t, cc, Eint0, a.dt, Eint) != 0);
-      Prim po = p;
-      po.pg = Eint * (a.gamma - 1);
-      const double Tf = po.pg * a.cp.Mu_tot_over_kB / po.ro;
-      if (Tf > a.cp.MaxT) po.pg *= a.cp.MaxT / Tf;
-      else if (Tf < a.cp.MinT) po.pg *= a.cp.MinT / Tf;
+      const double Eint0 = pg / (a.gamma - 1.0);
+      const double k1 = cool_dPdt<MODE>(t, cc, Eint0);
+      double Eint, Eint2 = 0.0;
+      fails += (cool_integrate<MODE>(t, cc, Eint0, k1, a.dt, Eint) != 0);
+      if (a.dE2) fails += (cool_integrate<MODE>(t, cc, Eint0, k1, a.dt2, Eint2) != 0);  // same P, same k1: the corrector's interval
+      asm volatile("" ::: "memory");
       // dU += PtoU(p') - PtoU(P): every component but the energy cancels exactly
-      Cons ui, uf;
+      const Prim p = load_prim<EQ>(a.P, c, g.vs, 0, 1, 2);
+      Cons ui;
       PtoU<EQ>(p, ui, a.gamma - 1.0);
-      PtoU<EQ>(po, uf, a.gamma - 1.0);
-      dE = uf.erg - ui.erg;
+      dE = cool_dE_of<EQ>(a, p, ui, Eint);
+      if (a.dE2) dE2 = cool_dE_of<EQ>(a, p, ui, Eint2);
     }
     if (a.dE) a.dE[c] = dE;
+    if (a.dE2) a.dE2[c] = dE2;
     if (a.dU) a.dU[g.vs + c] += dE;
   }
   if (fails && a.counters) atomicAdd((unsigned long long*)&a.counters[2], (unsigned long long)fails);
 }
 
 // calc_microphysics_dt / get_mp_timescales_no_radiation + mp_only_cooling::timescales
-template <int EQ>
+template <int EQ, int MODE>
 __global__ void __launch_bounds__(256) k_mp_dt(const __grid_constant__ CoolArgs a) {
   extern __shared__ double s_tab[];
   const CoolTab t = cool_tables_to_smem(a.cp, s_tab);
@@ -295,7 +354,7 @@ __global__ void __launch_bounds__(256) k_mp_dt(const __grid_constant__ CoolArgs 
     const double Eint = pg / (a.gamma - 1.0);
     const double T = pg * a.cp.Mu_tot_over_kB / ro;
     if (T >= 1.1 * a.cp.MinT) {
-      const double rate = fmax(fabs(cool_Edot(t, ro, T)), fabs(cool_Edot(t, ro, fmax(a.cp.MinT, 0.5 * T))));
+      const double rate = fmax(fabs(cool_Edot<MODE>(t, ro, T)), fabs(cool_Edot<MODE>(t, ro, fmax(a.cp.MinT, 0.5 * T))));
       my = fmin(my, Eint / rate);
     }
   }

@@ -82,7 +82,8 @@ struct pion_gpu_ctx {
   double* d_red = nullptr;  // 2 doubles for the dt all-reduce
   // microphysics (mp_only_cooling)
   CoolParams cool;
-  double *d_tables = nullptr, *mp_dE = nullptr;
+  double *d_tables = nullptr, *mp_dE = nullptr, *mp_dE2 = nullptr;  // cooling source of a stage (mp_dE2: the corrector's)
+  const double* mp_dE_stage = nullptr;                              // the one the next fused stage adds
   long long mp_failures = 0;
   // stellar-wind internal boundary: cell list (device linear indices) and reference states [nvar][n]
   long wind_n = 0;
@@ -127,7 +128,7 @@ static int make_state_tmap(const pion_gpu_ctx* c, double* base, int order, CUten
     enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   }
   int cw, rh, nb, tx, ty;
-  sweep_tma_box(c->cfg.eqntype, order, &cw, &rh, &nb, &tx, &ty);
+  sweep_tma_box(c->cfg.eqntype, order, c->ntr, &cw, &rh, &nb, &tx, &ty);
   if ((c->g.xoff + c->g.nb[0]) % 2 || tx % 2) {  // every box must start on a 16-byte boundary in x
     set_error("TMA sweep: tile boxes would start on odd x offsets");
     return 1;
@@ -146,6 +147,17 @@ static int make_state_tmap(const pion_gpu_ctx* c, double* base, int order, CUten
   }
   return 0;
 }
+
+// launch KERNEL<EQ, EP_cooling> for the cooling function of this context (mp_only_cooling::Edot's cases)
+#define PION_COOL_DISPATCH(mode, KERNEL, EQ, grid, block, smem, stream, args)          \
+  switch (mode) {                                                                      \
+    case 2: KERNEL<EQ, 2><<<grid, block, smem, stream>>>(args); break;                 \
+    case 4: KERNEL<EQ, 4><<<grid, block, smem, stream>>>(args); break;                 \
+    case 5: KERNEL<EQ, 5><<<grid, block, smem, stream>>>(args); break;                 \
+    case 6: KERNEL<EQ, 6><<<grid, block, smem, stream>>>(args); break;                 \
+    case 7: KERNEL<EQ, 7><<<grid, block, smem, stream>>>(args); break;                 \
+    default: KERNEL<EQ, 8><<<grid, block, smem, stream>>>(args); break;                \
+  }
 
 static int check_config(const pion_gpu_config& c) {
   if (c.ndim < 1 || c.ndim > 3) { set_error("ndim must be 1..3"); return 1; }
@@ -386,6 +398,7 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
     const double Mu = 1.40 * m_p, Mu_elec = 1.167 * m_p, Mu_ion = 1.273 * m_p;
     CoolParams& cp = c->cool;
     cp.mode = cfg->cooling;
+    cp.guess_ok = 0; cp.l2T0 = 0.f; cp.inv_l2step = 0.f;
     cp.nT = (cfg->cooling == 8) ? cfg->n_table : (cfg->cooling >= 4) ? cfg->n_spline : 0;
     cp.Mu = Mu; cp.Mu_elec = Mu_elec; cp.Mu_ion = Mu_ion;
     cp.smin = cfg->spline_min_slope; cp.smax = cfg->spline_max_slope;
@@ -403,6 +416,16 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
       for (int q = 0; q < 6; q++) memcpy(&h[(size_t)q * n], src[q], n * sizeof(double));
       for (int q = 1; q < 6; q++)
         for (int i = 0; i < n - 1; i++) h[(size_t)(5 + q) * n + i] = (h[(size_t)q * n + i + 1] - h[(size_t)q * n + i]) / (h[i + 1] - h[i]);
+      // log-uniform T column (the reference builds T_i = T_0 (T_max/T_0)^(i/(n-1))): interval guess from log2 T.
+      // Any strictly increasing table whose knots stay within a quarter step of that law qualifies; anything else
+      // keeps the binary search.  (The guess is only a starting point: the kernel corrects it against the table.)
+      cp.guess_ok = 0; cp.l2T0 = 0.f; cp.inv_l2step = 0.f;
+      if (n >= 3 && h[0] > 0.0) {
+        const double l0 = log2(h[0]), step = (log2(h[n - 1]) - l0) / (n - 1);
+        bool ok_guess = step > 0.0;
+        for (int i = 1; i < n && ok_guess; i++) ok_guess = h[i] > h[i - 1] && fabs(log2(h[i]) - (l0 + i * step)) < 0.25 * step;
+        if (ok_guess) { cp.guess_ok = 1; cp.l2T0 = (float)l0; cp.inv_l2step = (float)(1.0 / step); }
+      }
     } else if (cp.mode >= 4) {
       // natural cubic spline through the knots, as GSL's cspline builds it for the reference (tools/interpolate.cpp:
       // 59-118): c = y''/2 from the symmetric tridiagonal system, solved by forward elimination + back substitution
@@ -428,6 +451,7 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
     }
     ok &= cudaMalloc(&c->d_tables, h.size() * sizeof(double)) == cudaSuccess;
     ok &= cudaMalloc(&c->mp_dE, (size_t)g.vs * sizeof(double)) == cudaSuccess;
+    if (cfg->tmOOA == 2) ok &= cudaMalloc(&c->mp_dE2, (size_t)g.vs * sizeof(double)) == cudaSuccess && cudaMemset(c->mp_dE2, 0, (size_t)g.vs * sizeof(double)) == cudaSuccess;
     if (ok) {
       ok &= cudaMemcpy(c->d_tables, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
       ok &= cudaMemset(c->mp_dE, 0, (size_t)g.vs * sizeof(double)) == cudaSuccess;
@@ -477,7 +501,7 @@ extern "C" void pion_gpu_destroy(pion_gpu_ctx* c) {
   for (auto e : c->tev_pool) cudaEventDestroy(e);
   if (c->comm) ncclCommDestroy(c->comm);
   cudaFree(c->P); cudaFree(c->Ph); cudaFree(c->dU); cudaFree(c->eta); cudaFree(c->hll); cudaFree(c->hllf); cudaFree(c->mask);
-  cudaFree(c->d_dtmin); cudaFree(c->d_counters); cudaFree(c->d_red); cudaFree(c->d_tables); cudaFree(c->mp_dE); cudaFree(c->d_wind_idx); cudaFree(c->d_wind_val);
+  cudaFree(c->d_dtmin); cudaFree(c->d_counters); cudaFree(c->d_red); cudaFree(c->d_tables); cudaFree(c->mp_dE); cudaFree(c->mp_dE2); cudaFree(c->d_wind_idx); cudaFree(c->d_wind_val);
   for (int f = 0; f < 6; f++) { cudaFree(c->sendbuf[f]); cudaFree(c->recvbuf[f]); }
   for (int q = 0; q < 2; q++) {
     cudaFree(c->stage[q]);
@@ -792,11 +816,8 @@ static int queue_local_dt(pion_gpu_ctx* c) {
     a.dtmin = c->d_dtmin + 1; a.mp_timestep_limit = lim;
     const long ncell = (long)c->g.NG[0] * c->g.NG[1] * c->g.NG[2];
     const size_t smem = cool_smem_bytes(c->cool);
-    switch (c->cfg.eqntype) {
-      case PION_EQEUL: k_mp_dt<EQ_EULER><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
-      case PION_EQMHD: k_mp_dt<EQ_MHD><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
-      default: k_mp_dt<EQ_GLM><<<nblocks(ncell, 256, 148 * 8), 256, smem, c->stream>>>(a); break;
-    }
+    // (the kernel reads rho and p only: one instantiation per cooling function)
+    PION_COOL_DISPATCH(c->cool.mode, k_mp_dt, EQ_EULER, nblocks(ncell, 256, 148 * 8), 256, smem, c->stream, a)
     c->launches++;
     CUDA_OK(cudaGetLastError());
   }
@@ -985,7 +1006,7 @@ static void stage_tile_cells(const pion_gpu_ctx* c, int order, int* cx, int* cy)
   sweep_tile_cells(c->cfg.eqntype, cx, cy);
   if (c->have_tmap && !c->eta) {
     int cw, rh, nb;
-    sweep_tma_box(c->cfg.eqntype, order, &cw, &rh, &nb, cx, cy);
+    sweep_tma_box(c->cfg.eqntype, order, c->ntr, &cw, &rh, &nb, cx, cy);
   }
 }
 
@@ -1005,7 +1026,7 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
   a.Pb = Pb;
   a.out = out;
   a.dU = dU;
-  a.mp_dE = (fused && c->cfg.cooling) ? c->mp_dE : nullptr;
+  a.mp_dE = (fused && c->cfg.cooling) ? c->mp_dE_stage : nullptr;
   a.hll = c->hll;
   a.hllf = c->hllf;
   a.eta = c->eta;
@@ -1070,17 +1091,18 @@ static int launch_stage(pion_gpu_ctx* c, const double* S, const double* Pb, doub
 }
 
 // calc_noRT_microphysics_dU (time_integrator.cpp:438-489): always integrates from P
-static int launch_cooling(pion_gpu_ctx* c, double dt, double* dE, double* dU) {
+static int launch_cooling(pion_gpu_ctx* c, double dt, double* dE, double* dU, double dt2 = 0.0, double* dE2 = nullptr) {
   CoolArgs a;
   a.g = c->g; a.cp = c->cool; a.P = c->P; a.dE = dE; a.dU = dU; a.mask = c->mask; a.dt = dt; a.gamma = c->pp.gamma;
+  a.dE2 = dE2; a.dt2 = dt2;
   a.counters = c->d_counters; a.dtmin = nullptr; a.mp_timestep_limit = 0;
   const long ncell = (long)c->g.NG[0] * c->g.NG[1] * c->g.NG[2];
   const size_t smem = cool_smem_bytes(c->cool);
   const int blocks = nblocks(ncell, 128, 148 * 32);
   switch (c->cfg.eqntype) {
-    case PION_EQEUL: k_cooling_dU<EQ_EULER><<<blocks, 128, smem, c->stream>>>(a); break;
-    case PION_EQMHD: k_cooling_dU<EQ_MHD><<<blocks, 128, smem, c->stream>>>(a); break;
-    default: k_cooling_dU<EQ_GLM><<<blocks, 128, smem, c->stream>>>(a); break;
+    case PION_EQEUL: PION_COOL_DISPATCH(c->cool.mode, k_cooling_dU, EQ_EULER, blocks, 128, smem, c->stream, a) break;
+    case PION_EQMHD: PION_COOL_DISPATCH(c->cool.mode, k_cooling_dU, EQ_MHD, blocks, 128, smem, c->stream, a) break;
+    default: PION_COOL_DISPATCH(c->cool.mode, k_cooling_dU, EQ_GLM, blocks, 128, smem, c->stream, a) break;
   }
   c->launches++;
   CUDA_OK(cudaGetLastError());
@@ -1215,6 +1237,7 @@ extern "C" int pion_gpu_advance_time(pion_gpu_ctx* c, double* dt_done) {
     c->FV_dt = dt;
     // the single stage reads P's stencil and must not write P in place: go through Ph
     if (c->cfg.cooling && launch_cooling(c, dt, c->mp_dE, nullptr)) return 1;
+    c->mp_dE_stage = c->mp_dE;
     if (launch_preprocess(c, c->P, 1)) return 1;
     if (launch_stage(c, c->P, c->P, c->Ph, nullptr, dt, 1, true, true)) return 1;
     // P = Ph on the interior, then boundaries of both
@@ -1227,13 +1250,16 @@ extern "C" int pion_gpu_advance_time(pion_gpu_ctx* c, double* dt_done) {
   } else {
     // first_order_update(0.5 dt, OA2): Setdt(0.5dt), dynamics OA1, update Ph
     c->FV_dt = 0.5 * dt;
-    if (c->cfg.cooling && launch_cooling(c, 0.5 * dt, c->mp_dE, nullptr)) return 1;  // calc_microphysics_dU(0.5dt)
+    // calc_microphysics_dU(0.5dt) of the predictor AND calc_microphysics_dU(dt) of the corrector: both integrate from
+    // the start-of-step P (time_integrator.cpp:472), so one launch produces both source terms
+    if (c->cfg.cooling && launch_cooling(c, 0.5 * dt, c->mp_dE, nullptr, dt, c->mp_dE2)) return 1;
+    c->mp_dE_stage = c->mp_dE;
     if (launch_preprocess(c, c->P, 1)) return 1;
     // ... then boundaries of Ph (cstep=OA1 != maxstep=OA2), simtime = start of step
     if (stage_and_bcs(c, c->P, c->P, c->Ph, 0.5 * dt, 1, false, c->Ph, nullptr)) return 1;
     // second_order_update(dt, OA2): Setdt(dt), dynamics OA2 from Ph, update P
     c->FV_dt = dt;
-    if (c->cfg.cooling && launch_cooling(c, dt, c->mp_dE, nullptr)) return 1;  // from P again (time_integrator.cpp:472)
+    c->mp_dE_stage = c->mp_dE2;
     if (launch_preprocess(c, c->Ph, 2)) return 1;
     // ... then boundaries of P (and Ph == P): only P is kept current
     if (stage_and_bcs(c, c->Ph, c->P, c->P, dt, 2, true, c->P, nullptr)) return 1;

@@ -103,7 +103,8 @@ __device__ __forceinline__ unsigned long long dbl_ordered_bits(double x) {
 // grid_update_state_vector (time_integrator.cpp:881-958): U = PtoU(Pb) + dU,
 // out = UtoP(U) with floors; optionally the next step's CellTimeStep.
 template <int EQ>
-__device__ __forceinline__ int cell_advance_time_pb(const StageArgs& a, long c, const Prim& Pb, const Cons& acc, const double* acctr, int ntr, double& my_dt) {
+__device__ __forceinline__ int cell_advance_time_pb(const StageArgs& a, long c, const Prim& Pb, const Cons& acc, const double* acctr, int ntr, double& my_dt,
+                                                    const double* trb = nullptr, int trb_stride = 0) {
   constexpr int NB = nbase(EQ);
   const long vs = a.g.vs;
   Cons U;
@@ -122,7 +123,9 @@ __device__ __forceinline__ int cell_advance_time_pb(const StageArgs& a, long c, 
 #pragma unroll
   for (int q = 0; q < PION_MAXTR; q++) {
     if (q < ntr) {
-      double pb = __ldg(a.Pb + (long)(NB + q) * vs + c);
+      // base value of the tracer: from the caller's shared-memory tile when the base state IS the stencil state
+      // (predictor), else from HBM
+      double pb = trb ? trb[q * trb_stride] : __ldg(a.Pb + (long)(NB + q) * vs + c);
       if (a.pp.have_mp) pb *= scma_corr(pb);
       double u = pb * Pb.ro + acctr[q];
       double pn = pdiv(u, U.rho);
@@ -486,7 +489,7 @@ const char* launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream
 // cells per sweep tile along x / y (stage_sweep.cuh: 32 lanes, TY rows, one of each only produces fluxes)
 void sweep_tile_cells(int eq, int* cx, int* cy);  // eq: EQ_EULER / EQ_MHD / EQ_GLM
 bool sweep_tma_fits(int eq, int ntr);  // the TMA sweep kernel exists for this many tracers and its tile fits shared memory
-void sweep_tma_box(int eq, int order, int* cw, int* rh, int* nb, int* tx, int* ty);  // box of one TMA plane load of a stage of that order, cells per tile in x and y (stage_sweep_tma.cuh)
+void sweep_tma_box(int eq, int order, int ntr, int* cw, int* rh, int* nb, int* tx, int* ty);  // box of one TMA plane load of a stage of that order with ntr tracers, cells per tile in x and y (stage_sweep_tma.cuh)
 // flux-once sweep kernel (stage_sweep.cuh), instantiated in sweep_{euler,mhd,glm}.cu
 const char* launch_sweep_euler(int solver, int fkj, const StageArgs& a, cudaStream_t s);
 const char* launch_sweep_mhd(int solver, int fkj, const StageArgs& a, cudaStream_t s);

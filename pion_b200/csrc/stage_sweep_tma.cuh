@@ -54,13 +54,28 @@ namespace pion {
 #ifndef PION_TMA_RING1
 #define PION_TMA_RING1 4
 #endif
-__host__ __device__ constexpr int tma_ty(int eq, int order) { return (eq != EQ_EULER && order == 1) ? PION_TMA_TY1 : sweep_ty(eq); }
 __host__ __device__ constexpr int tma_ring(int eq, int order) { return (eq != EQ_EULER && order == 1) ? PION_TMA_RING1 : 4; }
 constexpr int TMA_TX = 32;                                            // cells a tile updates along x
 constexpr int TMA_CW = 36;                                            // tile columns: cells i0-2 .. i0+33
 __host__ __device__ constexpr int tma_rh(int ty) { return ty + 3; }  // tile rows
 __host__ __device__ constexpr int tma_plane_bytes(int nb, int ty) { return nb * tma_rh(ty) * TMA_CW * 8; }
 __host__ __device__ constexpr int tma_plane_stride(int nb, int ty) { return (tma_plane_bytes(nb, ty) + 127) / 128 * 128; }
+// dynamic shared memory of the TMA kernel: plane ring + y-flux slab + z-flux slots + x-edge slabs
+__host__ __device__ constexpr size_t tma_smem_bytes(int nv, int ty, int ring) {
+  return (size_t)ring * tma_plane_stride(nv, ty) + (size_t)2 * nv * ty * 32 * sizeof(double) + (size_t)3 * nv * ty * sizeof(double);
+}
+// shared memory one block may use so that `minb` blocks fit an SM (228 KB per SM, 1 KB reserved per block, 384 B static)
+__host__ __device__ constexpr size_t tma_smem_budget(int minb) { return (size_t)(228 * 1024) / minb - 1024 - 512; }
+// tracer counts the TMA kernel is instantiated for (tracers ride along as extra tile variables)
+constexpr int TMA_MAXTR = 2;
+// Tile rows for an equation set, stage order and tracer count: the equation set's row count (sweep_ty, or PION_TMA_TY1 for
+// first-order stages of MHD / GLM), reduced until the ring + slabs of nbase + ntr variables fit the shared memory:
+// Euler 8, 8, 7 rows for 0, 1, 2 tracers; ideal MHD 12, 12, 11; GLM 12, 11, 10.
+__host__ __device__ constexpr int tma_ty(int eq, int order, int ntr) {
+  int ty = (eq != EQ_EULER && order == 1) ? PION_TMA_TY1 : sweep_ty(eq);
+  while (ty > 4 && tma_smem_bytes(nbase(eq) + ntr, ty, tma_ring(eq, order)) > tma_smem_budget(sweep_minb(eq))) ty--;
+  return ty;
+}
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
@@ -346,6 +361,14 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   // light warp that of the cell beyond its x-edge face in plane k+1 -- and plane k+2's byte is requested ONE
   // PLANE AHEAD, so that the flux never waits on a global load
   unsigned w_k = 0, w_k1 = 0, we_k1 = 0;
+  // isdomain byte of the cell (stellar-wind boundaries only): requested ONE PLANE AHEAD like the face bytes (the
+  // synchronous load was 6 % of the Euler predictor's stall samples, profiles/r02p_*)
+  const unsigned char* mp = nullptr;
+  unsigned m_k = 1;
+  if (a.mask) {
+    mp = a.mask + gidx(g, i + g.nb[0], j + g.nb[1], k0 + g.nb[2]);
+    m_k = mp[0];
+  }
   const unsigned char* hp = nullptr;   // face byte of cell (i,j,k)
   const unsigned char* hpe = nullptr;  // light warp: face byte of cell (i0+32, j0+lane, k)
   if (SOLVER == SOLVE_HLLD) {
@@ -403,7 +426,10 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     for (int q = 0; q < NTRA; q++) acctr[q] = 0.0;
     // the centre state is RE-READ from the tile wherever it is needed (an LDS with an immediate offset is
     // cheaper than 18 registers held across the Riemann solver)
-    const bool domain = upd_xy && !warm && (a.mask ? (a.mask[c] != 0) : true);
+    // m_k: mask byte of plane k (the warm iteration, k = k0-1, already holds plane k0's and keeps it)
+    unsigned n_m = 1;
+    if (a.mask && !warm && !last) n_m = ldg_u8_now(mp + g.sz);
+    const bool domain = upd_xy && !warm && (m_k != 0);
     if (!warm && a.mp_dE && upd_xy) acc.erg = a.mp_dE[c];  // cooling source term (energy only)
 #ifdef PION_PB_PREFETCH
     // corrector: the base state P of this cell is read from HBM at the END of the iteration (cell_advance_time),
@@ -562,12 +588,13 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       if (light) hpe += g.sz;
     }
     if (warm) continue;
+    if (a.mask) { m_k = n_m; mp += g.sz; }
 
     if (domain) {
       Cons accx;  // grid frame == solver frame of x
       accx.rho = acc.rho; accx.erg = acc.erg; accx.mn = acc.m0; accx.mt1 = acc.m1; accx.mt2 = acc.m2;
       accx.bbn = acc.b0; accx.bbt1 = acc.b1; accx.bbt2 = acc.b2; accx.psi = acc.psi;
-      if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, lds_prim<EQ, VS>(p0, 0, 1, 2), accx, acctr, NTR, my_dt);
+      if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, lds_prim<EQ, VS>(p0, 0, 1, 2), accx, acctr, NTR, my_dt, p0 + NB * VS, VS);
       else status |= cell_advance_time<EQ>(a, c, accx, acctr, NTR, my_dt);
     } else if (upd_xy && a.out != a.S) {
       // cell cut out of the domain (time_integrator.cpp:905-908): state untouched
@@ -583,24 +610,17 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   stage_block_epilogue(a, my_dt, status);
 }
 
-// dynamic shared memory of the TMA kernel: plane ring + y-flux slab + z-flux slots + x-edge slabs
-__host__ __device__ constexpr size_t tma_smem_bytes(int nv, int ty, int ring) {
-  return (size_t)ring * tma_plane_stride(nv, ty) + (size_t)2 * nv * ty * 32 * sizeof(double) + (size_t)3 * nv * ty * sizeof(double);
-}
-constexpr size_t TMA_SMEM_MAX = 227 * 1024 - 1024;  // per-block opt-in limit minus the static part
-// tracer counts the TMA kernel is instantiated for
-constexpr int TMA_MAXTR = 1;
 __host__ __device__ constexpr bool tma_fits(int eq, int ntr) {
-  return ntr <= TMA_MAXTR && tma_smem_bytes(nbase(eq) + ntr, tma_ty(eq, 1), tma_ring(eq, 1)) <= TMA_SMEM_MAX &&
-         tma_smem_bytes(nbase(eq) + ntr, tma_ty(eq, 2), tma_ring(eq, 2)) <= TMA_SMEM_MAX;
+  return ntr <= TMA_MAXTR && tma_smem_bytes(nbase(eq) + ntr, tma_ty(eq, 1, ntr), tma_ring(eq, 1)) <= tma_smem_budget(sweep_minb(eq)) &&
+         tma_smem_bytes(nbase(eq) + ntr, tma_ty(eq, 2, ntr), tma_ring(eq, 2)) <= tma_smem_budget(sweep_minb(eq));
 }
 
 template <int EQ, int SOLVER, bool FKJ, int NTR, int ORDER>
 inline const char* launch_sweep_tma_o(const StageArgs& a, cudaStream_t s) {
-  constexpr int TY = tma_ty(EQ, ORDER), RING = tma_ring(EQ, ORDER), MINB = sweep_minb(EQ);
+  constexpr int TY = tma_ty(EQ, ORDER, NTR), RING = tma_ring(EQ, ORDER), MINB = sweep_minb(EQ);
   constexpr int NV = nbase(EQ) + NTR;
   static char name[160], extra[96];
-  static const char* nm = (snprintf(extra, sizeof extra, ",TY=%d|%d,RING=%d|%d,NTR=%d,ORDER=1|2 (TMA-staged stencil)", tma_ty(EQ, 1), tma_ty(EQ, 2),
+  static const char* nm = (snprintf(extra, sizeof extra, ",TY=%d|%d,RING=%d|%d,NTR=%d,ORDER=1|2 (TMA-staged stencil)", tma_ty(EQ, 1, NTR), tma_ty(EQ, 2, NTR),
                                     tma_ring(EQ, 1), tma_ring(EQ, 2), NTR),
                            kernel_variant_name(name, sizeof name, "k_stage_sweep_tma", EQ, SOLVER, FKJ, extra));
   const int bx = a.tx1 - a.tx0, by = a.ty1 - a.ty0, NZ = a.k_hi - a.k_lo;
@@ -643,16 +663,19 @@ inline const char* launch_sweep_any(const StageArgs& a, cudaStream_t s) {
   if constexpr (tma_fits(EQ, 1)) {
     if (tma && a.ntr == 1) return launch_sweep_tma_t<EQ, SOLVER, FKJ, 1>(a, s);
   }
+  if constexpr (tma_fits(EQ, 2)) {
+    if (tma && a.ntr == 2) return launch_sweep_tma_t<EQ, SOLVER, FKJ, 2>(a, s);
+  }
   return launch_sweep_t<EQ, SOLVER, FKJ>(a, s);
 }
 
 // box of one TMA plane load for an equation set (host side: tensor-map creation)
 inline bool sweep_tma_fits_impl(int eq, int ntr) { return tma_fits(eq, ntr); }
-inline void sweep_tma_box_impl(int eq, int order, int* cw, int* rh, int* nb, int* tx, int* ty) {
+inline void sweep_tma_box_impl(int eq, int order, int ntr, int* cw, int* rh, int* nb, int* tx, int* ty) {
   *tx = TMA_TX;
-  *ty = tma_ty(eq, order) - 1;
+  *ty = tma_ty(eq, order, ntr) - 1;
   *cw = TMA_CW;
-  *rh = tma_rh(tma_ty(eq, order));
+  *rh = tma_rh(tma_ty(eq, order, ntr));
   *nb = nbase(eq);
 }
 

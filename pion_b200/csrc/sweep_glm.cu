@@ -14,6 +14,6 @@ const char* launch_sweep_glm(int solver, int fkj, const StageArgs& a, cudaStream
   }
 }
 void sweep_tile_cells(int eq, int* cx, int* cy) { sweep_tile_cells_impl(eq, cx, cy); }
-void sweep_tma_box(int eq, int order, int* cw, int* rh, int* nb, int* tx, int* ty) { sweep_tma_box_impl(eq, order, cw, rh, nb, tx, ty); }
+void sweep_tma_box(int eq, int order, int ntr, int* cw, int* rh, int* nb, int* tx, int* ty) { sweep_tma_box_impl(eq, order, ntr, cw, rh, nb, tx, ty); }
 bool sweep_tma_fits(int eq, int ntr) { return sweep_tma_fits_impl(eq, ntr); }
 }  // namespace pion

@@ -56,6 +56,44 @@ def test_3d_multi_tile_tma_sweep(eqn, solver, av):
     run_pair(case_3d(eqn, solver, av, bcs="reflect-outflow", NG=(40, 26, 20)))
 
 
+@pytest.mark.parametrize("eqn,solver,av", [("euler", 8, 1), ("euler", 4, 0), ("euler", 6, 1), ("i-mhd", 7, 1), ("i-mhd", 4, 0),
+                                           ("glm-mhd", 7, 1), ("glm-mhd", 8, 0), ("glm-mhd", 4, 1)])
+@pytest.mark.parametrize("ntracer", [1, 2])
+def test_3d_multi_tile_tma_sweep_with_tracers(eqn, solver, av, ntracer):
+    """One and two tracers ride along as extra tile variables of the TMA sweep kernel; the tile loses rows as variables are
+    added (Euler 8 / 8 / 7 rows for 0 / 1 / 2 tracers, ideal MHD 12 / 12 / 11, GLM 12 / 11 / 10), so these grids span several
+    tiles of every one of those shapes, and the kernel variant that ran is checked."""
+    prob = case_3d(eqn, solver, av, bcs="mixed1", ntracer=ntracer, NG=(40, 26, 20))
+    run_pair(prob)
+    g = GpuSim(prob)
+    try:
+        g.set_state(random_state(prob, 3))
+        g.init_after_state()
+        g.run(1)
+        assert "k_stage_sweep_tma" in g.ctx.describe() and f"NTR={ntracer}" in g.ctx.describe(), g.ctx.describe()
+    finally:
+        g.close()
+
+
+def test_shock_problem_error_bound():
+    """Documented N-step bound on the reference's shock test problems at their BASELINE sizes (tools/shock_bound.py,
+    profiles/r02r_shock_problem_error_bounds.jsonl): double Mach reflection 260x80, Roe-CV, 300 steps: measured 1.0e-13
+    (3.4e-13 after the 600 steps to t = 0.2); advected field loop 128x64 GLM-MHD HLLD, 200 steps: measured < 5e-14.
+    Asserted with a margin of 50."""
+    import dataclasses
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import bench_configs as bc
+    cfgs = {c[0]: c for c in bc.configs(False)}
+    _, prob, ic, _, _ = cfgs["1 DMR 2-D Euler 260x80 solver 4"]
+    prob = dataclasses.replace(prob, finishtime=1e30)
+    run_pair(prob, nsteps=300, state=ic)
+    _, prob, ic, _, _ = cfgs["2 FieldLoop 2-D GLM-MHD 512x256 solver 7"]
+    prob = dataclasses.replace(prob, NG=(128, 64, 1), finishtime=1e30)
+    run_pair(prob, nsteps=200, state=ic)
+
+
 @pytest.mark.parametrize("bcs", ["outflow", "reflect-outflow", "mixed1", "mixed2"])
 @pytest.mark.parametrize("eqn,solver", [("glm-mhd", 7), ("euler", 8), ("i-mhd", 4)])
 def test_boundary_types(bcs, eqn, solver):

@@ -91,6 +91,11 @@ def test_exact_riemann_solver_rarefaction_and_cavitation_branches_bit_exact():
         run_pair(prob, nsteps=2, state=lambda p: diverging(p, 6.0))   # cavitation: du > 3 (c_l + c_r)
 
 
+@pytest.mark.parametrize("eqn,solver,av", [("euler", 8, 1), ("glm-mhd", 7, 1), ("i-mhd", 4, 0)])
+def test_two_tracers_bit_exact(eqn, solver, av):
+    run_pair(case_3d(eqn, solver, av, bcs="mixed1", ntracer=2, NG=(12, 10, 8)))
+
+
 def test_1d_and_first_order():
     run_pair(case_1d("i-mhd", 7, 1))
     run_pair(case_1d("euler", 8, 1, bcs=("reflecting", "inflow")))

@@ -14,6 +14,7 @@ for l in sys.stdin:
     d = json.loads(l); print('value=%.4g ms/step=%.3f stage_share=%.3f' % (d['value'], d['ms_per_step'], d['stage_share_of_step']))
 ")"
 done
+timeout 900 python tools/shock_bound.py > gpurun_out/shock_bound_$T.log 2>&1; echo "shock bound exit $?"
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/ab_${T}_default.log 2>&1
 grep -h '^{' gpurun_out/ab_${T}_default.log | python -c "
 import sys, json
