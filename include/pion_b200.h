@@ -36,7 +36,7 @@ extern "C" {
 /* integer codes are the reference's (constants.h:166-246, boundaries/boundaries.h:32-52) */
 enum { PION_EQEUL = 1, PION_EQMHD = 2, PION_EQGLM = 3 };
 enum { PION_COORD_CRT = 1, PION_COORD_CYL = 2, PION_COORD_SPH = 3 };
-enum { PION_FLUX_LF = 0, PION_FLUX_RSLINEAR = 1, PION_FLUX_RSEXACT = 2, PION_FLUX_RSHYBRID = 3, PION_FLUX_ROE = 4, PION_FLUX_ROE_PV = 5, PION_FLUX_FVS = 6, PION_FLUX_HLLD = 7, PION_FLUX_HLL = 8 };  /* 1-3, 5, 6: Euler only; 0 forces first order */
+enum { PION_FLUX_LF = 0, PION_FLUX_RSLINEAR = 1, PION_FLUX_RSEXACT = 2, PION_FLUX_RSHYBRID = 3, PION_FLUX_ROE = 4, PION_FLUX_ROE_PV = 5, PION_FLUX_FVS = 6, PION_FLUX_HLLD = 7, PION_FLUX_HLL = 8 };  /* 2, 3, 5, 6: Euler only (1 with MHD = the linear MHD solver of riemannMHD.cpp); 0 forces first order */
 enum { PION_AV_NONE = 0, PION_AV_FKJ98 = 1, PION_AV_HCORR = 3, PION_AV_HCORR_FKJ98 = 4 };
 enum {
   PION_BC_PERIODIC = 1, PION_BC_OUTFLOW = 2, PION_BC_INFLOW = 3, PION_BC_REFLECTING = 4, PION_BC_FIXED = 5,
@@ -66,7 +66,7 @@ typedef struct pion_gpu_config {
   int nvar, ntracer;   /* SimPM.nvar, SimPM.ntracer (tracers are the last ntracer variables) */
   int eqntype;         /* SimPM.eqntype */
   int coord_sys;       /* SimPM.coord_sys: Cartesian 1-3D, cylindrical (z,R) 2-D, spherical 1-D Euler */
-  int solver;          /* SimPM.solverType: 0 Lax-Friedrichs, 1 / 2 / 3 linear / exact / hybrid Riemann solver (Euler), 4 Roe-CV, 5 Roe-PV, 6 FVS, 7 HLLD, 8 HLL */
+  int solver;          /* SimPM.solverType: 0 Lax-Friedrichs, 1 / 2 / 3 linear / exact / hybrid Riemann solver (Euler; MHD: 1 only), 4 Roe-CV, 5 Roe-PV, 6 FVS, 7 HLLD, 8 HLL */
   int artviscosity;    /* SimPM.artviscosity: 0,1,3,4 */
   int spOOA, tmOOA;    /* SimPM.spOOA / tmOOA: (1,1) or (2,2) */
   double gamma, cfl, etav;

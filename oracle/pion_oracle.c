@@ -1197,6 +1197,171 @@ static void euler_inviscid_flux(pion_oracle *s, const double *Pl, const double *
     abort();
   }
 }
+/* ---------------------------------------------------------------------------------------------------------
+ * riemann_MHD: the linear MHD Riemann solver (solverType 1 with the MHD equations; Falle, Komissarov & Joarder 1998
+ * with the Roe & Balsara eigenvector normalisation), Riemann_solvers/riemannMHD.cpp.
+ * Solver-frame variables (enum rsvars, riemannMHD.h:56-65): RRO, RPG, RVX, RVY, RVZ, RBY, RBZ (+ RBX as a parameter).
+ * ------------------------------------------------------------------------------------------------------- */
+/* eqns_mhd_ideal::SetAvgState (eqns_mhd_adiabatic.cpp:501-543), called once by the riemann_MHD constructor
+ * (riemannMHD.cpp:120) in direction XX: the solver's reference vector is RefVec[RO], RefVec[PG], a tenth of the fast
+ * speed of RefVec (rotated so that B lies in the x-z plane) three times, |B(RefVec)| three times */
+static void rs_mhd_refvec(const pion_oracle *s, double *refvel01, double *refB) {
+  double rv[8];
+  for (int v = 0; v < 8; v++) rv[v] = s->cfg.refvec[v];
+  const double g = s->gamma;
+  double angle = rv[BY] * rv[BY] + rv[BX] * rv[BX], refvel;
+  for (int pass = 0; pass < 1; pass++) {
+    if (angle > 10. * MACHINEACCURACY) {
+      angle = M_PI / 2. - asin(rv[BY] / sqrt(angle));
+      if (rv[BX] < 0) angle = -angle;
+      for (int sgn = 0; sgn < 2; sgn++) { /* rotateXY(angle), cfast, rotateXY(-angle) (:423-437) */
+        const double th = sgn ? -angle : angle;
+        const double ct = cos(th), st = sin(th);
+        double vx = rv[VX] * ct - rv[VY] * st, vy = rv[VX] * st + rv[VY] * ct;
+        rv[VX] = vx; rv[VY] = vy;
+        vx = rv[BX] * ct - rv[BY] * st; vy = rv[BX] * st + rv[BY] * ct;
+        rv[BX] = vx; rv[BY] = vy;
+        if (!sgn) {
+          const double ch = sqrt(g * rv[PG] / rv[RO]); /* eqns_mhd_ideal::cfast (:246-257) */
+          double t1 = ch * ch + (rv[BX] * rv[BX] + rv[BY] * rv[BY] + rv[BZ] * rv[BZ]) / rv[RO];
+          double t2 = 4. * ch * ch * rv[BX] * rv[BX] / rv[RO];
+          t2 = fmax(MACHINEACCURACY, t1 * t1 - t2);
+          refvel = sqrt((t1 + sqrt(t2)) / 2.);
+        }
+      }
+    } else { /* maxspeed == cfast (eqns_mhd_adiabatic.h:120-123) */
+      const double ch = sqrt(g * rv[PG] / rv[RO]);
+      double t1 = ch * ch + (rv[BX] * rv[BX] + rv[BY] * rv[BY] + rv[BZ] * rv[BZ]) / rv[RO];
+      double t2 = 4. * ch * ch * rv[BX] * rv[BX] / rv[RO];
+      t2 = fmax(MACHINEACCURACY, t1 * t1 - t2);
+      refvel = sqrt((t1 + sqrt(t2)) / 2.);
+    }
+  }
+  *refB = sqrt(rv[BX] * rv[BX] + rv[BY] * rv[BY] + rv[BZ] * rv[BZ]);
+  *refvel01 = 0.1 * refvel;
+}
+/* riemann_MHD::JMs_riemann_solve, mode 1 (riemannMHD.cpp:165-400) with get_sound_speeds (:555-765), get_eigenvalues
+ * (:768-777), RoeBalsara_evectors (:965-1115), calculate_wave_strengths (:813-846), get_pstar (:849-960).
+ * l, r, ans: grid-frame primitive vectors; returns 1 where the reference calls rep.error. */
+static int rs_mhd_solve(pion_oracle *s, const double *l, const double *rgt, double *ans) {
+  enum { RRO = 0, RPG = 1, RVX = 2, RVY = 3, RVZ = 4, RBY = 5, RBZ = 6, RBX = 7 };
+  enum { FN = 0, AN = 1, SN = 2, CT = 3, SP = 4, AP = 5, FP = 6 };
+  const int ix[8] = {RO, PG, s->eVX, s->eVY, s->eVZ, s->eBY, s->eBZ, s->eBX}; /* code2solvervars (:443-475) */
+  const double g = s->gamma;
+  const double smallB = MACHINEACCURACY, tinyB = smallB * smallB * smallB;
+  double L[8], R[8], M[8], ps[8], ev[7], pdiff[7], str[7], lev[7][7], rev[7][7];
+  for (int v = 0; v < 8; v++) { L[v] = l[ix[v]]; R[v] = rgt[ix[v]]; M[v] = 0.5 * (L[v] + R[v]); ps[v] = 0.0; }
+  for (int v = 0; v < s->nv; v++) ans[v] = 0.0; /* RS_pstar[v >= 8] is never written: zero */
+  const double ansBX = M[RBX];
+  ps[RBX] = ansBX;
+  /* same-state shortcut (:227-268): solver-frame differences over the UNROTATED entries 0..6 of the reference vector */
+  double refvel01, refB;
+  rs_mhd_refvec(s, &refvel01, &refB);
+  const double refn[7] = {s->cfg.refvec[RO], s->cfg.refvec[PG], refvel01, refvel01, refvel01, refB, refB};
+  double diff = 0.;
+  for (int i = 0; i < 7; i++) diff += fabs(R[i] - L[i]) / (fabs(refn[i]) + TINYVALUE);
+  int fail = 0;
+  if (diff < 1.e-6) {
+    for (int v = 0; v < 7; v++) ps[v] = M[v];
+  } else {
+    /* get_sound_speeds */
+    const double ch = sqrt(g * M[RPG] / M[RRO]);
+    const double bx = ansBX / sqrt(M[RRO]);
+    const double ca = fabs(bx);
+    const double bt = sqrt((M[RBY] * M[RBY] + M[RBZ] * M[RBZ]) / M[RRO]);
+    double betay, betaz;
+    if (bt > tinyB) { betay = M[RBY] / sqrt(M[RRO]) / bt; betaz = M[RBZ] / sqrt(M[RRO]) / bt; }
+    else { betay = 1. / sqrt(2.); betaz = 1. / sqrt(2.); }
+    if ((ch / ((ca < bt) ? bt : ca)) < sqrt(smallB)) fail = 1;
+    double temp1 = ch * ch + bx * bx + bt * bt;
+    double temp2 = 4. * ch * ch * bx * bx;
+    if ((temp2 = temp1 * temp1 - temp2) < MACHINEACCURACY) temp2 = MACHINEACCURACY;
+    double cf = sqrt((temp1 + sqrt(temp2)) / 2.);
+    if ((temp2 = temp1 - sqrt(temp2)) < MACHINEACCURACY) temp2 = MACHINEACCURACY;
+    double cs = sqrt(temp2 / 2.);
+    if (cs > ch) cs = ch - smallB;
+    if (ch > cf) cf = ch + smallB;
+    if (cs > ca) cs = ca - smallB;
+    if (cs <= 0. || cs > ca) cs = ca / 2.;
+    if (ca > cf) cf = ca + smallB;
+    double alphaf = 0., alphas = 0., cf2diff;
+    if ((cf2diff = cf * cf - cs * cs) > smallB) {
+      if ((alphaf = ch * ch - cs * cs) <= smallB) alphaf = 0.;
+      if ((alphas = cf * cf - ch * ch) <= smallB) alphas = 0.;
+      if ((alphaf = sqrt(alphaf / cf2diff)) > 1.) alphaf = 1.;
+      if ((alphas = sqrt(alphas / cf2diff)) > 1.) alphas = 1.;
+    } else {
+      fail = 1; /* "Near Triple degeneracy point": rep.error */
+    }
+    if ((cf <= 0.) || (cs < 0.) || (ca < 0.) || (ch <= 0.)) fail = 1;
+    if (!fail) {
+      /* get_eigenvalues */
+      ev[FN] = M[RVX] - cf; ev[FP] = M[RVX] + cf; ev[AN] = M[RVX] - ca; ev[AP] = M[RVX] + ca;
+      ev[SN] = M[RVX] - cs; ev[SP] = M[RVX] + cs; ev[CT] = M[RVX];
+      /* RoeBalsara_evectors */
+      const double r2 = sqrt(2.);
+      const int sBx = (ansBX < 0.) ? -1 : 1;
+      const double sro = sqrt(M[RRO]);
+      lev[FN][RRO] = 0.0; lev[FN][RVX] = -alphaf * cf; lev[FN][RVY] = alphas * cs * sBx * betay; lev[FN][RVZ] = alphas * cs * sBx * betaz;
+      lev[FN][RPG] = alphaf / M[RRO]; lev[FN][RBY] = alphas * ch * betay / sro; lev[FN][RBZ] = alphas * ch * betaz / sro;
+      lev[AN][RRO] = 0.; lev[AN][RVX] = 0.; lev[AN][RVY] = sBx * betaz / r2; lev[AN][RVZ] = -sBx * betay / r2;
+      lev[AN][RPG] = 0.; lev[AN][RBY] = betaz / sro / r2; lev[AN][RBZ] = -betay / sro / r2;
+      lev[SN][RRO] = 0.0; lev[SN][RVX] = -alphas * cs; lev[SN][RVY] = -alphaf * cf * sBx * betay; lev[SN][RVZ] = -alphaf * cf * sBx * betaz;
+      lev[SN][RPG] = alphas / M[RRO]; lev[SN][RBY] = -alphaf * ch * betay / sro; lev[SN][RBZ] = -alphaf * ch * betaz / sro;
+      lev[CT][RRO] = 1.; lev[CT][RVX] = 0.; lev[CT][RVY] = 0.; lev[CT][RVZ] = 0.; lev[CT][RPG] = -1 / ch / ch; lev[CT][RBY] = 0.; lev[CT][RBZ] = 0.;
+      lev[SP][RRO] = 0.0; lev[SP][RVX] = -lev[SN][RVX]; lev[SP][RVY] = -lev[SN][RVY]; lev[SP][RVZ] = -lev[SN][RVZ];
+      lev[SP][RPG] = lev[SN][RPG]; lev[SP][RBY] = lev[SN][RBY]; lev[SP][RBZ] = lev[SN][RBZ];
+      lev[AP][RRO] = 0.; lev[AP][RVX] = 0.; lev[AP][RVY] = lev[AN][RVY]; lev[AP][RVZ] = lev[AN][RVZ];
+      lev[AP][RPG] = 0.; lev[AP][RBY] = -lev[AN][RBY]; lev[AP][RBZ] = -lev[AN][RBZ];
+      lev[FP][RRO] = 0.0; lev[FP][RVX] = -lev[FN][RVX]; lev[FP][RVY] = -lev[FN][RVY]; lev[FP][RVZ] = -lev[FN][RVZ];
+      lev[FP][RPG] = lev[FN][RPG]; lev[FP][RBY] = lev[FN][RBY]; lev[FP][RBZ] = lev[FN][RBZ];
+      rev[FN][RRO] = alphaf * M[RRO]; rev[FN][RVX] = lev[FN][RVX]; rev[FN][RVY] = lev[FN][RVY]; rev[FN][RVZ] = lev[FN][RVZ];
+      rev[FN][RPG] = alphaf * M[RRO] * ch * ch; rev[FN][RBY] = lev[FN][RBY] * M[RRO]; rev[FN][RBZ] = lev[FN][RBZ] * M[RRO];
+      rev[AN][RRO] = 0.; rev[AN][RVX] = 0.; rev[AN][RVY] = lev[AN][RVY]; rev[AN][RVZ] = lev[AN][RVZ];
+      rev[AN][RPG] = 0.; rev[AN][RBY] = lev[AN][RBY] * M[RRO]; rev[AN][RBZ] = lev[AN][RBZ] * M[RRO];
+      rev[SN][RRO] = alphas * M[RRO]; rev[SN][RVX] = lev[SN][RVX]; rev[SN][RVY] = lev[SN][RVY]; rev[SN][RVZ] = lev[SN][RVZ];
+      rev[SN][RPG] = alphas * M[RRO] * ch * ch; rev[SN][RBY] = lev[SN][RBY] * M[RRO]; rev[SN][RBZ] = lev[SN][RBZ] * M[RRO];
+      rev[CT][RRO] = 1.0; rev[CT][RVX] = 0.; rev[CT][RVY] = 0.; rev[CT][RVZ] = 0.; rev[CT][RPG] = 0.; rev[CT][RBY] = 0.; rev[CT][RBZ] = 0.;
+      rev[SP][RRO] = rev[SN][RRO]; rev[SP][RVX] = -rev[SN][RVX]; rev[SP][RVY] = -rev[SN][RVY]; rev[SP][RVZ] = -rev[SN][RVZ];
+      rev[SP][RPG] = rev[SN][RPG]; rev[SP][RBY] = rev[SN][RBY]; rev[SP][RBZ] = rev[SN][RBZ];
+      rev[AP][RRO] = 0.; rev[AP][RVX] = 0.; rev[AP][RVY] = rev[AN][RVY]; rev[AP][RVZ] = rev[AN][RVZ];
+      rev[AP][RPG] = 0.; rev[AP][RBY] = -rev[AN][RBY]; rev[AP][RBZ] = -rev[AN][RBZ];
+      rev[FP][RRO] = rev[FN][RRO]; rev[FP][RVX] = -rev[FN][RVX]; rev[FP][RVY] = -rev[FN][RVY]; rev[FP][RVZ] = -rev[FN][RVZ];
+      rev[FP][RPG] = rev[FN][RPG]; rev[FP][RBY] = rev[FN][RBY]; rev[FP][RBZ] = rev[FN][RBZ];
+      const double a22 = 1. / (2. * ch * ch);
+      for (int i = 0; i < 7; i++) { lev[FN][i] *= a22; lev[SN][i] *= a22; lev[SP][i] *= a22; lev[FP][i] *= a22; }
+      /* calculate_wave_strengths: strength = left eigenvector . (right - left), summed in rsvars order */
+      for (int i = 0; i < 7; i++) pdiff[i] = R[i] - L[i];
+      for (int w = 0; w < 7; w++) {
+        double t = 0.0;
+        for (int i = 0; i < 7; i++) t += lev[w][i] * pdiff[i];
+        str[w] = t;
+      }
+      /* get_pstar: cross the waves with negative speed from the left; at a (nearly) stationary contact average
+       * with the state reached from the right */
+      int i = 0;
+      const double evalacc = 1.e-4;
+      for (int j = 0; j < 7; j++) ps[j] = L[j];
+      while ((i < 7) && (ev[i] < 0.)) {
+        for (int j = 0; j < 7; j++) ps[j] += str[i] * rev[i][j];
+        i++;
+      }
+      if (fabs(M[RVX]) < (evalacc * ch)) {
+        i = 6;
+        for (int j = 0; j < 7; j++) pdiff[j] = R[j];
+        while ((i >= 0) && (ev[i] > 0.)) {
+          for (int j = 0; j < 7; j++) pdiff[j] -= str[i] * rev[i][j];
+          i--;
+        }
+        for (int v = 0; v < 7; v++) ps[v] = 0.5 * (ps[v] + pdiff[v]);
+      }
+      if (ps[RPG] < 0.) ps[RPG] = refn[RPG] * BASEPG;
+      if (ps[RRO] < 0.) ps[RRO] = refn[RRO] * BASEPG;
+    }
+  }
+  for (int v = 0; v < 8; v++) ans[ix[v]] = ps[v]; /* solver2codevars (:480-512) */
+  return fail;
+}
 /* FV_solver_mhd_ideal_adi::inviscid_flux (solver_eqn_mhd_adi.cpp:102-198) */
 static void mhd_ideal_inviscid_flux(pion_oracle *s, long cl, long cr, const double *Pl, const double *Pr, double *flux,
                                     double *pstar) {
@@ -1205,6 +1370,11 @@ static void mhd_ideal_inviscid_flux(pion_oracle *s, long cl, long cr, const doub
   if (s->cfg.solver == PO_FLUX_LF) { /* :132-136 */
     lax_friedrichs_flux(s, Pl, Pr, flux);
     for (int v = 0; v < s->nv; v++) pstar[v] = 0.5 * (Pl[v] + Pr[v]);
+  } else if (s->cfg.solver >= 1 && s->cfg.solver <= 3) { /* :160-166: riemann_MHD only knows the linear solve: modes 2, 3 are fatal */
+    if (s->cfg.solver != 1 || rs_mhd_solve(s, Pl, Pr, pstar)) s->nfail_riemann++;
+    double us[PO_MAXVAR] = {0};
+    mhd_ideal_PtoU(s, pstar, us); /* PtoFlux = PtoU + PUtoFlux (eqns_base.cpp:230-240); pstar[SI] is zero */
+    mhd_PUtoFlux(s, pstar, us, flux);
   } else if (s->cfg.solver == PO_FLUX_ROE) {
     mhd_RoeCV(s, Pl, Pr, s->HC_etamax, pstar, flux);
   } else if (s->cfg.solver == PO_FLUX_HLLD) {

@@ -54,7 +54,7 @@ struct PhysParams {
   int have_mp;
   double lf_c;         // Lax-Friedrichs only: dx / FV_dt (set per stage launch)
   double lf_ndim;      // ... and FV_gndim
-  double rs_refvec[5]; // linear / exact / hybrid Riemann solvers: riemann_Euler::eq_refvec = RefVec[RO, PG] and 0.1 c(RefVec) three times (SetAvgState)
+  double rs_refvec[5]; // linear / exact / hybrid Riemann solvers: Euler riemann_Euler::eq_refvec = RefVec[RO, PG] and 0.1 c(RefVec) three times; MHD {RefVec[RO], RefVec[PG], 0.1 cfast(RefVec), |B(RefVec)|} (SetAvgState)
 };
 
 __device__ __forceinline__ double sq(double x) { return x * x; }
@@ -787,6 +787,152 @@ __device__ inline int hydro_JMs(const Prim& l, const Prim& rg, const PhysParams&
   return fail;
 }
 
+// ---------------------------------------------------------------------------
+// riemann_MHD: the linear MHD Riemann solver (solverType 1 with the MHD equations; Falle, Komissarov & Joarder 1998 with the
+// Roe & Balsara eigenvector normalisation): JMs_riemann_solve mode 1 (Riemann_solvers/riemannMHD.cpp:165-400), get_sound_speeds
+// (:555-765), get_eigenvalues (:768-777), RoeBalsara_evectors (:965-1115), calculate_wave_strengths (:813-846), get_pstar
+// (:849-960), then PtoFlux(pstar).  Solver-frame variables in the reference's order RRO, RPG, RVX, RVY, RVZ, RBY, RBZ (the Prim
+// fields ro, pg, vn, vt1, vt2, bt1, bt2; bn is the parameter B_x).  Plain IEEE arithmetic as written in the reference: gather
+// kernel only, not a performance path.  Returns 1 where the reference calls rep.error.
+// pp.rs_refvec = {RefVec[RO], RefVec[PG], 0.1 cfast(RefVec), |B(RefVec)|} (eqns_mhd_ideal::SetAvgState, built on the host).
+// ---------------------------------------------------------------------------
+__device__ inline int mhd_JMs_linear(const Prim& l, const Prim& r, const PhysParams& pp, Cons& flux, Prim& pstar) {
+  enum { RRO = 0, RPG = 1, RVX = 2, RVY = 3, RVZ = 4, RBY = 5, RBZ = 6 };
+  enum { FN = 0, AN = 1, SN = 2, CT = 3, SP = 4, AP = 5, FP = 6 };
+  const double g = pp.gamma;
+  const double smallB = PION_MACHINEACCURACY, tinyB = smallB * smallB * smallB;
+  const double L[7] = {l.ro, l.pg, l.vn, l.vt1, l.vt2, l.bt1, l.bt2}, R[7] = {r.ro, r.pg, r.vn, r.vt1, r.vt2, r.bt1, r.bt2};
+  double M[7], ps[7];
+#pragma unroll
+  for (int v = 0; v < 7; v++) M[v] = 0.5 * (L[v] + R[v]);
+  const double ansBX = 0.5 * (l.bn + r.bn);
+  const double refn[7] = {pp.rs_refvec[0], pp.rs_refvec[1], pp.rs_refvec[2], pp.rs_refvec[2], pp.rs_refvec[2], pp.rs_refvec[3], pp.rs_refvec[3]};
+  double diff = 0.;
+#pragma unroll
+  for (int i = 0; i < 7; i++) diff += fabs(R[i] - L[i]) / (fabs(refn[i]) + PION_TINYVALUE);
+  int fail = 0;
+  if (diff < 1.e-6) {  // same-state shortcut (:227-268)
+#pragma unroll
+    for (int v = 0; v < 7; v++) ps[v] = M[v];
+  } else {
+    const double sro = sqrt(M[RRO]);
+    const double ch = sqrt(g * M[RPG] / M[RRO]);
+    const double bx = ansBX / sro;
+    const double ca = fabs(bx);
+    const double bt = sqrt((M[RBY] * M[RBY] + M[RBZ] * M[RBZ]) / M[RRO]);
+    double betay, betaz;
+    if (bt > tinyB) { betay = M[RBY] / sro / bt; betaz = M[RBZ] / sro / bt; }
+    else { betay = 1. / sqrt(2.); betaz = 1. / sqrt(2.); }
+    if ((ch / ((ca < bt) ? bt : ca)) < sqrt(smallB)) fail = 1;
+    double temp1 = ch * ch + bx * bx + bt * bt;
+    double temp2 = 4. * ch * ch * bx * bx;
+    if ((temp2 = temp1 * temp1 - temp2) < PION_MACHINEACCURACY) temp2 = PION_MACHINEACCURACY;
+    double cf = sqrt((temp1 + sqrt(temp2)) / 2.);
+    if ((temp2 = temp1 - sqrt(temp2)) < PION_MACHINEACCURACY) temp2 = PION_MACHINEACCURACY;
+    double cs = sqrt(temp2 / 2.);
+    if (cs > ch) cs = ch - smallB;
+    if (ch > cf) cf = ch + smallB;
+    if (cs > ca) cs = ca - smallB;
+    if (cs <= 0. || cs > ca) cs = ca / 2.;
+    if (ca > cf) cf = ca + smallB;
+    double alphaf = 0., alphas = 0., cf2diff;
+    if ((cf2diff = cf * cf - cs * cs) > smallB) {
+      if ((alphaf = ch * ch - cs * cs) <= smallB) alphaf = 0.;
+      if ((alphas = cf * cf - ch * ch) <= smallB) alphas = 0.;
+      if ((alphaf = sqrt(alphaf / cf2diff)) > 1.) alphaf = 1.;
+      if ((alphas = sqrt(alphas / cf2diff)) > 1.) alphas = 1.;
+    } else {
+      fail = 1;  // "Near Triple degeneracy point": rep.error in the reference
+    }
+    if ((cf <= 0.) || (cs < 0.) || (ca < 0.) || (ch <= 0.)) fail = 1;
+#pragma unroll
+    for (int v = 0; v < 7; v++) ps[v] = 0.0;
+    if (!fail) {
+      const double ev[7] = {M[RVX] - cf, M[RVX] - ca, M[RVX] - cs, M[RVX], M[RVX] + cs, M[RVX] + ca, M[RVX] + cf};
+      const double r2 = sqrt(2.);
+      const double sBx = (ansBX < 0.) ? -1.0 : 1.0;
+      // the three independent left eigenvectors (negative fast, Alfven, slow) and the contact; the positive ones differ
+      // from them by the signs of the velocity (fast, slow) or field (Alfven) components
+      double lev[7][7], rev[7][7];
+#pragma unroll
+      for (int w = 0; w < 7; w++)
+#pragma unroll
+        for (int i = 0; i < 7; i++) lev[w][i] = rev[w][i] = 0.0;
+      lev[FN][RVX] = -alphaf * cf; lev[FN][RVY] = alphas * cs * sBx * betay; lev[FN][RVZ] = alphas * cs * sBx * betaz;
+      lev[FN][RPG] = alphaf / M[RRO]; lev[FN][RBY] = alphas * ch * betay / sro; lev[FN][RBZ] = alphas * ch * betaz / sro;
+      lev[AN][RVY] = sBx * betaz / r2; lev[AN][RVZ] = -sBx * betay / r2;
+      lev[AN][RBY] = betaz / sro / r2; lev[AN][RBZ] = -betay / sro / r2;
+      lev[SN][RVX] = -alphas * cs; lev[SN][RVY] = -alphaf * cf * sBx * betay; lev[SN][RVZ] = -alphaf * cf * sBx * betaz;
+      lev[SN][RPG] = alphas / M[RRO]; lev[SN][RBY] = -alphaf * ch * betay / sro; lev[SN][RBZ] = -alphaf * ch * betaz / sro;
+      lev[CT][RRO] = 1.; lev[CT][RPG] = -1 / ch / ch;
+      lev[SP][RVX] = -lev[SN][RVX]; lev[SP][RVY] = -lev[SN][RVY]; lev[SP][RVZ] = -lev[SN][RVZ];
+      lev[SP][RPG] = lev[SN][RPG]; lev[SP][RBY] = lev[SN][RBY]; lev[SP][RBZ] = lev[SN][RBZ];
+      lev[AP][RVY] = lev[AN][RVY]; lev[AP][RVZ] = lev[AN][RVZ]; lev[AP][RBY] = -lev[AN][RBY]; lev[AP][RBZ] = -lev[AN][RBZ];
+      lev[FP][RVX] = -lev[FN][RVX]; lev[FP][RVY] = -lev[FN][RVY]; lev[FP][RVZ] = -lev[FN][RVZ];
+      lev[FP][RPG] = lev[FN][RPG]; lev[FP][RBY] = lev[FN][RBY]; lev[FP][RBZ] = lev[FN][RBZ];
+      rev[FN][RRO] = alphaf * M[RRO]; rev[FN][RVX] = lev[FN][RVX]; rev[FN][RVY] = lev[FN][RVY]; rev[FN][RVZ] = lev[FN][RVZ];
+      rev[FN][RPG] = alphaf * M[RRO] * ch * ch; rev[FN][RBY] = lev[FN][RBY] * M[RRO]; rev[FN][RBZ] = lev[FN][RBZ] * M[RRO];
+      rev[AN][RVY] = lev[AN][RVY]; rev[AN][RVZ] = lev[AN][RVZ]; rev[AN][RBY] = lev[AN][RBY] * M[RRO]; rev[AN][RBZ] = lev[AN][RBZ] * M[RRO];
+      rev[SN][RRO] = alphas * M[RRO]; rev[SN][RVX] = lev[SN][RVX]; rev[SN][RVY] = lev[SN][RVY]; rev[SN][RVZ] = lev[SN][RVZ];
+      rev[SN][RPG] = alphas * M[RRO] * ch * ch; rev[SN][RBY] = lev[SN][RBY] * M[RRO]; rev[SN][RBZ] = lev[SN][RBZ] * M[RRO];
+      rev[CT][RRO] = 1.0;
+      rev[SP][RRO] = rev[SN][RRO]; rev[SP][RVX] = -rev[SN][RVX]; rev[SP][RVY] = -rev[SN][RVY]; rev[SP][RVZ] = -rev[SN][RVZ];
+      rev[SP][RPG] = rev[SN][RPG]; rev[SP][RBY] = rev[SN][RBY]; rev[SP][RBZ] = rev[SN][RBZ];
+      rev[AP][RVY] = rev[AN][RVY]; rev[AP][RVZ] = rev[AN][RVZ]; rev[AP][RBY] = -rev[AN][RBY]; rev[AP][RBZ] = -rev[AN][RBZ];
+      rev[FP][RRO] = rev[FN][RRO]; rev[FP][RVX] = -rev[FN][RVX]; rev[FP][RVY] = -rev[FN][RVY]; rev[FP][RVZ] = -rev[FN][RVZ];
+      rev[FP][RPG] = rev[FN][RPG]; rev[FP][RBY] = rev[FN][RBY]; rev[FP][RBZ] = rev[FN][RBZ];
+      const double a22 = 1. / (2. * ch * ch);
+#pragma unroll
+      for (int i = 0; i < 7; i++) { lev[FN][i] *= a22; lev[SN][i] *= a22; lev[SP][i] *= a22; lev[FP][i] *= a22; }
+      double pdiff[7], str[7];
+#pragma unroll
+      for (int i = 0; i < 7; i++) pdiff[i] = R[i] - L[i];
+#pragma unroll
+      for (int w = 0; w < 7; w++) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 7; i++) t += lev[w][i] * pdiff[i];
+        str[w] = t;
+      }
+      // get_pstar: the eigenvalues are ordered, so "while (ev[i] < 0)" crosses the first n waves
+#pragma unroll
+      for (int j = 0; j < 7; j++) ps[j] = L[j];
+      bool go = true;
+#pragma unroll
+      for (int w = 0; w < 7; w++) {
+        go = go && (ev[w] < 0.);
+        if (go) {
+#pragma unroll
+          for (int j = 0; j < 7; j++) ps[j] += str[w] * rev[w][j];
+        }
+      }
+      if (fabs(M[RVX]) < (1.e-4 * ch)) {  // (nearly) stationary contact: average with the state reached from the right
+#pragma unroll
+        for (int j = 0; j < 7; j++) pdiff[j] = R[j];
+        go = true;
+#pragma unroll
+        for (int w = 6; w >= 0; w--) {
+          go = go && (ev[w] > 0.);
+          if (go) {
+#pragma unroll
+            for (int j = 0; j < 7; j++) pdiff[j] -= str[w] * rev[w][j];
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < 7; v++) ps[v] = 0.5 * (ps[v] + pdiff[v]);
+      }
+      if (ps[RPG] < 0.) ps[RPG] = refn[RPG] * 1.e-5;  // BASEPG, constants.h:336
+      if (ps[RRO] < 0.) ps[RRO] = refn[RRO] * 1.e-5;
+    }
+  }
+  pstar.ro = ps[RRO]; pstar.pg = ps[RPG]; pstar.vn = ps[RVX]; pstar.vt1 = ps[RVY]; pstar.vt2 = ps[RVZ];
+  pstar.bt1 = ps[RBY]; pstar.bt2 = ps[RBZ]; pstar.bn = ansBX; pstar.psi = 0.0;
+  Cons u;
+  PtoU_mhd_ideal(pstar, u, g - 1.0);
+  PUtoFlux<EQ_MHD>(pstar, u, flux);
+  return fail;
+}
+
 // HLLD_MHD::HLLD_signal_speeds (HLLD_MHD.cpp:342-368); Bx is the same on both
 // sides in the GLM case but the formula is kept general.
 __device__ __forceinline__ void hlld_speeds(const Prim& L, const Prim& R, double g, double& Sl, double& Sr) {
@@ -1202,6 +1348,9 @@ __device__ __forceinline__ void intercell_flux(const Prim& eL, const Prim& eR, c
     }
     if (SOLVER == SOLVE_LF) {
       lax_friedrichs<EQ_MHD>(l, r, pp, flux, pstar);
+    } else if (SOLVER == SOLVE_RSLINEAR) {
+      const int f = mhd_JMs_linear(l, r, pp, flux, pstar);
+      if (rs_fail) *rs_fail |= f;
     } else if (SOLVER == SOLVE_ROE) {
       mhd_RoeCV(l, r, pp, hc_etamax, flux, pstar);
     } else if (SOLVER == SOLVE_HLLD && !use_hll) {

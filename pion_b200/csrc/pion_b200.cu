@@ -167,12 +167,12 @@ static int check_config(const pion_gpu_config& c) {
   if (c.coord_sys == PION_COORD_CYL && c.ndim != 2) { set_error("Cylindrical coordinates only implemented for 2d axial symmetry"); return 1; }
   if (c.coord_sys == PION_COORD_SPH && (c.ndim != 1 || c.eqntype != PION_EQEUL)) { set_error("Spherical coordinates only implemented for 1D Euler"); return 1; }
   if (c.coord_sys != PION_COORD_CRT && c.n_wind > 0) { set_error("stellar-wind boundary: only Cartesian grids are built"); return 1; }
-  // 1, 2, 3: linear / exact / hybrid Riemann solvers -- built for the Euler equations (riemann.cpp); the MHD linear
-  // solver of riemannMHD.cpp is not
-  const bool euler_only = (c.solver == PION_FLUX_ROE_PV || c.solver == PION_FLUX_FVS || (c.solver >= 1 && c.solver <= 3));
+  // 1, 2, 3: linear / exact / hybrid Riemann solvers (riemann.cpp) for the Euler equations; riemann_MHD only has the
+  // linear solve (riemannMHD.cpp:176-183: modes 2 and 3 end in rep.error "MODE i: Don't know what to do")
+  const bool euler_only = (c.solver == PION_FLUX_ROE_PV || c.solver == PION_FLUX_FVS || c.solver == PION_FLUX_RSEXACT || c.solver == PION_FLUX_RSHYBRID);
   if (c.solver != PION_FLUX_LF && c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL && !euler_only) { set_error("solver must be 0 (Lax-Friedrichs), 1-3 (linear / exact / hybrid Riemann solver, Euler), 4 (Roe-CV), 5 (Roe-PV), 6 (FVS), 7 (HLLD) or 8 (HLL)"); return 1; }
   // solver_eqn_mhd_adi.cpp:132-198: the MHD solvers have no Roe-PV / FVS branch ("what sort of flux solver do you mean???")
-  if (euler_only && c.eqntype != PION_EQEUL) { set_error("solvers 1-3 (linear / exact / hybrid; the MHD linear solver is not built), 5 (Roe-PV) and 6 (FVS) are for the Euler equations only"); return 1; }
+  if (euler_only && c.eqntype != PION_EQEUL) { set_error("solvers 2, 3 (exact / hybrid Riemann solver: riemann_MHD only knows the linear solve), 5 (Roe-PV) and 6 (FVS) are for the Euler equations only"); return 1; }
   if (c.eqntype == PION_EQEUL && c.solver == PION_FLUX_HLLD) { set_error("HLLD needs MHD equations"); return 1; }
   if (c.artviscosity != 0 && c.artviscosity != 1 && c.artviscosity != 3 && c.artviscosity != 4) { set_error("artviscosity must be 0,1,3,4"); return 1; }
   if (!((c.spOOA == 1 && c.tmOOA == 1) || (c.spOOA == 2 && c.tmOOA == 2))) { set_error("Bad OOA requests; choose (1,1) or (2,2)"); return 1; }
@@ -366,6 +366,41 @@ extern "C" pion_gpu_ctx* pion_gpu_create(const pion_gpu_config* cfg) {
   pp.rs_refvec[0] = cfg->refvec[0];
   pp.rs_refvec[1] = cfg->refvec[1];
   pp.rs_refvec[2] = pp.rs_refvec[3] = pp.rs_refvec[4] = 0.1 * sqrt(cfg->gamma * cfg->refvec[1] / cfg->refvec[0]);
+  if (cfg->eqntype != PION_EQEUL) {
+    // eqns_mhd_ideal::SetAvgState (eqns_mhd_adiabatic.cpp:501-543, called by the riemann_MHD constructor in direction XX):
+    // reference velocity = a tenth of the fast speed of RefVec rotated about z so that B_y = 0, reference field = |B(RefVec)|
+    // of the vector rotated there and back
+    double rv[8];
+    for (int v = 0; v < 8; v++) rv[v] = cfg->refvec[v];
+    const double g = cfg->gamma;
+    auto cfast = [&]() {
+      const double ch = sqrt(g * rv[1] / rv[0]);
+      const double t1 = ch * ch + (rv[5] * rv[5] + rv[6] * rv[6] + rv[7] * rv[7]) / rv[0];
+      double t2 = 4. * ch * ch * rv[5] * rv[5] / rv[0];
+      t2 = fmax(PION_MACHINEACCURACY, t1 * t1 - t2);
+      return sqrt((t1 + sqrt(t2)) / 2.);
+    };
+    auto rot = [&](double th) {
+      const double ct = cos(th), st = sin(th);
+      double vx = rv[2] * ct - rv[3] * st, vy = rv[2] * st + rv[3] * ct;
+      rv[2] = vx; rv[3] = vy;
+      vx = rv[5] * ct - rv[6] * st; vy = rv[5] * st + rv[6] * ct;
+      rv[5] = vx; rv[6] = vy;
+    };
+    double angle = rv[6] * rv[6] + rv[5] * rv[5], refvel;
+    if (angle > 10. * PION_MACHINEACCURACY) {
+      angle = M_PI / 2. - asin(rv[6] / sqrt(angle));
+      if (rv[5] < 0) angle = -angle;
+      rot(angle);
+      refvel = cfast();
+      rot(-angle);
+    } else {
+      refvel = cfast();
+    }
+    pp.rs_refvec[2] = 0.1 * refvel;
+    pp.rs_refvec[3] = sqrt(rv[5] * rv[5] + rv[6] * rv[6] + rv[7] * rv[7]);
+    pp.rs_refvec[4] = 0.0;
+  }
   pp.min_temp = cfg->min_temperature;
   pp.max_temp = cfg->max_temperature;
   pp.have_mp = cfg->cooling ? 1 : 0;

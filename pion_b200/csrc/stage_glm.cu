@@ -6,6 +6,10 @@ const char* launch_stage_glm(int solver, int fkj, const StageArgs& a, cudaStream
     if (fkj) return launch_stage_t<EQ_GLM, SOLVE_LF, true>(a, s);
     else return launch_stage_t<EQ_GLM, SOLVE_LF, false>(a, s);
   }
+  if (solver == SOLVE_RSLINEAR) {
+    if (fkj) return launch_stage_t<EQ_GLM, SOLVE_RSLINEAR, true>(a, s);
+    else return launch_stage_t<EQ_GLM, SOLVE_RSLINEAR, false>(a, s);
+  }
   if (solver == SOLVE_ROE) {
     if (fkj) return launch_stage_t<EQ_GLM, SOLVE_ROE, true>(a, s);
     else return launch_stage_t<EQ_GLM, SOLVE_ROE, false>(a, s);

@@ -6,6 +6,10 @@ const char* launch_stage_mhd(int solver, int fkj, const StageArgs& a, cudaStream
     if (fkj) return launch_stage_t<EQ_MHD, SOLVE_LF, true>(a, s);
     else return launch_stage_t<EQ_MHD, SOLVE_LF, false>(a, s);
   }
+  if (solver == SOLVE_RSLINEAR) {
+    if (fkj) return launch_stage_t<EQ_MHD, SOLVE_RSLINEAR, true>(a, s);
+    else return launch_stage_t<EQ_MHD, SOLVE_RSLINEAR, false>(a, s);
+  }
   if (solver == SOLVE_ROE) {
     if (fkj) return launch_stage_t<EQ_MHD, SOLVE_ROE, true>(a, s);
     else return launch_stage_t<EQ_MHD, SOLVE_ROE, false>(a, s);

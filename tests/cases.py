@@ -1,8 +1,8 @@
 """Shared parity-case definitions (equation set x solver x viscosity x boundaries)."""
 from harness import Problem
 
-EQ_SOLVERS = [("euler", 8), ("euler", 4), ("euler", 5), ("euler", 6), ("euler", 0), ("euler", 1), ("euler", 2), ("euler", 3), ("i-mhd", 8), ("i-mhd", 7), ("i-mhd", 4), ("i-mhd", 0),
-              ("glm-mhd", 8), ("glm-mhd", 7), ("glm-mhd", 4), ("glm-mhd", 0)]
+EQ_SOLVERS = [("euler", 8), ("euler", 4), ("euler", 5), ("euler", 6), ("euler", 0), ("euler", 1), ("euler", 2), ("euler", 3), ("i-mhd", 8), ("i-mhd", 7), ("i-mhd", 4), ("i-mhd", 0), ("i-mhd", 1),
+              ("glm-mhd", 8), ("glm-mhd", 7), ("glm-mhd", 4), ("glm-mhd", 0), ("glm-mhd", 1)]
 AVS = [0, 1, 3, 4]
 DX = 0.0625  # cells must be cubic (uniform_grid.cpp:866-874); a power of two keeps xmax exact
 

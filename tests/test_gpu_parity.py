@@ -75,6 +75,27 @@ def test_3d_multi_tile_tma_sweep_with_tracers(eqn, solver, av, ntracer):
         g.close()
 
 
+@pytest.mark.parametrize("eqn", ["i-mhd", "glm-mhd"])
+@pytest.mark.parametrize("kind", ["tiny", "v0", "bt0", "bx0", "b0", "hot"])
+def test_mhd_linear_riemann_solver_branches(eqn, kind):
+    """riemann_MHD (solverType 1 with MHD): the same-state shortcut, stationary contacts, the degenerate field
+    configurations and a strong-gradient state; no solver failure is counted."""
+    from test_oracle_vs_ref import _mhd_linear_state
+    if kind == "hot":
+        run_pair(case_3d(eqn, 1, 1, bcs="reflect-outflow", NG=(18, 14, 10)), nsteps=2, state=hot_sphere_state)
+        return
+    prob = case_2d(eqn, 1, 1, bcs="outflow")
+    run_pair(prob, nsteps=3, state=_mhd_linear_state(kind))
+    g = GpuSim(prob)
+    try:
+        g.set_state(_mhd_linear_state(kind)(prob))
+        g.init_after_state()
+        g.run(2)
+        assert g.ctx.riemann_failures() == 0
+    finally:
+        g.close()
+
+
 def test_shock_problem_error_bound():
     """Documented N-step bound on the reference's shock test problems at their BASELINE sizes (tools/shock_bound.py,
     profiles/r02r_shock_problem_error_bounds.jsonl): double Mach reflection 260x80, Roe-CV, 300 steps: measured 1.0e-13

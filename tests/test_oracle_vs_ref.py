@@ -91,6 +91,43 @@ def test_exact_riemann_solver_rarefaction_and_cavitation_branches_bit_exact():
         run_pair(prob, nsteps=2, state=lambda p: diverging(p, 6.0))   # cavitation: du > 3 (c_l + c_r)
 
 
+def _mhd_linear_state(kind):
+    def f(p):
+        P = random_state(p, 9, amp=0.3)
+        if kind == "tiny":  # nearly uniform: the same-state shortcut of riemann_MHD::JMs_riemann_solve (riemannMHD.cpp:227-268)
+            m = P.mean(axis=(1, 2, 3), keepdims=True)
+            P = m + (P - m) * 1e-7
+            P[1, :, P.shape[2] // 2, P.shape[3] // 2] *= 1.5
+        elif kind == "v0":   # stationary contacts: get_pstar averages the left- and right-going solutions (:849-960)
+            P[2:5] = 0.0
+        elif kind == "bt0":  # no tangential field: beta_y = beta_z = 1/sqrt 2 (:645-655)
+            P[6:8] = 0.0
+        elif kind == "bx0":  # no normal field along x and y: c_a = 0, c_s = c_a / 2 (:690-700)
+            P[5] = 0.0
+            P[6] = 0.0
+        elif kind == "b0":   # hydrodynamic limit
+            P[5:8] = 0.0
+        return P
+    return f
+
+
+@pytest.mark.parametrize("eqn", ["i-mhd", "glm-mhd"])
+@pytest.mark.parametrize("av", [0, 1])
+def test_mhd_linear_riemann_solver_bit_exact(eqn, av):
+    """solverType 1 with the MHD equations: riemann_MHD (riemannMHD.cpp), second and first order, strong gradients."""
+    run_pair(case_2d(eqn, 1, av, bcs="outflow"), nsteps=3)
+    run_pair(case_3d(eqn, 1, av, bcs="mixed1", ntracer=1), nsteps=2)
+    run_pair(case_3d(eqn, 1, av, bcs="reflect-outflow", NG=(18, 14, 10)), nsteps=2, state=hot_sphere_state)
+    run_pair(case_3d(eqn, 1, av, bcs="mixed2", NG=(9, 7, 5), ooa=1), nsteps=2, state=hot_sphere_state)
+    run_pair(case_2d(eqn, 1, av, bcs="outflow"), nsteps=2, amp=2.0)
+
+
+@pytest.mark.parametrize("eqn", ["i-mhd", "glm-mhd"])
+@pytest.mark.parametrize("kind", ["tiny", "v0", "bt0", "bx0", "b0"])
+def test_mhd_linear_riemann_solver_degenerate_branches_bit_exact(eqn, kind):
+    run_pair(case_2d(eqn, 1, 1, bcs="outflow"), nsteps=3, state=_mhd_linear_state(kind))
+
+
 @pytest.mark.parametrize("eqn,solver,av", [("euler", 8, 1), ("glm-mhd", 7, 1), ("i-mhd", 4, 0)])
 def test_two_tracers_bit_exact(eqn, solver, av):
     run_pair(case_3d(eqn, solver, av, bcs="mixed1", ntracer=2, NG=(12, 10, 8)))
