@@ -170,7 +170,7 @@ static int check_config(const pion_gpu_config& c) {
   // 1, 2, 3: linear / exact / hybrid Riemann solvers (riemann.cpp) for the Euler equations; riemann_MHD only has the
   // linear solve (riemannMHD.cpp:176-183: modes 2 and 3 end in rep.error "MODE i: Don't know what to do")
   const bool euler_only = (c.solver == PION_FLUX_ROE_PV || c.solver == PION_FLUX_FVS || c.solver == PION_FLUX_RSEXACT || c.solver == PION_FLUX_RSHYBRID);
-  if (c.solver != PION_FLUX_LF && c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL && !euler_only) { set_error("solver must be 0 (Lax-Friedrichs), 1-3 (linear / exact / hybrid Riemann solver, Euler), 4 (Roe-CV), 5 (Roe-PV), 6 (FVS), 7 (HLLD) or 8 (HLL)"); return 1; }
+  if (c.solver != PION_FLUX_LF && c.solver != PION_FLUX_RSLINEAR && c.solver != PION_FLUX_ROE && c.solver != PION_FLUX_HLLD && c.solver != PION_FLUX_HLL && !euler_only) { set_error("solver must be 0 (Lax-Friedrichs), 1-3 (linear / exact / hybrid Riemann solver, Euler), 4 (Roe-CV), 5 (Roe-PV), 6 (FVS), 7 (HLLD) or 8 (HLL)"); return 1; }
   // solver_eqn_mhd_adi.cpp:132-198: the MHD solvers have no Roe-PV / FVS branch ("what sort of flux solver do you mean???")
   if (euler_only && c.eqntype != PION_EQEUL) { set_error("solvers 2, 3 (exact / hybrid Riemann solver: riemann_MHD only knows the linear solve), 5 (Roe-PV) and 6 (FVS) are for the Euler equations only"); return 1; }
   if (c.eqntype == PION_EQEUL && c.solver == PION_FLUX_HLLD) { set_error("HLLD needs MHD equations"); return 1; }

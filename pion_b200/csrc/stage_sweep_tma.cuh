@@ -530,12 +530,21 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         const int rn = min(row + 1, TY - 1);
         const Cons Fl = cons_from_smem<EQ, TY>(sbuf, row, lane);
         const Cons Fhy = cons_from_smem<EQ, TY>(sbuf, rn, lane);
+        // the tracer fluxes are read BEFORE this thread says it is done with the slab (they used to be read after the
+        // arrive: a warp already waiting to publish plane k+1 could overwrite them -- seen as a 1e-2 tracer error of
+        // the slower -DPION_STRICT build, r02t)
+        double Fltr[NTRA], Fhytr[NTRA];
+#pragma unroll
+        for (int q = 0; q < NTR; q++) {
+          Fltr[q] = sbuf[(NB + q) * CS + row * 32 + lane];
+          Fhytr[q] = sbuf[(NB + q) * CS + rn * 32 + lane];
+        }
         mbar_arrive(&s_free);
         cons_diff(D, Fl, Fhy);
         acc_sources<EQ, VS, 1>(acc, C, uB, p0 - CW, p0 + CW, dt, idx, hdtdx);
         acc_flux_diff<EQ, 1>(acc, D, dt, idx, dtdx);
 #pragma unroll
-        for (int q = 0; q < NTR; q++) PION_ACCTR(q, sbuf[(NB + q) * CS + row * 32 + lane], sbuf[(NB + q) * CS + rn * 32 + lane])
+        for (int q = 0; q < NTR; q++) PION_ACCTR(q, Fltr[q], Fhytr[q])
       } else if (f == 1) {
         {  // the flux through this cell's low z face was computed one plane ago: thread-private slot in shared memory
           const Cons Fz = cons_from_smem<EQ, TY>(s_fz, row, lane);
