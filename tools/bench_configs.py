@@ -108,7 +108,11 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--only", default="", help="comma-separated config numbers, e.g. 3,5")
+    ap.add_argument("--lib", default=None, help="another build of libpion_b200.so (kernel A/B experiments)")
     args = ap.parse_args()
+    if args.lib:
+        from pion_b200.capi import load_library
+        load_library(args.lib)
     tables = load_cooling_tables()
     rows = []
     for name, prob, icfn, nsteps, cpu_div in configs(args.quick):
