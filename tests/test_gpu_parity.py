@@ -89,7 +89,26 @@ def test_mhd_linear_riemann_solver_branches(eqn, kind):
     # step on (riemannMHD.cpp:645-655 only switches to 1/sqrt 2 below 1e-46): the Alfven / slow eigenvectors then point
     # somewhere else on every build of the same arithmetic.  The flux does not depend on that direction analytically
     # (Falle et al. 1998), numerically to ~1e-11 per step: measured 2.7e-11 after three steps.
-    run_pair(prob, nsteps=3, state=_mhd_linear_state(kind), tol=1e-9 if kind in ("bt0", "b0") else None)
+    if kind == "b0":
+        # no field at all: B stays rounding noise (~1e-17) on both sides, a relative error of it means nothing --
+        # the hydrodynamic variables must agree, and the field must stay noise
+        o, g0 = OracleSim(prob), GpuSim(prob)
+        try:
+            P = _mhd_linear_state(kind)(prob)
+            for sim in (o, g0):
+                sim.set_state(P)
+                sim.init_after_state()
+            o.run(3)
+            g0.run(3)
+            Po, Pg = o.get_state(0), g0.get_state(0)
+            assert rel_err(Pg[:5], Po[:5]).max() < 1e-9
+            assert np.max(np.abs(Pg[5:8])) < 1e-12 and np.max(np.abs(Po[5:8])) < 1e-12
+            assert g0.ctx.riemann_failures() == 0
+        finally:
+            o.close()
+            g0.close()
+        return
+    run_pair(prob, nsteps=3, state=_mhd_linear_state(kind), tol=1e-9 if kind == "bt0" else None)
     g = GpuSim(prob)
     try:
         g.set_state(_mhd_linear_state(kind)(prob))
