@@ -448,9 +448,19 @@ __global__ void __launch_bounds__(32 * TY, MINB)
 #endif
     }
 #endif
+    // Order of the three solves of a plane.  Default x, z, y: the y fluxes of plane k+1 are published by the LAST solve of
+    // an iteration and consumed by the FIRST of the next, so every warp waits there for the slowest one.  PION_TMA_YMID:
+    // x, y, z -- the publish moves to the middle slot: one solve of slack between publish and consume, and one between
+    // "slab read by everybody" and its overwrite (instead of none and two).
 #pragma unroll 1
+#ifdef PION_TMA_YMID
+    for (int sl = (warm && !light) ? 1 : 0; sl < 3; sl++) {
+      const int f = (sl == 0) ? 0 : (sl == 1) ? 2 : 1;
+      if (f == 2 && last) continue;
+#else
     for (int f = (warm && !light) ? 1 : 0; f < 3; f++) {
       if (f == 2 && last) break;
+#endif
       Cons Fnew;
       cons_zero<EQ>(Fnew);
       double Ftr[NTRA];
