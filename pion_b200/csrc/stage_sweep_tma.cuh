@@ -453,22 +453,24 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     // x, y, z -- the publish moves to the middle slot: one solve of slack between publish and consume, and one between
     // "slab read by everybody" and its overwrite (instead of none and two).  MEASURED (r02x, parity green): 18.00 vs 17.86 ms
     // per 512^3 GLM-HLLD stage, Wind3D 14.94 vs 14.74 ms per step -- the waits at the slab barriers are not what bounds the kernel.
+    // Euler: three COPIES of the (small) solver with f a compile-time constant in each -- no loop-carried register moves, no
+    // runtime dispatch on the face: +5 % on the 256^3 blast wave, +1.3 % on Wind3D (r02z).  For MHD / GLM the unrolled form
+    // does not fit the instruction cache (52-61 KB of code with ONE copy of HLLD; the unrolled trial of round 1 stalled on
+    // instruction fetch), so there it stays a real loop.
+    constexpr bool UNROLL_FACES = (EQ == EQ_EULER);
 #if defined(PION_TMA_YMID)
 #pragma unroll 1
     for (int sl = (warm && !light) ? 1 : 0; sl < 3; sl++) {
       const int f = (sl == 0) ? 0 : (sl == 1) ? 2 : 1;
       if (f == 2 && last) continue;
-#elif defined(PION_TMA_UNROLL_EULER)
-    // Euler: three COPIES of the (small) solver, f a compile-time constant in each: no loop-carried register moves, no
-    // runtime dispatch on the face (for MHD / GLM the unrolled form does not fit the instruction cache, see the header)
-#pragma unroll(EQ == EQ_EULER ? 3 : 1)
-    for (int f = 0; f < 3; f++) {
-      if (f == 0 && warm && !light) continue;
-      if (f == 2 && last) continue;
 #else
-#pragma unroll 1
-    for (int f = (warm && !light) ? 1 : 0; f < 3; f++) {
-      if (f == 2 && last) break;
+#pragma unroll(UNROLL_FACES ? 3 : 1)
+    for (int f = UNROLL_FACES ? 0 : ((warm && !light) ? 1 : 0); f < 3; f++) {
+      if (UNROLL_FACES && f == 0 && warm && !light) continue;
+      if (f == 2 && last) {
+        if (UNROLL_FACES) continue;
+        else break;
+      }
 #endif
       Cons Fnew;
       cons_zero<EQ>(Fnew);
