@@ -1205,37 +1205,34 @@ static void euler_inviscid_flux(pion_oracle *s, const double *Pl, const double *
 /* eqns_mhd_ideal::SetAvgState (eqns_mhd_adiabatic.cpp:501-543), called once by the riemann_MHD constructor
  * (riemannMHD.cpp:120) in direction XX: the solver's reference vector is RefVec[RO], RefVec[PG], a tenth of the fast
  * speed of RefVec (rotated so that B lies in the x-z plane) three times, |B(RefVec)| three times */
+/* eqns_mhd_ideal::cfast (eqns_mhd_adiabatic.cpp:246-257) of an unrotated 8-vector */
+static double rs_mhd_cfast_nat(const double *rv, double g) {
+  const double ch = sqrt(g * rv[PG] / rv[RO]);
+  double t1 = ch * ch + (rv[BX] * rv[BX] + rv[BY] * rv[BY] + rv[BZ] * rv[BZ]) / rv[RO];
+  double t2 = 4. * ch * ch * rv[BX] * rv[BX] / rv[RO];
+  t2 = fmax(MACHINEACCURACY, t1 * t1 - t2);
+  return sqrt((t1 + sqrt(t2)) / 2.);
+}
+/* eqns_mhd_ideal::rotateXY (:423-437) */
+static void rs_mhd_rotateXY(double *rv, double th) {
+  const double ct = cos(th), st = sin(th);
+  double vx = rv[VX] * ct - rv[VY] * st, vy = rv[VX] * st + rv[VY] * ct;
+  rv[VX] = vx; rv[VY] = vy;
+  vx = rv[BX] * ct - rv[BY] * st; vy = rv[BX] * st + rv[BY] * ct;
+  rv[BX] = vx; rv[BY] = vy;
+}
 static void rs_mhd_refvec(const pion_oracle *s, double *refvel01, double *refB) {
   double rv[8];
   for (int v = 0; v < 8; v++) rv[v] = s->cfg.refvec[v];
-  const double g = s->gamma;
   double angle = rv[BY] * rv[BY] + rv[BX] * rv[BX], refvel;
-  for (int pass = 0; pass < 1; pass++) {
-    if (angle > 10. * MACHINEACCURACY) {
-      angle = M_PI / 2. - asin(rv[BY] / sqrt(angle));
-      if (rv[BX] < 0) angle = -angle;
-      for (int sgn = 0; sgn < 2; sgn++) { /* rotateXY(angle), cfast, rotateXY(-angle) (:423-437) */
-        const double th = sgn ? -angle : angle;
-        const double ct = cos(th), st = sin(th);
-        double vx = rv[VX] * ct - rv[VY] * st, vy = rv[VX] * st + rv[VY] * ct;
-        rv[VX] = vx; rv[VY] = vy;
-        vx = rv[BX] * ct - rv[BY] * st; vy = rv[BX] * st + rv[BY] * ct;
-        rv[BX] = vx; rv[BY] = vy;
-        if (!sgn) {
-          const double ch = sqrt(g * rv[PG] / rv[RO]); /* eqns_mhd_ideal::cfast (:246-257) */
-          double t1 = ch * ch + (rv[BX] * rv[BX] + rv[BY] * rv[BY] + rv[BZ] * rv[BZ]) / rv[RO];
-          double t2 = 4. * ch * ch * rv[BX] * rv[BX] / rv[RO];
-          t2 = fmax(MACHINEACCURACY, t1 * t1 - t2);
-          refvel = sqrt((t1 + sqrt(t2)) / 2.);
-        }
-      }
-    } else { /* maxspeed == cfast (eqns_mhd_adiabatic.h:120-123) */
-      const double ch = sqrt(g * rv[PG] / rv[RO]);
-      double t1 = ch * ch + (rv[BX] * rv[BX] + rv[BY] * rv[BY] + rv[BZ] * rv[BZ]) / rv[RO];
-      double t2 = 4. * ch * ch * rv[BX] * rv[BX] / rv[RO];
-      t2 = fmax(MACHINEACCURACY, t1 * t1 - t2);
-      refvel = sqrt((t1 + sqrt(t2)) / 2.);
-    }
+  if (angle > 10. * MACHINEACCURACY) {
+    angle = M_PI / 2. - asin(rv[BY] / sqrt(angle));
+    if (rv[BX] < 0) angle = -angle;
+    rs_mhd_rotateXY(rv, angle);
+    refvel = rs_mhd_cfast_nat(rv, s->gamma);
+    rs_mhd_rotateXY(rv, -angle);
+  } else {
+    refvel = rs_mhd_cfast_nat(rv, s->gamma); /* maxspeed == cfast (eqns_mhd_adiabatic.h:120-123) */
   }
   *refB = sqrt(rv[BX] * rv[BX] + rv[BY] * rv[BY] + rv[BZ] * rv[BZ]);
   *refvel01 = 0.1 * refvel;
