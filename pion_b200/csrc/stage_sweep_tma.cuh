@@ -108,6 +108,21 @@ __device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* map
       : "memory");
 }
 
+// -DPION_RACE_STRESS: pseudo-random per-warp delays at the points where warps hand data to each other (slab publish /
+// release, x-edge publish, plane refill), so that the parity suite runs under timings the normal build never produces.
+// An ordering bug then shows as a parity failure (the tracer-slab read after release of r02t was found that way, by accident,
+// on the slower strict build).  Compiled out by default.
+#ifdef PION_RACE_STRESS
+__device__ __forceinline__ void stress_delay(unsigned tag) {
+  unsigned h = ((threadIdx.x >> 5) + 1u) * 2654435761u ^ (blockIdx.x * 40503u) ^ (tag * 0x9E3779B9u) ^ (unsigned)clock();
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+  h = __shfl_sync(0xffffffffu, h, 0);  // one decision per warp
+  if ((h & 3u) == 0) __nanosleep(100u + (h >> 8) % 4000u);
+}
+#else
+__device__ __forceinline__ void stress_delay(unsigned) {}
+#endif
+
 // one flag byte, issued HERE (volatile: the compiler may not sink it to its first use, a whole plane later)
 __device__ __forceinline__ unsigned ldg_u8_now(const unsigned char* p) {
   unsigned v;
@@ -508,6 +523,7 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       Cons D;
       if (f == 0) {
         if (light) {  // publish the x-edge fluxes of plane k+1 (covered by this iteration's arrive on s_bar)
+          stress_delay(6);
           if (lane < TY - 1 && !last) {
             // three buffers: this store runs ahead of the wait below, i.e. possibly while slower warps
             // still read the x-edge fluxes of plane k
@@ -521,8 +537,10 @@ __global__ void __launch_bounds__(32 * TY, MINB)
           if (warm) continue;
         }
         // the previous iteration published this plane's y fluxes and x-edge fluxes
+        stress_delay(1);
         mbar_wait_spin(&s_bar, phase);
         phase ^= 1u;
+        stress_delay(2);
         Cons Fh = cons_shfl_down<EQ>(Fnew);
         double Fhtr[NTRA];
 #pragma unroll
@@ -561,6 +579,7 @@ __global__ void __launch_bounds__(32 * TY, MINB)
           Fhytr[q] = sbuf[(NB + q) * CS + rn * 32 + lane];
         }
         mbar_arrive(&s_free);
+        stress_delay(3);
         cons_diff(D, Fl, Fhy);
         acc_sources<EQ, VS, 1>(acc, C, uB, p0 - CW, p0 + CW, dt, idx, hdtdx);
         acc_flux_diff<EQ, 1>(acc, D, dt, idx, dtdx);
@@ -588,6 +607,7 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         // warp to get here refills that buffer with plane k+3 (needed by the next iteration's z flux), so
         // nobody spins on an "empty" barrier.  A warp cannot be a whole iteration ahead (s_bar), so the
         // running count identifies the iteration.
+        stress_delay(5);
         __syncwarp();
         if (lane == 0 && !light) {
           __threadfence_block();
@@ -602,6 +622,7 @@ __global__ void __launch_bounds__(32 * TY, MINB)
         }
       } else {
         double* nbuf = s_flux;  // the slab now takes plane k+1 ...
+        stress_delay(4);
         if (!warm) {            // ... once everybody has read plane k out of it
           mbar_wait_spin(&s_free, fphase);
           fphase ^= 1u;
