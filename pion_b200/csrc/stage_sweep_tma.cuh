@@ -32,6 +32,7 @@
 // the TMA unit; those values only reach threads whose results are discarded.
 #pragma once
 #include <cuda.h>
+#include <cstdint>
 #include <cstdlib>
 #include "stage_sweep.cuh"
 
@@ -66,6 +67,19 @@ __host__ __device__ constexpr size_t tma_smem_bytes(int nv, int ty, int ring) {
 }
 // shared memory one block may use so that `minb` blocks fit an SM (228 KB per SM, 1 KB reserved per block, 384 B static)
 __host__ __device__ constexpr size_t tma_smem_budget(int minb) { return (size_t)(228 * 1024) / minb - 1024 - 512; }
+// The corrector reads the cell's BASE state P (not the stencil state Ph) for cell_advance_time: nine / six global loads whose
+// latency shows as long-scoreboard stalls (Euler corrector: 1.8 warps per issue, `profiles/r02A_wind384_*`; next to >= 203 KB of
+// shared memory only 28 KB of L1 remain, so prefetch.global.L1 did not help).  Where the shared memory has room (Euler with
+// at most one tracer; MHD / GLM tiles fill it), every thread copies its own cell's base state into a THREAD-PRIVATE slot with
+// cp.async at the top of the iteration and reads it back three solves later: no registers held, no barrier needed.
+__host__ __device__ constexpr bool tma_pb_stage(int eq, int order, int nv, int ty) {
+#ifdef PION_NO_PB_STAGE
+  return false;
+#else
+  return eq == EQ_EULER && order == 2 &&
+         tma_smem_bytes(nv, ty, 4) + 128 + (size_t)nv * (ty - 1) * 32 * sizeof(double) <= tma_smem_budget(sweep_minb(eq));
+#endif
+}
 // tracer counts the TMA kernel is instantiated for (tracers ride along as extra tile variables)
 constexpr int TMA_MAXTR = 2;
 // Tile rows for an equation set, stage order and tracer count: the equation set's row count (sweep_ty, or PION_TMA_TY1 for
@@ -99,6 +113,10 @@ __device__ __forceinline__ void mbar_wait_spin(unsigned long long* bar, unsigned
     if (!ok) __nanosleep(PION_SPIN_SLEEP);
 #endif
   } while (!ok);
+}
+// 8-byte asynchronous copy global -> shared (LDGSTS), completion by cp.async.wait_all of the issuing thread
+__device__ __forceinline__ void cp_async_f64(double* dst_smem, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* map, unsigned long long* bar, int x, int y, int z) {
   asm volatile(
@@ -313,6 +331,9 @@ __global__ void __launch_bounds__(32 * TY, MINB)
   __shared__ unsigned long long s_bar;       // y-flux slab + x-edge fluxes published (all threads arrive)
   __shared__ unsigned long long s_free;      // y-flux slab read by everybody (the slab is single-buffered)
   double* const s_fz = s_flux + SLAB;        // [NV][TY][32] thread-private: the z flux carried to the next plane
+  constexpr bool PBS = tma_pb_stage(EQ, ORDER, NV, TY);
+  // [NV][TY-1][32] thread-private: the cell's base state, staged by cp.async (128-byte aligned behind the x-edge slabs)
+  double* const s_pb = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_xedge + 3 * XSLAB) + 127) & ~(uintptr_t)127);
   __shared__ unsigned long long s_full[RING];   // plane buffer filled (TMA transaction bytes)
   __shared__ unsigned s_done;                // consumer warps that have finished reading plane k-1 (running count)
 
@@ -446,6 +467,12 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     if (a.mask && !warm && !last) n_m = ldg_u8_now(mp + g.sz);
     const bool domain = upd_xy && !warm && (m_k != 0);
     if (!warm && a.mp_dE && upd_xy) acc.erg = a.mp_dE[c];  // cooling source term (energy only)
+    const bool pb_staged = PBS && !pb_is_s;
+    if (pb_staged && domain) {
+#pragma unroll
+      for (int v = 0; v < NV; v++) cp_async_f64(s_pb + (v * (TY - 1) + row) * 32 + lane, a.Pb + (long)v * vs + c);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 #ifdef PION_PB_PREFETCH
     // corrector: the base state P of this cell is read from HBM at the END of the iteration (cell_advance_time),
     // three Riemann solves from here; ask for its lines now so that those loads hit L1 (ncu: long-scoreboard
@@ -645,8 +672,15 @@ __global__ void __launch_bounds__(32 * TY, MINB)
       Cons accx;  // grid frame == solver frame of x
       accx.rho = acc.rho; accx.erg = acc.erg; accx.mn = acc.m0; accx.mt1 = acc.m1; accx.mt2 = acc.m2;
       accx.bbn = acc.b0; accx.bbt1 = acc.b1; accx.bbt2 = acc.b2; accx.psi = acc.psi;
-      if (pb_is_s) status |= cell_advance_time_pb<EQ>(a, c, lds_prim<EQ, VS>(p0, 0, 1, 2), accx, acctr, NTR, my_dt, p0 + NB * VS, VS);
-      else status |= cell_advance_time<EQ>(a, c, accx, acctr, NTR, my_dt);
+      if (pb_is_s) {
+        status |= cell_advance_time_pb<EQ>(a, c, lds_prim<EQ, VS>(p0, 0, 1, 2), accx, acctr, NTR, my_dt, p0 + NB * VS, VS);
+      } else if (pb_staged) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        const double* q = s_pb + row * 32 + lane;  // own slot: variable v at q[v (TY-1) 32]
+        status |= cell_advance_time_pb<EQ>(a, c, lds_prim<EQ, (TY - 1) * 32>(q, 0, 1, 2), accx, acctr, NTR, my_dt, q + NB * (TY - 1) * 32, (TY - 1) * 32);
+      } else {
+        status |= cell_advance_time<EQ>(a, c, accx, acctr, NTR, my_dt);
+      }
     } else if (upd_xy && a.out != a.S) {
       // cell cut out of the domain (time_integrator.cpp:905-908): state untouched
       for (int v = 0; v < NV; v++) a.out[(long)v * vs + c] = a.S[(long)v * vs + c];
@@ -688,7 +722,7 @@ inline const char* launch_sweep_tma_o(const StageArgs& a, cudaStream_t s) {
     while (kchunk > 8 && (long)bx * by * ((NZ + kchunk - 1) / kchunk) < 148L * 4) kchunk >>= 1;
     grid = dim3(bx, by, (NZ + kchunk - 1) / kchunk);
   }
-  constexpr size_t smem = tma_smem_bytes(NV, TY, RING);
+  constexpr size_t smem = tma_smem_bytes(NV, TY, RING) + (tma_pb_stage(EQ, ORDER, NV, TY) ? 128 + (size_t)NV * (TY - 1) * 32 * sizeof(double) : 0);
   // the opt-in is per DEVICE: one flag per ordinal (a process may hold contexts on several GPUs)
   static bool attr_done[PION_MAX_DEVICES] = {false};
   const int dev = current_device_slot();
