@@ -33,6 +33,20 @@ CASES = {
     "euler_roepv_fkj_2d_outflow": (case_2d("euler", 5, 1, bcs="outflow"), 4),
 }
 
+# round 2: Lax-Friedrichs (0), the Euler linear / exact / hybrid Riemann solvers (1-3), the MHD linear Riemann solver (1),
+# and two tracers on 3-D multi-tile grids (extra tile variables of the TMA sweep kernel)
+CASES.update({
+    "euler_lf_2d_outflow": (case_2d("euler", 0, 1, bcs="outflow"), 4),
+    "imhd_lf_3d_mixed": (case_3d("i-mhd", 0, 0, bcs="mixed1", NG=(10, 8, 6)), 4),
+    "euler_rslinear_fkj_2d_outflow": (case_2d("euler", 1, 1, bcs="outflow"), 4),
+    "euler_rsexact_3d_tracer": (case_3d("euler", 2, 0, bcs="reflect-outflow", ntracer=1, NG=(10, 8, 6)), 3),
+    "euler_rshybrid_fkj_2d_reflect": (case_2d("euler", 3, 1, bcs="reflect-outflow"), 4),
+    "imhd_rslinear_fkj_3d_mixed": (case_3d("i-mhd", 1, 1, bcs="mixed1", NG=(10, 8, 6)), 4),
+    "glm_rslinear_2d_outflow": (case_2d("glm-mhd", 1, 0, bcs="outflow"), 4),
+    "glm_hlld_fkj_3d_two_tracers_tiles": (case_3d("glm-mhd", 7, 1, bcs="mixed1", ntracer=2, NG=(36, 14, 10)), 3),
+    "euler_hll_fkj_3d_two_tracers_tiles": (case_3d("euler", 8, 1, bcs="reflect-outflow", ntracer=2, NG=(36, 14, 10)), 3),
+})
+
 # x100 pressure ellipsoid (harness.hot_sphere_state): thousands of cells trip the HLLD -> HLL switch, next to
 # reflecting walls where the ideal-MHD HLLD contact speed is an exact zero; the second case spans 2 x 2 tiles and
 # 2 z chunks of the TMA sweep kernel
