@@ -56,6 +56,47 @@ def test_config_validation_matches_reference_errors():
     assert b"Bad OOA requests" in lib.pion_gpu_last_error()  # time_integrator.cpp:130
 
 
+def test_every_supported_equation_solver_pair_passes_the_configuration_check():
+    """check_config runs before the device is touched, so it can be exercised here: every (equation set, solverType,
+    artviscosity) the parity suite uses must get PAST it (on this GPU-less host that means the next error, "no CUDA device"),
+    and what the reference rejects must be rejected with a message (solver_eqn_mhd_adi.cpp:132-198, riemannMHD.cpp:176-183,
+    mp_only_cooling.cpp:418)."""
+    import dataclasses
+    import torch
+    from cases import AVS, EQ_SOLVERS, case_2d, case_cooling
+    from harness import gpu_config, load_cooling_tables
+    from pion_b200.capi import load_library
+    lib = load_library()
+
+    def create_error(prob, tables=None):
+        cfg, keep = gpu_config(prob, tables=tables)
+        h = lib.pion_gpu_create(ctypes.byref(cfg))
+        if h:
+            lib.pion_gpu_destroy(h)
+            return b""
+        return lib.pion_gpu_last_error()
+
+    have_gpu = torch.cuda.is_available()
+    for eqn, solver in EQ_SOLVERS:
+        for av in AVS:
+            err = create_error(case_2d(eqn, solver, av))
+            assert err == (b"" if have_gpu else err) and (have_gpu or b"no CUDA device" in err), (eqn, solver, av, err)
+    for flag in (2, 4, 5, 6, 7, 8):
+        prob = dataclasses.replace(case_cooling("euler", 8), cooling=flag)
+        from harness import tables_for
+        err = create_error(prob, tables=tables_for(prob))
+        assert have_gpu or b"no CUDA device" in err, (flag, err)
+    # rejected like the reference
+    for eqn, solver, word in (("i-mhd", 2, b"Euler equations only"), ("glm-mhd", 3, b"Euler equations only"), ("i-mhd", 5, b"Euler equations only"),
+                              ("glm-mhd", 6, b"Euler equations only"), ("euler", 7, b"HLLD needs MHD"), ("euler", 9, b"solver must be")):
+        err = create_error(case_2d(eqn, solver, 0))
+        assert word in err, (eqn, solver, err)
+    err = create_error(dataclasses.replace(case_cooling("euler", 8), cooling=3), tables=load_cooling_tables())
+    assert b"cooling flag" in err, err
+    err = create_error(case_2d("euler", 8, 2))
+    assert b"artviscosity" in err, err
+
+
 def test_decompose_domain_matches_mcmd():
     """MCMDcontrol::decomposeDomain: 8 ranks on a cube -> 2x2x2, rank = nx*ny*iz + nx*iy + ix."""
     from harness import Problem, gpu_config
