@@ -1,7 +1,7 @@
 #!/bin/bash
 # Developer script: round-2 record of one build = full GPU suite, smoke(), default bench line (e2e + CPU baseline +
 # parity), reference arm, ncu launch list, full ncu capture of the stage kernel (predictor + corrector) and of the
-# cooling kernel of the Wind3D-style configuration, per-config throughput.  usage: tools/gpu_r02n.sh <tag>
+# cooling kernel of the Wind3D-style configuration, per-config throughput.  usage: tools/gpu_record_all.sh <tag>
 TAG=${1:-r02n}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Developer script: parity of a variant library on the 3-D cases, then A/B against the default build.  usage: gpu_r02x.sh <tag> <variant>
+# Developer script: parity of a variant library on the 3-D cases, then A/B against the default build.  usage: tools/gpu_variant_ab.sh <tag> <variant>
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T=${1:-r02x}; V=${2:-ymid}
