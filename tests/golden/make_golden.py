@@ -88,6 +88,29 @@ TEST_PROBLEMS = {
                                               "BW_interface": 1.0e50, "BW_amb2_RO": 0.0, "BW_amb2_PG": 0.0, "BW_amb2_VX": 0.0,
                                               "BW_amb2_VY": 0.0, "BW_amb2_VZ": 0.0, "InitIons": "LEAVE"}), 12),
 }
+
+
+# The reference's shock-tube known-answer INPUTS (ics/shock_tube.cpp:473-810): Toro's tests 1-5 (Euler), Brio & Wu, Falle's fast /
+# slow shocks and Ryu & Jones 1a (ideal MHD), 1-D, 128 cells, 40 steps, states written by the reference's own IC class
+def _shock_tube(num, eqn, solver, gamma, av=1):
+    return Problem(ndim=1, NG=(128, 1, 1), eqn=eqn, solver=solver, artviscosity=av, etav=0.1, gamma=gamma, cfl=0.4, xmax=(1.0, 1.0, 1.0),
+                   bcs=("outflow", "outflow") + ("periodic",) * 4, ics="ShockTube",
+                   extra={"STnumber": num, "STshockpos": 0.5, "STangleXY": 0, "STangleXZ": 0})
+
+
+SHOCK_TUBES = {
+    "st_toro1_euler_hll": (_shock_tube(1, "euler", 8, 1.4), 40),
+    "st_toro2_euler_exact": (_shock_tube(2, "euler", 2, 1.4, av=0), 40),
+    "st_toro3_euler_roe": (_shock_tube(3, "euler", 4, 1.4), 40),
+    "st_toro4_euler_hybrid": (_shock_tube(4, "euler", 3, 1.4), 40),
+    "st_toro5_euler_fvs": (_shock_tube(5, "euler", 6, 1.4), 40),
+    "st_briowu_imhd_hlld": (_shock_tube(7, "i-mhd", 7, 2.0), 40),
+    "st_briowu_imhd_linear": (_shock_tube(7, "i-mhd", 1, 2.0), 40),
+    "st_falle_fs_imhd_roe": (_shock_tube(9, "i-mhd", 4, 5.0 / 3.0), 40),
+    "st_falle_ss_imhd_hll": (_shock_tube(10, "i-mhd", 8, 5.0 / 3.0), 40),
+    "st_ryujones1a_imhd_hlld": (_shock_tube(15, "i-mhd", 7, 5.0 / 3.0, av=0), 40),
+}
+TEST_PROBLEMS.update(SHOCK_TUBES)
 CASES.update(TEST_PROBLEMS)
 
 # Per-cell cooling source term (mp_only_cooling, EP_cooling 8) on cgs states; `dense` puts the
