@@ -110,6 +110,20 @@ SHOCK_TUBES = {
     "st_falle_ss_imhd_hll": (_shock_tube(10, "i-mhd", 8, 5.0 / 3.0), 40),
     "st_ryujones1a_imhd_hlld": (_shock_tube(15, "i-mhd", 7, 5.0 / 3.0, av=0), 40),
 }
+# more of the reference's own test problems (ics/basic_tests.cpp): Liska & Wendroff implosion (test_problems/LiskaWendroffImplosion,
+# reflecting walls), Orszag-Tang vortex (:680-735) and Stone's Kelvin-Helmholtz set-up (:814-870; the IC class forces gamma = 1.4
+# and seeds its noise with srand(975)), at 48 x 48
+MORE_TEST_PROBLEMS = {
+    "tp_LWI_n048_roe": (Problem(ndim=2, NG=(48, 48, 1), eqn="euler", solver=4, artviscosity=0, etav=0.15, gamma=1.4, cfl=0.3,
+                                xmax=(0.3, 0.3, 1.0), bcs=("reflecting",) * 4 + ("periodic",) * 2, ics="LiskaWendroffImplosion"), 20),
+    "tp_OrszagTang_n048_glm_hlld": (Problem(ndim=2, NG=(48, 48, 1), eqn="glm-mhd", solver=7, artviscosity=1, etav=0.1, gamma=5.0 / 3.0, cfl=0.4,
+                                            xmax=(1.0, 1.0, 1.0), ics="OrszagTang", extra={"OTVbeta": 3.333333333, "OTVmach": 1.0}), 20),
+    "tp_KHStone_n048_euler_hll": (Problem(ndim=2, NG=(48, 48, 1), eqn="euler", solver=8, artviscosity=1, etav=0.1, gamma=1.4, cfl=0.4,
+                                          xmin=(-0.5, -0.5, 0.0), xmax=(0.5, 0.5, 1.0), ics="KelvinHelmholzStone"), 20),
+    "tp_KHStone_n048_imhd_hlld": (Problem(ndim=2, NG=(48, 48, 1), eqn="i-mhd", solver=7, artviscosity=1, etav=0.1, gamma=1.4, cfl=0.4,
+                                          xmin=(-0.5, -0.5, 0.0), xmax=(0.5, 0.5, 1.0), ics="KelvinHelmholzStone"), 20),
+}
+TEST_PROBLEMS.update(MORE_TEST_PROBLEMS)
 TEST_PROBLEMS.update(SHOCK_TUBES)
 CASES.update(TEST_PROBLEMS)
 
