@@ -128,6 +128,47 @@ def test_mhd_linear_riemann_solver_degenerate_branches_bit_exact(eqn, kind):
     run_pair(case_2d(eqn, 1, 1, bcs="outflow"), nsteps=3, state=_mhd_linear_state(kind))
 
 
+def _stone_mhd_blastwave(bfield, eqn, solver):
+    """test_problems/MHD_Blastwave2D/params_MHD_blastwave2D_UG_B*_n256.txt at 32 x 48 (Stone's MHD blast wave, periodic)."""
+    from harness import Problem
+    return Problem(ndim=2, NG=(32, 48, 1), eqn=eqn, solver=solver, artviscosity=1, etav=0.1, gamma=1.6666666666666666666667, cfl=0.3,
+                   xmin=(-0.5, -0.75, 0.0), xmax=(0.5, 0.75, 1.0), ics="BlastWave",
+                   extra={"BWradius": 0.1, "BWpressure": 0.1, "BWdensity": 1.0, "BWmagfieldX": bfield, "BWmagfieldY": bfield, "BWmagfieldZ": 0.0,
+                          "BW_energy": 0.471238898038, "BW_nzones": 3.2, "BW_blast_dens": 1.0, "BW_interface": 1.0e50, "BW_amb2_RO": 0.0,
+                          "BW_amb2_PG": 0.0, "BW_amb2_VX": 0.0, "BW_amb2_VY": 0.0, "BW_amb2_VZ": 0.0, "InitIons": "LEAVE"})
+
+
+@pytest.mark.parametrize("bfield", [0.25066282746310002, 2.5066282746310002, 25.066282746310002])
+@pytest.mark.parametrize("eqn,solver", [("glm-mhd", 7), ("i-mhd", 4), ("glm-mhd", 1)])
+def test_reference_mhd_blastwave_problem_bit_exact(bfield, eqn, solver):
+    """The reference's MHD blast wave (plasma beta from 1.6 down to 1.6e-4) from its own IC class: 15 steps, oracle == reference."""
+    prob = _stone_mhd_blastwave(bfield, eqn, solver)
+    r = RefSim(prob, run_ics=True)
+    P0 = r.get_state(0)
+    r.close()
+    assert np.max(np.abs(P0[5])) > 0.0
+    run_pair(prob, nsteps=15, state=lambda p: P0)
+
+
+@pytest.mark.parametrize("solver,av", [(4, 1), (8, 1), (4, 4), (6, 1)])
+def test_reference_oblique_shock_problem_bit_exact(solver, av):
+    """test_problems/ObliqueShock/params_oblique_shock_M25.txt at 50 x 25: a Mach-25 shock at 2 degrees to the grid from the
+    reference's ShockTube IC class (custom pre / post-shock states, cgs units), outflow + FIXED boundaries."""
+    from harness import Problem
+    prob = Problem(ndim=2, NG=(50, 25, 1), eqn="euler", solver=solver, artviscosity=av, etav=0.15, gamma=1.666666666666666666, cfl=0.4,
+                   xmax=(1.0e17, 0.5e17, 1.0), bcs=("outflow", "fixed", "outflow", "outflow", "periodic", "periodic"), ics="ShockTube",
+                   refvec=(1.0e-22, 1.0e-12, 1.0e6, 1.0e6, 1.0e6) + (1.0,) * 11,
+                   extra={"STnumber": -7, "STangleXY": 2.0, "STangleXZ": 0.0, "STshockpos": 4.0e16,
+                          "STpostvecRO": 3.9808917197e-22, "STpostvecPG": 7.8100000000e-10, "STpostvecVX": -8.2074451397e05,
+                          "STpostvecVY": 0.0, "STpostvecVZ": 0.0, "STprevecRO": 1.0e-22, "STprevecPG": 1.0e-12,
+                          "STprevecVX": -3.237486122e6, "STprevecVY": 0.0, "STprevecVZ": 0.0})
+    r = RefSim(prob, run_ics=True)
+    P0 = r.get_state(0)
+    r.close()
+    assert P0[0].max() > 3.0e-22 and P0[0].min() < 1.1e-22
+    run_pair(prob, nsteps=15, state=lambda p: P0)
+
+
 @pytest.mark.parametrize("eqn,solver,av", [("euler", 8, 1), ("glm-mhd", 7, 1), ("i-mhd", 4, 0)])
 def test_two_tracers_bit_exact(eqn, solver, av):
     run_pair(case_3d(eqn, solver, av, bcs="mixed1", ntracer=2, NG=(12, 10, 8)))
