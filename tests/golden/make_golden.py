@@ -123,6 +123,24 @@ MORE_TEST_PROBLEMS = {
     "tp_KHStone_n048_imhd_hlld": (Problem(ndim=2, NG=(48, 48, 1), eqn="i-mhd", solver=7, artviscosity=1, etav=0.1, gamma=1.4, cfl=0.4,
                                           xmin=(-0.5, -0.5, 0.0), xmax=(0.5, 0.5, 1.0), ics="KelvinHelmholzStone"), 20),
 }
+# the reference's curvilinear blast waves: test_problems/blastwave_axi2d/params_axi2dBW_HalfPlane_NR016.txt (cylindrical (z,R),
+# Roe-CV) and test_problems/blastwave_sph1d/params_sphBW_n128.txt (1-D spherical, the shipped HYBRID Riemann solver, and HLL)
+_BW = {"BWpressure": 1.38e-11, "BWdensity": 2.34e-22, "BWmagfieldX": 0.0, "BWmagfieldY": 0.0, "BWmagfieldZ": 0.0, "BW_energy": 1.0e51,
+       "BW_nzones": 2, "BW_blast_dens": 2.34e-22, "BW_interface": 1.0e50, "BW_amb2_RO": 0.0, "BW_amb2_PG": 0.0, "BW_amb2_VX": 0.0,
+       "BW_amb2_VY": 0.0, "BW_amb2_VZ": 0.0, "InitIons": "LEAVE"}
+_BWREF = (2.34e-22, 1.38e-11, 1e6, 1e6, 1e6) + (1.0,) * 11
+MORE_TEST_PROBLEMS.update({
+    "tp_BWaxi2D_halfplane_n016_roe": (Problem(ndim=2, NG=(32, 16, 1), eqn="euler", solver=4, artviscosity=1, etav=0.1, gamma=1.666666666666666666666,
+                                              cfl=0.3, coords="cylindrical", xmin=(-30.86e18, 0.0, 0.0), xmax=(30.86e18, 30.86e18, 1.0),
+                                              bcs=("outflow", "outflow", "reflecting", "outflow", "periodic", "periodic"), ics="BlastWave",
+                                              extra=_BW, refvec=_BWREF), 20),
+    "tp_BWsph1D_n128_hybrid": (Problem(ndim=1, NG=(128, 1, 1), eqn="euler", solver=3, artviscosity=1, etav=0.1, gamma=1.666666666666666666666, cfl=0.3,
+                                       coords="spherical", xmin=(0.0, 0.0, 0.0), xmax=(30.86e18, 1.0, 1.0),
+                                       bcs=("reflecting", "outflow") + ("periodic",) * 4, ics="BlastWave", extra=_BW, refvec=_BWREF), 20),
+    "tp_BWsph1D_n128_hll": (Problem(ndim=1, NG=(128, 1, 1), eqn="euler", solver=8, artviscosity=1, etav=0.1, gamma=1.666666666666666666666, cfl=0.3,
+                                    coords="spherical", xmin=(0.0, 0.0, 0.0), xmax=(30.86e18, 1.0, 1.0),
+                                    bcs=("reflecting", "outflow") + ("periodic",) * 4, ics="BlastWave", extra=_BW, refvec=_BWREF), 20),
+})
 TEST_PROBLEMS.update(MORE_TEST_PROBLEMS)
 TEST_PROBLEMS.update(SHOCK_TUBES)
 CASES.update(TEST_PROBLEMS)
