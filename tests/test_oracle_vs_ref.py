@@ -150,6 +150,25 @@ def test_reference_mhd_blastwave_problem_bit_exact(bfield, eqn, solver):
     run_pair(prob, nsteps=15, state=lambda p: P0)
 
 
+@pytest.mark.parametrize("eqn,solver,av", [("glm-mhd", 4, 1), ("glm-mhd", 7, 1), ("i-mhd", 8, 1), ("glm-mhd", 4, 4)])
+def test_reference_mhd_axisymmetric_blastwave_problem_bit_exact(eqn, solver, av):
+    """test_problems/blastwave_axi2d/params_MHDaxi2dBW_HalfPlane_NR128.txt at 32 x 16 cells: cylindrical (z, R), axial field with
+    plasma beta 1, reflecting axis -- the geometric source terms and area-weighted divergence of the MHD equations."""
+    from harness import Problem
+    prob = Problem(ndim=2, NG=(32, 16, 1), eqn=eqn, solver=solver, artviscosity=av, etav=0.15, gamma=1.666666666666666666666, cfl=0.2,
+                   coords="cylindrical", xmin=(-30.86e18, 0.0, 0.0), xmax=(30.86e18, 30.86e18, 1.0),
+                   bcs=("outflow", "outflow", "reflecting", "outflow", "periodic", "periodic"), ics="BlastWave",
+                   refvec=(2.34e-22, 1.38e-11, 1e6, 1e6, 1e6, 5e-6, 5e-6, 5e-6, 5e-6) + (1.0,) * 7,
+                   extra={"BWpressure": 1.38e-11, "BWdensity": 2.34e-22, "BWmagfieldX": 5.25357e-06, "BWmagfieldY": 0.0, "BWmagfieldZ": 0.0,
+                          "BW_energy": 1.0e51, "BW_nzones": 2, "BW_blast_dens": 2.34e-22, "BW_interface": 1.0e50, "BW_amb2_RO": 0.0,
+                          "BW_amb2_PG": 0.0, "BW_amb2_VX": 0.0, "BW_amb2_VY": 0.0, "BW_amb2_VZ": 0.0, "InitIons": "LEAVE"})
+    r = RefSim(prob, run_ics=True)
+    P0 = r.get_state(0)
+    r.close()
+    assert np.max(np.abs(P0[5])) > 0.0
+    run_pair(prob, nsteps=15, state=lambda p: P0)
+
+
 @pytest.mark.parametrize("solver,av", [(4, 1), (8, 1), (4, 4), (6, 1)])
 def test_reference_oblique_shock_problem_bit_exact(solver, av):
     """test_problems/ObliqueShock/params_oblique_shock_M25.txt at 50 x 25: a Mach-25 shock at 2 degrees to the grid from the
