@@ -193,6 +193,26 @@ def test_two_tracers_bit_exact(eqn, solver, av):
     run_pair(case_3d(eqn, solver, av, bcs="mixed1", ntracer=2, NG=(12, 10, 8)))
 
 
+@pytest.mark.parametrize("eqn,solver", [("euler", 8), ("euler", 4), ("i-mhd", 7), ("i-mhd", 4)])
+def test_negative_pressure_floor_path_bit_exact(eqn, solver):
+    """Cold, highly supersonic random flow (p ~ 1e-7 rho v^2): the conservative update leaves dozens to hundreds of cells with a
+    negative pressure, which UtoP resets (SET_NEGATIVE_PRESSURE_TO_FIXED_TEMPERATURE, eqns_hydro_adiabatic.cpp:117-205,
+    eqns_mhd_adiabatic.cpp:110-224) -- oracle == reference on that path, and the path is really taken."""
+    def cold(p):
+        P = random_state(p, 3, amp=3.0)
+        P[1] *= 1e-7
+        return P
+    prob = case_2d(eqn, solver, 1, bcs="outflow")
+    run_pair(prob, nsteps=3, state=cold)
+    o = OracleSim(prob)
+    o.set_state(cold(prob))
+    o.init_after_state()
+    o.run(3)
+    counts = o.error_counts()
+    o.close()
+    assert counts[0] == 0 and counts[1] > 10, counts
+
+
 def test_1d_and_first_order():
     run_pair(case_1d("i-mhd", 7, 1))
     run_pair(case_1d("euler", 8, 1, bcs=("reflecting", "inflow")))
