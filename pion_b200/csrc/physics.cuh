@@ -1076,12 +1076,20 @@ __device__ __forceinline__ void mhd_HLLD(const Prim& L, const Prim& R, const Phy
 
   flux.rho = K_mn + c2 * (rho_s - K_ro);
   flux.mn = (K_mn * K_vn + K_pg + pm_K - K_bn * K_bn) + c2 * (lam2 * rho_s - K_mn);
-  flux.mt1 = (K_mn * K_vt1 - K_bn * K_bt1) + c2 * (vys * rho_s - K_mt1) + c1 * ((vy_ss - vys) * rho_s);
-  flux.mt2 = (K_mn * K_vt2 - K_bn * K_bt2) + c2 * (vzs * rho_s - K_mt2) + c1 * ((vz_ss - vzs) * rho_s);
-  flux.erg = (K_vn * (K_erg + K_pg + pm_K) - K_bn * vb_own) + c2 * (erg_s - K_erg) + c1 * derg_ss;
+  // The ** jumps are only FORMED in the ** region (c1 != 0): beyond a strong rarefaction the star density of the side that is
+  // NOT used can be negative, its square root -- and with it every ** quantity -- a NaN, and 0 x NaN is not 0.  The reference
+  // never evaluates the ** states outside that region (HLLD_MHD.cpp:292-333).  Found by the negative-pressure-reset probe
+  // (plasma beta 1e-7, tools/floor_probe.py); same arithmetic, bit for bit, wherever every quantity is finite (checked on
+  // 4e5 interfaces with a host build of this header).
+  const bool in_ss = (c1 != 0.0);
+  const double j_vy = in_ss ? (vy_ss - vys) : 0.0, j_vz = in_ss ? (vz_ss - vzs) : 0.0;
+  const double j_by = in_ss ? (by_ss - bys) : 0.0, j_bz = in_ss ? (bz_ss - bzs) : 0.0, j_erg = in_ss ? derg_ss : 0.0;
+  flux.mt1 = (K_mn * K_vt1 - K_bn * K_bt1) + c2 * (vys * rho_s - K_mt1) + c1 * (j_vy * rho_s);
+  flux.mt2 = (K_mn * K_vt2 - K_bn * K_bt2) + c2 * (vzs * rho_s - K_mt2) + c1 * (j_vz * rho_s);
+  flux.erg = (K_vn * (K_erg + K_pg + pm_K) - K_bn * vb_own) + c2 * (erg_s - K_erg) + c1 * j_erg;
   flux.bbn = c2 * (BX - K_bn);
-  flux.bbt1 = (K_vn * K_bt1 - K_vt1 * K_bn) + c2 * (bys - K_bt1) + c1 * (by_ss - bys);
-  flux.bbt2 = (K_vn * K_bt2 - K_vt2 * K_bn) + c2 * (bzs - K_bt2) + c1 * (bz_ss - bzs);
+  flux.bbt1 = (K_vn * K_bt1 - K_vt1 * K_bn) + c2 * (bys - K_bt1) + c1 * j_by;
+  flux.bbt2 = (K_vn * K_bt2 - K_vt2 * K_bn) + c2 * (bzs - K_bt2) + c1 * j_bz;
   flux.psi = 0.0;
 
   if (NEED_PSTAR) {
