@@ -1,0 +1,48 @@
+"""Developer script: the device physics header compiled for the host (see tests/test_device_physics_on_host.py) against the
+oracle over 18 000 extreme interfaces per (equation set, solver, viscosity): counts where the device form is non-finite while the
+oracle is finite, the reverse, both, and the worst relative flux difference.  Round 2 result: the device form is never non-finite
+where the reference is finite (the reverse happens for Roe-PV + FKJ98, as in the reference itself); worst difference 4.8e-12."""
+import sys, ctypes as C, subprocess, shutil, tempfile
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent / 'tests'))
+import numpy as np
+import test_device_physics_on_host as T
+from pathlib import Path
+from harness import OracleSim
+from cases import case_3d
+# build host lib the same way as the fixture
+d = Path(tempfile.mkdtemp())
+fm = (T.CSRC / "fastmath.cuh").read_text().replace("#include <cuda_runtime.h>", '#include "shim.h"').replace('asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));', "r = pion_rcp_approx(x);").replace('asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));', "y = pion_rsqrt_approx(x);")
+ph = (T.CSRC / "physics.cuh").read_text().replace("#include <cuda_runtime.h>", '#include "shim.h"')
+a = ph.index('  asm("{\\n\\t.reg .pred p;'); b = ph.index("__double2hiint(b)));", a) + len("__double2hiint(b)));")
+ph = ph[:a] + "  if ((__double2hiint(a) ^ __double2hiint(b)) >= 0) e = fma(m, h, e);" + ph[b:]
+(d/"fastmath.cuh").write_text(fm); (d/"physics.cuh").write_text(ph)
+for f in ("shim.h","host_flux.cpp"): shutil.copy(T.HERE/f, d/f)
+subprocess.run(["g++","-O1","-std=c++17","-fPIC","-shared","-ffp-contract=fast","-mfma","-I",str(d),str(d/"host_flux.cpp"),"-o",str(d/"l.so")],check=True)
+lib = C.CDLL(str(d/"l.so")); lib.host_intercell_flux.restype = C.c_int
+lib.host_intercell_flux.argtypes = [C.c_int]*3 + [C.c_void_p]*3 + [C.c_int, C.c_double, C.c_int, C.c_void_p]
+flux = np.zeros(9)
+for eqn, solver in T.CASES:
+    for av in (0, 1):
+        prob = case_3d(eqn, solver, av); nphys = {"euler":5,"i-mhd":8,"glm-mhd":9}[eqn]
+        o = OracleSim(prob)
+        if eqn == "glm-mhd": o.set_glm_speeds(prob.cfl*prob.dx/T.CHYP, prob.dx, 0.25/prob.dx)
+        par = np.array([prob.gamma, prob.etav if av else 0.0, T.CHYP if eqn=="glm-mhd" else 0.0, prob.refvec[0]] + T.solver_refvec(prob))
+        rng = np.random.default_rng(7)
+        res = {}
+        for kind in ("cold", "supersonic", "strong"):
+            L, R = T.interfaces(kind, 6000, nphys, rng)
+            hostbad = refbad = both = 0; worst = 0.0
+            for q in range(L.shape[0]):
+                ax = q % 3
+                Fo = np.zeros(9); Fo[:nphys] = o.intercell_flux(ax, L[q,:nphys], R[q,:nphys])[:nphys]
+                l, r = T.frame(L[q], ax), T.frame(R[q], ax)
+                lib.host_intercell_flux(T.EQN[eqn], solver, av, l.ctypes.data, r.ctypes.data, par.ctypes.data, 0, 0.0, ax, flux.ctypes.data)
+                Fh = T.unframe_flux(flux, ax)
+                fo, fh = np.all(np.isfinite(Fo)), np.all(np.isfinite(Fh))
+                if fo and not fh: hostbad += 1
+                elif fh and not fo: refbad += 1
+                elif not fo and not fh: both += 1
+                else: worst = max(worst, np.max(np.abs(Fh-Fo))/max(np.max(np.abs(Fo)),1e-300))
+            res[kind] = (hostbad, refbad, both, "%.1e" % worst)
+        o.close()
+        print(eqn, solver, av, res, flush=True)
