@@ -42,7 +42,7 @@ def hostlib(tmp_path_factory):
     for f in ("shim.h", "host_flux.cpp"):
         shutil.copy(HERE / f, d / f)
     so = d / "libhost_physics.so"
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=fast", "-mfma", "-I", str(d), str(d / "host_flux.cpp"), "-o", str(so)],
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=fast", "-I", str(d), str(d / "host_flux.cpp"), "-o", str(so)],
                    check=True)
     lib = C.CDLL(str(so))
     lib.host_intercell_flux.restype = C.c_int

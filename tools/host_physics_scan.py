@@ -17,7 +17,7 @@ a = ph.index('  asm("{\\n\\t.reg .pred p;'); b = ph.index("__double2hiint(b)));"
 ph = ph[:a] + "  if ((__double2hiint(a) ^ __double2hiint(b)) >= 0) e = fma(m, h, e);" + ph[b:]
 (d/"fastmath.cuh").write_text(fm); (d/"physics.cuh").write_text(ph)
 for f in ("shim.h","host_flux.cpp"): shutil.copy(T.HERE/f, d/f)
-subprocess.run(["g++","-O1","-std=c++17","-fPIC","-shared","-ffp-contract=fast","-mfma","-I",str(d),str(d/"host_flux.cpp"),"-o",str(d/"l.so")],check=True)
+subprocess.run(["g++","-O1","-std=c++17","-fPIC","-shared","-ffp-contract=fast","-I",str(d),str(d/"host_flux.cpp"),"-o",str(d/"l.so")],check=True)
 lib = C.CDLL(str(d/"l.so")); lib.host_intercell_flux.restype = C.c_int
 lib.host_intercell_flux.argtypes = [C.c_int]*3 + [C.c_void_p]*3 + [C.c_int, C.c_double, C.c_int, C.c_void_p]
 flux = np.zeros(9)
